@@ -1,0 +1,220 @@
+"""ctypes access to the CHECKER libraries -- test infrastructure only.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import
+this module; nothing under sopot_b200/ does.
+
+Two interchangeable checkers, same call surface:
+  kind="port"       oracle/libsopot_oracle.so   plain-C restatement (oracle/sopot_oracle.c)
+  kind="reference"  oracle/_ref/libsopot_ref.so the unmodified reference compiled from
+                    /root/reference through oracle/ref_harness.cpp (exists where it was built)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_sz = ctypes.c_size_t
+_d = ctypes.c_double
+_i = ctypes.c_int
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if n is not None and a.ndim == 0:
+        a = np.full(n, float(a))
+    return a
+
+
+def build(force: bool = False) -> None:
+    """(Re)build the checker libraries with oracle/Makefile."""
+    subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []) + ["all"], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def have_reference() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libsopot_ref.so"))
+
+
+class Checker:
+    def __init__(self, kind: str = "port"):
+        self.kind = kind
+        if kind == "port":
+            path, self.pfx = os.path.join(_HERE, "libsopot_oracle.so"), "orc_"
+            if not os.path.exists(path):
+                build()
+        elif kind == "reference":
+            path, self.pfx = os.path.join(_HERE, "_ref", "libsopot_ref.so"), "ref_"
+        else:
+            raise ValueError(kind)
+        self.lib = ctypes.CDLL(path)
+        self.path = path
+
+    def _fn(self, name, argtypes, restype=_i):
+        f = getattr(self.lib, self.pfx + name)
+        f.argtypes, f.restype = argtypes, restype
+        return f
+
+    def hardware_threads(self) -> int:
+        return int(self._fn("hardware_threads", [])())
+
+    # ---------------- config 1 ----------------
+    def ho_rk4(self, m, k, c, x0, v0, t0, t1, dt, store_every=0, n_snap=0, nthreads=1):
+        k = _f64(k); n = k.size
+        m, c, x0, v0 = (_f64(a, n) for a in (m, c, x0, v0))
+        fin = np.empty((2, n)); tl = np.empty(n)
+        traj = np.full((n_snap, 2, n), np.nan) if store_every else None
+        self._fn("ho_rk4", [_sz] + [_dp] * 5 + [_d] * 3 + [_sz, _dp, _dp, _dp, _i])(
+            n, _p(m), _p(k), _p(c), _p(x0), _p(v0), t0, t1, dt, store_every, _p(fin), _p(traj), _p(tl),
+            nthreads)
+        return fin, traj, tl
+
+    # ---------------- config 2 ----------------
+    def dpend_rk4(self, m1, m2, L1, L2, g, th1, th2, w1, w2, t0, t1, dt, store_every=0, n_snap=0,
+                  nthreads=1):
+        th1 = _f64(th1); n = th1.size
+        m1, m2, L1, L2, g, th2, w1, w2 = (_f64(a, n) for a in (m1, m2, L1, L2, g, th2, w1, w2))
+        fin = np.empty((4, n)); tl = np.empty(n)
+        traj = np.full((n_snap, 4, n), np.nan) if store_every else None
+        self._fn("dpend_rk4", [_sz] + [_dp] * 9 + [_d] * 3 + [_sz, _dp, _dp, _dp, _i])(
+            n, _p(m1), _p(m2), _p(L1), _p(L2), _p(g), _p(th1), _p(th2), _p(w1), _p(w2), t0, t1, dt,
+            store_every, _p(fin), _p(traj), _p(tl), nthreads)
+        return fin, traj, tl
+
+    def dpend_rhs(self, m1, m2, L1, L2, g, state):
+        state = _f64(state); n = state.shape[1]
+        m1, m2, L1, L2, g = (_f64(a, n) for a in (m1, m2, L1, L2, g))
+        out = np.empty((4, n))
+        self._fn("dpend_rhs", [_sz] + [_dp] * 7)(n, _p(m1), _p(m2), _p(L1), _p(L2), _p(g), _p(state),
+                                                  _p(out))
+        return out
+
+    # ---------------- config 3 ----------------
+    def cartpole_linearize(self, x, u, mc, m, L, g, nthreads=1):
+        x = _f64(x); P = x.shape[1]
+        u, mc, m, L, g = (_f64(a, P) for a in (u, mc, m, L, g))
+        A = np.empty((16, P)); B = np.empty((4, P))
+        if self.kind == "port":
+            st = np.zeros(P, dtype=np.int32)
+            self._fn("cartpole_linearize", [_sz] + [_dp] * 8 + [_ip, _i])(
+                P, _p(x), _p(u), _p(mc), _p(m), _p(L), _p(g), _p(A), _p(B),
+                st.ctypes.data_as(_ip), nthreads)
+        else:
+            self._fn("cartpole_linearize", [_sz] + [_dp] * 8 + [_i])(
+                P, _p(x), _p(u), _p(mc), _p(m), _p(L), _p(g), _p(A), _p(B), nthreads)
+        return A, B
+
+    def cartpole_rk4(self, mc, m, L, g, s0, force, t0, t1, dt, nthreads=1):
+        s0 = _f64(s0); n = s0.shape[1]
+        mc, m, L, g, force = (_f64(a, n) for a in (mc, m, L, g, force))
+        fin = np.empty((4, n))
+        self._fn("cartpole_rk4", [_sz] + [_dp] * 6 + [_d] * 3 + [_dp, _i])(
+            n, _p(mc), _p(m), _p(L), _p(g), _p(s0), _p(force), t0, t1, dt, _p(fin), nthreads)
+        return fin
+
+    # ---------------- config 4 ----------------
+    @staticmethod
+    def _tab(t, cols):
+        if t is None:
+            return 0, None
+        t = _f64(t)
+        assert t.ndim == 2 and t.shape[1] == cols
+        return t.shape[0], t
+
+    def rocket_rk4(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, t_end, dt,
+                   store_every=0, n_snap=0, want_stats=True, nthreads=1):
+        elev = _f64(elev); n = elev.size
+        az, diam, g0 = (_f64(a, n) for a in (az, diam, g0))
+        er, engine = self._tab(engine, 8)
+        mr, mass_tab = self._tab(mass_tab, 2)
+        xr, ix_tab = self._tab(ix_tab, 2)
+        yr, iyz_tab = self._tab(iyz_tab, 2)
+        fin = np.empty((14, n))
+        stats = np.empty((8, n)) if want_stats else None
+        traj = np.full((n_snap, 14, n), np.nan) if store_every else None
+        rc = self._fn("rocket_rk4", [_sz] + [_dp] * 4 + [_sz, _dp] * 4 + [_d, _d, _sz, _dp, _dp, _dp, _i])(
+            n, _p(elev), _p(az), _p(diam), _p(g0), er, _p(engine), mr, _p(mass_tab), xr, _p(ix_tab),
+            yr, _p(iyz_tab), t_end, dt, store_every, _p(fin), _p(traj), _p(stats), nthreads)
+        assert rc == 0
+        return fin, stats, traj
+
+    def rocket_rhs(self, elev, az, diam, g0, engine, mass_tab, state):
+        state = _f64(state); n = state.shape[1]
+        er, engine = self._tab(engine, 8)
+        mr, mass_tab = self._tab(mass_tab, 2)
+        out = np.empty((14, n))
+        rc = self._fn("rocket_rhs", [_sz, _d, _d, _d, _d, _sz, _dp, _sz, _dp, _dp, _dp])(
+            n, elev, az, diam, g0, er, _p(engine), mr, _p(mass_tab), _p(state), _p(out))
+        assert rc == 0
+        return out
+
+    def engine_thrust(self, engine, tq, patm):
+        er, engine = self._tab(engine, 8)
+        tq, patm = _f64(tq), _f64(patm)
+        out = np.empty(tq.size)
+        self._fn("engine_thrust", [_sz, _dp, _sz, _dp, _dp, _dp])(er, _p(engine), tq.size, _p(tq),
+                                                                   _p(patm), _p(out))
+        return out
+
+    def atmosphere(self, h):
+        h = _f64(h)
+        T, P, rho, a = (np.empty(h.size) for _ in range(4))
+        self._fn("atmosphere", [_sz] + [_dp] * 5)(h.size, _p(h), _p(T), _p(P), _p(rho), _p(a))
+        return T, P, rho, a
+
+    # ---------------- config 5 ----------------
+    def grid2d_rhs(self, rows, cols, topo, mass, spacing, k, c, state):
+        state = _f64(state).ravel()
+        out = np.empty_like(state)
+        if self.kind == "port":
+            self._fn("grid2d_rhs", [_sz, _sz, _i, _d, _d, _d, _d, _dp, _dp])(
+                rows, cols, topo, mass, spacing, k, c, _p(state), _p(out))
+        else:
+            rc = self._fn("grid2d", [_sz, _sz, _i, _d, _d, _d, _d, _dp, _i, _d, _sz, _dp])(
+                rows, cols, topo, mass, spacing, k, c, _p(state), 0, 0.0, 0, _p(out))
+            if rc < 0:
+                raise KeyError("grid size not instantiated in the reference harness")
+        return out
+
+    def grid2d_rk4(self, rows, cols, topo, mass, spacing, k, c, dt, n_steps, state, nthreads=1):
+        state = _f64(state).ravel().copy()
+        if self.kind == "port":
+            rc = self._fn("grid2d_rk4", [_sz, _sz, _i, _d, _d, _d, _d, _d, _sz, _dp, _i])(
+                rows, cols, topo, mass, spacing, k, c, dt, n_steps, _p(state), nthreads)
+            assert rc == n_steps
+            return state
+        out = np.empty_like(state)
+        rc = self._fn("grid2d", [_sz, _sz, _i, _d, _d, _d, _d, _dp, _i, _d, _sz, _dp])(
+            rows, cols, topo, mass, spacing, k, c, _p(state), 1, dt, n_steps, _p(out))
+        if rc < 0:
+            raise KeyError("grid size not instantiated in the reference harness")
+        assert rc == n_steps, (rc, n_steps)
+        return out
+
+    def grid2d_initial_state(self, rows, cols, spacing, mass=1.0, k=1.0, c=0.0, topo=0):
+        out = np.empty(4 * rows * cols)
+        if self.kind == "port":
+            self._fn("grid2d_initial_state", [_sz, _sz, _d, _dp])(rows, cols, spacing, _p(out))
+        else:
+            rc = self._fn("grid2d", [_sz, _sz, _i, _d, _d, _d, _d, _dp, _i, _d, _sz, _dp])(
+                rows, cols, topo, mass, spacing, k, c, _p(out), 2, 0.0, 0, _p(out))
+            if rc < 0:
+                raise KeyError("grid size not instantiated in the reference harness")
+        return out
+
+    def rk4_num_steps(self, t0, t1, dt) -> int:
+        if self.kind != "port":
+            raise NotImplementedError
+        return int(self._fn("rk4_num_steps", [_d, _d, _d], _sz)(t0, t1, dt))

@@ -1,0 +1,357 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Thin extern "C" driver around the UNMODIFIED reference headers, which are included
+// from where they lie under /root/reference (-I/root/reference); no reference source is
+// copied into this repository. It is compiled by oracle/Makefile into
+// oracle/_ref/libsopot_ref.so with the reference's own arithmetic flags
+// (g++ -std=c++20 -O3, no -march, no fast-math => no FMA contraction; CMakeLists.txt:7-9,33-35).
+//
+// Every entry point integrates through the reference's own public API exactly the way
+// its tests do (tests/compile_time_test.cpp:126-136): makeTypedODESystem -> lambda that
+// copies the StateView into a std::vector -> createRK4Solver().solve(...).
+// Ensemble entry points fan instances out over std::thread (one system + one solver per
+// thread: both are non re-entrant, core/solver.hpp:48-49).
+#include "core/typed_component.hpp"
+#include "core/solver.hpp"
+#include "core/linearization.hpp"
+#include "physics/harmonic_oscillator.hpp"
+#include "physics/pendulum/double_pendulum.hpp"
+#include "physics/control/cart_n_pendulum.hpp"
+#include "physics/connected_masses/connectivity_matrix_2d.hpp"
+#include "rocket/rocket.hpp"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <unistd.h>
+
+using namespace sopot;
+
+namespace {
+
+template <class F>
+void parallel_for(size_t n, int nthreads, F&& body) {
+    if (nthreads <= 1 || n <= 1) { for (size_t i = 0; i < n; ++i) body(i); return; }
+    std::atomic<size_t> next{0};
+    const size_t chunk = 16;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                size_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                size_t e = b + chunk < n ? b + chunk : n;
+                for (size_t i = b; i < e; ++i) body(i);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+// Copy every `store_every`-th stored step (and always the last) of a SolutionResult.
+// traj layout: [n_snap][dim][n_inst] ; final layout: [dim][n_inst]
+template <class Sys>
+SolutionResult solve_system(const Sys& sys, double t0, double t1, double dt) {
+    auto solver = createRK4Solver();
+    auto derivs = [&sys](double t, StateView sv) {
+        std::vector<double> v(sv.begin(), sv.end());
+        return sys.computeDerivatives(t, v);
+    };
+    return solver.solve(derivs, sys.getStateDimension(), t0, t1, dt, sys.getInitialState());
+}
+
+void scatter_result(const SolutionResult& r, size_t dim, size_t i, size_t n,
+                    size_t store_every, double* final_out, double* traj_out, double* t_last) {
+    const auto& last = r.states.back();
+    for (size_t d = 0; d < dim; ++d) final_out[d * n + i] = last[d];
+    if (t_last) t_last[i] = r.times.back();
+    if (traj_out && store_every) {
+        size_t snap = 0;
+        for (size_t s = store_every; s < r.states.size(); s += store_every, ++snap)
+            for (size_t d = 0; d < dim; ++d) traj_out[(snap * dim + d) * n + i] = r.states[s][d];
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- config 1: damped harmonic oscillator (physics/harmonic_oscillator.hpp:44-85) ----
+int ref_ho_rk4(size_t n, const double* m, const double* k, const double* c, const double* x0,
+               const double* v0, double t0, double t1, double dt, size_t store_every,
+               double* final_out, double* traj_out, double* t_last, int nthreads) {
+    parallel_for(n, nthreads, [&](size_t i) {
+        auto sys = makeTypedODESystem<double>(
+            physics::HarmonicOscillator<double>(m[i], k[i], c[i], x0[i], v0[i]));
+        auto r = solve_system(sys, t0, t1, dt);
+        scatter_result(r, 2, i, n, store_every, final_out, traj_out, t_last);
+    });
+    return 0;
+}
+
+// ---- config 2: double pendulum (physics/pendulum/double_pendulum.hpp:68-179) ----
+int ref_dpend_rk4(size_t n, const double* m1, const double* m2, const double* L1, const double* L2,
+                  const double* g, const double* th1, const double* th2, const double* w1,
+                  const double* w2, double t0, double t1, double dt, size_t store_every,
+                  double* final_out, double* traj_out, double* t_last, int nthreads) {
+    parallel_for(n, nthreads, [&](size_t i) {
+        auto sys = makeTypedODESystem<double>(pendulum::DoublePendulum<double>(
+            m1[i], m2[i], L1[i], L2[i], g[i], th1[i], th2[i], w1[i], w2[i]));
+        auto r = solve_system(sys, t0, t1, dt);
+        scatter_result(r, 4, i, n, store_every, final_out, traj_out, t_last);
+    });
+    return 0;
+}
+
+// derivative evaluation only (single RHS), for per-call parity
+int ref_dpend_rhs(size_t n, const double* m1, const double* m2, const double* L1, const double* L2,
+                  const double* g, const double* state /*[4][n]*/, double* out /*[4][n]*/) {
+    for (size_t i = 0; i < n; ++i) {
+        auto sys = makeTypedODESystem<double>(
+            pendulum::DoublePendulum<double>(m1[i], m2[i], L1[i], L2[i], g[i]));
+        std::vector<double> s{state[i], state[n + i], state[2 * n + i], state[3 * n + i]};
+        auto d = sys.computeDerivatives(0.0, s);
+        for (int j = 0; j < 4; ++j) out[j * n + i] = d[j];
+    }
+    return 0;
+}
+
+// ---- config 3: cart-pole linearization via Dual<double,5> ----
+// makeLinearizer<4,1> (core/linearization.hpp:121-126) around CartNPendulum<1,Dual<double,5>>
+// (physics/control/cart_n_pendulum.hpp:143-221) with setControlForce(u[0]) inside the lambda.
+int ref_cartpole_linearize(size_t P, const double* x /*[4][P]*/, const double* u /*[P]*/,
+                           const double* mc, const double* m, const double* L, const double* g,
+                           double* A /*[16][P]*/, double* B /*[4][P]*/, int nthreads) {
+    using Lin = SystemLinearizer<4, 1>;
+    using D = Lin::DualT;
+    parallel_for(P, nthreads, [&](size_t p) {
+        control::CartNPendulum<1, D> plant(mc[p], {m[p]}, {L[p]}, g[p]);
+        auto sys = makeTypedODESystem<D>(std::move(plant));
+        auto lin = makeLinearizer<4, 1>(
+            [&sys](D t, const Lin::DualState& xs, const Lin::DualInput& us) {
+                sys.template getComponent<0>().setControlForce(us[0]);
+                std::vector<D> sv(xs.begin(), xs.end());
+                auto d = sys.computeDerivatives(t, sv);
+                Lin::DualDerivative out;
+                for (size_t i = 0; i < 4; ++i) out[i] = d[i];
+                return out;
+            });
+        auto r = lin.linearize(0.0, {x[p], x[P + p], x[2 * P + p], x[3 * P + p]}, {u[p]});
+        for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 4; ++j) A[(i * 4 + j) * P + p] = r.A[i][j];
+            B[i * P + p] = r.B[i][0];
+        }
+    });
+    return 0;
+}
+
+// plain-double cart-pole integration with a constant force (CartNPendulum<1,double>)
+int ref_cartpole_rk4(size_t n, const double* mc, const double* m, const double* L, const double* g,
+                     const double* s0 /*[4][n]*/, const double* force, double t0, double t1,
+                     double dt, double* final_out, int nthreads) {
+    parallel_for(n, nthreads, [&](size_t i) {
+        control::CartNPendulum<1, double> plant(mc[i], {m[i]}, {L[i]}, g[i],
+                                                {s0[i], s0[n + i], s0[2 * n + i], s0[3 * n + i]});
+        plant.setControlForce(force[i]);
+        auto sys = makeTypedODESystem<double>(std::move(plant));
+        sys.template getComponent<0>().setControlForce(force[i]);
+        auto r = solve_system(sys, t0, t1, dt);
+        scatter_result(r, 4, i, n, 0, final_out, nullptr, nullptr);
+    });
+    return 0;
+}
+
+// ---- config 4: 6-DOF rocket ----
+// The 11 components of Rocket<T>::SystemType (rocket/rocket.hpp:73-85) composed by hand so
+// that gravity can be jittered (Rocket<T> has no gravity setter). Tables reach the reference
+// only through CSV files (rocket/interpolated_engine.hpp:61-85, rocket_body.hpp:55-85), so
+// they are written with %.17g (round-trips through std::stod exactly).
+static std::string write_csv(const std::string& dir, const char* name, size_t rows, size_t cols,
+                             const double* data /*row-major*/) {
+    std::string path = dir + "/" + name;
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return path;
+    for (size_t r = 0; r < rows; ++r) {
+        for (size_t c = 0; c < cols; ++c)
+            std::fprintf(f, c ? ",%.17g" : "%.17g", data[r * cols + c]);
+        std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+    return path;
+}
+
+struct RocketTables {
+    std::string dir;
+    std::string engine, mass, ix, iyz;
+};
+
+// stats layout [8][n]: apogee, apogee_t, max_speed, max_speed_t, burnout_alt, burnout_speed,
+// downrange_E (final state[1]), downrange_N (final state[2])   (rocket/simulation_result.hpp:151-189)
+int ref_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg, const double* diameter,
+                   const double* g0, size_t engine_rows, const double* engine /*[rows][8]*/,
+                   size_t mass_rows, const double* mass_tab /*[rows][2]*/,
+                   size_t ix_rows, const double* ix_tab, size_t iyz_rows, const double* iyz_tab,
+                   double t_end, double dt, size_t store_every, double* final_out /*[14][n]*/,
+                   double* traj_out, double* stats_out /*[8][n] or null*/, int nthreads) {
+    using namespace sopot::rocket;
+    char tmpl[] = "/tmp/sopot_ref_XXXXXX";
+    char* d = mkdtemp(tmpl);
+    if (!d) return 1;
+    std::string dir(d);
+    std::string f_eng = engine_rows ? write_csv(dir, "sim_engine.csv", engine_rows, 8, engine) : "";
+    std::string f_mass = mass_rows ? write_csv(dir, "sim_mass.csv", mass_rows, 2, mass_tab) : "";
+    std::string f_ix = ix_rows ? write_csv(dir, "sim_ix.csv", ix_rows, 2, ix_tab) : "";
+    std::string f_iyz = iyz_rows ? write_csv(dir, "sim_iyz.csv", iyz_rows, 2, iyz_tab) : "";
+
+    // load tables once; components are copied per instance
+    InterpolatedEngine<double> engine0;
+    if (engine_rows) engine0.loadFromFile(f_eng);
+    RocketBody<double> body0;
+    if (mass_rows) body0.loadMass(f_mass);
+    if (ix_rows) body0.loadInertiaX(f_ix);
+    if (iyz_rows) body0.loadInertiaYZ(f_iyz);
+    const double burn = engine0.getBurnTime();
+
+    parallel_for(n, nthreads, [&](size_t i) {
+        RotationKinematics<double> att;
+        att.setInitialFromLauncherAngles(elev_deg[i], az_deg[i]);
+        auto sys = makeTypedODESystem<double>(
+            SimulationTime<double>(), TranslationKinematics<double>(), TranslationDynamics<double>(),
+            std::move(att), RotationDynamics<double>(), StandardAtmosphere<double>(),
+            Gravity<double>(g0[i]), RocketBody<double>(body0), InterpolatedEngine<double>(engine0),
+            AxisymmetricAerodynamics<double>(diameter[i]), ForceAggregator<double>());
+        auto r = solve_system(sys, 0.0, t_end, dt);
+        scatter_result(r, 14, i, n, store_every, final_out, traj_out, nullptr);
+        if (stats_out) {
+            // same scan as SimulationResult::computeStatistics (rocket/simulation_result.hpp:151-189)
+            double apogee = 0, apogee_t = 0, vmax = 0, vmax_t = 0, bo_alt = 0, bo_spd = 0;
+            for (size_t s = 0; s < r.size(); ++s) {
+                double t = r.times[s];
+                const auto& st = r.states[s];
+                double alt = st[3];
+                double spd = std::sqrt(st[4] * st[4] + st[5] * st[5] + st[6] * st[6]);
+                if (alt > apogee) { apogee = alt; apogee_t = t; }
+                if (spd > vmax) { vmax = spd; vmax_t = t; }
+                if (burn > 0 && std::abs(t - burn) < 0.1) { bo_alt = alt; bo_spd = spd; }
+            }
+            const auto& last = r.states.back();
+            double v[8] = {apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd, last[1], last[2]};
+            for (int j = 0; j < 8; ++j) stats_out[j * n + i] = v[j];
+        }
+    });
+    for (auto* p : {&f_eng, &f_mass, &f_ix, &f_iyz}) if (!p->empty()) unlink(p->c_str());
+    rmdir(dir.c_str());
+    return 0;
+}
+
+// single RHS evaluation of the full rocket at given states [14][n] (shared config)
+int ref_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0,
+                   size_t engine_rows, const double* engine, size_t mass_rows, const double* mass_tab,
+                   const double* state, double* out) {
+    using namespace sopot::rocket;
+    char tmpl[] = "/tmp/sopot_ref_XXXXXX";
+    char* d = mkdtemp(tmpl);
+    if (!d) return 1;
+    std::string dir(d);
+    std::string f_eng = write_csv(dir, "sim_engine.csv", engine_rows, 8, engine);
+    std::string f_mass = write_csv(dir, "sim_mass.csv", mass_rows, 2, mass_tab);
+    InterpolatedEngine<double> engine0; engine0.loadFromFile(f_eng);
+    RocketBody<double> body0; body0.loadMass(f_mass);
+    RotationKinematics<double> att; att.setInitialFromLauncherAngles(elev_deg, az_deg);
+    auto sys = makeTypedODESystem<double>(
+        SimulationTime<double>(), TranslationKinematics<double>(), TranslationDynamics<double>(),
+        std::move(att), RotationDynamics<double>(), StandardAtmosphere<double>(),
+        Gravity<double>(g0), std::move(body0), std::move(engine0),
+        AxisymmetricAerodynamics<double>(diameter), ForceAggregator<double>());
+    for (size_t i = 0; i < n; ++i) {
+        std::vector<double> s(14);
+        for (int j = 0; j < 14; ++j) s[j] = state[j * n + i];
+        auto dv = sys.computeDerivatives(0.0, s);
+        for (int j = 0; j < 14; ++j) out[j * n + i] = dv[j];
+    }
+    unlink(f_eng.c_str()); unlink(f_mass.c_str()); rmdir(dir.c_str());
+    return 0;
+}
+
+// engine precompute columns (pressure ratio, mass flow, engine force) as the reference derives
+// them at load time (rocket/interpolated_engine.hpp:176-252), observed through the public API:
+// not directly exposed, so we expose thrust magnitude at (t, P_atm) instead.
+int ref_engine_thrust(size_t engine_rows, const double* engine, size_t nq, const double* tq,
+                      const double* patm, double* thrust) {
+    using namespace sopot::rocket;
+    char tmpl[] = "/tmp/sopot_ref_XXXXXX";
+    char* d = mkdtemp(tmpl);
+    if (!d) return 1;
+    std::string dir(d);
+    std::string f_eng = write_csv(dir, "sim_engine.csv", engine_rows, 8, engine);
+    InterpolatedEngine<double> e; e.loadFromFile(f_eng);
+    for (size_t i = 0; i < nq; ++i) thrust[i] = e.computeThrustMagnitude(tq[i], patm[i]);
+    unlink(f_eng.c_str()); rmdir(dir.c_str());
+    return 0;
+}
+
+int ref_atmosphere(size_t n, const double* h, double* T, double* P, double* rho, double* a) {
+    sopot::rocket::StandardAtmosphere<double> atm;
+    for (size_t i = 0; i < n; ++i) {
+        T[i] = atm.computeTemperature(h[i]); P[i] = atm.computePressure(h[i]);
+        rho[i] = atm.computeDensity(h[i]); a[i] = atm.computeSpeedOfSound(h[i]);
+    }
+    return 0;
+}
+
+// ---- config 5: templated grid2d (physics/connected_masses/connectivity_matrix_2d.hpp:156-198) ----
+// Only small sizes are instantiable (6x6 takes 101 s to compile); topology: 0 quad, 1 quad+diagonals
+// (makeGrid2DSystem<...,true>), 2 triangular (makeTriangularGridSystem).
+} // extern "C"
+namespace {
+template <size_t R, size_t C, int Topo>
+auto make_grid(double mass, double spacing, double k, double c) {
+    using namespace sopot::connected_masses;
+    if constexpr (Topo == 0) return makeGrid2DSystem<double, R, C, false>(mass, spacing, k, c);
+    else if constexpr (Topo == 1) return makeGrid2DSystem<double, R, C, true>(mass, spacing, k, c);
+    else return makeTriangularGridSystem<double, R, C>(mass, spacing, k, c);
+}
+template <size_t R, size_t C, int Topo>
+int grid_run(double mass, double spacing, double k, double c, const double* state, int mode,
+             double dt, size_t n_steps, double* out) {
+    auto sys = make_grid<R, C, Topo>(mass, spacing, k, c);
+    const size_t dim = 4 * R * C;
+    std::vector<double> s(state, state + dim);
+    if (mode == 0) {                       // one RHS
+        auto d = sys.computeDerivatives(0.0, s);
+        std::memcpy(out, d.data(), dim * sizeof(double));
+    } else if (mode == 1) {                // RK4Solver::solve for n_steps
+        auto solver = createRK4Solver();
+        auto derivs = [&sys](double t, StateView sv) {
+            std::vector<double> v(sv.begin(), sv.end());
+            return sys.computeDerivatives(t, v);
+        };
+        auto r = solver.solve(derivs, dim, 0.0, dt * (double)n_steps, dt, s);
+        std::memcpy(out, r.states.back().data(), dim * sizeof(double));
+        return (int)(r.states.size() - 1);
+    } else {                               // initial state
+        auto s0 = sys.getInitialState();
+        std::memcpy(out, s0.data(), dim * sizeof(double));
+    }
+    return 0;
+}
+} // namespace
+
+extern "C" {
+#define GRID_CASE(R, C, T) if (rows == R && cols == C && topo == T) \
+    return grid_run<R, C, T>(mass, spacing, k, c, state, mode, dt, n_steps, out);
+
+// returns -1 when (rows, cols, topo) is not one of the instantiated sizes
+int ref_grid2d(size_t rows, size_t cols, int topo, double mass, double spacing, double k, double c,
+               const double* state, int mode, double dt, size_t n_steps, double* out) {
+    GRID_CASE(2, 2, 0) GRID_CASE(3, 3, 0) GRID_CASE(4, 5, 0) GRID_CASE(2, 5, 0)
+    GRID_CASE(3, 3, 1) GRID_CASE(4, 4, 1) GRID_CASE(3, 4, 2) GRID_CASE(4, 4, 2)
+    return -1;
+}
+
+} // extern "C"
