@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- RK4 instance-steps/s (FP64) of the B200 ensemble engine, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): double-pendulum ensemble,
+4 Mi instances per GPU, RK4 dt = 1e-3 over 10 s = 10 000 steps per instance.  One bench "step" is one
+pass of the hot path over that batch = ONE launch of rk4_ensemble_kernel<DpendSys> (4.19e10
+instance-steps).  Ensembles shard trivially: every rank integrates its own 4 Mi instances, there is no
+data-path collective ("scaling": "weak"); torch.distributed (NCCL) is used only for the barrier and the
+max-over-ranks of the device time.
+
+  value     instance-steps/s with inputs resident in HBM (device pointers), CUDA-event timed.
+  e2e       the same pass through the C-ABI with HOST buffers (pinned): H2D of the 9 parameter arrays and
+            D2H of the final state + status inside the timed region.
+  roofline  FP64: algorithmic flops (204 per instance-step, SURVEY.md section 8d: every + - * / and every
+            transcendental = 1 flop) / kernel time, against the DFMA issue peak measured in this run by
+            sopot_b200_measure_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure).
+  cpu_baseline  the reference's own CPU RK4 (oracle/_ref when it was built, else the oracle port) on
+            all host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 22
+N_STEPS = 10000
+DT = 1e-3
+FLOP_PER_INSTANCE_STEP = 204.0
+METRIC = "RK4 instance-steps/s (FP64)"
+UNIT = "instance-steps/s"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples drawing more than half the maximum power seen
+        load = [s for s, p in zip(sm, power) if power and p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(seconds_target: float, force_kind: str | None = None):
+    """Time the reference's CPU RK4 on the double-pendulum workload; returns (inst-steps/s, cores, kind, sample)."""
+    from oracle.oracle_py import Checker, build, have_reference
+    from sopot_b200 import workloads as W
+    build()
+    kind = force_kind or ("reference" if have_reference() else "port")
+    chk = Checker(kind)
+    cores = chk.hardware_threads()
+    w = W.dpend_ensemble(64 * cores, seed=2)
+    args = [w[k] for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+    t = time.perf_counter()
+    chk.dpend_rk4(*args, 0.0, 0.5, DT, nthreads=cores)                    # probe: 500 steps
+    probe = time.perf_counter() - t
+    rate = 64 * cores * 500 / max(probe, 1e-6)
+    n = int(max(cores * 8, min(N_PER_GPU, rate * seconds_target / N_STEPS)))
+    n = (n // cores) * cores or cores
+    w = W.dpend_ensemble(N_PER_GPU, seed=2)                                # the SAME inputs as the GPU run, first n
+    args = [w[k][:n].copy() for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+    t = time.perf_counter()
+    chk.dpend_rk4(*args, 0.0, 10.0, DT, nthreads=cores)
+    el = time.perf_counter() - t
+    sample = f"first {n} of the {N_PER_GPU} instances x {N_STEPS} steps, {cores} threads, {el:.1f} s wall"
+    return n * N_STEPS / el, cores, kind, sample, el
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    rates, ms = [], []
+    for i in range(args.warmup + args.steps):
+        r, cores, kind, sample, el = cpu_reference_rate(4.0 if i < args.warmup else 12.0)
+        if i >= args.warmup:
+            rates.append(r); ms.append(el * 1e3)
+    v = statistics.mean(rates)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "double pendulum ensemble, RK4 dt=1e-3 over 10 s (10000 steps/instance); "
+                                   "each step = a bounded sample of the 4Mi-instance batch on the host CPU",
+                       "instances_per_gpu": N_PER_GPU, "n_steps": N_STEPS, "dt": DT},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def other_configs(eng, hbm_peak, fp64_peak):
+    """One timed pass (after one warm-up) of the other four BASELINE configs at full size, N = 1."""
+    from sopot_b200 import workloads as W
+    from sopot_b200.capi import FP_CONTRACT, FP_STRICT, MEM_DEVICE
+    out = {}
+
+    def timed(fn, reps=2):
+        fn(); eng.sync()
+        best = 1e30
+        for _ in range(reps):
+            eng.event_record(2); fn(); eng.event_record(3)
+            best = min(best, eng.elapsed_ms(2, 3))
+        return best
+
+    # config 1: oscillator 1 Mi x 1000 steps, final-state mode (FP64 bound, 44 flop / instance-step)
+    n = 1 << 20
+    w = W.ho_ensemble(n)
+    d = {k: eng.to_device(w[k]) for k in ("m", "k", "c", "x0", "v0")}
+    st = eng.empty((2, n))
+    ms = timed(lambda: eng.ho_rk4(d["m"], d["k"], d["c"], d["x0"], d["v0"], n, 0.0, 0.01, 1000, mem=MEM_DEVICE,
+                                  fp_mode=FP_CONTRACT, want_status=False, state_out=st, sync=False), 3)
+    out["ho_1Mi_x1000"] = {"ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3),
+                           "fp64_frac": 44.0 * n * 1000 / (ms * 1e-3) / 1e12 / fp64_peak}
+    # config 3: 1 Mi linearizations, HBM bound, 200 B / point
+    P = 1 << 20
+    w = W.cartpole_points(P)
+    dx, du = eng.to_device(w["x"]), eng.to_device(w["u"])
+    A, B = eng.empty((16, P)), eng.empty((4, P))
+    ms = timed(lambda: eng.cartpole_linearize(1.0, 0.1, 0.5, 9.81, dx, du, P, mem=MEM_DEVICE, A=A, B=B,
+                                              want_status=False, sync=False), 5)
+    out["cartpole_linearize_1Mi"] = {"ms": ms, "points_per_s": P / (ms * 1e-3), "GBs": 200.0 * P / (ms * 1e-3) / 1e9,
+                                     "hbm_frac": 200.0 * P / (ms * 1e-3) / 1e9 / hbm_peak}
+    for a in (dx, du, A, B, st, *d.values()):
+        a.free()
+    # config 4: rocket Monte Carlo 1 Mi x 3000 steps + dispersion reduction
+    n = 1 << 20
+    w = W.rocket_ensemble(n)
+    d = {k: eng.to_device(w[k]) for k in ("elev", "az", "diam", "g0")}
+    st, stats = eng.empty((14, n)), eng.empty((8, n))
+    ms = timed(lambda: eng.rocket_rk4(d["elev"], d["az"], d["diam"], d["g0"], w["engine"], w["mass_tab"], None, None, n,
+                                      0.01, 3000, mem=MEM_DEVICE, want_status=False, state_out=st, stats_out=stats,
+                                      sync=False), 1)
+    disp = eng.dispersion_stats(stats)
+    out["rocket_1Mi_x3000"] = {"ms": ms, "instance_steps_per_s": n * 3000 / (ms * 1e-3),
+                               "apogee_mean_m": disp[0]["mean"], "apogee_std_m": disp[0]["stddev"]}
+    for a in (st, stats, *d.values()):
+        a.free()
+    # config 5: grid2d 8192^2, 10 RK4 steps (544 B / mass-step)
+    p = W.GRID2D_PARAMS
+    n = 8192
+    gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
+    for mode, name in ((FP_STRICT, "strict"), (FP_CONTRACT, "contract")):
+        ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False), 1) / 10.0
+        out[f"grid2d_8192x8192_{name}"] = {"ms_per_step": ms, "mass_steps_per_s": n * n / (ms * 1e-3),
+                                           "GBs": 544.0 * n * n / (ms * 1e-3) / 1e9,
+                                           "hbm_frac": 544.0 * n * n / (ms * 1e-3) / 1e9 / hbm_peak}
+    state.free()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=N_PER_GPU, help="instances per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other four configs and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    from sopot_b200 import workloads as W
+    from sopot_b200.capi import FP_CONTRACT, MEM_DEVICE, MEM_HOST, Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [Engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    eng = Engine(local, nccl_id, rank, world)
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.instances
+    w = W.dpend_ensemble(n, seed=2 + rank)
+    keys = ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")
+    dev = {k: eng.to_device(w[k]) for k in keys}
+    d_state = eng.empty((4, n))
+    d_status = None
+
+    def step_device():
+        eng.dpend_rk4(*[dev[k] for k in keys], n, 0.0, DT, N_STEPS, mem=MEM_DEVICE, fp_mode=FP_CONTRACT,
+                      want_status=False, state_out=d_state, sync=False)
+
+    # ---- device-resident timing: W warm-up, then exactly K steps between barriers ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    eng.event_record(0)
+    for _ in range(args.steps):
+        step_device()
+    eng.event_record(1)
+    ms_total = eng.elapsed_ms(0, 1)
+    barrier()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    host = {k: eng.pinned((n,)) for k in keys}
+    for k in keys:
+        host[k][:] = w[k]
+    h_state = eng.pinned((4, n))
+
+    def step_host():
+        eng.dpend_rk4(*[host[k] for k in keys], n, 0.0, DT, N_STEPS, mem=MEM_HOST, fp_mode=FP_CONTRACT,
+                      want_status=False, state_out=h_state, sync=False)
+
+    step_host()
+    barrier()
+    eng.event_record(4)
+    for _ in range(args.steps):
+        step_host()
+    eng.event_record(5)
+    ms_e2e = eng.elapsed_ms(4, 5)
+    barrier()
+    checksum = float(np.sum(h_state[:, :: max(1, n // 4096)]))       # the D2H result is really read
+    assert np.isfinite(checksum)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = (float(x) for x in t.cpu())
+
+    total_units = float(n) * N_STEPS * world * args.steps
+    value = total_units / (ms_total * 1e-3)
+    e2e_value = total_units / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        fp64_peak = eng.measure_fp64_peak()
+        hbm_peak_live = eng.measure_hbm_peak(1 << 30)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = hbm_peak_live, "measured live (sopot_b200_measure_hbm_peak)"
+        if os.path.exists(peaks_path):
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        kernel_ms = ms_total / max(launches, 1) if world == 1 else None
+        per_gpu_rate = float(n) * N_STEPS * args.steps / (ms_total * 1e-3)
+        achieved = FLOP_PER_INSTANCE_STEP * per_gpu_rate / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "double pendulum ensemble (BASELINE configs[1]): m=L=1, g=9.81, theta~U(-3,3), "
+                                   "RK4 dt=1e-3 over 10 s = 10000 steps/instance, one kernel launch per step",
+                       "instances_per_gpu": n, "n_steps": N_STEPS, "dt": DT, "fp_mode": "contract",
+                       "l2": "inputs larger than L2 (9 arrays x %d MiB per step)" % (n * 8 >> 20),
+                       "parallelism": "ensemble sharded over %d GPU(s), no data-path collective" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 9 * n * 8, "d2h_bytes_per_step": 4 * n * 8,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "rk4_ensemble_kernel<DpendSys,false>", "kernel_ms": kernel_ms,
+                         "flop_per_unit": FLOP_PER_INSTANCE_STEP,
+                         "peak_source": "DFMA issue rate measured in this run (sopot_b200_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm_copy_live_gbs": hbm_peak_live},
+        }
+        if not args.no_extras and world == 1:
+            try:
+                for a in list(dev.values()) + [d_state]:
+                    a.free()
+                line["other_configs"] = other_configs(eng, hbm_peak, fp64_peak)
+            except Exception as e:                      # extras must never cost the headline number
+                line["other_configs"] = {"error": repr(e)}
+            try:
+                r, cores, kind, sample, _ = cpu_reference_rate(12.0)
+                line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,209 @@
+/*
+ * sopot_b200.h -- C ABI of the B200-native batched ODE integration engine for SOPOT.
+ *
+ * The reference (jedrzejmichalczyk/sopot) is a header-only C++20 template library with no FFI of
+ * its own: the boundary below is what a host-language binding for the
+ * RK4-ensemble hot path would bind.  Each entry point names the reference interface it replaces
+ * (file:line under the reference tree).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *  - One ctx per host thread / GPU.  Every call is enqueued on the ctx stream and returns
+ *    immediately; results are valid after sopot_b200_sync().  Return value: 0 on success, a
+ *    SOPOT_B200_E* code otherwise, text in sopot_b200_last_error().  Nothing throws across the ABI
+ *    (the reference throws std::invalid_argument / std::runtime_error; the C++ header layer
+ *    re-throws from these codes).
+ *  - Caller owns every buffer.  `mem` in the options says whether the pointers of that call are
+ *    device (SOPOT_B200_MEM_DEVICE) or host (SOPOT_B200_MEM_HOST) addresses; host buffers are
+ *    staged through a ctx-owned device arena (H2D before, D2H after, same stream).
+ *  - Ensemble data is SoA: element i of component d lives at base[d * n + i].
+ *  - Per-instance parameters: a parameter pointer addresses n doubles, or ONE double when its bit
+ *    is set in `broadcast` (bit index = position of the field in the params struct).
+ *  - fp_mode: SOPOT_B200_FP_CONTRACT lets the compiler fuse a*b+c into DFMA and replaces x/6.0
+ *    style divisions by reciprocal multiplies (<= 1e-12 relative per step against the reference);
+ *    SOPOT_B200_FP_STRICT evaluates every operation with the reference's association and IEEE
+ *    rounding (no contraction): bit-identical to the reference wherever no libm transcendental is
+ *    involved (oscillator, grid2d), and differing only by the libm last-ulp elsewhere.
+ *  - status[i] (optional, int32): 0 ok, SOPOT_B200_ST_NONFINITE, SOPOT_B200_ST_SINGULAR
+ *    (the reference throws "mass matrix is singular", physics/control/cart_n_pendulum.hpp:331-333).
+ */
+#ifndef SOPOT_B200_H
+#define SOPOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOPOT_B200_ABI_VERSION 1
+
+enum {
+    SOPOT_B200_OK = 0,
+    SOPOT_B200_EINVAL = 1,      /* bad argument (reference: std::invalid_argument in ctors) */
+    SOPOT_B200_ECUDA = 2,       /* CUDA runtime error */
+    SOPOT_B200_ENCCL = 3,       /* NCCL error / NCCL not loadable */
+    SOPOT_B200_ENOMEM = 4,
+    SOPOT_B200_ENODEVICE = 5    /* no usable sm_100 device: there is NO CPU fallback */
+};
+
+enum { SOPOT_B200_MEM_DEVICE = 0, SOPOT_B200_MEM_HOST = 1 };
+enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
+enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2 };
+
+typedef struct sopot_b200_ctx sopot_b200_ctx;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context.  nccl_unique_id: NULL for a single-GPU ctx; otherwise the 128 bytes produced by
+ * sopot_b200_nccl_unique_id() on rank 0 and distributed by the host (torch.distributed, MPI, ...).
+ * NCCL is dlopen()ed (libnccl.so.2) only when nranks > 1.
+ * ------------------------------------------------------------------------------------------- */
+int  sopot_b200_abi_version(void);
+int  sopot_b200_nccl_unique_id(void* out128);
+int  sopot_b200_init(sopot_b200_ctx** out, int device, const void* nccl_unique_id, int rank, int nranks);
+void sopot_b200_destroy(sopot_b200_ctx* ctx);
+const char* sopot_b200_last_error(const sopot_b200_ctx* ctx);   /* ctx may be NULL: last init error */
+int  sopot_b200_sync(sopot_b200_ctx* ctx);
+/* adopt an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int  sopot_b200_set_stream(sopot_b200_ctx* ctx, void* cuda_stream);
+int  sopot_b200_device_info(sopot_b200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                            size_t* global_mem_bytes, char* name, size_t name_len);
+
+/* device / pinned-host memory so that a host language without a CUDA binding can drive the engine */
+int  sopot_b200_malloc(sopot_b200_ctx* ctx, size_t bytes, void** dptr);
+int  sopot_b200_free(sopot_b200_ctx* ctx, void* dptr);
+int  sopot_b200_host_alloc(sopot_b200_ctx* ctx, size_t bytes, void** hptr);   /* pinned */
+int  sopot_b200_host_free(sopot_b200_ctx* ctx, void* hptr);
+int  sopot_b200_memcpy_h2d(sopot_b200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  sopot_b200_memcpy_d2h(sopot_b200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  sopot_b200_memcpy_d2d(sopot_b200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  sopot_b200_memset(sopot_b200_ctx* ctx, void* dst, int byte, size_t bytes);
+
+/* CUDA-event timing on the ctx stream (slots 0..15) and launch accounting */
+int  sopot_b200_event_record(sopot_b200_ctx* ctx, int slot);
+int  sopot_b200_event_elapsed_ms(sopot_b200_ctx* ctx, int slot_begin, int slot_end, float* ms); /* syncs on slot_end */
+uint64_t sopot_b200_launch_count(const sopot_b200_ctx* ctx);   /* kernels this library launched on ctx */
+
+/* RK4Solver::solve loop count, core/solver.hpp:91,127: while (t < t_end - dt*0.5) t += dt */
+size_t sopot_b200_rk4_num_steps(double t0, double t1, double dt);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ensemble RK4: replaces createRK4Solver().solve(derivs, dim, t0, t1, dt, y0) (core/solver.hpp:63-140)
+ * over TypedODESystem<double, ...>::computeDerivatives (core/typed_component.hpp:410-414), for n
+ * independent instances at once.  state_out[dim][n] = state after n_steps steps.
+ * traj_out (optional): snapshot s (0-based) = state after (s+1)*store_every steps, layout
+ * [n_steps / store_every][dim][n].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t mem;          /* SOPOT_B200_MEM_* for every pointer of the call          */
+    uint32_t fp_mode;      /* SOPOT_B200_FP_*                                         */
+    size_t   store_every;  /* 0: final state only                                     */
+    uint32_t broadcast;    /* bit i: i-th params pointer addresses a single double    */
+    uint32_t reserved;
+} sopot_b200_rk4_opts;
+
+/* physics::HarmonicOscillator<double>(mass, k, c, x0, v0), physics/harmonic_oscillator.hpp:44-85 */
+typedef struct { const double *m, *k, *c, *x0, *v0; } sopot_b200_ho_params;
+int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n, double t0, double dt,
+                      size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out /*[2][n]*/,
+                      double* traj_out, int32_t* status);
+
+/* pendulum::DoublePendulum<double>(m1, m2, L1, L2, g, th1, th2, w1, w2),
+ * physics/pendulum/double_pendulum.hpp:68-179 */
+typedef struct { const double *m1, *m2, *L1, *L2, *g, *th1, *th2, *w1, *w2; } sopot_b200_dpend_params;
+int sopot_b200_dpend_rk4(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n, double t0,
+                         double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
+                         double* state_out /*[4][n]*/, double* traj_out, int32_t* status);
+/* one derivative evaluation per instance (computeDerivatives), state/out [4][n] */
+int sopot_b200_dpend_rhs(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n,
+                         const sopot_b200_rk4_opts* opts, const double* state, double* out);
+
+/* control::CartNPendulum<1,double>(mc, {m}, {L}, g, {x,th,xd,w}) with a constant control force
+ * (setControlForce), physics/control/cart_n_pendulum.hpp:83-221 */
+typedef struct { const double *mc, *m, *L, *g, *x, *th, *xd, *w, *force; } sopot_b200_cartpole_params;
+int sopot_b200_cartpole_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n, double t0,
+                            double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
+                            double* state_out /*[4][n]*/, double* traj_out, int32_t* status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched linearization: replaces makeLinearizer<4,1>(f).linearize(t, x, u)
+ * (core/linearization.hpp:75-126) around CartNPendulum<1, Dual<double,5>> for P operating points.
+ * x0 [4][P], u0 [P]; A [4*4][P] (A[i][j] at (i*4+j)*P + p), B [4][P].
+ * opts->broadcast bits: 0 mc, 1 m, 2 L, 3 g.   opts->store_every is ignored.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const double *mc, *m, *L, *g; } sopot_b200_cartpole_plant;
+int sopot_b200_cartpole_linearize(sopot_b200_ctx* ctx, const sopot_b200_cartpole_plant* plant,
+                                  const double* x0, const double* u0, size_t P,
+                                  const sopot_b200_rk4_opts* opts, double* A, double* B, int32_t* status);
+
+/* ---------------------------------------------------------------------------------------------
+ * 6-DOF rocket Monte Carlo: replaces rocket::simulateRocket(rocket, t_end, dt) +
+ * SimulationResult::computeStatistics (rocket/rocket.hpp:268-303, rocket/simulation_result.hpp:151-189)
+ * for n trajectories of Rocket<double>::SystemType (rocket/rocket.hpp:73-85, 14 states).
+ * Tables are shared by the ensemble and always HOST pointers, row-major:
+ *   engine [engine_rows][8]: time, throat_d, exit_d, p_comb, T_comb, gamma, mol_mass, efficiency
+ *          (rocket/interpolated_engine.hpp:66-79; the isentropic precompute of :176-252 runs here,
+ *          on the host, once);  mass/ix/iyz [rows][2]: time, value (rocket/rocket_body.hpp:55-85);
+ *   rows == 0 means "not loaded" (constants 100 / 10 / 100, rocket_body.hpp:36-39; no thrust).
+ * Per trajectory (broadcast bits 0..3): launcher elevation / azimuth [deg] (Rocket::setLauncher),
+ * reference diameter [m] (setDiameter), gravity (Gravity<T>(g)).
+ * state_out [14][n]; stats_out [8][n] (optional): apogee, apogee_time, max_speed, max_speed_time,
+ * burnout_altitude, burnout_speed, final East, final North.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const double *elevation_deg, *azimuth_deg, *diameter, *gravity;
+    size_t engine_rows; const double* engine;
+    size_t mass_rows;   const double* mass;
+    size_t ix_rows;     const double* ix;
+    size_t iyz_rows;    const double* iyz;
+} sopot_b200_rocket_params;
+int sopot_b200_rocket_rk4(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n, double dt,
+                          size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out,
+                          double* traj_out, double* stats_out, int32_t* status);
+/* one derivative evaluation per instance, state/out [14][n] (per-trajectory params as above) */
+int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n,
+                          const sopot_b200_rk4_opts* opts, const double* state, double* out);
+
+/* Dispersion statistics over per-trajectory rows (e.g. stats_out above): for each of `rows` rows of
+ * values[rows][n_local]: count, sum, sum of squares, min, max -- reduced on the device, then summed /
+ * min-maxed over all ranks of the ctx with NCCL (one allreduce(sum) + one allreduce(min) + one (max)).
+ * out[rows] on the HOST, identical on every rank.  Non-finite entries are skipped and counted. */
+typedef struct { double count, sum, sumsq, min, max, mean, stddev, nonfinite; } sopot_b200_dispersion;
+int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* values, size_t rows, size_t n_local,
+                                uint32_t mem, sopot_b200_dispersion* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * grid2d mass-spring cloth: replaces RK4Solver::solve over makeGrid2DSystem<double,R,C,Diag> /
+ * makeTriangularGridSystem (physics/connected_masses/connectivity_matrix_2d.hpp:156-266) at
+ * runtime sizes.  State is AoS [rows][cols][x,y,vx,vy], row-major (grid_2d.hpp:97-99).
+ * topology: 0 quad, 1 quad + diagonals (IncludeDiagonals=true), 2 triangular.
+ * Multi-GPU: each rank of the ctx owns the contiguous slab rows [row_begin, row_begin + rows_local)
+ * of the global grid and `state` addresses only that slab; one boundary row is exchanged with each
+ * neighbour before every RK stage (NCCL send/recv over NVLink).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    size_t rows, cols;            /* GLOBAL grid size                         */
+    size_t row_begin, rows_local; /* this rank's slab (whole grid if 1 rank)  */
+    int    topology;
+    double mass, spacing, stiffness, damping;
+} sopot_b200_grid2d_params;
+int sopot_b200_grid2d_initial_state(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* g, uint32_t mem,
+                                    double* state);
+int sopot_b200_grid2d_rk4(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* g, double dt, size_t n_steps,
+                          const sopot_b200_rk4_opts* opts, double* state /* in/out */);
+/* one derivative evaluation (computeDerivatives) of the local slab; single-rank ctx only */
+int sopot_b200_grid2d_rhs(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* g,
+                          const sopot_b200_rk4_opts* opts, const double* state, double* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Roofline denominators measured on this device: dependent-free DFMA issue rate (FP64 TFLOP/s,
+ * FMA = 2 flop) and a device copy (GB/s, read + write).  Used by bench.py; MEASURED_PEAKS.json has
+ * no FP64 figure.
+ * ------------------------------------------------------------------------------------------- */
+int sopot_b200_measure_fp64_peak(sopot_b200_ctx* ctx, double* tflops);
+int sopot_b200_measure_hbm_peak(sopot_b200_ctx* ctx, size_t bytes, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOPOT_B200_H */

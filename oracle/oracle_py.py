@@ -32,10 +32,10 @@ def _p(a):
 
 
 def _f64(a, n=None):
-    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    if n is not None and a.ndim == 0:
-        a = np.full(n, float(a))
-    return a
+    a = np.asarray(a, dtype=np.float64)
+    if n is not None and a.size == 1 and n != 1:
+        a = np.full(n, float(a.reshape(-1)[0]))
+    return np.ascontiguousarray(a)
 
 
 def build(force: bool = False) -> None:

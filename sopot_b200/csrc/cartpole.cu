@@ -1,0 +1,203 @@
+// cartpole.cu -- CartNPendulum plant (physics/control/cart_n_pendulum.hpp:143-221, :319-359) on the
+// device, generic over the scalar (Real<S> for integration, DualR<N,S> for linearization), plus
+//   K1 instantiation  sopot_b200_cartpole_rk4        (constant control force)
+//   K2                sopot_b200_cartpole_linearize  = SystemLinearizer<4,1>::linearize
+//                     (core/linearization.hpp:75-114) with Dual<double,5>.
+#include "dual.cuh"
+#include "ensemble.cuh"
+
+// Generic N-link plant.  Arrays are indexed with compile-time constants only (full unrolling; row
+// swaps of the partial-pivot search are predicated element swaps), so everything stays in registers.
+template <int NL, class T>
+struct CartPlant {
+    static constexpr int NDOF = NL + 1;
+    double mc, m[NL], L[NL], g;
+
+    // returns 0 or SOPOT_B200_ST_SINGULAR; deriv/local layout [x, th_1..th_N, xd, w_1..w_N]
+    __device__ __forceinline__ int derivatives(const T (&local)[2 * NDOF], const T& F, T (&deriv)[2 * NDOF]) const {
+        using SC = ScalarOf<T>;
+        const T gT = SC::make(g);
+        T s[NL], c[NL], omega[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {                    // :155-161
+            r_sincos(local[1 + i], s[i], c[i]);
+            omega[i] = local[NDOF + 1 + i];
+        }
+        double Mtail[NL];                                  // tailMass, :134-138
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = i; j < NL; ++j) sum += m[j];
+            Mtail[i] = sum;
+        }
+        T A[NDOF][NDOF], b[NDOF];
+        T total = SC::make(mc);                            // :172-174
+#pragma unroll
+        for (int i = 0; i < NL; ++i) total = total + SC::make(m[i]);
+        A[0][0] = total;
+        b[0] = F;                                          // :176
+#pragma unroll
+        for (int a = 0; a < NL; ++a) {                     // :177-182
+            const T coupling = SC::make(Mtail[a]) * SC::make(L[a]) * c[a];
+            A[0][1 + a] = coupling;
+            A[1 + a][0] = coupling;
+            b[0] = b[0] + SC::make(Mtail[a]) * SC::make(L[a]) * s[a] * omega[a] * omega[a];
+        }
+#pragma unroll
+        for (int a = 0; a < NL; ++a) {                     // :185-203
+            T rhs_a = SC::make(Mtail[a]) * gT * SC::make(L[a]) * s[a];
+#pragma unroll
+            for (int bb = 0; bb < NL; ++bb) {
+                const int mx = a > bb ? a : bb;
+                const T cab = c[a] * c[bb] + s[a] * s[bb];
+                A[1 + a][1 + bb] = SC::make(Mtail[mx]) * SC::make(L[a]) * SC::make(L[bb]) * cab;
+                if (bb != a) {
+                    const T sab = s[a] * c[bb] - c[a] * s[bb];
+                    rhs_a = rhs_a - SC::make(Mtail[mx]) * SC::make(L[a]) * SC::make(L[bb]) * sab * omega[bb] * omega[bb];
+                }
+            }
+            b[1 + a] = rhs_a;
+        }
+        // solveLinearSystem, :319-359: Gaussian elimination, partial pivoting on |value|
+        int st = 0;
+#pragma unroll
+        for (int col = 0; col < NDOF; ++col) {
+            int pivot = col;
+            double best = fabs(sb_value_of(A[col][col]));
+#pragma unroll
+            for (int row = col + 1; row < NDOF; ++row) {
+                const double mag = fabs(sb_value_of(A[row][col]));
+                if (mag > best) { best = mag; pivot = row; }
+            }
+            if (best < 1e-15) st = SOPOT_B200_ST_SINGULAR;  // the reference throws here
+#pragma unroll
+            for (int row = col + 1; row < NDOF; ++row) {
+                if (row == pivot) {
+#pragma unroll
+                    for (int j = 0; j < NDOF; ++j) { const T t = A[col][j]; A[col][j] = A[row][j]; A[row][j] = t; }
+                    const T t = b[col]; b[col] = b[row]; b[row] = t;
+                }
+            }
+#pragma unroll
+            for (int row = col + 1; row < NDOF; ++row) {
+                const T factor = A[row][col] / A[col][col];
+#pragma unroll
+                for (int j = col; j < NDOF; ++j) A[row][j] = A[row][j] - factor * A[col][j];
+                b[row] = b[row] - factor * b[col];
+            }
+        }
+        T x[NDOF];
+#pragma unroll
+        for (int i = NDOF - 1; i >= 0; --i) {
+            T sum = b[i];
+#pragma unroll
+            for (int j = i + 1; j < NDOF; ++j) sum = sum - A[i][j] * x[j];
+            x[i] = sum / A[i][i];
+        }
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) { deriv[i] = local[NDOF + i]; deriv[NDOF + i] = x[i]; }   // :206-219
+        return st;
+    }
+};
+
+// ---- K1: cart-pole (N = 1) integration with a constant force ----------------------------------------
+struct CartpoleSys {
+    static constexpr int DIM = 4;
+    static constexpr int BLOCK = 128;
+    struct DevParams { ParamRef mc, m, L, g, x, th, xd, w, force; };
+    template <bool S> struct Inst { CartPlant<1, Real<S>> plant; Real<S> F; };
+    template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
+    template <bool S>
+    static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
+        in.plant.mc = P.mc.at(i); in.plant.m[0] = P.m.at(i); in.plant.L[0] = P.L.at(i); in.plant.g = P.g.at(i);
+        in.F = Real<S>(P.force.at(i));
+        y[0] = Real<S>(P.x.at(i)); y[1] = Real<S>(P.th.at(i)); y[2] = Real<S>(P.xd.at(i)); y[3] = Real<S>(P.w.at(i));
+    }
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
+        return in.plant.derivatives(y, in.F, dy);
+    }
+    template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
+    template <bool S>
+    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[4]) {}
+};
+
+SB_EXPORT int sopot_b200_cartpole_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n,
+                                      double t0, double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
+                                      double* state_out, double* traj_out, int32_t* status) {
+    EnsembleArgs a{ctx, n, t0, dt, n_steps, opts, state_out, traj_out, status};
+    int rc = sb_check_ensemble(a, p);
+    if (rc) return rc;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_ensemble_arena_bytes(9, 4, n, n_steps, opts, traj_out, status, 0))))
+        return rc;
+    const double* user[9] = {p->mc, p->m, p->L, p->g, p->x, p->th, p->xd, p->w, p->force};
+    ParamRef r[9];
+    if ((rc = sb_stage_params(sg, user, 9, n, opts->broadcast, r))) return rc;
+    CartpoleSys::DevParams P{r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]};
+    return sb_launch_ensemble<CartpoleSys>(a, P, sg);
+}
+
+// ---- K2: batched linearization, one operating point per thread ------------------------------------
+// Dual<double,5> = 6 doubles per scalar, the whole 2x2 solve stays in registers.  Inputs and the 20
+// Jacobian entries are SoA, so every load and store of a warp is one fully coalesced 256 B segment:
+// 200 algorithmic bytes per point, HBM-bound.
+template <bool S>
+__global__ void __launch_bounds__(128)
+cartpole_linearize_kernel(ParamRef mc, ParamRef m, ParamRef L, ParamRef g, const double* __restrict__ x0,
+                          const double* __restrict__ u0, size_t P, double* __restrict__ A,
+                          double* __restrict__ B, int32_t* __restrict__ status) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    using D = DualR<5, S>;
+    CartPlant<1, D> plant;
+    plant.mc = mc.at(p); plant.m[0] = m.at(p); plant.L[0] = L.at(p); plant.g = g.at(p);
+    D xs[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xs[i] = D::variable(__ldg(x0 + (size_t)i * P + p), i);   // linearization.hpp:86-89
+    const D us = D::variable(__ldg(u0 + p), 4);                                           // :92-95
+    const int st = plant.derivatives(xs, us, d);
+    const double bad = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) A[(size_t)(i * 4 + j) * P + p] = st ? bad : d[i].d[j].v;   // :102-111
+        B[(size_t)i * P + p] = st ? bad : d[i].d[4].v;
+    }
+    if (status) status[p] = st;
+}
+
+SB_EXPORT int sopot_b200_cartpole_linearize(sopot_b200_ctx* ctx, const sopot_b200_cartpole_plant* plant,
+                                            const double* x0, const double* u0, size_t P,
+                                            const sopot_b200_rk4_opts* opts, double* A, double* B,
+                                            int32_t* status) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!plant || !x0 || !u0 || !opts || !A || !B) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 4 * sb_align(P * 8) + sb_align(4 * P * 8) + sb_align(P * 8) +
+                                                 sb_align(16 * P * 8) + sb_align(4 * P * 8) + sb_align(P * 4) + 4096)))
+        return rc;
+    const double* user[4] = {plant->mc, plant->m, plant->L, plant->g};
+    ParamRef r[4];
+    if ((rc = sb_stage_params(sg, user, 4, P, opts->broadcast, r))) return rc;
+    const void *d_x, *d_u; void *d_A, *d_B, *d_st;
+    if ((rc = sg.in(x0, 4 * P * 8, &d_x))) return rc;
+    if ((rc = sg.in(u0, P * 8, &d_u))) return rc;
+    if ((rc = sg.out(A, 16 * P * 8, &d_A))) return rc;
+    if ((rc = sg.out(B, 4 * P * 8, &d_B))) return rc;
+    if ((rc = sg.out(status, P * 4, &d_st))) return rc;
+    if (P) {
+        const unsigned grid = sb_grid_for(P, 128);
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT)
+            cartpole_linearize_kernel<true><<<grid, 128, 0, ctx->stream>>>(r[0], r[1], r[2], r[3], (const double*)d_x,
+                (const double*)d_u, P, (double*)d_A, (double*)d_B, (int32_t*)d_st);
+        else
+            cartpole_linearize_kernel<false><<<grid, 128, 0, ctx->stream>>>(r[0], r[1], r[2], r[3], (const double*)d_x,
+                (const double*)d_u, P, (double*)d_A, (double*)d_B, (int32_t*)d_st);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}

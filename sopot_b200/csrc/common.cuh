@@ -1,0 +1,143 @@
+// common.cuh -- context, error plumbing, host<->device staging and the Real<Strict> scalar used by
+// every kernel of libsopot_b200.so.  sm_100a only; there is no CPU path in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sopot_b200.h"
+
+#define SB_EXPORT extern "C" __attribute__((visibility("default")))
+
+struct NcclApi;   // context.cu
+
+struct sopot_b200_ctx {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;          // halo / overlap work
+    cudaEvent_t events[16] = {};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // internal cross-stream ordering
+    uint64_t launches = 0;
+    std::string error;
+    // grow-only device arena used to stage HOST-pointer calls
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    // persistent scratch for device-pointer calls (grid work vectors, reduction partials)
+    char* scratch = nullptr;
+    size_t scratch_cap = 0;
+    // NCCL (nranks > 1)
+    void* nccl_comm = nullptr;
+    const NcclApi* nccl = nullptr;
+};
+
+int sb_fail(sopot_b200_ctx* ctx, int code, const char* fmt, ...);
+int sb_cuda_fail(sopot_b200_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define SB_CUDA(ctx, expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) return sb_cuda_fail((ctx), _e, #expr, __FILE__, __LINE__);   \
+    } while (0)
+
+#define SB_CHECK_LAUNCH(ctx)                                                                \
+    do {                                                                                    \
+        (ctx)->launches++;                                                                  \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) return sb_cuda_fail((ctx), _e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// ---- arena staging -------------------------------------------------------------------------
+int sb_arena_begin(sopot_b200_ctx* ctx, size_t total_bytes);          // ensure capacity, reset bump
+void* sb_arena_take(sopot_b200_ctx* ctx, size_t bytes);               // 256 B aligned bump allocation
+int sb_scratch(sopot_b200_ctx* ctx, size_t bytes, void** out);        // persistent scratch >= bytes
+inline size_t sb_align(size_t b) { return (b + 255) & ~size_t(255); }
+
+// A call's view of its buffers: for MEM_DEVICE the user pointers are used as they are; for MEM_HOST
+// inputs are copied into the arena up front and outputs are copied back by finish().
+struct Staging {
+    sopot_b200_ctx* ctx;
+    bool host;
+    struct Out { void* user; void* dev; size_t bytes; };
+    std::vector<Out> outs;
+    Staging(sopot_b200_ctx* c, uint32_t mem) : ctx(c), host(mem == SOPOT_B200_MEM_HOST) {}
+    // returns the device address to read from (nullptr stays nullptr)
+    int in(const void* user, size_t bytes, const void** dev);
+    int out(void* user, size_t bytes, void** dev);
+    int finish();
+};
+
+// ---- per-instance parameter access -----------------------------------------------------------
+// A parameter is an array of n doubles or (broadcast) a single double.
+struct ParamRef {
+    const double* p;
+    size_t stride;   // 1 or 0
+    __device__ __forceinline__ double at(size_t i) const { return __ldg(p + i * stride); }
+};
+
+// ---- Real<Strict> ----------------------------------------------------------------------------
+// Strict = true : every + - * is a separately rounded IEEE operation (__dadd_rn/__dmul_rn are never
+//                 contracted into DFMA), divisions and sqrt are the IEEE-correct CUDA defaults: the
+//                 arithmetic of the reference's g++ -O3 build without -march (no FMA).
+// Strict = false: plain operators; nvcc (-fmad=true) contracts a*b+c into DFMA.
+template <bool Strict>
+struct Real {
+    double v;
+    __host__ __device__ __forceinline__ Real() : v(0.0) {}
+    __host__ __device__ __forceinline__ Real(double x) : v(x) {}
+    __host__ __device__ __forceinline__ explicit operator double() const { return v; }
+};
+
+#ifdef __CUDA_ARCH__
+#define SB_ADD(a, b) __dadd_rn((a), (b))
+#define SB_MUL(a, b) __dmul_rn((a), (b))
+#else
+#define SB_ADD(a, b) ((a) + (b))
+#define SB_MUL(a, b) ((a) * (b))
+#endif
+
+template <bool S> __host__ __device__ __forceinline__ Real<S> operator+(Real<S> a, Real<S> b) {
+    if constexpr (S) return Real<S>(SB_ADD(a.v, b.v)); else return Real<S>(a.v + b.v);
+}
+template <bool S> __host__ __device__ __forceinline__ Real<S> operator-(Real<S> a, Real<S> b) {
+    if constexpr (S) return Real<S>(SB_ADD(a.v, -b.v)); else return Real<S>(a.v - b.v);
+}
+template <bool S> __host__ __device__ __forceinline__ Real<S> operator*(Real<S> a, Real<S> b) {
+    if constexpr (S) return Real<S>(SB_MUL(a.v, b.v)); else return Real<S>(a.v * b.v);
+}
+template <bool S> __host__ __device__ __forceinline__ Real<S> operator/(Real<S> a, Real<S> b) {
+    return Real<S>(a.v / b.v);   // IEEE division in both modes (-prec-div=true)
+}
+template <bool S> __host__ __device__ __forceinline__ Real<S> operator-(Real<S> a) { return Real<S>(-a.v); }
+template <bool S> __host__ __device__ __forceinline__ Real<S>& operator+=(Real<S>& a, Real<S> b) { a = a + b; return a; }
+template <bool S> __host__ __device__ __forceinline__ Real<S>& operator-=(Real<S>& a, Real<S> b) { a = a - b; return a; }
+template <bool S> __host__ __device__ __forceinline__ Real<S>& operator*=(Real<S>& a, Real<S> b) { a = a * b; return a; }
+// mixed with double literals
+#define SB_MIXED(op)                                                                               \
+    template <bool S> __host__ __device__ __forceinline__ Real<S> operator op(Real<S> a, double b) { return a op Real<S>(b); } \
+    template <bool S> __host__ __device__ __forceinline__ Real<S> operator op(double a, Real<S> b) { return Real<S>(a) op b; }
+SB_MIXED(+) SB_MIXED(-) SB_MIXED(*) SB_MIXED(/)
+#undef SB_MIXED
+template <bool S> __host__ __device__ __forceinline__ bool operator<(Real<S> a, Real<S> b) { return a.v < b.v; }
+template <bool S> __host__ __device__ __forceinline__ bool operator>(Real<S> a, Real<S> b) { return a.v > b.v; }
+template <bool S> __host__ __device__ __forceinline__ bool operator<=(Real<S> a, Real<S> b) { return a.v <= b.v; }
+template <bool S> __host__ __device__ __forceinline__ bool operator>=(Real<S> a, Real<S> b) { return a.v >= b.v; }
+
+template <bool S> __device__ __forceinline__ Real<S> r_sqrt(Real<S> a) { return Real<S>(sqrt(a.v)); }
+template <bool S> __device__ __forceinline__ Real<S> r_sin(Real<S> a) { return Real<S>(sin(a.v)); }
+template <bool S> __device__ __forceinline__ Real<S> r_cos(Real<S> a) { return Real<S>(cos(a.v)); }
+template <bool S> __device__ __forceinline__ void r_sincos(Real<S> a, Real<S>& s, Real<S>& c) {
+    double sv, cv; sincos(a.v, &sv, &cv); s = Real<S>(sv); c = Real<S>(cv);
+}
+// x / d where the reference divides: IEEE division when Strict, reciprocal multiply otherwise
+template <bool S> __device__ __forceinline__ Real<S> r_div_const(Real<S> a, double d) {
+    if constexpr (S) return Real<S>(a.v / d); else return Real<S>(a.v * (1.0 / d));
+}
+
+inline unsigned sb_grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }

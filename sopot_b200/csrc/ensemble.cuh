@@ -1,0 +1,166 @@
+// ensemble.cuh -- K1: the fused four-stage RK4 step of core/solver.hpp:91-132 for an ensemble of
+// independent instances, one instance per thread, state and stage vectors register-resident for all
+// n_steps (no global traffic inside the time loop except optional strided trajectory snapshots).
+//
+// RK4 association (core/solver.hpp:95-125):  k_i = dt * f(.)  then
+//     y += (k1 + 2.0*k2 + 2.0*k3 + k4) / 6.0      evaluated left to right.
+// The running accumulator  S <- k1; S <- S + 2.0*k2; S <- S + 2.0*k3; y <- y + (S + k4)/6.0
+// reproduces ((k1 + 2k2) + 2k3) + k4 exactly (2.0*k is exact), so only one stage vector is live.
+//
+// A System provides:
+//   static constexpr int DIM;
+//   struct DevParams;                       // kernel argument (ParamRef per parameter, tables, ...)
+//   template <bool S> struct Inst;          // per-instance constants held in registers
+//   template <bool S> static __device__ void load(const DevParams&, size_t i, Inst<S>&, Real<S>(&y)[DIM]);
+//   template <bool S> static __device__ int  rhs(const Inst<S>&, const Real<S>(&y)[DIM], Real<S>(&dy)[DIM]);
+//   template <bool S> static __device__ void observe(Inst<S>&, double t, const Real<S>(&y)[DIM]);   // after each step
+//   template <bool S> static __device__ void finish(const DevParams&, const Inst<S>&, size_t i, size_t n, const Real<S>(&y)[DIM]);
+#pragma once
+#include "common.cuh"
+
+template <class Sys, bool S>
+__device__ __forceinline__ int rk4_step(const typename Sys::template Inst<S>& in,
+                                        Real<S> (&y)[Sys::DIM], const Real<S> dt) {
+    constexpr int D = Sys::DIM;
+    Real<S> k[D], acc[D], tmp[D];
+    int st = Sys::template rhs<S>(in, y, k);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { k[d] = k[d] * dt; acc[d] = k[d]; tmp[d] = y[d] + 0.5 * k[d]; }
+    st |= Sys::template rhs<S>(in, tmp, k);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { k[d] = k[d] * dt; acc[d] = acc[d] + 2.0 * k[d]; tmp[d] = y[d] + 0.5 * k[d]; }
+    st |= Sys::template rhs<S>(in, tmp, k);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { k[d] = k[d] * dt; acc[d] = acc[d] + 2.0 * k[d]; tmp[d] = y[d] + k[d]; }
+    st |= Sys::template rhs<S>(in, tmp, k);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { k[d] = k[d] * dt; y[d] = y[d] + r_div_const(acc[d] + k[d], 6.0); }
+    return st;
+}
+
+template <class Sys, bool S>
+__global__ void __launch_bounds__(Sys::BLOCK)
+rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double t0, const double dt_,
+                    const size_t n_steps, const size_t store_every, double* __restrict__ state_out,
+                    double* __restrict__ traj_out, int32_t* __restrict__ status) {
+    constexpr int D = Sys::DIM;
+    Sys::template block_setup<S>(P);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Sys::template Inst<S> in;
+    Real<S> y[D];
+    Sys::template load<S>(P, i, in, y);
+    const Real<S> dt(dt_);
+    double t = t0;                       // accumulated like the reference: t += dt (core/solver.hpp:127)
+    Sys::template observe<S>(in, t, y);  // the reference stores the initial condition (:87-88)
+    int st = 0;
+    size_t until_snap = store_every, snap = 0;
+    for (size_t step = 0; step < n_steps; ++step) {
+        st |= rk4_step<Sys, S>(in, y, dt);
+        t += dt_;
+        Sys::template observe<S>(in, t, y);
+        if (store_every && --until_snap == 0) {
+            until_snap = store_every;
+            if (traj_out) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) traj_out[(snap * D + d) * n + i] = y[d].v;
+            }
+            ++snap;
+        }
+    }
+    bool finite = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { state_out[(size_t)d * n + i] = y[d].v; finite &= isfinite(y[d].v); }
+    Sys::template finish<S>(P, in, i, n, y);
+    if (status) status[i] = (st & SOPOT_B200_ST_SINGULAR) ? SOPOT_B200_ST_SINGULAR
+                          : (finite ? SOPOT_B200_ST_OK : SOPOT_B200_ST_NONFINITE);
+}
+
+// single derivative evaluation per instance (computeDerivatives), state/out [DIM][n]
+template <class Sys, bool S>
+__global__ void __launch_bounds__(Sys::BLOCK)
+rhs_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double* __restrict__ state,
+                    double* __restrict__ out) {
+    constexpr int D = Sys::DIM;
+    Sys::template block_setup<S>(P);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Sys::template Inst<S> in;
+    Real<S> y[D], dy[D];
+    Sys::template load<S>(P, i, in, y);
+#pragma unroll
+    for (int d = 0; d < D; ++d) y[d] = Real<S>(state[(size_t)d * n + i]);
+    Sys::template rhs<S>(in, y, dy);
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[(size_t)d * n + i] = dy[d].v;
+}
+
+// ---- host-side helpers shared by the ensemble entry points -------------------------------------
+struct EnsembleArgs {
+    sopot_b200_ctx* ctx;
+    size_t n;
+    double t0, dt;
+    size_t n_steps;
+    const sopot_b200_rk4_opts* opts;
+    double* state_out;
+    double* traj_out;
+    int32_t* status;
+};
+
+inline int sb_check_ensemble(const EnsembleArgs& a, const void* params) {
+    if (!a.ctx) return SOPOT_B200_EINVAL;
+    if (!params || !a.opts || !a.state_out)
+        return sb_fail(a.ctx, SOPOT_B200_EINVAL, "params, opts and state_out must be non-NULL");
+    if (a.opts->mem > 1 || a.opts->fp_mode > 1) return sb_fail(a.ctx, SOPOT_B200_EINVAL, "bad opts");
+    if (!(a.dt > 0.0)) return sb_fail(a.ctx, SOPOT_B200_EINVAL, "dt must be positive");
+    if (a.traj_out && a.opts->store_every == 0)
+        return sb_fail(a.ctx, SOPOT_B200_EINVAL, "traj_out needs store_every > 0");
+    return SOPOT_B200_OK;
+}
+
+// stage `count` per-instance parameters (each n doubles, or 1 when its broadcast bit is set)
+inline int sb_stage_params(Staging& sg, const double* const* user, int count, size_t n,
+                           uint32_t broadcast, ParamRef* refs) {
+    for (int j = 0; j < count; ++j) {
+        if (!user[j]) return sb_fail(sg.ctx, SOPOT_B200_EINVAL, "parameter pointer %d is NULL", j);
+        const bool bc = (broadcast >> j) & 1u;
+        const void* dev = nullptr;
+        int rc = sg.in(user[j], (bc ? 1 : n) * sizeof(double), &dev);
+        if (rc) return rc;
+        refs[j].p = static_cast<const double*>(dev);
+        refs[j].stride = bc ? 0 : 1;
+    }
+    return SOPOT_B200_OK;
+}
+
+inline size_t sb_ensemble_arena_bytes(int n_params, int dim, size_t n, size_t n_steps,
+                                      const sopot_b200_rk4_opts* o, bool traj, bool status, size_t extra) {
+    size_t snaps = (traj && o->store_every) ? n_steps / o->store_every : 0;
+    return (size_t)n_params * sb_align(n * 8) + sb_align((size_t)dim * n * 8) +
+           sb_align(snaps * dim * n * 8) + (status ? sb_align(n * 4) : 0) + extra + 4096;
+}
+
+template <class Sys>
+int sb_launch_ensemble(const EnsembleArgs& a, const typename Sys::DevParams& P, Staging& sg) {
+    sopot_b200_ctx* ctx = a.ctx;
+    const size_t n = a.n;
+    const size_t snaps = (a.traj_out && a.opts->store_every) ? a.n_steps / a.opts->store_every : 0;
+    void *d_state = nullptr, *d_traj = nullptr, *d_status = nullptr;
+    int rc;
+    if ((rc = sg.out(a.state_out, (size_t)Sys::DIM * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(a.traj_out, snaps * Sys::DIM * n * 8, &d_traj))) return rc;
+    if ((rc = sg.out(a.status, n * 4, &d_status))) return rc;
+    if (n) {
+        const unsigned grid = sb_grid_for(n, Sys::BLOCK);
+        if (a.opts->fp_mode == SOPOT_B200_FP_STRICT)
+            rk4_ensemble_kernel<Sys, true><<<grid, Sys::BLOCK, 0, ctx->stream>>>(
+                P, n, a.t0, a.dt, a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
+                (int32_t*)d_status);
+        else
+            rk4_ensemble_kernel<Sys, false><<<grid, Sys::BLOCK, 0, ctx->stream>>>(
+                P, n, a.t0, a.dt, a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
+                (int32_t*)d_status);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}

@@ -1,0 +1,150 @@
+// ho_dpend.cu -- K1 instantiations for the two small analytic systems:
+//   config 1  physics::HarmonicOscillator   (physics/harmonic_oscillator.hpp:75-85)
+//   config 2  pendulum::DoublePendulum      (physics/pendulum/double_pendulum.hpp:126-179)
+#include "ensemble.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// HarmonicOscillator::derivatives: {v, T(-k/m)*x - T(c/m)*v}.  The two quotients are loop
+// invariant; hoisting them out of the time loop is bit-identical to dividing on every call.
+// ------------------------------------------------------------------------------------------------
+struct HoSys {
+    static constexpr int DIM = 2;
+    static constexpr int BLOCK = 128;
+    struct DevParams { ParamRef m, k, c, x0, v0; };
+    template <bool S> struct Inst { Real<S> a, b; };   // a = -k/m, b = c/m
+    template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
+    template <bool S>
+    static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[2]) {
+        const double m = P.m.at(i), k = P.k.at(i), c = P.c.at(i);
+        in.a = Real<S>(-k / m);
+        in.b = Real<S>(c / m);
+        y[0] = Real<S>(P.x0.at(i));
+        y[1] = Real<S>(P.v0.at(i));
+    }
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[2], Real<S> (&dy)[2]) {
+        dy[0] = y[1];
+        dy[1] = in.a * y[0] - in.b * y[1];
+        return 0;
+    }
+    template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[2]) {}
+    template <bool S>
+    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[2]) {}
+};
+
+SB_EXPORT int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n, double t0,
+                                double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
+                                double* state_out, double* traj_out, int32_t* status) {
+    EnsembleArgs a{ctx, n, t0, dt, n_steps, opts, state_out, traj_out, status};
+    int rc = sb_check_ensemble(a, p);
+    if (rc) return rc;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_ensemble_arena_bytes(5, 2, n, n_steps, opts, traj_out, status, 0))))
+        return rc;
+    const double* user[5] = {p->m, p->k, p->c, p->x0, p->v0};
+    ParamRef r[5];
+    if ((rc = sb_stage_params(sg, user, 5, n, opts->broadcast, r))) return rc;
+    HoSys::DevParams P{r[0], r[1], r[2], r[3], r[4]};
+    return sb_launch_ensemble<HoSys>(a, P, sg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DoublePendulum::derivatives.  Parameter-only products are hoisted in the reference's own
+// association: m2*L2*w2*w2*sd = (((m2*L2)*w2)*w2)*sd,  (m1+m2)*g*s1 = ((m1+m2)*g)*s1,
+// -L1*w1*w1*sd = (((-L1)*w1)*w1)*sd, so the Strict instantiation performs exactly the reference's
+// operations on every call.  sin(delta) and cos(delta) share one argument reduction (sincos).
+// In contract mode the two divisions by det become one reciprocal and two multiplies.
+// ------------------------------------------------------------------------------------------------
+struct DpendSys {
+    static constexpr int DIM = 4;
+    static constexpr int BLOCK = 128;
+    struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
+    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g; };
+    template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
+    template <bool S>
+    static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
+        const Real<S> m1(P.m1.at(i)), m2(P.m2.at(i)), L1(P.L1.at(i)), L2(P.L2.at(i)), g(P.g.at(i));
+        in.a11 = (m1 + m2) * L1;        // :162
+        in.m2L2 = m2 * L2;
+        in.m12g = (m1 + m2) * g;
+        in.negL1 = -L1;
+        in.L1 = L1; in.L2 = L2; in.g = g;
+        y[0] = Real<S>(P.th1.at(i)); y[1] = Real<S>(P.th2.at(i));
+        y[2] = Real<S>(P.w1.at(i));  y[3] = Real<S>(P.w2.at(i));
+    }
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
+        const Real<S> theta1 = y[0], theta2 = y[1], omega1 = y[2], omega2 = y[3];
+        const Real<S> delta = theta1 - theta2;                       // :145
+        Real<S> sin_delta, cos_delta;
+        r_sincos(delta, sin_delta, cos_delta);
+        const Real<S> sin_theta1 = r_sin(theta1), sin_theta2 = r_sin(theta2);
+        const Real<S> a12 = in.m2L2 * cos_delta;                     // :163
+        const Real<S> a21 = in.L1 * cos_delta;                       // :164
+        const Real<S> a22 = in.L2;
+        const Real<S> b1 = in.m2L2 * omega2 * omega2 * sin_delta - in.m12g * sin_theta1;   // :168
+        const Real<S> b2 = in.negL1 * omega1 * omega1 * sin_delta - in.g * sin_theta2;     // :169
+        const Real<S> det = in.a11 * a22 - a12 * a21;                // :172
+        const Real<S> n1 = b1 * a22 - b2 * a12;                      // :174
+        const Real<S> n2 = in.a11 * b2 - a21 * b1;                   // :175
+        dy[0] = omega1;
+        dy[1] = omega2;
+        if constexpr (S) { dy[2] = n1 / det; dy[3] = n2 / det; }
+        else { const Real<S> inv = Real<S>(1.0) / det; dy[2] = n1 * inv; dy[3] = n2 * inv; }
+        return 0;
+    }
+    template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
+    template <bool S>
+    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[4]) {}
+};
+
+static int dpend_stage(sopot_b200_ctx* ctx, Staging& sg, const sopot_b200_dpend_params* p, size_t n,
+                       uint32_t broadcast, DpendSys::DevParams& P) {
+    const double* user[9] = {p->m1, p->m2, p->L1, p->L2, p->g, p->th1, p->th2, p->w1, p->w2};
+    ParamRef r[9];
+    int rc = sb_stage_params(sg, user, 9, n, broadcast, r);
+    if (rc) return rc;
+    (void)ctx;
+    P = DpendSys::DevParams{r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]};
+    return SOPOT_B200_OK;
+}
+
+SB_EXPORT int sopot_b200_dpend_rk4(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n,
+                                   double t0, double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
+                                   double* state_out, double* traj_out, int32_t* status) {
+    EnsembleArgs a{ctx, n, t0, dt, n_steps, opts, state_out, traj_out, status};
+    int rc = sb_check_ensemble(a, p);
+    if (rc) return rc;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_ensemble_arena_bytes(9, 4, n, n_steps, opts, traj_out, status, 0))))
+        return rc;
+    DpendSys::DevParams P;
+    if ((rc = dpend_stage(ctx, sg, p, n, opts->broadcast, P))) return rc;
+    return sb_launch_ensemble<DpendSys>(a, P, sg);
+}
+
+SB_EXPORT int sopot_b200_dpend_rhs(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n,
+                                   const sopot_b200_rk4_opts* opts, const double* state, double* out) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    // the ICs are overwritten by `state`; reuse th1 as a valid pointer when the caller passes none
+    sopot_b200_dpend_params q = *p;
+    if (!q.th1) q.th1 = state; if (!q.th2) q.th2 = state; if (!q.w1) q.w1 = state; if (!q.w2) q.w2 = state;
+    if (sg.host && (rc = sb_arena_begin(ctx, 9 * sb_align(n * 8) + 2 * sb_align(4 * n * 8) + 4096))) return rc;
+    DpendSys::DevParams P;
+    if ((rc = dpend_stage(ctx, sg, &q, n, opts->broadcast, P))) return rc;
+    const void* d_state; void* d_out;
+    if ((rc = sg.in(state, 4 * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(out, 4 * n * 8, &d_out))) return rc;
+    if (n) {
+        const unsigned grid = sb_grid_for(n, DpendSys::BLOCK);
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT)
+            rhs_ensemble_kernel<DpendSys, true><<<grid, DpendSys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        else
+            rhs_ensemble_kernel<DpendSys, false><<<grid, DpendSys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}

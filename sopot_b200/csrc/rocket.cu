@@ -1,0 +1,451 @@
+// rocket.cu -- K1 instantiation for the 6-DOF rocket, Rocket<double>::SystemType
+// (rocket/rocket.hpp:73-85): 11 components, 14 states
+//   [0] t  [1..3] pos ENU  [4..6] vel ENU  [7..10] q1..q4 (scalar last)  [11..13] body rates.
+//
+// One trajectory per thread, state + RK4 accumulators register-resident.  Each distinct state
+// function is evaluated ONCE per derivative call (the reference's registry re-evaluates its whole
+// sub-tree on every query, core/typed_component.hpp:249-261; state functions are pure, so the
+// de-duplicated evaluation is value-identical):
+//   rotation matrix R(q)        1x  (reference: 4x  -- thrust, aero force in/out, aero moment)
+//   atmosphere P(h), T(h)       1x  (reference: pow() 3x -- thrust, force density, moment density)
+//   body velocity, airspeed     1x  (reference: 2x)
+//   mass(t)                     1x  (reference: 2x)
+// Terms the reference multiplies by an exact zero are dropped where that cannot change a value:
+//   thrust_body = (T,0,0)  =>  R*thrust_body = (R00*T, R10*T, R20*T)      (quaternion.hpp:115-122)
+//   omega_quat.q4 = 0      =>  the q*p4 products vanish                    (quaternion.hpp:80-90)
+//   Cl = Cs = 0 without coefficient tables (axisymmetric_aero.hpp:154,166) => lift and side force
+//   are +-0 and the two atan2 / sin / cos that only feed them are not evaluated.
+// Engine / mass / inertia tables and the 7-layer atmosphere are staged in shared memory by every
+// block; all lanes of a warp read the same time interval (state[0] advances identically in every
+// instance), so table reads are shared-memory broadcasts.
+#include "ensemble.cuh"
+#include <cmath>
+#include <vector>
+
+namespace {
+
+// StandardAtmosphere, rocket/standard_atmosphere.hpp:18-32.  pow_exp = g0*M/(R*lapse) (:64) and
+// exp_den = R*T_base (:62) are formed on the host in the reference's order.
+struct AtmLayer { double h_top, P_base, T_base, lapse, h_base, pow_exp, exp_den; };
+__constant__ AtmLayer c_atm[7];
+
+constexpr double kAtmR = 8.3144598, kAtmM = 0.0289644, kAtmGamma = 1.4, kAtmG0 = 9.80665;
+constexpr double kAtmP0 = 101325.0, kAtmT0 = 288.15;
+constexpr double kAtmRs = kAtmR / kAtmM;
+constexpr double kEnginePi = 3.14159265358979323846;   // interpolated_engine.hpp:34
+constexpr double kAeroPi = 3.14159265358979;            // axisymmetric_aero.hpp:56 (truncated, literal)
+
+struct RocketTablesDev {
+    // one packed device buffer: engine columns time, exit_d, p_comb, press_ratio, engine_force
+    // (5 * er), then mass time/value (2 * mr), ix (2 * xr), iyz (2 * yr)
+    const double* packed;
+    int er, mr, xr, yr;
+    double burn_time;
+    int use_interp;
+};
+
+template <bool S>
+struct Lerp {   // io/interpolation.hpp:49-71 on a shared time grid
+    int i;          // interval index, or -1: clamp low, -2: clamp high
+    Real<S> t;      // (x - x0) / (x1 - x0)
+    __device__ __forceinline__ Real<S> eval(const double* y, int n) const {
+        if (i == -1) return Real<S>(y[0]);
+        if (i == -2) return Real<S>(y[n - 1]);
+        const Real<S> y0(y[i]), y1(y[i + 1]);
+        return y0 + t * (y1 - y0);
+    }
+};
+
+template <bool S>
+__device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv) {
+    Lerp<S> L;
+    L.t = Real<S>(0.0);
+    if (xv <= x[0]) { L.i = -1; return L; }
+    if (xv >= x[n - 1]) { L.i = -2; return L; }
+    int lo = 0, hi = n;                       // std::lower_bound: first element >= xv
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < xv) lo = mid + 1; else hi = mid; }
+    const int i = lo > 0 ? lo - 1 : 0;
+    const Real<S> x0(x[i]), x1(x[i + 1]);
+    L.i = i;
+    L.t = (Real<S>(xv) - x0) / (x1 - x0);
+    return L;
+}
+
+template <bool S>
+__device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S>& T) {
+    const double h = alt.v;
+    if (h <= 0) { P = Real<S>(kAtmP0); T = Real<S>(kAtmT0); return; }          // :45,:57
+    if (h >= 100000.0) { P = Real<S>(1e-4); T = Real<S>(186.95); return; }      // :46,:58
+    int li = 0;
+#pragma unroll
+    for (int k = 6; k >= 0; --k) if (h <= c_atm[k].h_top) li = k;              // first layer with h <= h_top
+    const AtmLayer l = c_atm[li];
+    const Real<S> dh = alt - Real<S>(l.h_base);
+    if (fabs(l.lapse) < 1e-10) {
+        T = Real<S>(l.T_base);
+        // P_base * exp(-(g0*M) * (h - h_base) / (R*T_base))                    :62
+        const Real<S> arg = Real<S>(-(kAtmG0 * kAtmM)) * dh / Real<S>(l.exp_den);
+        P = Real<S>(l.P_base) * Real<S>(exp(arg.v));
+    } else {
+        const Real<S> Tl = Real<S>(l.T_base) + Real<S>(l.lapse) * dh;           // :50, :63
+        T = Tl;
+        const Real<S> ratio = Real<S>(l.T_base) / Tl;
+        P = Real<S>(l.P_base) * Real<S>(pow(ratio.v, l.pow_exp));               // :64
+    }
+}
+
+}  // namespace
+
+struct RocketSys {
+    static constexpr int DIM = 14;
+    static constexpr int BLOCK = 128;
+    struct DevParams {
+        ParamRef elev, az, diam, g;
+        RocketTablesDev tab;
+        double* stats_out;   // [8][n] or nullptr
+    };
+    template <bool S> struct Inst {
+        Real<S> g, area, len;
+        const double* tb;          // shared-memory copy of the packed tables
+        int er, mr, xr, yr, use_interp;
+        double burn;
+        double apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd;
+    };
+    static size_t smem_bytes(const DevParams& P) {
+        return sizeof(double) * (size_t)(5 * P.tab.er + 2 * P.tab.mr + 2 * P.tab.xr + 2 * P.tab.yr);
+    }
+    template <bool S> static __device__ __forceinline__ void block_setup(const DevParams& P) {
+        extern __shared__ double s_tab[];
+        const int total = 5 * P.tab.er + 2 * P.tab.mr + 2 * P.tab.xr + 2 * P.tab.yr;
+        for (int j = threadIdx.x; j < total; j += blockDim.x) s_tab[j] = P.tab.packed[j];
+        __syncthreads();
+    }
+    template <bool S>
+    static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[14]) {
+        extern __shared__ double s_tab[];
+        in.tb = s_tab;
+        in.er = P.tab.er; in.mr = P.tab.mr; in.xr = P.tab.xr; in.yr = P.tab.yr;
+        in.use_interp = P.tab.use_interp; in.burn = P.tab.burn_time;
+        const double d = P.diam.at(i);
+        in.g = Real<S>(P.g.at(i));
+        in.area = Real<S>(kAeroPi) * Real<S>(d) * Real<S>(d) / Real<S>(4.0);   // axisymmetric_aero.hpp:56
+        in.len = Real<S>(d);
+        in.apogee = 0; in.apogee_t = 0; in.vmax = 0; in.vmax_t = 0; in.bo_alt = 0; in.bo_spd = 0;
+#pragma unroll
+        for (int k = 0; k < 14; ++k) y[k] = Real<S>(0.0);
+        // Quaternion::from_launcher_angles, rocket/quaternion.hpp:164-190
+        const Real<S> deg2rad = Real<S>(3.14159265358979323846 / 180.0);
+        const Real<S> yaw = (Real<S>(90.0) - Real<S>(P.az.at(i))) * deg2rad;
+        const Real<S> pitch = Real<S>(P.elev.at(i)) * deg2rad;
+        Real<S> sy, cy, sp, cp;
+        r_sincos(yaw * Real<S>(0.5), sy, cy);
+        r_sincos(pitch * Real<S>(0.5), sp, cp);
+        y[7] = sy * sp; y[8] = (-cy) * sp; y[9] = sy * cp; y[10] = cy * cp;
+    }
+
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&s)[14], Real<S> (&d)[14]) {
+        using R = Real<S>;
+        const R time = s[0], alt = s[3];
+        const R q1 = s[7], q2 = s[8], q3 = s[9], q4 = s[10];
+        const R wx = s[11], wy = s[12], wz = s[13];
+        const double* tb = in.tb;
+        const double* eng_t = tb;
+        const double* mass_t = tb + 5 * in.er;
+        const double* ix_t = mass_t + 2 * in.mr;
+        const double* iyz_t = ix_t + 2 * in.xr;
+
+        // ---- rotation matrix, quaternion.hpp:94-112 (once) ----
+        const R q1_2 = q1 * q1, q2_2 = q2 * q2, q3_2 = q3 * q3, q4_2 = q4 * q4;
+        const R q1q2 = q1 * q2, q1q3 = q1 * q3, q1q4 = q1 * q4, q2q3 = q2 * q3, q2q4 = q2 * q4, q3q4 = q3 * q4;
+        const R R00 = q4_2 + q1_2 - q2_2 - q3_2, R01 = R(2.0) * (q1q2 - q3q4), R02 = R(2.0) * (q1q3 + q2q4);
+        const R R10 = R(2.0) * (q1q2 + q3q4), R11 = q4_2 - q1_2 + q2_2 - q3_2, R12 = R(2.0) * (q2q3 - q1q4);
+        const R R20 = R(2.0) * (q1q3 - q2q4), R21 = R(2.0) * (q2q3 + q1q4), R22 = q4_2 - q1_2 - q2_2 + q3_2;
+
+        // ---- body velocity and airspeed, axisymmetric_aero.hpp:177-188 ----
+        const R vbx = R00 * s[4] + R10 * s[5] + R20 * s[6];
+        const R vby = R01 * s[4] + R11 * s[5] + R21 * s[6];
+        const R vbz = R02 * s[4] + R12 * s[5] + R22 * s[6];
+        const R airspeed = r_sqrt(vbx * vbx + vby * vby + vbz * vbz);
+        const bool aero_on = !(airspeed.v < 1.0);
+
+        // ---- mass and inertia, rocket_body.hpp:121-179 ----
+        R mass(100.0), Ix(10.0), Iyz(100.0);
+        if (in.use_interp) {
+            if (in.mr) mass = lerp_locate<S>(mass_t, in.mr, time.v).eval(mass_t + in.mr, in.mr);
+            if (in.xr) Ix = lerp_locate<S>(ix_t, in.xr, time.v).eval(ix_t + in.xr, in.xr);
+            if (in.yr) Iyz = lerp_locate<S>(iyz_t, in.yr, time.v).eval(iyz_t + in.yr, in.yr);
+        }
+
+        // ---- thrust, interpolated_engine.hpp:103-152 ----
+        const bool burning = in.er > 0 && time.v <= in.burn;
+        R P(0.0), T(0.0);
+        if (burning || aero_on) atmosphere<S>(alt, P, T);
+        R thrust(0.0);
+        if (burning) {
+            const Lerp<S> L = lerp_locate<S>(eng_t, in.er, time.v);
+            const R d_exit = L.eval(eng_t + in.er, in.er);
+            const R p_comb = L.eval(eng_t + 2 * in.er, in.er);
+            const R press_ratio = L.eval(eng_t + 3 * in.er, in.er);
+            const R exit_area = R(kEnginePi) * d_exit * d_exit / R(4.0);
+            const R exit_pressure = p_comb * press_ratio;
+            const R engine_force = L.eval(eng_t + 4 * in.er, in.er);
+            thrust = engine_force + exit_area * (exit_pressure - P);
+        }
+
+        // ---- aerodynamic force (ENU) and damping moment (body) ----
+        R Fax(0.0), Fay(0.0), Faz(0.0), Mx(0.0), My(0.0), Mz(0.0);
+        if (aero_on) {
+            const R density = P / (R(kAtmRs) * T);                               // standard_atmosphere.hpp:70
+            const R dynp = R(0.5) * density * airspeed * airspeed;                // :198
+            const R qS = dynp * in.area;                                          // :212
+            R ux(0.0), uy(0.0), uz(0.0);
+            if (!(airspeed.v < 1e-15)) { ux = vbx / airspeed; uy = vby / airspeed; uz = vbz / airspeed; }
+            const R drag = qS * R(0.3);                                           // Cd default, :142
+            const R fbx = (-ux) * drag, fby = (-uy) * drag, fbz = (-uz) * drag;   // :228
+            Fax = R00 * fbx + R01 * fby + R02 * fbz;                              // :251-253
+            Fay = R10 * fbx + R11 * fby + R12 * fbz;
+            Faz = R20 * fbx + R21 * fby + R22 * fbz;
+            const R qSd = qS * in.len;                                            // :271
+            const R damping = in.len / airspeed;                                  // :274
+            const R cq = R(-450.0) * qSd * damping;                               // :275, :283-287
+            Mx = cq * wx; My = cq * wy; Mz = cq * wz;
+        }
+
+        // ---- ForceAggregator, force_aggregator.hpp:61-79 : (F_gravity + F_thrust) + F_aero ----
+        const R Fx = R00 * thrust + Fax;
+        const R Fy = R10 * thrust + Fay;
+        const R Fz = ((-in.g) * mass + R20 * thrust) + Faz;
+
+        d[0] = R(1.0);                                                            // simulation_time.hpp:46-54
+        d[1] = s[4]; d[2] = s[5]; d[3] = s[6];                                    // translation_kinematics.hpp:46-55
+        d[4] = Fx / mass; d[5] = Fy / mass; d[6] = Fz / mass;                     // translation_dynamics.hpp:35-42
+        d[7] = ((q4 * wx + q2 * wz) - q3 * wy) * R(0.5);                          // quaternion.hpp:80-90
+        d[8] = ((q4 * wy - q1 * wz) + q3 * wx) * R(0.5);
+        d[9] = ((q4 * wz + q1 * wy) - q2 * wx) * R(0.5);
+        d[10] = (((-(q1 * wx)) - q2 * wy) - q3 * wz) * R(0.5);
+        d[11] = (Mx - (Iyz - Iyz) * wy * wz) / Ix;                                // rotation_dynamics.hpp:42-44
+        d[12] = (My - (Ix - Iyz) * wx * wz) / Iyz;
+        d[13] = (Mz - (Iyz - Ix) * wx * wy) / Iyz;
+        return 0;
+    }
+
+    // SimulationResult::computeStatistics, rocket/simulation_result.hpp:151-189, fused into the loop
+    template <bool S>
+    static __device__ __forceinline__ void observe(Inst<S>& in, double t, const Real<S> (&y)[14]) {
+        const double alt = y[3].v;
+        const Real<S> sp2 = y[4] * y[4] + y[5] * y[5] + y[6] * y[6];
+        const double spd = sqrt(sp2.v);
+        if (alt > in.apogee) { in.apogee = alt; in.apogee_t = t; }
+        if (spd > in.vmax) { in.vmax = spd; in.vmax_t = t; }
+        if (in.burn > 0 && fabs(t - in.burn) < 0.1) { in.bo_alt = alt; in.bo_spd = spd; }
+    }
+    template <bool S>
+    static __device__ __forceinline__ void finish(const DevParams& P, const Inst<S>& in, size_t i, size_t n,
+                                                  const Real<S> (&y)[14]) {
+        if (!P.stats_out) return;
+        double* o = P.stats_out + i;
+        o[0] = in.apogee; o[n] = in.apogee_t; o[2 * n] = in.vmax; o[3 * n] = in.vmax_t;
+        o[4 * n] = in.bo_alt; o[5 * n] = in.bo_spd; o[6 * n] = y[1].v; o[7 * n] = y[2].v;
+    }
+};
+
+// ---- host side ------------------------------------------------------------------------------------
+namespace {
+
+// LinearInterpolator::interpolate (io/interpolation.hpp:49-71) on host columns
+double host_lerp(const std::vector<double>& x, const double* y, double xv) {
+    const size_t n = x.size();
+    if (n == 0) return 0.0;
+    if (xv <= x.front()) return y[0];
+    if (xv >= x.back()) return y[n - 1];
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (x[mid] < xv) lo = mid + 1; else hi = mid; }
+    size_t i = lo ? lo - 1 : 0;
+    const double t = (xv - x[i]) / (x[i + 1] - x[i]);
+    return y[i] + t * (y[i + 1] - y[i]);
+}
+
+// InterpolatedEngine::computePressureRatio, interpolated_engine.hpp:225-252
+double nozzle_pressure_ratio(double k, double area_ratio) {
+    double pr = 0.01;
+    for (int it = 0; it < 20; ++it) {
+        double M2 = (2.0 / (k - 1.0)) * (std::pow(1.0 / pr, (k - 1.0) / k) - 1.0);
+        if (M2 < 0) M2 = 0;
+        const double M = std::sqrt(M2);
+        const double term = (2.0 / (k + 1.0)) * (1.0 + (k - 1.0) / 2.0 * M2);
+        const double area_calc = (1.0 / M) * std::pow(term, (k + 1.0) / (2.0 * (k - 1.0)));
+        if (std::fabs(area_calc - area_ratio) < 0.001 * area_ratio) break;
+        pr *= (area_calc > area_ratio) ? 0.95 : 1.05;
+        if (pr < 1e-6) pr = 1e-6;
+        if (pr > 1.0) pr = 1.0;
+    }
+    return pr;
+}
+
+// Pack the host tables for the device: the load-time precompute of InterpolatedEngine
+// (interpolated_engine.hpp:176-222) happens here, once per call, on the host.
+void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, RocketTablesDev& tab) {
+    const size_t er = p->engine_rows, mr = p->mass_rows, xr = p->ix_rows, yr = p->iyz_rows;
+    out.assign(5 * er + 2 * mr + 2 * xr + 2 * yr, 0.0);
+    if (er) {
+        std::vector<double> t(er), col(8 * er);
+        for (size_t r = 0; r < er; ++r)
+            for (int c = 0; c < 8; ++c) col[c * er + r] = p->engine[r * 8 + c];
+        for (size_t r = 0; r < er; ++r) t[r] = col[r];
+        double* o_t = out.data();
+        double* o_exit = o_t + er; double* o_pc = o_exit + er; double* o_pr = o_pc + er; double* o_f = o_pr + er;
+        for (size_t r = 0; r < er; ++r) {
+            const double tt = t[r];
+            const double k = host_lerp(t, &col[5 * er], tt), d_throat = host_lerp(t, &col[1 * er], tt);
+            const double d_exit = host_lerp(t, &col[2 * er], tt), pc = host_lerp(t, &col[3 * er], tt);
+            const double temp = host_lerp(t, &col[4 * er], tt), mol = host_lerp(t, &col[6 * er], tt);
+            const double eff = host_lerp(t, &col[7 * er], tt);
+            const double throat_area = kEnginePi * d_throat * d_throat / 4.0;
+            const double exit_area = kEnginePi * d_exit * d_exit / 4.0;
+            const double ratio = nozzle_pressure_ratio(k, exit_area / throat_area);
+            const double throat_pressure = pc * std::pow(2.0 / (k + 1.0), k / (k - 1.0));
+            const double throat_temp = temp * (2.0 / (k + 1.0));
+            const double Rspec = kAtmR / mol;
+            const double throat_density = throat_pressure / (Rspec * throat_temp);
+            const double throat_velocity = std::sqrt(k * Rspec * throat_temp);
+            double mdot = throat_density * throat_velocity * throat_area;
+            if (mdot < 0) mdot = 0;
+            const double exit_velocity =
+                eff * std::sqrt(2.0 * k / (k - 1.0) * Rspec * temp * (1.0 - std::pow(ratio, (k - 1.0) / k)));
+            o_t[r] = tt; o_exit[r] = col[2 * er + r]; o_pc[r] = col[3 * er + r];
+            o_pr[r] = ratio; o_f[r] = mdot * exit_velocity;
+        }
+    }
+    double* o = out.data() + 5 * er;
+    auto put2 = [&](size_t rows, const double* src) {
+        for (size_t r = 0; r < rows; ++r) { o[r] = src[2 * r]; o[rows + r] = src[2 * r + 1]; }
+        o += 2 * rows;
+    };
+    put2(mr, p->mass); put2(xr, p->ix); put2(yr, p->iyz);
+    tab.er = (int)er; tab.mr = (int)mr; tab.xr = (int)xr; tab.yr = (int)yr;
+    tab.burn_time = er ? p->engine[(er - 1) * 8] : 0.0;
+    tab.use_interp = (mr || xr || yr) ? 1 : 0;
+}
+
+int upload_atmosphere(sopot_b200_ctx* ctx) {
+    static const double L[7][5] = {
+        {11000.0, 101325.0, 288.15, -0.0065, 0.0},   {20000.0, 22632.0, 216.65, 0.0, 11000.0},
+        {32000.0, 5474.89, 216.65, 0.001, 20000.0},  {47000.0, 868.02, 228.65, 0.0028, 32000.0},
+        {51000.0, 110.91, 270.65, 0.0, 47000.0},     {71000.0, 66.94, 270.65, -0.0028, 51000.0},
+        {100000.0, 3.96, 214.65, -0.002, 71000.0}};
+    AtmLayer h[7];
+    for (int i = 0; i < 7; ++i) {
+        h[i] = AtmLayer{L[i][0], L[i][1], L[i][2], L[i][3], L[i][4], 0.0, kAtmR * L[i][2]};
+        if (std::fabs(L[i][3]) >= 1e-10) h[i].pow_exp = kAtmG0 * kAtmM / (kAtmR * L[i][3]);
+    }
+    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_atm, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    return SOPOT_B200_OK;
+}
+
+int rocket_prepare(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n, uint32_t broadcast,
+                   Staging& sg, RocketSys::DevParams& P) {
+    if ((p->engine_rows && !p->engine) || (p->mass_rows && !p->mass) || (p->ix_rows && !p->ix) ||
+        (p->iyz_rows && !p->iyz))
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "table pointer is NULL with rows > 0");
+    if (p->engine_rows == 1 || p->mass_rows == 1 || p->ix_rows == 1 || p->iyz_rows == 1)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "interpolation tables need at least 2 rows");
+    int rc;
+    if ((rc = upload_atmosphere(ctx))) return rc;
+    std::vector<double> packed;
+    pack_tables(p, packed, P.tab);
+    if (packed.size() * 8 > 200 * 1024)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "tables exceed the 200 KiB shared-memory staging budget");
+    // the packed tables always travel host -> device (tables are host pointers by contract)
+    void* d_tab = nullptr;
+    if ((rc = sb_scratch(ctx, packed.size() * 8 + 256, &d_tab))) return rc;
+    if (!packed.empty()) {
+        SB_CUDA(ctx, cudaMemcpyAsync(d_tab, packed.data(), packed.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `packed` is a local
+    }
+    P.tab.packed = static_cast<const double*>(d_tab);
+    const double* user[4] = {p->elevation_deg, p->azimuth_deg, p->diameter, p->gravity};
+    ParamRef r[4];
+    if ((rc = sb_stage_params(sg, user, 4, n, broadcast, r))) return rc;
+    P.elev = r[0]; P.az = r[1]; P.diam = r[2]; P.g = r[3];
+    P.stats_out = nullptr;
+    return SOPOT_B200_OK;
+}
+
+template <bool S>
+int rocket_set_smem(sopot_b200_ctx* ctx, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(rk4_ensemble_kernel<RocketSys, S>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        SB_CUDA(ctx, cudaFuncSetAttribute(rhs_ensemble_kernel<RocketSys, S>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return SOPOT_B200_OK;
+}
+
+}  // namespace
+
+SB_EXPORT int sopot_b200_rocket_rk4(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n, double dt,
+                                    size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out,
+                                    double* traj_out, double* stats_out, int32_t* status) {
+    EnsembleArgs a{ctx, n, 0.0, dt, n_steps, opts, state_out, traj_out, status};
+    int rc = sb_check_ensemble(a, p);
+    if (rc) return rc;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_ensemble_arena_bytes(4, 14, n, n_steps, opts, traj_out, status,
+                                                                     sb_align(8 * n * 8)))))
+        return rc;
+    RocketSys::DevParams P;
+    if ((rc = rocket_prepare(ctx, p, n, opts->broadcast, sg, P))) return rc;
+    void* d_stats = nullptr;
+    if ((rc = sg.out(stats_out, 8 * n * 8, &d_stats))) return rc;
+    P.stats_out = static_cast<double*>(d_stats);
+
+    const size_t smem = RocketSys::smem_bytes(P);
+    const size_t snaps = (traj_out && opts->store_every) ? n_steps / opts->store_every : 0;
+    void *d_state = nullptr, *d_traj = nullptr, *d_status = nullptr;
+    if ((rc = sg.out(state_out, 14 * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(traj_out, snaps * 14 * n * 8, &d_traj))) return rc;
+    if ((rc = sg.out(status, n * 4, &d_status))) return rc;
+    if (n) {
+        const unsigned grid = sb_grid_for(n, RocketSys::BLOCK);
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT) {
+            if ((rc = rocket_set_smem<true>(ctx, smem))) return rc;
+            rk4_ensemble_kernel<RocketSys, true><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(
+                P, n, 0.0, dt, n_steps, opts->store_every, (double*)d_state, (double*)d_traj, (int32_t*)d_status);
+        } else {
+            if ((rc = rocket_set_smem<false>(ctx, smem))) return rc;
+            rk4_ensemble_kernel<RocketSys, false><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(
+                P, n, 0.0, dt, n_steps, opts->store_every, (double*)d_state, (double*)d_traj, (int32_t*)d_status);
+        }
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}
+
+SB_EXPORT int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n,
+                                    const sopot_b200_rk4_opts* opts, const double* state, double* out) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 4 * sb_align(n * 8) + 2 * sb_align(14 * n * 8) + 4096))) return rc;
+    RocketSys::DevParams P;
+    if ((rc = rocket_prepare(ctx, p, n, opts->broadcast, sg, P))) return rc;
+    const void* d_state; void* d_out;
+    if ((rc = sg.in(state, 14 * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(out, 14 * n * 8, &d_out))) return rc;
+    const size_t smem = RocketSys::smem_bytes(P);
+    if (n) {
+        const unsigned grid = sb_grid_for(n, RocketSys::BLOCK);
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT) {
+            if ((rc = rocket_set_smem<true>(ctx, smem))) return rc;
+            rhs_ensemble_kernel<RocketSys, true><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        } else {
+            if ((rc = rocket_set_smem<false>(ctx, smem))) return rc;
+            rhs_ensemble_kernel<RocketSys, false><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        }
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}

@@ -1,0 +1,96 @@
+"""Regenerate tests/golden/*.npz from the UNMODIFIED reference compiled in the build container.
+
+    python tests/golden/make_golden.py          (needs oracle/_ref/libsopot_ref.so, i.e. /root/reference)
+
+Every array named ref_* below is an output of the reference's own code path (makeTypedODESystem ->
+createRK4Solver().solve, makeLinearizer<4,1>, Rocket component system, makeGrid2DSystem), driven by
+oracle/ref_harness.cpp; inputs are stored beside them so the fixtures do not depend on any RNG.
+The reference's own tests contain almost no numeric goldens for this path;
+the known answers quoted in BASELINE.md section 2 are asserted in tests/test_oracle.py as well.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.oracle_py import Checker  # noqa: E402
+from sopot_b200 import workloads as W  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    R = Checker("reference")
+    # ---- config 1 ----
+    w = W.ho_ensemble(64)
+    w["m"][0], w["k"][0], w["c"][0], w["x0"][0] = 2.0, 9.0, 0.1, 1.5          # README nominal first
+    fin, traj, tl = R.ho_rk4(w["m"], w["k"], w["c"], w["x0"], w["v0"], 0.0, 10.0, 0.01, 100, 10)
+    np.savez(os.path.join(OUT, "ho.npz"), m=w["m"], k=w["k"], c=w["c"], x0=w["x0"], v0=w["v0"],
+             ref_final=fin, ref_traj=traj, ref_t_last=tl)
+    # ---- config 2 ----
+    w = W.dpend_ensemble(16)
+    w["th1"][0], w["th2"][0] = np.pi / 4, np.pi / 6                           # BASELINE.md nominal first
+    w["th1"][1], w["th2"][1] = 3.0, 3.0                                       # most chaotic survey case
+    args = [w[k] for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+    fin, traj, _ = R.dpend_rk4(*args, 0.0, 10.0, 1e-3, 1000, 10)
+    st = np.stack([np.linspace(-3, 3, 32), np.linspace(3, -2, 32), np.linspace(-4, 4, 32), np.linspace(5, -5, 32)])
+    rhs = R.dpend_rhs(1.3, 0.7, 0.9, 1.1, 9.81, st)
+    # shadow twins: theta1 nudged by one ulp
+    th1n = np.nextafter(w["th1"], np.inf)
+    args_n = [w["m1"], w["m2"], w["L1"], w["L2"], w["g"], th1n, w["th2"], w["w1"], w["w2"]]
+    _, traj_n, _ = R.dpend_rk4(*args_n, 0.0, 10.0, 1e-3, 1000, 10)
+    np.savez(os.path.join(OUT, "dpend.npz"), **{k: w[k] for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")},
+             ref_final=fin, ref_traj=traj, ref_traj_twin=traj_n, rhs_state=st, ref_rhs=rhs)
+    # ---- config 3 ----
+    w = W.cartpole_points(256)
+    w["x"][:, 0] = 0.0; w["u"][0] = 0.0                                       # upright
+    w["x"][:, 1] = [0.1, 0.3, -0.2, 0.5]; w["u"][1] = 1.5                     # BASELINE.md point
+    A, B = R.cartpole_linearize(w["x"], w["u"], w["mc"], w["m"], w["L"], w["g"])
+    fin = R.cartpole_rk4(w["mc"][:16], w["m"][:16], w["L"][:16], w["g"][:16], w["x"][:, :16], w["u"][:16], 0.0, 2.0, 0.01)
+    np.savez(os.path.join(OUT, "cartpole.npz"), x=w["x"], u=w["u"], mc=w["mc"], m=w["m"], L=w["L"], g=w["g"],
+             ref_A=A, ref_B=B, ref_rk4_final=fin)
+    # ---- config 4 ----
+    w = W.rocket_ensemble(8)
+    w["elev"][0], w["az"][0], w["diam"][0], w["g0"][0] = 85.0, 0.0, 0.16, 9.80665
+    fin, stats, traj = R.rocket_rk4(w["elev"], w["az"], w["diam"], w["g0"], w["engine"], w["mass_tab"], None, None,
+                                    30.0, 0.01, 500, 6)
+    h = np.concatenate([np.linspace(-100, 101000, 401), [0, 11000, 20000, 32000, 47000, 51000, 71000, 100000]])
+    T, P, rho, a = R.atmosphere(h)
+    tq = np.linspace(-0.1, 3.7, 77); pa = np.linspace(101325, 60000, 77)
+    thrust = R.engine_thrust(w["engine"], tq, pa)
+    rhs_state = traj[:, :, :4].transpose(1, 0, 2).reshape(14, -1).copy()      # states along real trajectories
+    rhs = R.rocket_rhs(85.0, 0.0, 0.16, 9.80665, w["engine"], w["mass_tab"], rhs_state)
+    ix = np.array([[0.0, 0.12], [3.5, 0.09]]); iyz = np.array([[0.0, 8.0], [3.5, 6.5]])
+    fin2, stats2, _ = R.rocket_rk4(w["elev"][:4], w["az"][:4], w["diam"][:4], w["g0"][:4], w["engine"], w["mass_tab"],
+                                   ix, iyz, 10.0, 0.01)
+    np.savez(os.path.join(OUT, "rocket.npz"), elev=w["elev"], az=w["az"], diam=w["diam"], g0=w["g0"],
+             engine=w["engine"], mass_tab=w["mass_tab"], ref_final=fin, ref_stats=stats, ref_traj=traj,
+             atm_h=h, ref_atm_T=T, ref_atm_P=P, ref_atm_rho=rho, ref_atm_a=a, thrust_t=tq, thrust_patm=pa,
+             ref_thrust=thrust, rhs_state=rhs_state, ref_rhs=rhs, ix_tab=ix, iyz_tab=iyz, ref_final_inertia=fin2,
+             ref_stats_inertia=stats2)
+    # ---- config 5 ----
+    rng = np.random.Generator(np.random.MT19937(5))
+    out = {}
+    for (r, c, t) in [(2, 2, 0), (3, 3, 0), (4, 5, 0), (2, 5, 0), (3, 3, 1), (4, 4, 1), (3, 4, 2), (4, 4, 2)]:
+        s0 = R.grid2d_initial_state(r, c, 0.5, topo=t)
+        s = s0 + rng.normal(0, 0.1, s0.shape)
+        key = f"g{r}x{c}t{t}"
+        out[key + "_init"] = s0
+        out[key + "_state"] = s
+        out[key + "_rhs"] = R.grid2d_rhs(r, c, t, 1.3, 0.5, 50.0, 0.5, s)
+        out[key + "_rk4"] = R.grid2d_rk4(r, c, t, 1.3, 0.5, 50.0, 0.5, 1e-3, 200, s)
+    # a degenerate state: two coincident masses (len < 1e-10 clamp, indexed_spring_2d.hpp:125)
+    s = R.grid2d_initial_state(3, 3, 0.5)
+    s[4 * 4 + 0], s[4 * 4 + 1] = s[4 * 3 + 0], s[4 * 3 + 1]
+    out["g3x3t0_degenerate_state"] = s
+    out["g3x3t0_degenerate_rhs"] = R.grid2d_rhs(3, 3, 0, 1.0, 0.5, 50.0, 0.5, s)
+    np.savez(os.path.join(OUT, "grid2d.npz"), **out)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

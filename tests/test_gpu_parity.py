@@ -1,0 +1,306 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Tolerances (north_star): <= 1e-12 relative per step, <= 1e-9 relative on the final state, relative =
+max-norm over the state vector of one instance.  FP_STRICT is additionally required to be
+BIT-IDENTICAL wherever the path contains no libm transcendental (oscillator, grid2d): there the only
+possible difference to the reference is FMA contraction, which strict mode forbids.
+The chaotic double pendulum uses the shadow-twin rule of SURVEY.md section 8c beyond t = 1 s.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from sopot_b200 import workloads as W
+from sopot_b200.capi import FP_CONTRACT, FP_STRICT, MEM_DEVICE, MEM_HOST, ST_NONFINITE, ST_OK
+
+pytestmark = pytest.mark.gpu
+
+PER_STEP = 1e-12
+FINAL = 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ config 1
+def test_ho_golden_bit_exact_strict(engine):
+    g = golden("ho")
+    st, traj, status = engine.ho_rk4(g["m"], g["k"], g["c"], g["x0"], g["v0"], 64, 0.0, 0.01, 1000, fp_mode=FP_STRICT,
+                                     store_every=100)
+    assert np.array_equal(st, g["ref_final"]) and np.array_equal(traj, g["ref_traj"])
+    assert st[0, 0] == -0.82129045056399141 and st[1, 0] == -1.7419130577838189      # README known answer
+    assert np.all(status == ST_OK)
+
+
+def test_ho_contract_within_tolerance(engine, port):
+    g = golden("ho")
+    one, _, _ = engine.ho_rk4(g["m"], g["k"], g["c"], g["x0"], g["v0"], 64, 0.0, 0.01, 1, fp_mode=FP_CONTRACT)
+    ref1, _, _ = port.ho_rk4(g["m"], g["k"], g["c"], g["x0"], g["v0"], 0.0, 0.01, 0.01)
+    assert rel_err(one, ref1).max() <= PER_STEP
+    st, traj, _ = engine.ho_rk4(g["m"], g["k"], g["c"], g["x0"], g["v0"], 64, 0.0, 0.01, 1000, fp_mode=FP_CONTRACT,
+                                store_every=100)
+    assert rel_err(st, g["ref_final"]).max() <= FINAL
+    assert rel_err(traj, g["ref_traj"], axis=1).max() <= FINAL
+
+
+@pytest.mark.parametrize("mem", [MEM_HOST, MEM_DEVICE])
+def test_ho_full_config_vs_oracle(engine, port, mem):
+    """BASELINE config 1 at full size (2^20 instances, 1000 steps): strict == oracle bit for bit on a
+    contiguous + strided sample, contract within 1e-9; host and device pointer paths agree exactly."""
+    n = 1 << 20
+    w = W.ho_ensemble(n)
+    st, _, status = engine.ho_rk4(w["m"], w["k"], w["c"], w["x0"], w["v0"], n, 0.0, 0.01, 1000, mem=mem, fp_mode=FP_STRICT)
+    st = st.download() if mem == MEM_DEVICE else st
+    status = status.download() if mem == MEM_DEVICE else status
+    idx = np.concatenate([np.arange(2048), np.arange(0, n, 997), [n - 1]])
+    ref, _, _ = port.ho_rk4(w["m"][idx], w["k"][idx], w["c"][idx], w["x0"][idx], w["v0"][idx], 0.0, 10.0, 0.01, nthreads=4)
+    assert np.array_equal(st[:, idx], ref)
+    assert np.all(status == ST_OK)
+    fast, _, _ = engine.ho_rk4(w["m"], w["k"], w["c"], w["x0"], w["v0"], n, 0.0, 0.01, 1000, mem=mem, fp_mode=FP_CONTRACT)
+    fast = fast.download() if mem == MEM_DEVICE else fast
+    assert rel_err(fast, st).max() <= FINAL
+
+
+def test_ho_edge_cases(engine):
+    # empty ensemble, single instance, ragged size (not a multiple of the block), broadcast parameters
+    st, _, _ = engine.ho_rk4(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), 0, 0.0, 0.01, 10)
+    assert st.shape == (2, 0)
+    a, _, _ = engine.ho_rk4([2.0], [9.0], [0.1], [1.5], [0.0], 1, 0.0, 0.01, 1000, fp_mode=FP_STRICT)
+    assert a[0, 0] == -0.82129045056399141
+    n = 1000 + 37
+    k = 9.0 * (1 + 0.01 * np.arange(n) / n)
+    b, _, _ = engine.ho_rk4(2.0, k, 0.1, 1.5, 0.0, n, 0.0, 0.01, 100, fp_mode=FP_STRICT)            # scalars broadcast
+    c, _, _ = engine.ho_rk4(np.full(n, 2.0), k, np.full(n, 0.1), np.full(n, 1.5), np.zeros(n), n, 0.0, 0.01, 100, fp_mode=FP_STRICT)
+    assert np.array_equal(b, c)
+    # zero steps returns the initial condition; non-finite input is flagged, never thrown
+    z, _, _ = engine.ho_rk4(2.0, k, 0.1, 1.5, 0.25, n, 0.0, 0.01, 0)
+    assert np.all(z[0] == 1.5) and np.all(z[1] == 0.25)
+    bad, _, status = engine.ho_rk4(2.0, np.where(np.arange(n) == 5, np.nan, k), 0.1, 1.5, 0.0, n, 0.0, 0.01, 10)
+    assert status[5] == ST_NONFINITE and status.sum() == ST_NONFINITE
+    # linearity of the (linear) oscillator flow: scaling the IC scales the solution (size-independent property)
+    s1, _, _ = engine.ho_rk4(2.0, k, 0.1, 1.5, 0.0, n, 0.0, 0.01, 500, fp_mode=FP_STRICT)
+    s2, _, _ = engine.ho_rk4(2.0, k, 0.1, 3.0, 0.0, n, 0.0, 0.01, 500, fp_mode=FP_STRICT)
+    assert np.array_equal(2.0 * s1, s2)     # power-of-two scaling commutes with every rounding
+
+
+def test_bad_arguments_report_errors(engine):
+    from sopot_b200.capi import SopotB200Error
+    with pytest.raises(SopotB200Error, match="dt must be positive"):
+        engine.ho_rk4([2.0], [9.0], [0.1], [1.5], [0.0], 1, 0.0, -0.01, 10)
+    with pytest.raises(SopotB200Error):
+        engine.grid2d_rk4(engine.grid2d_params(1, 5, 0, 1.0, 0.5, 50.0, 0.5), 1e-3, 1, np.zeros((5, 4)))
+
+
+# ------------------------------------------------------------------------------------------------ config 2
+def _dp_args(g):
+    return [g[k] for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+
+
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_dpend_single_rhs_and_single_step(engine, port, fp):
+    g = golden("dpend")
+    rhs = engine.dpend_rhs(1.3, 0.7, 0.9, 1.1, 9.81, g["rhs_state"], fp_mode=fp)
+    assert rel_err(rhs, g["ref_rhs"]).max() <= PER_STEP
+    w = W.dpend_ensemble(4096, seed=21)
+    args = _dp_args(w)
+    one, _, _ = engine.dpend_rk4(*args, 4096, 0.0, 1e-3, 1, fp_mode=fp)
+    ref1, _, _ = port.dpend_rk4(*args, 0.0, 1e-3, 1e-3, nthreads=4)
+    assert rel_err(one, ref1).max() <= PER_STEP
+
+
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_dpend_golden_shadow_twin(engine, fp):
+    """<= 1e-9 at t = 1 s (hard gate); later snapshots: error <= C * (separation of the reference run
+    from its own 1-ulp-perturbed twin) + 1e-9, C = 1e3 (10^4 steps each contribute an ulp-level
+    perturbation of their own)."""
+    g = golden("dpend")
+    st, traj, status = engine.dpend_rk4(*_dp_args(g), 16, 0.0, 1e-3, 10000, fp_mode=fp, store_every=1000)
+    assert np.all(status == ST_OK)
+    err = rel_err(traj, g["ref_traj"], axis=1)                 # [snap][instance]
+    twin = rel_err(g["ref_traj_twin"], g["ref_traj"], axis=1)
+    assert err[0].max() <= FINAL, err[0]
+    assert np.all(err <= 1e3 * twin + FINAL), (err / (twin + 1e-300)).max()
+    assert np.array_equal(st, traj[-1])
+    # the documented non-chaotic nominal case stays inside 1e-9 for the whole 10 s
+    assert err[:, 0].max() <= FINAL
+
+
+def test_dpend_full_horizon_sample_vs_oracle(engine, port):
+    n = 1 << 16
+    w = W.dpend_ensemble(n)
+    args = _dp_args(w)
+    st, _, status = engine.dpend_rk4(*args, n, 0.0, 1e-3, 1000, fp_mode=FP_CONTRACT)
+    idx = np.arange(0, n, 257)
+    ref, _, _ = port.dpend_rk4(*[a[idx] for a in args], 0.0, 1.0, 1e-3, nthreads=4)
+    assert rel_err(st[:, idx], ref).max() <= FINAL
+    assert np.all(status == ST_OK)
+    # device-resident call gives the same bits as the host-staged call
+    d, _, _ = engine.dpend_rk4(*args, n, 0.0, 1e-3, 1000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT)
+    assert np.array_equal(d.download(), st)
+
+
+# ------------------------------------------------------------------------------------------------ config 3
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_cartpole_linearize_golden(engine, fp):
+    g = golden("cartpole")
+    P = g["u"].size
+    A, B, status = engine.cartpole_linearize(g["mc"], g["m"], g["L"], g["g"], g["x"], g["u"], P, fp_mode=fp)
+    scale = np.maximum(np.abs(g["ref_A"]).max(axis=0), 1.0)
+    assert (np.abs(A - g["ref_A"]).max(axis=0) / scale).max() <= PER_STEP
+    assert (np.abs(B - g["ref_B"]).max(axis=0) / np.maximum(np.abs(g["ref_B"]).max(axis=0), 1.0)).max() <= PER_STEP
+    assert np.all(status == ST_OK)
+    A4 = A.reshape(4, 4, P)
+    # structure the reference tests assert (tests/inverted_pendulum_test.cpp:186-203): kinematic rows exact
+    assert np.all(A4[0, 2] == 1.0) and np.all(A4[1, 3] == 1.0) and np.all(A4[0, [0, 1, 3]] == 0.0) and np.all(B[:2] == 0.0)
+
+
+def test_cartpole_linearize_full_config(engine, port):
+    P = 1 << 20
+    w = W.cartpole_points(P)
+    A, B, status = engine.cartpole_linearize(1.0, 0.1, 0.5, 9.81, w["x"], w["u"], P, fp_mode=FP_CONTRACT)   # broadcast plant
+    idx = np.arange(0, P, 101)
+    rA, rB = port.cartpole_linearize(w["x"][:, idx], w["u"][idx], 1.0, 0.1, 0.5, 9.81, nthreads=4)
+    assert (np.abs(A[:, idx] - rA).max(axis=0) / np.maximum(np.abs(rA).max(axis=0), 1.0)).max() <= PER_STEP
+    assert (np.abs(B[:, idx] - rB).max(axis=0) / np.maximum(np.abs(rB).max(axis=0), 1.0)).max() <= PER_STEP
+    assert np.all(status == ST_OK)
+    dx, du = engine.to_device(w["x"]), engine.to_device(w["u"])
+    Ad, Bd, _ = engine.cartpole_linearize(1.0, 0.1, 0.5, 9.81, dx, du, P, mem=MEM_DEVICE, fp_mode=FP_CONTRACT)
+    assert np.array_equal(Ad.download(), A) and np.array_equal(Bd.download(), B)
+
+
+def test_cartpole_rk4_golden(engine):
+    g = golden("cartpole")
+    x = g["x"][:, :16]
+    st, _, status = engine.cartpole_rk4(g["mc"][:16], g["m"][:16], g["L"][:16], g["g"][:16], x[0], x[1], x[2], x[3],
+                                        g["u"][:16], 16, 0.0, 0.01, 200, fp_mode=FP_STRICT)
+    assert rel_err(st, g["ref_rk4_final"]).max() <= FINAL
+    assert np.all(status == ST_OK)
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_rocket_rhs_golden(engine, fp):
+    g = golden("rocket")
+    out = engine.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], g["rhs_state"], fp_mode=fp)
+    ref = g["ref_rhs"]
+    # derivative blocks have very different magnitudes: compare each physical block with its own scale
+    for lo, hi in ((0, 1), (1, 4), (4, 7), (7, 11), (11, 14)):
+        scale = np.maximum(np.abs(ref[lo:hi]).max(axis=0), 1e-6)
+        assert (np.abs(out[lo:hi] - ref[lo:hi]).max(axis=0) / scale).max() <= 1e-11, (lo, hi)
+
+
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_rocket_golden_trajectories(engine, fp):
+    g = golden("rocket")
+    st, stats, traj, status = engine.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None,
+                                                None, 8, 0.01, 3000, fp_mode=fp, store_every=500)
+    assert np.all(status == ST_OK)
+    assert rel_err(st, g["ref_final"]).max() <= FINAL
+    assert rel_err(traj, g["ref_traj"], axis=1).max() <= FINAL
+    ref = g["ref_stats"]
+    assert np.all(np.abs(stats - ref) <= FINAL * np.maximum(np.abs(ref), 1.0))
+    assert np.array_equal(stats[[1, 3]], ref[[1, 3]])          # apogee / max-speed times are exact step times
+
+
+def test_rocket_inertia_tables_and_single_step(engine, port):
+    g = golden("rocket")
+    st, stats, _, _ = engine.rocket_rk4(g["elev"][:4], g["az"][:4], g["diam"][:4], g["g0"][:4], g["engine"], g["mass_tab"],
+                                        g["ix_tab"], g["iyz_tab"], 4, 0.01, 1000, fp_mode=FP_STRICT)
+    assert rel_err(st, g["ref_final_inertia"]).max() <= FINAL
+    one, _, _, _ = engine.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None, None, 8,
+                                     0.01, 1, fp_mode=FP_CONTRACT, want_stats=False)
+    ref1, _, _ = port.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None, None, 0.01, 0.01)
+    assert rel_err(one, ref1).max() <= PER_STEP
+    # no tables at all: constants 100 / 10 / 100, no thrust (rocket_body.hpp:36-39) -> ballistic drop stays on the pad
+    st0, _, _, _ = engine.rocket_rk4(g["elev"][:4], g["az"][:4], g["diam"][:4], g["g0"][:4], None, None, None, None, 4, 0.01, 100)
+    ref0, _, _ = port.rocket_rk4(g["elev"][:4], g["az"][:4], g["diam"][:4], g["g0"][:4], None, None, None, None, 1.0, 0.01)
+    assert rel_err(st0, ref0).max() <= FINAL
+
+
+def test_rocket_monte_carlo_sample_and_dispersion(engine, port):
+    n = 1 << 14
+    w = W.rocket_ensemble(n)
+    st, stats, _, status = engine.rocket_rk4(w["elev"], w["az"], w["diam"], w["g0"], w["engine"], w["mass_tab"], None, None,
+                                             n, 0.01, 3000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT)
+    hstats, hst = stats.download(), st.download()
+    assert np.all(status.download() == ST_OK)
+    idx = np.arange(0, n, 509)
+    rfin, rstats, _ = port.rocket_rk4(w["elev"][idx], w["az"][idx], w["diam"][idx], w["g0"][idx], w["engine"], w["mass_tab"],
+                                      None, None, 30.0, 0.01, nthreads=4)
+    assert rel_err(hst[:, idx], rfin).max() <= FINAL
+    assert np.all(np.abs(hstats[:, idx] - rstats) <= FINAL * np.maximum(np.abs(rstats), 1.0))
+    # K4: device reduction of the per-trajectory rows against numpy
+    disp = engine.dispersion_stats(stats)
+    for r, d in enumerate(disp):
+        row = hstats[r]
+        assert d["count"] == n and d["nonfinite"] == 0
+        assert d["min"] == row.min() and d["max"] == row.max()
+        assert abs(d["mean"] - row.mean()) <= 1e-12 * max(abs(row.mean()), 1.0)
+        assert abs(d["stddev"] - row.std()) <= 1e-6 * max(row.std(), 1e-9)
+    # non-finite entries are skipped and counted, ragged sizes reduce correctly
+    v = np.arange(7 * 1001, dtype=np.float64).reshape(7, 1001)
+    v[3, 17] = np.nan
+    d = engine.dispersion_stats(v)
+    assert d[3]["nonfinite"] == 1 and d[3]["count"] == 1000 and d[0]["sum"] == v[0].sum() and d[6]["max"] == v[6].max()
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+GRID_CASES = [(2, 2, 0), (3, 3, 0), (4, 5, 0), (2, 5, 0), (3, 3, 1), (4, 4, 1), (3, 4, 2), (4, 4, 2)]
+
+
+@pytest.mark.parametrize("r,c,t", GRID_CASES)
+def test_grid2d_golden_bit_exact(engine, r, c, t):
+    """Strict mode == the templated reference system bit for bit (rhs and 200 RK4Solver steps)."""
+    g = golden("grid2d")
+    key = f"g{r}x{c}t{t}"
+    gp = engine.grid2d_params(r, c, t, 1.3, 0.5, 50.0, 0.5)
+    assert np.array_equal(engine.grid2d_initial_state(gp).ravel(), g[key + "_init"])
+    s = g[key + "_state"].reshape(-1, 4).copy()
+    assert np.array_equal(engine.grid2d_rhs(gp, s, fp_mode=FP_STRICT).ravel(), g[key + "_rhs"])
+    out = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_STRICT)
+    assert np.array_equal(out.ravel(), g[key + "_rk4"])
+    fast = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_CONTRACT)
+    assert rel_err(fast.ravel(), g[key + "_rk4"]).max() <= FINAL
+
+
+def test_grid2d_degenerate_spring(engine):
+    g = golden("grid2d")
+    gp = engine.grid2d_params(3, 3, 0, 1.0, 0.5, 50.0, 0.5)
+    out = engine.grid2d_rhs(gp, g["g3x3t0_degenerate_state"].reshape(-1, 4).copy(), fp_mode=FP_STRICT)
+    assert np.array_equal(out.ravel(), g["g3x3t0_degenerate_rhs"], equal_nan=True)
+
+
+@pytest.mark.parametrize("rows,cols,topo", [(64, 96, 0), (33, 257, 0), (48, 40, 1), (40, 48, 2), (513, 70, 0)])
+def test_grid2d_medium_vs_oracle_bit_exact(engine, port, rows, cols, topo):
+    p = W.GRID2D_PARAMS
+    s0 = W.grid2d_state(rows, cols, p["spacing"])
+    gp = engine.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"])
+    ref_rhs = port.grid2d_rhs(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], s0)
+    assert np.array_equal(engine.grid2d_rhs(gp, s0.copy(), fp_mode=FP_STRICT).ravel(), ref_rhs)
+    ref = port.grid2d_rk4(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], 25, s0, nthreads=4)
+    got = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_STRICT)
+    assert np.array_equal(got.ravel(), ref)
+    dev = engine.to_device(s0)
+    engine.grid2d_rk4(gp, p["dt"], 25, dev, fp_mode=FP_STRICT)
+    assert np.array_equal(dev.download().ravel(), ref)
+    fast = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_CONTRACT)
+    assert rel_err(fast.ravel(), ref).max() <= FINAL
+
+
+def test_grid2d_large_properties(engine, port):
+    """2048^2 (too big for the oracle to integrate in seconds): size-independent properties --
+    rest grid is a fixed point; total momentum stays at zero (internal forces cancel,
+    tests/verify_grid_physics.cpp:116); top-left 64x64 block after 3 steps equals the oracle run on a
+    512x512 crop (influence travels <= 4 rows per step, so the crop's far boundary cannot be felt)."""
+    p = W.GRID2D_PARAMS
+    n = 2048
+    gp = engine.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    rest = engine.grid2d_initial_state(gp, mem=MEM_DEVICE)
+    engine.grid2d_rk4(gp, p["dt"], 5, rest, fp_mode=FP_STRICT)
+    r = rest.download()
+    assert np.array_equal(r, W.grid2d_state(n, n, p["spacing"], bump=False))
+    s0 = W.grid2d_state(n, n, p["spacing"])
+    dev = engine.to_device(s0)
+    engine.grid2d_rk4(gp, p["dt"], 3, dev, fp_mode=FP_STRICT)
+    out = dev.download().reshape(n, n, 4)
+    assert np.abs(out[..., 2:].sum(axis=(0, 1))).max() < 1e-9
+    crop = np.ascontiguousarray(s0.reshape(n, n, 4)[:512, :512]).reshape(-1, 4)
+    ref = port.grid2d_rk4(512, 512, 0, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], 3, crop, nthreads=8).reshape(512, 512, 4)
+    assert np.array_equal(out[:64, :64], ref[:64, :64])
