@@ -49,7 +49,8 @@ enum {
 
 enum { SOPOT_B200_MEM_DEVICE = 0, SOPOT_B200_MEM_HOST = 1 };
 enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
-enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2 };
+enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2,
+       SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */ };
 
 typedef struct sopot_b200_ctx sopot_b200_ctx;
 

@@ -15,7 +15,8 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int32, 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsopot_b200.so")
+# SOPOT_B200_LIB lets tools/ load an experimental build of the same library (never a different backend)
+LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libsopot_b200.so")
 
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1

@@ -104,7 +104,7 @@ struct CartPlant {
 // ---- K1: cart-pole (N = 1) integration with a constant force ----------------------------------------
 struct CartpoleSys {
     static constexpr int DIM = 4;
-    static constexpr int BLOCK = 128;
+    static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
     struct DevParams { ParamRef mc, m, L, g, x, th, xd, w, force; };
     template <bool S> struct Inst { CartPlant<1, Real<S>> plant; Real<S> F; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
@@ -120,7 +120,7 @@ struct CartpoleSys {
     }
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
     template <bool S>
-    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[4]) {}
+    static __device__ __forceinline__ int finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[4]) { return 0; }
 };
 
 SB_EXPORT int sopot_b200_cartpole_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n,

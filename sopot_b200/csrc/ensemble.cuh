@@ -8,13 +8,13 @@
 // reproduces ((k1 + 2k2) + 2k3) + k4 exactly (2.0*k is exact), so only one stage vector is live.
 //
 // A System provides:
-//   static constexpr int DIM;
+//   static constexpr int DIM, BLOCK, IPT (instances per thread), MIN_BLOCKS (launch-bounds hint);
 //   struct DevParams;                       // kernel argument (ParamRef per parameter, tables, ...)
 //   template <bool S> struct Inst;          // per-instance constants held in registers
 //   template <bool S> static __device__ void load(const DevParams&, size_t i, Inst<S>&, Real<S>(&y)[DIM]);
 //   template <bool S> static __device__ int  rhs(const Inst<S>&, const Real<S>(&y)[DIM], Real<S>(&dy)[DIM]);
 //   template <bool S> static __device__ void observe(Inst<S>&, double t, const Real<S>(&y)[DIM]);   // after each step
-//   template <bool S> static __device__ void finish(const DevParams&, const Inst<S>&, size_t i, size_t n, const Real<S>(&y)[DIM]);
+//   template <bool S> static __device__ int  finish(const DevParams&, const Inst<S>&, size_t i, size_t n, const Real<S>(&y)[DIM]);
 #pragma once
 #include "common.cuh"
 
@@ -38,42 +38,69 @@ __device__ __forceinline__ int rk4_step(const typename Sys::template Inst<S>& in
     return st;
 }
 
+// IPT = instances per thread (Sys::IPT): IPT independent instances are advanced in lock-step by one
+// thread, which gives the scheduler IPT independent dependency chains per warp (FP64 latency hiding)
+// while per-system constants held in registers are shared.  Instance j of a thread is
+// (blockIdx.x*IPT + j)*blockDim.x + threadIdx.x, so every load and store stays fully coalesced.
 template <class Sys, bool S>
-__global__ void __launch_bounds__(Sys::BLOCK)
+__global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS)
 rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double t0, const double dt_,
                     const size_t n_steps, const size_t store_every, double* __restrict__ state_out,
                     double* __restrict__ traj_out, int32_t* __restrict__ status) {
     constexpr int D = Sys::DIM;
+    constexpr int IPT = Sys::IPT;
     Sys::template block_setup<S>(P);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    typename Sys::template Inst<S> in;
-    Real<S> y[D];
-    Sys::template load<S>(P, i, in, y);
+    const size_t base = (size_t)blockIdx.x * IPT * blockDim.x + threadIdx.x;
+    if (base >= n) return;
+    typename Sys::template Inst<S> in[IPT];
+    Real<S> y[IPT][D];
+    size_t idx[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const size_t i = base + (size_t)j * blockDim.x;
+        idx[j] = i < n ? i : base;           // a ragged tail re-computes instance `base` and discards it
+        Sys::template load<S>(P, idx[j], in[j], y[j]);
+    }
     const Real<S> dt(dt_);
-    double t = t0;                       // accumulated like the reference: t += dt (core/solver.hpp:127)
-    Sys::template observe<S>(in, t, y);  // the reference stores the initial condition (:87-88)
-    int st = 0;
+    double t = t0;                           // accumulated like the reference: t += dt (core/solver.hpp:127)
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);   // initial condition is stored (:87-88)
+    int st[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) st[j] = 0;
     size_t until_snap = store_every, snap = 0;
     for (size_t step = 0; step < n_steps; ++step) {
-        st |= rk4_step<Sys, S>(in, y, dt);
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) st[j] |= rk4_step<Sys, S>(in[j], y[j], dt);
         t += dt_;
-        Sys::template observe<S>(in, t, y);
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);
         if (store_every && --until_snap == 0) {
             until_snap = store_every;
             if (traj_out) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) traj_out[(snap * D + d) * n + i] = y[d].v;
+                for (int j = 0; j < IPT; ++j) {
+                    if (j == 0 || base + (size_t)j * blockDim.x < n) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) traj_out[(snap * D + d) * n + idx[j]] = y[j][d].v;
+                    }
+                }
             }
             ++snap;
         }
     }
-    bool finite = true;
 #pragma unroll
-    for (int d = 0; d < D; ++d) { state_out[(size_t)d * n + i] = y[d].v; finite &= isfinite(y[d].v); }
-    Sys::template finish<S>(P, in, i, n, y);
-    if (status) status[i] = (st & SOPOT_B200_ST_SINGULAR) ? SOPOT_B200_ST_SINGULAR
-                          : (finite ? SOPOT_B200_ST_OK : SOPOT_B200_ST_NONFINITE);
+    for (int j = 0; j < IPT; ++j) {
+        if (j > 0 && base + (size_t)j * blockDim.x >= n) continue;
+        const size_t i = idx[j];
+        bool finite = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { state_out[(size_t)d * n + i] = y[j][d].v; finite &= isfinite(y[j][d].v); }
+        const int sj = st[j] | Sys::template finish<S>(P, in[j], i, n, y[j]);
+        if (status) status[i] = (sj & SOPOT_B200_ST_SINGULAR) ? SOPOT_B200_ST_SINGULAR
+                              : !finite ? SOPOT_B200_ST_NONFINITE
+                              : (sj & SOPOT_B200_ST_RANGE) ? SOPOT_B200_ST_RANGE : SOPOT_B200_ST_OK;
+    }
 }
 
 // single derivative evaluation per instance (computeDerivatives), state/out [DIM][n]
@@ -151,7 +178,7 @@ int sb_launch_ensemble(const EnsembleArgs& a, const typename Sys::DevParams& P, 
     if ((rc = sg.out(a.traj_out, snaps * Sys::DIM * n * 8, &d_traj))) return rc;
     if ((rc = sg.out(a.status, n * 4, &d_status))) return rc;
     if (n) {
-        const unsigned grid = sb_grid_for(n, Sys::BLOCK);
+        const unsigned grid = sb_grid_for(n, Sys::BLOCK * Sys::IPT);
         if (a.opts->fp_mode == SOPOT_B200_FP_STRICT)
             rk4_ensemble_kernel<Sys, true><<<grid, Sys::BLOCK, 0, ctx->stream>>>(
                 P, n, a.t0, a.dt, a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,

@@ -2,6 +2,7 @@
 //   config 1  physics::HarmonicOscillator   (physics/harmonic_oscillator.hpp:75-85)
 //   config 2  pendulum::DoublePendulum      (physics/pendulum/double_pendulum.hpp:126-179)
 #include "ensemble.cuh"
+#include "trig.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // HarmonicOscillator::derivatives: {v, T(-k/m)*x - T(c/m)*v}.  The two quotients are loop
@@ -9,7 +10,7 @@
 // ------------------------------------------------------------------------------------------------
 struct HoSys {
     static constexpr int DIM = 2;
-    static constexpr int BLOCK = 128;
+    static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
     struct DevParams { ParamRef m, k, c, x0, v0; };
     template <bool S> struct Inst { Real<S> a, b; };   // a = -k/m, b = c/m
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
@@ -29,7 +30,7 @@ struct HoSys {
     }
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[2]) {}
     template <bool S>
-    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[2]) {}
+    static __device__ __forceinline__ int finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[2]) { return 0; }
 };
 
 SB_EXPORT int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n, double t0,
@@ -55,9 +56,18 @@ SB_EXPORT int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
 // operations on every call.  sin(delta) and cos(delta) share one argument reduction (sincos).
 // In contract mode the two divisions by det become one reciprocal and two multiplies.
 // ------------------------------------------------------------------------------------------------
+#ifndef SB_DPEND_BLOCK
+#define SB_DPEND_BLOCK 128
+#endif
+#ifndef SB_DPEND_IPT
+#define SB_DPEND_IPT 1
+#endif
+#ifndef SB_DPEND_MINB
+#define SB_DPEND_MINB 1
+#endif
 struct DpendSys {
     static constexpr int DIM = 4;
-    static constexpr int BLOCK = 128;
+    static constexpr int BLOCK = SB_DPEND_BLOCK, IPT = SB_DPEND_IPT, MIN_BLOCKS = SB_DPEND_MINB;
     struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
     template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
@@ -76,9 +86,22 @@ struct DpendSys {
     static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
         const Real<S> theta1 = y[0], theta2 = y[1], omega1 = y[2], omega2 = y[3];
         const Real<S> delta = theta1 - theta2;                       // :145
-        Real<S> sin_delta, cos_delta;
-        r_sincos(delta, sin_delta, cos_delta);
-        const Real<S> sin_theta1 = r_sin(theta1), sin_theta2 = r_sin(theta2);
+        Real<S> sin_delta, cos_delta, sin_theta1, sin_theta2;
+        int st = 0;
+        if constexpr (S) {
+            r_sincos(delta, sin_delta, cos_delta);
+            sin_theta1 = r_sin(theta1); sin_theta2 = r_sin(theta2);
+        } else {
+            // trig.cuh (<= 1.6 ulp, branch-free; range checked once in finish()).  sin/cos of delta come
+            // from the angle-difference identities instead of a third argument reduction + polynomial
+            // pair: 46 instead of 63 FP64 operations per derivative call; absolute error <= 4e-16, i.e.
+            // far inside the 1e-12 per-step tolerance of this mode.
+            Real<S> c1, c2;
+            sbtrig::sincos(theta1.v, sin_theta1.v, c1.v);
+            sbtrig::sincos(theta2.v, sin_theta2.v, c2.v);
+            sin_delta = sin_theta1 * c2 - c1 * sin_theta2;
+            cos_delta = c1 * c2 + sin_theta1 * sin_theta2;
+        }
         const Real<S> a12 = in.m2L2 * cos_delta;                     // :163
         const Real<S> a21 = in.L1 * cos_delta;                       // :164
         const Real<S> a22 = in.L2;
@@ -90,12 +113,15 @@ struct DpendSys {
         dy[0] = omega1;
         dy[1] = omega2;
         if constexpr (S) { dy[2] = n1 / det; dy[3] = n2 / det; }
-        else { const Real<S> inv = Real<S>(1.0) / det; dy[2] = n1 * inv; dy[3] = n2 * inv; }
-        return 0;
+        else { const Real<S> inv(sbtrig::rcp_fast(det.v)); dy[2] = n1 * inv; dy[3] = n2 * inv; }
+        return st;
     }
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
     template <bool S>
-    static __device__ __forceinline__ void finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&)[4]) {}
+    static __device__ __forceinline__ int finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&y)[4]) {
+        if constexpr (S) return 0;
+        else return fmax(fabs(y[0].v), fabs(y[1].v)) > 0.5 * sbtrig::kMaxArg ? SOPOT_B200_ST_RANGE : 0;
+    }
 };
 
 static int dpend_stage(sopot_b200_ctx* ctx, Staging& sg, const sopot_b200_dpend_params* p, size_t n,

@@ -98,7 +98,7 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
 
 struct RocketSys {
     static constexpr int DIM = 14;
-    static constexpr int BLOCK = 128;
+    static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
     struct DevParams {
         ParamRef elev, az, diam, g;
         RocketTablesDev tab;
@@ -241,12 +241,13 @@ struct RocketSys {
         if (in.burn > 0 && fabs(t - in.burn) < 0.1) { in.bo_alt = alt; in.bo_spd = spd; }
     }
     template <bool S>
-    static __device__ __forceinline__ void finish(const DevParams& P, const Inst<S>& in, size_t i, size_t n,
+    static __device__ __forceinline__ int finish(const DevParams& P, const Inst<S>& in, size_t i, size_t n,
                                                   const Real<S> (&y)[14]) {
-        if (!P.stats_out) return;
+        if (!P.stats_out) return 0;
         double* o = P.stats_out + i;
         o[0] = in.apogee; o[n] = in.apogee_t; o[2 * n] = in.vmax; o[3 * n] = in.vmax_t;
         o[4 * n] = in.bo_alt; o[5 * n] = in.bo_spd; o[6 * n] = y[1].v; o[7 * n] = y[2].v;
+        return 0;
     }
 };
 

@@ -134,7 +134,8 @@ SB_EXPORT int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* val
 
 SB_EXPORT int sopot_b200_measure_fp64_peak(sopot_b200_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return SOPOT_B200_EINVAL;
-    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    // short (~1 ms) bursts, best of 10: the burst figure for a kernel timed alone (B200_PROFILING.md)
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1024;
     void* scr;
     int rc = sb_scratch(ctx, (size_t)blocks * threads * 8, &scr);
     if (rc) return rc;
@@ -142,7 +143,7 @@ SB_EXPORT int sopot_b200_measure_fp64_peak(sopot_b200_ctx* ctx, double* tflops) 
     SB_CUDA(ctx, cudaEventCreate(&e0));
     SB_CUDA(ctx, cudaEventCreate(&e1));
     double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {
+    for (int rep = 0; rep < 11; ++rep) {
         SB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
         dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)scr, iters, 1.0000001, 1e-9);
         SB_CHECK_LAUNCH(ctx);

@@ -1,0 +1,125 @@
+// trig.cuh -- lean double-precision sin / sincos for the FP64-bound ensemble kernels.
+//
+// Why: in rk4_ensemble_kernel<DpendSys> built on CUDA's libdevice sin()/sincos(), only 39 % of the
+// executed instructions were FP64 (ncu, profiles/r1_dpend_opmix_libdevice.txt): per instance-step 178
+// UMOV (64-bit polynomial constants re-materialised in the loop), 64 FSEL, 56 LOP3, 52 MOV, 24 LDG of
+// the coefficient table, 24 F2I/I2F and 32 BSSY/BSYNC for the Payne-Hanek slow path kept the issue
+// slots 77 % busy while the FP64 pipe sat at 60 %.  The routines below keep the same accuracy class
+// (Cody-Waite 3-term reduction with FMA, fdlibm __kernel_sin/__kernel_cos minimax polynomials,
+// error ~1 ulp on the reduced range) with ~10 non-FP64 instructions per call:
+//   * quadrant by the 1.5*2^52 magic-number add (no F2I/I2F, which run on the quarter-rate XU pipe),
+//   * coefficients in uniform registers for the whole time loop (see c_trig below),
+//   * no data-dependent branch and no slow path: |x| <= 1e9 is the caller's contract (checked once per
+//     derivative call; beyond it the instance is flagged SOPOT_B200_ST_RANGE).
+// Only the FP_CONTRACT instantiations use these; FP_STRICT keeps libdevice.
+#pragma once
+
+#ifdef __CUDACC__
+#define SB_HD __host__ __device__ __forceinline__
+#else
+#define SB_HD inline
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#endif
+
+namespace sbtrig {
+
+constexpr double kTwoOverPi = 0x1.45f306dc9c883p-1;
+constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52
+constexpr double kPio2Hi = 0x1.921fb54442d18p+0;         // pi/2 = Hi + Mid + Lo to ~160 bits
+constexpr double kPio2Mid = 0x1.1a62633145c07p-54;
+constexpr double kPio2Lo = -0x1.f1976b7ed8fbcp-110;
+constexpr double kMaxArg = 1.0e9;                        // measured: <= 1.6 ulp for |x| <= 1e10 (tests/cpp/trig_accuracy.cpp)
+// fdlibm k_sin.c / k_cos.c minimax coefficients on [-pi/4, pi/4]
+constexpr double kS1 = -1.66666666666666324348e-01, kS2 = 8.33333333332248946124e-03,
+                 kS3 = -1.98412698298579493134e-04, kS4 = 2.75573137070700676789e-06,
+                 kS5 = -2.50507602534068634195e-08, kS6 = 1.58969099521155010221e-10;
+constexpr double kC1 = 4.16666666666666019037e-02, kC2 = -1.38888888888741095749e-03,
+                 kC3 = 2.48015872894767294178e-05, kC4 = -2.75573143513906633035e-07,
+                 kC5 = 2.08757232129817482790e-09, kC6 = -1.13596475577881948265e-11;
+
+SB_HD int lo_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    uint64_t u; std::memcpy(&u, &x, 8); return (int)(uint32_t)u;
+#endif
+}
+SB_HD double flip_sign_if(double x, int neg_mask_bit31) {     // xor bit 31 of the high word
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ neg_mask_bit31, __double2loint(x));
+#else
+    uint64_t u; std::memcpy(&u, &x, 8); u ^= (uint64_t)(uint32_t)neg_mask_bit31 << 32; std::memcpy(&x, &u, 8); return x;
+#endif
+}
+
+// Coefficient placement matters more than instruction count on sm_100a (tools/microbench/fp64_mix.cu,
+// profiles/r1_dpend_notes.md): a DFMA whose three sources are three distinct vector registers is limited
+// by register-file read bandwidth to ~3 cycles per warp instruction, 2 cycles with an operand from a
+// UNIFORM register.  Literals are re-materialised by ptxas with an UMOV pair at every use, per-thread
+// registers cost the third RF read, but a __constant__ table read with STATIC indices is loaded once
+// (LDCU.128) into uniform registers that stay live across the whole time loop and feed DFMA directly.
+#ifdef __CUDACC__
+__constant__ double c_trig[17] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
+                                  kC1, kC2, kC3, kC4, kC5, kC6};
+#endif
+constexpr double h_trig[17] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
+                               kC1, kC2, kC3, kC4, kC5, kC6};
+#ifdef __CUDA_ARCH__
+#define SB_TRIG(i) c_trig[i]
+#else
+#define SB_TRIG(i) h_trig[i]
+#endif
+
+// x = q*(pi/2) + r, |r| <= pi/4 (+ rounding), q returned modulo 2^32 (only its low 2 bits matter)
+SB_HD void reduce(double x, double& r, int& q) {
+    double j = fma(x, SB_TRIG(0), SB_TRIG(1));
+    q = lo_word(j);
+    j -= SB_TRIG(1);
+    r = fma(-j, SB_TRIG(2), x);
+    r = fma(-j, SB_TRIG(3), r);
+    r = fma(-j, SB_TRIG(4), r);
+}
+
+// both sin and cos of x (two polynomials, quadrant swap and sign fix)
+SB_HD void sincos(double x, double& s, double& c) {
+    double r; int q;
+    reduce(x, r, q);
+    const double z = r * r;
+    double ps = fma(z, SB_TRIG(10), SB_TRIG(9)); ps = fma(z, ps, SB_TRIG(8)); ps = fma(z, ps, SB_TRIG(7));
+    ps = fma(z, ps, SB_TRIG(6)); ps = fma(z, ps, SB_TRIG(5));
+    double pc = fma(z, SB_TRIG(16), SB_TRIG(15)); pc = fma(z, pc, SB_TRIG(14)); pc = fma(z, pc, SB_TRIG(13));
+    pc = fma(z, pc, SB_TRIG(12)); pc = fma(z, pc, SB_TRIG(11));
+    const double sr = fma(z * r, ps, r);                    // sin(r)
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));    // cos(r)
+    const bool odd = q & 1;
+    const double sv = odd ? cr : sr, cv = odd ? sr : cr;
+    s = flip_sign_if(sv, (q << 30) & 0x80000000);           // sin < 0 in quadrants 2, 3
+    c = flip_sign_if(cv, ((q + 1) << 30) & 0x80000000);     // cos < 0 in quadrants 1, 2
+}
+
+// sin(x) only (both polynomials, one select: cheaper on the RF than selecting 6 coefficient pairs)
+SB_HD double sin1(double x) {
+    double s, c;
+    sincos(x, s, c);
+    return s;
+}
+
+// 1/x to ~1 ulp for normal, finite x: MUFU.RCP64H seed + two Newton steps, no special-case branch
+// (the IEEE division sequence carries a data-dependent slow path; callers guarantee |x| in the normal range).
+SB_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
+}  // namespace sbtrig

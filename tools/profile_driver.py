@@ -1,0 +1,54 @@
+"""Small, short workloads for ncu captures (one config per call):  python tools/profile_driver.py <config>"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sopot_b200 import workloads as W  # noqa: E402
+from sopot_b200.capi import FP_CONTRACT, FP_STRICT, MEM_DEVICE, Engine  # noqa: E402
+
+cfg = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+eng = Engine(0)
+if cfg == "dpend":
+    n = 1 << 20
+    w = W.dpend_ensemble(n)
+    keys = ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")
+    d = [eng.to_device(w[k]) for k in keys]
+    st = eng.empty((4, n))
+    for _ in range(reps):
+        eng.dpend_rk4(*d, n, 0.0, 1e-3, 1000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, want_status=False, state_out=st)
+elif cfg == "ho":
+    n = 1 << 20
+    w = W.ho_ensemble(n)
+    d = [eng.to_device(w[k]) for k in ("m", "k", "c", "x0", "v0")]
+    st = eng.empty((2, n))
+    for _ in range(reps):
+        eng.ho_rk4(*d, n, 0.0, 0.01, 1000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, want_status=False, state_out=st)
+elif cfg == "lin":
+    P = 1 << 20
+    w = W.cartpole_points(P)
+    dx, du = eng.to_device(w["x"]), eng.to_device(w["u"])
+    A, B = eng.empty((16, P)), eng.empty((4, P))
+    for _ in range(reps):
+        eng.cartpole_linearize(1.0, 0.1, 0.5, 9.81, dx, du, P, mem=MEM_DEVICE, A=A, B=B, want_status=False)
+elif cfg == "rocket":
+    n = 1 << 18
+    w = W.rocket_ensemble(n)
+    d = [eng.to_device(w[k]) for k in ("elev", "az", "diam", "g0")]
+    st, stats = eng.empty((14, n)), eng.empty((8, n))
+    for _ in range(reps):
+        eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, 600, mem=MEM_DEVICE, want_status=False,
+                       state_out=st, stats_out=stats)
+elif cfg in ("grid", "grid_strict"):
+    p = W.GRID2D_PARAMS
+    n = 8192
+    gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
+    eng.grid2d_rk4(gp, p["dt"], reps, state, fp_mode=FP_STRICT if cfg == "grid_strict" else FP_CONTRACT)
+else:
+    raise SystemExit("unknown config " + cfg)
+eng.sync()
+print("done", cfg, eng.launch_count())
+eng.close()
