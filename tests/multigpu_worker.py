@@ -1,0 +1,66 @@
+"""Worker for tests/test_multigpu.py: run under torchrun with one rank per GPU.
+Checks (1) dispersion statistics all-reduced over NCCL == numpy on the concatenated data,
+(2) slab-decomposed grid2d with per-stage halo exchange == the single-GPU run bit for bit,
+(3) ensemble sharding: concatenated shard results == one-GPU results bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sopot_b200 import workloads as W  # noqa: E402
+from sopot_b200.capi import FP_CONTRACT, FP_STRICT, Engine  # noqa: E402
+from sopot_b200.distributed import dist_env, make_engine, partition, slab  # noqa: E402
+
+rank, world, local = dist_env()
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+eng = make_engine()
+
+# (1) dispersion over ranks
+rng = np.random.default_rng(123)
+full = rng.normal(5.0, 2.0, (6, 100003))
+full[2, 77] = np.inf
+b, e = partition(full.shape[1], rank, world)
+d = eng.dispersion_stats(np.ascontiguousarray(full[:, b:e]))
+for r in range(6):
+    row = full[r][np.isfinite(full[r])]
+    assert d[r]["count"] == row.size and d[r]["nonfinite"] == full.shape[1] - row.size, (rank, r, d[r])
+    assert d[r]["min"] == row.min() and d[r]["max"] == row.max()
+    assert abs(d[r]["mean"] - row.mean()) < 1e-12 * abs(row.mean()) and abs(d[r]["stddev"] - row.std()) < 1e-9
+
+# (2) grid2d slabs vs single domain (computed redundantly on every rank with a private single-rank engine)
+p = W.GRID2D_PARAMS
+for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2, 3), (1024, 1024, 0, 4)):
+    s0 = W.grid2d_state(rows, cols, p["spacing"]).reshape(rows, cols, 4)
+    solo = Engine(local)
+    ref = solo.grid2d_rk4(solo.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], steps,
+                          s0.reshape(-1, 4).copy(), fp_mode=FP_STRICT).reshape(rows, cols, 4)
+    solo.close()
+    rb, rl = slab(rows, rank, world)
+    gp = eng.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], row_begin=rb, rows_local=rl)
+    mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT)
+    assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo)
+    dev = eng.to_device(s0[rb:rb + rl].reshape(-1, 4).copy())
+    eng.grid2d_rk4(gp, p["dt"], steps, dev, fp_mode=FP_STRICT)
+    assert np.array_equal(dev.download().reshape(rl, cols, 4), ref[rb:rb + rl])
+    init = eng.grid2d_initial_state(gp).reshape(rl, cols, 4)
+    assert np.array_equal(init, W.grid2d_state(rows, cols, p["spacing"], bump=False).reshape(rows, cols, 4)[rb:rb + rl])
+
+# (3) ensemble sharding is exact: shard == slice of the whole
+n = 50001
+w = W.dpend_ensemble(n)
+keys = ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")
+b, e = partition(n, rank, world)
+part, _, _ = eng.dpend_rk4(*[w[k][b:e] for k in keys], e - b, 0.0, 1e-3, 300, fp_mode=FP_CONTRACT)
+solo = Engine(local)
+whole, _, _ = solo.dpend_rk4(*[w[k] for k in keys], n, 0.0, 1e-3, 300, fp_mode=FP_CONTRACT)
+solo.close()
+assert np.array_equal(part, whole[:, b:e])
+
+dist.barrier()
+eng.close()
+dist.destroy_process_group()
+print(f"rank {rank}/{world} multigpu ok", flush=True)
