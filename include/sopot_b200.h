@@ -108,6 +108,9 @@ typedef struct { const double *m, *k, *c, *x0, *v0; } sopot_b200_ho_params;
 int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n, double t0, double dt,
                       size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out /*[2][n]*/,
                       double* traj_out, int32_t* status);
+/* one derivative evaluation per instance (TypedODESystem::computeDerivatives), state/out [2][n] */
+int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n,
+                      const sopot_b200_rk4_opts* opts, const double* state, double* out);
 
 /* pendulum::DoublePendulum<double>(m1, m2, L1, L2, g, th1, th2, w1, w2),
  * physics/pendulum/double_pendulum.hpp:68-179 */
@@ -125,6 +128,8 @@ typedef struct { const double *mc, *m, *L, *g, *x, *th, *xd, *w, *force; } sopot
 int sopot_b200_cartpole_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n, double t0,
                             double dt, size_t n_steps, const sopot_b200_rk4_opts* opts,
                             double* state_out /*[4][n]*/, double* traj_out, int32_t* status);
+int sopot_b200_cartpole_rhs(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n,
+                            const sopot_b200_rk4_opts* opts, const double* state, double* out);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched linearization: replaces makeLinearizer<4,1>(f).linearize(t, x, u)

@@ -93,6 +93,8 @@ SYMBOLS = {
     "sopot_b200_rk4_num_steps": (c_size_t, [c_double, c_double, c_double]),
     "sopot_b200_ho_rk4": (c_int, [_ctx, POINTER(HoParams), c_size_t, c_double, c_double, c_size_t,
                                   POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
+    "sopot_b200_ho_rhs": (c_int, [_ctx, POINTER(HoParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
+    "sopot_b200_cartpole_rhs": (c_int, [_ctx, POINTER(CartpoleParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_dpend_rk4": (c_int, [_ctx, POINTER(DpendParams), c_size_t, c_double, c_double, c_size_t,
                                      POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
     "sopot_b200_dpend_rhs": (c_int, [_ctx, POINTER(DpendParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),

@@ -139,6 +139,33 @@ SB_EXPORT int sopot_b200_cartpole_rk4(sopot_b200_ctx* ctx, const sopot_b200_cart
     return sb_launch_ensemble<CartpoleSys>(a, P, sg);
 }
 
+SB_EXPORT int sopot_b200_cartpole_rhs(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p, size_t n,
+                                      const sopot_b200_rk4_opts* opts, const double* state, double* out) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 9 * sb_align(n * 8) + 2 * sb_align(4 * n * 8) + 4096))) return rc;
+    sopot_b200_cartpole_params q = *p;
+    if (!q.x) q.x = state; if (!q.th) q.th = state; if (!q.xd) q.xd = state; if (!q.w) q.w = state;
+    const double* user[9] = {q.mc, q.m, q.L, q.g, q.x, q.th, q.xd, q.w, q.force};
+    ParamRef r[9];
+    if ((rc = sb_stage_params(sg, user, 9, n, opts->broadcast, r))) return rc;
+    CartpoleSys::DevParams P{r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]};
+    const void* d_state; void* d_out;
+    if ((rc = sg.in(state, 4 * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(out, 4 * n * 8, &d_out))) return rc;
+    if (n) {
+        const unsigned grid = sb_grid_for(n, CartpoleSys::BLOCK);
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT)
+            rhs_ensemble_kernel<CartpoleSys, true><<<grid, CartpoleSys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        else
+            rhs_ensemble_kernel<CartpoleSys, false><<<grid, CartpoleSys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}
+
 // ---- K2: batched linearization, one operating point per thread ------------------------------------
 // Dual<double,5> = 6 doubles per scalar, the whole 2x2 solve stays in registers.  Inputs and the 20
 // Jacobian entries are SoA, so every load and store of a warp is one fully coalesced 256 B segment:

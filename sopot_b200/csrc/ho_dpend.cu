@@ -49,6 +49,38 @@ SB_EXPORT int sopot_b200_ho_rk4(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
     return sb_launch_ensemble<HoSys>(a, P, sg);
 }
 
+// one derivative evaluation per instance for any ensemble System (computeDerivatives, N instances)
+template <class Sys>
+static int launch_rhs(sopot_b200_ctx* ctx, const typename Sys::DevParams& P, Staging& sg, size_t n, bool strict,
+                      const double* state, double* out) {
+    const void* d_state; void* d_out; int rc;
+    if ((rc = sg.in(state, Sys::DIM * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(out, Sys::DIM * n * 8, &d_out))) return rc;
+    if (n) {
+        const unsigned grid = sb_grid_for(n, Sys::BLOCK);
+        if (strict) rhs_ensemble_kernel<Sys, true><<<grid, Sys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        else rhs_ensemble_kernel<Sys, false><<<grid, Sys::BLOCK, 0, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}
+
+SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params* p, size_t n,
+                                const sopot_b200_rk4_opts* opts, const double* state, double* out) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 5 * sb_align(n * 8) + 2 * sb_align(2 * n * 8) + 4096))) return rc;
+    sopot_b200_ho_params q = *p;
+    if (!q.x0) q.x0 = state; if (!q.v0) q.v0 = state;      // ICs are overwritten by `state`
+    const double* user[5] = {q.m, q.k, q.c, q.x0, q.v0};
+    ParamRef r[5];
+    if ((rc = sb_stage_params(sg, user, 5, n, opts->broadcast, r))) return rc;
+    HoSys::DevParams P{r[0], r[1], r[2], r[3], r[4]};
+    return launch_rhs<HoSys>(ctx, P, sg, n, opts->fp_mode == SOPOT_B200_FP_STRICT, state, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // DoublePendulum::derivatives.  Parameter-only products are hoisted in the reference's own
 // association: m2*L2*w2*w2*sd = (((m2*L2)*w2)*w2)*sd,  (m1+m2)*g*s1 = ((m1+m2)*g)*s1,

@@ -1,0 +1,225 @@
+// sopot/core/typed_component.hpp -- composition API of the reference (core/typed_component.hpp) on top of
+// the B200 engine: TypedComponent<N,T>, TypedRegistry, TypedODESystem, makeTypedODESystem, query<Tag>.
+//
+// What is the same: component base (state_size, LocalState, offsets, getGlobalState), compile-time
+// registry dispatch of compute(Tag, state[, registry]) with "first provider in pack order wins, registry
+// aware overload preferred" (reference :208-222, :249-261), constexpr state offsets (:306-325),
+// getInitialState gathering (:377-398), hasFunction / computeStateFunction(s) / getComponent.
+//
+// What is different, on purpose: components carry NO host derivative code.  computeDerivatives() and
+// RK4Solver::solve() launch the CUDA kernels of libsopot_b200.so through b200::SystemBinding<Components...>
+// -- a compile-time map from a component pack to its C-ABI entry points, specialised beside each shipped
+// component.  A pack without a binding fails to compile with a message instead of silently running on the
+// host (there is no CPU fallback).  State functions (positions, energies, ...) are pure functions of the
+// state vector (docs/COMPONENT_GUIDELINES.md:396-407) and stay ordinary host code: they are diagnostics,
+// not the hot path.
+#pragma once
+#include <array>
+#include <concepts>
+#include <span>
+#include <stdexcept>
+#include <string_view>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../b200/engine.hpp"
+#include "../b200/trace.hpp"
+#include "scalar.hpp"
+#include "state_function_tags.hpp"
+
+namespace sopot {
+
+template <size_t N, Scalar T> class TypedComponent;
+
+template <typename C>
+concept TypedComponentConcept = requires {
+    typename C::scalar_type;
+    typename C::LocalState;
+    typename C::LocalDerivative;
+    { C::state_size } -> std::convertible_to<size_t>;
+};
+template <typename C>
+concept HasInitialState = requires(const C& c) { { c.getInitialLocalState() } -> std::same_as<typename C::LocalState>; };
+template <typename C>
+concept HasIdentification = requires(const C& c) {
+    { c.getComponentType() } -> std::convertible_to<std::string_view>;
+    { c.getComponentName() } -> std::convertible_to<std::string_view>;
+};
+template <typename C, typename Tag, typename T>
+concept TypedProvidesStateFunctionSpan = TypedComponentConcept<C> && StateTagConcept<Tag> &&
+    requires(const C& c, std::span<const T> s) { { c.compute(Tag{}, s) }; };
+template <typename C, typename Tag, typename T, typename Registry>
+concept TypedProvidesRegistryAwareStateFunctionSpan = TypedComponentConcept<C> && StateTagConcept<Tag> &&
+    requires(const C& c, std::span<const T> s, const Registry& r) { { c.compute(Tag{}, s, r) }; };
+template <typename C, typename Tag, typename T, typename Registry>
+concept TypedProvidesStateFunction =
+    TypedProvidesStateFunctionSpan<C, Tag, T> || TypedProvidesRegistryAwareStateFunctionSpan<C, Tag, T, Registry>;
+
+template <typename Registry, typename Tag>
+concept RegistryProvides = requires { { Registry::template hasFunction<Tag>() } -> std::convertible_to<bool>; } &&
+                           Registry::template hasFunction<Tag>();
+
+template <StateTagConcept Tag, typename Registry, typename T>
+    requires RegistryProvides<Registry, Tag>
+inline auto query(const Registry& registry, std::span<const T> state) { return registry.template computeFunction<Tag>(state); }
+template <StateTagConcept Tag, typename Registry, typename T>
+    requires RegistryProvides<Registry, Tag>
+inline auto query(const Registry& registry, const std::vector<T>& state) { return registry.template computeFunction<Tag>(state); }
+
+template <size_t StateSize, Scalar T = double>
+class TypedComponent {
+public:
+    using scalar_type = T;
+    static constexpr size_t state_size = StateSize;
+    using LocalState = ScalarState<T, StateSize>;
+    using LocalDerivative = ScalarState<T, StateSize>;
+    size_t getStateOffset() const noexcept { return m_state_offset; }
+    void setStateOffset(size_t o) noexcept { m_state_offset = o; }
+    void setOffset(size_t o) noexcept { m_state_offset = o; }
+protected:
+    size_t m_state_offset{0};
+    T getGlobalState(std::span<const T> g, size_t i) const { return g[m_state_offset + i]; }
+    LocalState extractLocalState(std::span<const T> g) const {
+        LocalState l;
+        for (size_t i = 0; i < StateSize; ++i) l[i] = g[m_state_offset + i];
+        return l;
+    }
+};
+
+template <typename T, TypedComponentConcept... Components>
+class TypedRegistry {
+    std::tuple<const Components&...> m_components;
+    using Self = TypedRegistry<T, Components...>;
+    template <StateTagConcept Tag>
+    static constexpr size_t providerIndex() {       // first component in pack order that provides Tag
+        size_t idx = sizeof...(Components), i = 0;
+        ((idx == sizeof...(Components) && TypedProvidesStateFunction<Components, Tag, T, Self> ? (idx = i) : 0, ++i), ...);
+        return idx;
+    }
+public:
+    explicit constexpr TypedRegistry(const Components&... c) : m_components(c...) {}
+    template <StateTagConcept Tag>
+    static constexpr bool hasFunction() { return (TypedProvidesStateFunction<Components, Tag, T, Self> || ...); }
+    template <StateTagConcept Tag>
+    auto computeFunction(std::span<const T> state) const {
+        static_assert(hasFunction<Tag>(), "No component provides this state function");
+        const auto& provider = std::get<providerIndex<Tag>()>(m_components);
+        using P = std::decay_t<decltype(provider)>;
+        if constexpr (TypedProvidesRegistryAwareStateFunctionSpan<P, Tag, T, Self>) return provider.compute(Tag{}, state, *this);
+        else return provider.compute(Tag{}, state);
+    }
+    template <StateTagConcept Tag>
+    auto computeFunction(const std::vector<T>& state) const { return computeFunction<Tag>(std::span<const T>(state)); }
+    static constexpr size_t component_count() { return sizeof...(Components); }
+    template <size_t I> constexpr const auto& getComponent() const { return std::get<I>(m_components); }
+};
+
+namespace b200 {
+// Compile-time map: component pack -> device entry points.  Specialised next to the shipped components:
+//   static constexpr bool available = true;  static constexpr size_t dim;
+//   static std::vector<double> rhs(Engine&, const std::tuple<Cs...>&, const std::vector<double>& state);
+//   static EnsembleResult solve(Engine&, const std::tuple<Cs...>&, const std::vector<double>& y0, size_t n_steps,
+//                               double t0, double dt, const EnsembleOptions&);
+template <typename... Components> struct SystemBinding { static constexpr bool available = false; };
+}  // namespace b200
+
+template <typename T, TypedComponentConcept... Components>
+class TypedODESystem {
+    std::tuple<Components...> m_components;
+    TypedRegistry<T, Components...> m_registry;
+    static constexpr size_t m_total = (Components::state_size + ...);
+    using RegistryType = TypedRegistry<T, Components...>;
+    static constexpr auto offsets() {
+        std::array<size_t, sizeof...(Components) + 1> o{};
+        size_t acc = 0, i = 0;
+        ((o[i++] = acc, acc += Components::state_size), ...);
+        o[sizeof...(Components)] = acc;
+        return o;
+    }
+    static constexpr auto offset_array = offsets();
+public:
+    using scalar_type = T;
+    using Binding = b200::SystemBinding<Components...>;
+
+    explicit TypedODESystem(Components... c)
+        : m_components(std::move(c)...), m_registry(std::get<Components>(m_components)...) {
+        [this]<size_t... I>(std::index_sequence<I...>) {
+            (std::get<I>(m_components).setStateOffset(offset_array[I]), ...);
+            (std::get<I>(m_components).setOffset(offset_array[I]), ...);
+        }(std::make_index_sequence<sizeof...(Components)>{});
+    }
+    // the registry refers to the tuple members: moving / copying a system would leave it dangling
+    // (same hazard as the reference) -- forbidden here instead of undefined
+    TypedODESystem(const TypedODESystem&) = delete;
+    TypedODESystem& operator=(const TypedODESystem&) = delete;
+
+    // TypedODESystem::computeDerivatives (reference :410-414): one derivative evaluation, on the device.
+    // T = double -> rhs_ensemble_kernel with N = 1; T = Dual<double,K> -> the batched linearization kernel
+    // (value + Jacobian of the plant) followed by the chain rule over the caller's seeds.
+    std::vector<T> computeDerivatives(T /*t*/, const std::vector<T>& state) const {
+        static_assert(Binding::available, "this component pack has no B200 binding: only the shipped systems can be "
+                                          "evaluated (sopot-b200 has no host fallback)");
+        if (state.size() != m_total) throw std::invalid_argument("state has the wrong dimension");
+        if constexpr (std::is_same_v<T, double>) {
+            std::vector<double> out = Binding::rhs(b200::Engine::shared(), m_components, state);
+            if (auto* tr = b200::detail::active_trace()) {           // see b200/trace.hpp
+                tr->calls++;
+                tr->returned = out;
+                const std::tuple<Components...> snap = m_components;
+                tr->solve = [snap](b200::Engine& e, const std::vector<double>& y0, size_t n_steps, double t0, double dt,
+                                   const b200::EnsembleOptions& o) { return Binding::solve(e, snap, y0, n_steps, t0, dt, o); };
+                tr->rhs = [snap](b200::Engine& e, const std::vector<double>& y) { return Binding::rhs(e, snap, y); };
+            }
+            return out;
+        } else {
+            return Binding::rhs_dual(b200::Engine::shared(), m_components, state);
+        }
+    }
+    static constexpr size_t getStateDimension() noexcept { return m_total; }
+    std::vector<T> getInitialState() const {
+        std::vector<T> s(m_total);
+        [this, &s]<size_t... I>(std::index_sequence<I...>) {
+            ([&] {
+                using C = std::tuple_element_t<I, std::tuple<Components...>>;
+                if constexpr (C::state_size > 0) {
+                    const auto& c = std::get<I>(m_components);
+                    const auto l = c.getInitialLocalState();
+                    for (size_t j = 0; j < C::state_size; ++j) s[c.getStateOffset() + j] = l[j];
+                }
+            }(), ...);
+        }(std::make_index_sequence<sizeof...(Components)>{});
+        return s;
+    }
+    template <StateTagConcept Tag> static constexpr bool hasFunction() { return RegistryType::template hasFunction<Tag>(); }
+    template <StateTagConcept Tag> auto computeStateFunction(const std::vector<T>& s) const { return m_registry.template computeFunction<Tag>(s); }
+    template <StateTagConcept Tag> auto computeStateFunction(std::span<const T> s) const { return m_registry.template computeFunction<Tag>(s); }
+    template <StateTagConcept... Tags>
+    auto computeStateFunctions(const std::vector<T>& s) const {
+        static_assert(sizeof...(Tags) > 0, "Must specify at least one function");
+        static_assert((hasFunction<Tags>() && ...), "All requested functions must be available");
+        return std::tuple{m_registry.template computeFunction<Tags>(s)...};
+    }
+    template <size_t I>
+        requires(I < sizeof...(Components))
+    constexpr const auto& getComponent() const { return std::get<I>(m_components); }
+    static constexpr size_t getComponentCount() noexcept { return sizeof...(Components); }
+    const auto& getRegistry() const { return m_registry; }
+    const std::tuple<Components...>& components() const { return m_components; }
+    std::vector<double> stateValues(const std::vector<T>& s) const {
+        std::vector<double> v(s.size());
+        for (size_t i = 0; i < s.size(); ++i) v[i] = value_of(s[i]);
+        return v;
+    }
+};
+
+template <typename T = double, TypedComponentConcept... Components>
+auto makeTypedODESystem(Components&&... c) {
+    return TypedODESystem<T, std::decay_t<Components>...>(std::forward<Components>(c)...);
+}
+
+template <typename S> struct is_typed_ode_system : std::false_type {};
+template <typename T, typename... C> struct is_typed_ode_system<TypedODESystem<T, C...>> : std::true_type {};
+
+}  // namespace sopot

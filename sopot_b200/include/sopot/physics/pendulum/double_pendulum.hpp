@@ -1,0 +1,143 @@
+// pendulum::DoublePendulum<T> -- Lagrangian double pendulum, state [theta1, theta2, omega1, omega2].
+// Interface of physics/pendulum/double_pendulum.hpp:34-337; the Cramer-rule derivative (:126-179) is
+// DpendSys in csrc/ho_dpend.cu.
+#pragma once
+#include <array>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include "../../core/typed_component.hpp"
+#include "tags.hpp"
+
+namespace sopot::pendulum {
+
+template <Scalar T = double>
+class DoublePendulum final : public TypedComponent<4, T> {
+public:
+    using Base = TypedComponent<4, T>;
+    using typename Base::LocalState;
+    using typename Base::LocalDerivative;
+
+    explicit DoublePendulum(double mass1, double mass2, double length1, double length2, double gravity = 9.81,
+                            double theta1_0 = 0.0, double theta2_0 = 0.0, double omega1_0 = 0.0, double omega2_0 = 0.0)
+        : m_m1(mass1), m_m2(mass2), m_L1(length1), m_L2(length2), m_g(gravity), m_ic{theta1_0, theta2_0, omega1_0, omega2_0} {
+        auto need = [](double v, const char* what) {
+            if (v <= 0.0) throw std::invalid_argument(std::string(what) + " must be positive (got " + std::to_string(v) + ")");
+        };
+        need(mass1, "Mass 1"); need(mass2, "Mass 2"); need(length1, "Length 1"); need(length2, "Length 2");
+    }
+    LocalState getInitialLocalState() const { return {T(m_ic[0]), T(m_ic[1]), T(m_ic[2]), T(m_ic[3])}; }
+    std::string_view getComponentType() const { return "DoublePendulum"; }
+    std::string_view getComponentName() const { return "DoublePendulum"; }
+
+    T compute(mass1::Angle, std::span<const T> s) const { return this->getGlobalState(s, 0); }
+    T compute(mass1::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 2); }
+    T compute(mass2::Angle, std::span<const T> s) const { return this->getGlobalState(s, 1); }
+    T compute(mass2::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 3); }
+    T compute(mass1::Mass, std::span<const T>) const { return T(m_m1); }
+    T compute(mass2::Mass, std::span<const T>) const { return T(m_m2); }
+    T compute(system::Length1, std::span<const T>) const { return T(m_L1); }
+    T compute(system::Length2, std::span<const T>) const { return T(m_L2); }
+    std::array<T, 2> compute(mass1::CartesianPosition, std::span<const T> s) const {
+        using std::sin; using std::cos;
+        const T th1 = this->getGlobalState(s, 0);
+        return {T(m_L1) * sin(th1), -T(m_L1) * cos(th1)};
+    }
+    std::array<T, 2> compute(mass1::CartesianVelocity, std::span<const T> s) const {
+        using std::sin; using std::cos;
+        const T th1 = this->getGlobalState(s, 0), w1 = this->getGlobalState(s, 2);
+        return {T(m_L1) * cos(th1) * w1, T(m_L1) * sin(th1) * w1};
+    }
+    std::array<T, 2> compute(mass2::CartesianPosition, std::span<const T> s) const {
+        using std::sin; using std::cos;
+        const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
+        return {T(m_L1) * sin(th1) + T(m_L2) * sin(th2), -T(m_L1) * cos(th1) - T(m_L2) * cos(th2)};
+    }
+    std::array<T, 2> compute(mass2::CartesianVelocity, std::span<const T> s) const {
+        using std::sin; using std::cos;
+        const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
+        const T w1 = this->getGlobalState(s, 2), w2 = this->getGlobalState(s, 3);
+        return {T(m_L1) * cos(th1) * w1 + T(m_L2) * cos(th2) * w2, T(m_L1) * sin(th1) * w1 + T(m_L2) * sin(th2) * w2};
+    }
+    T compute(system::KineticEnergy, std::span<const T> s) const {
+        using std::cos;
+        const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
+        const T w1 = this->getGlobalState(s, 2), w2 = this->getGlobalState(s, 3);
+        const T L1(m_L1), L2(m_L2);
+        const T v1 = L1 * L1 * w1 * w1;
+        const T v2 = L1 * L1 * w1 * w1 + L2 * L2 * w2 * w2 + T(2.0) * L1 * L2 * w1 * w2 * cos(th1 - th2);
+        return T(0.5) * T(m_m1) * v1 + T(0.5) * T(m_m2) * v2;
+    }
+    T compute(system::PotentialEnergy, std::span<const T> s) const {
+        using std::cos;
+        const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
+        return -T(m_g) * ((T(m_m1) + T(m_m2)) * T(m_L1) * cos(th1) + T(m_m2) * T(m_L2) * cos(th2));
+    }
+    T compute(system::TotalEnergy, std::span<const T> s) const {
+        return compute(system::KineticEnergy{}, s) + compute(system::PotentialEnergy{}, s);
+    }
+    double getMass1() const { return m_m1; }
+    double getMass2() const { return m_m2; }
+    double getLength1() const { return m_L1; }
+    double getLength2() const { return m_L2; }
+    double getGravity() const { return m_g; }
+private:
+    double m_m1, m_m2, m_L1, m_L2, m_g;
+    std::array<double, 4> m_ic;
+};
+
+struct DoublePendulumEnsemble {
+    size_t n;
+    b200::Param mass1, mass2, length1, length2, gravity, theta1, theta2, omega1, omega2;
+    sopot_b200_dpend_params params(uint32_t& bc) const {
+        const b200::Param* f[9] = {&mass1, &mass2, &length1, &length2, &gravity, &theta1, &theta2, &omega1, &omega2};
+        bc = 0;
+        for (int j = 0; j < 9; ++j) bc |= (f[j]->broadcast(n) ? 1u : 0u) << j;
+        return {f[0]->data(), f[1]->data(), f[2]->data(), f[3]->data(), f[4]->data(), f[5]->data(), f[6]->data(),
+                f[7]->data(), f[8]->data()};
+    }
+    b200::EnsembleResult integrate(b200::Engine& eng, size_t n_steps, double t0, double dt, const b200::EnsembleOptions& o) const {
+        uint32_t bc;
+        const auto p = params(bc);
+        const auto opts = b200::make_opts(o, bc);
+        b200::EnsembleResult r;
+        r.n = n; r.dim = 4; r.n_steps = n_steps; r.store_every = o.store_every;
+        r.state.resize(4 * n);
+        r.trajectory.resize(r.snapshots() * 4 * n);
+        if (o.want_status) r.status.resize(n);
+        eng.check(sopot_b200_dpend_rk4(eng.ctx(), &p, n, t0, dt, n_steps, &opts, r.state.data(),
+                                       r.trajectory.empty() ? nullptr : r.trajectory.data(),
+                                       o.want_status ? r.status.data() : nullptr));
+        eng.sync();
+        return r;
+    }
+};
+
+}  // namespace sopot::pendulum
+
+namespace sopot::b200 {
+template <>
+struct SystemBinding<pendulum::DoublePendulum<double>> {
+    static constexpr bool available = true;
+    using Tuple = std::tuple<pendulum::DoublePendulum<double>>;
+    static pendulum::DoublePendulumEnsemble one(const Tuple& t, const std::vector<double>& y) {
+        const auto& c = std::get<0>(t);
+        return {1, c.getMass1(), c.getMass2(), c.getLength1(), c.getLength2(), c.getGravity(), y[0], y[1], y[2], y[3]};
+    }
+    static std::vector<double> rhs(Engine& eng, const Tuple& t, const std::vector<double>& s) {
+        const auto e = one(t, s);
+        uint32_t bc;
+        const auto p = e.params(bc);
+        EnsembleOptions o; o.fp_mode = FpMode::Strict;
+        const auto opts = make_opts(o, 0);
+        std::vector<double> out(4);
+        eng.check(sopot_b200_dpend_rhs(eng.ctx(), &p, 1, &opts, s.data(), out.data()));
+        eng.sync();
+        return out;
+    }
+    static EnsembleResult solve(Engine& eng, const Tuple& t, const std::vector<double>& y0, size_t n_steps, double t0,
+                                double dt, const EnsembleOptions& o) {
+        return one(t, y0).integrate(eng, n_steps, t0, dt, o);
+    }
+};
+}  // namespace sopot::b200

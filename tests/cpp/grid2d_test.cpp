@@ -1,0 +1,78 @@
+// Grid tests in the shape of the reference's tests/grid_2d_test.cpp (3x3 quad :13-106, 4x4 cloth with
+// diagonals :111-190) and tests/verify_grid_physics.cpp (equilibrium force < 1e-10 :76, hand-computed spring
+// force :151).  The reference tests only print; the known answers here come from the unmodified templated
+// makeGrid2DSystem compiled by oracle/ and integrated with RK4Solver::solve.  The grid kernel in strict mode
+// is bit-identical to it (no libm call on this path).  Needs a B200.
+#include <cstdio>
+#include <sopot/physics/connected_masses/grid_2d.hpp>
+#include "check.hpp"
+
+using namespace sopot;
+using namespace sopot::connected_masses;
+
+int main() {
+    auto system = makeGrid2DSystem<double, 3, 3, false>(1.0, 1.0, 10.0, 0.5);
+    ASSERT_TRUE(system.getStateDimension() == 36);
+    auto state = system.getInitialState();
+    for (size_t r = 0; r < 3; ++r)
+        for (size_t c = 0; c < 3; ++c) {
+            ASSERT_TRUE(state[(r * 3 + c) * 4 + 0] == double(c) && state[(r * 3 + c) * 4 + 1] == double(r));
+            ASSERT_TRUE(state[(r * 3 + c) * 4 + 2] == 0.0 && state[(r * 3 + c) * 4 + 3] == 0.0);
+        }
+    // rest grid: no force anywhere
+    for (double v : system.computeDerivatives(0.0, state)) ASSERT_NEAR(v, 0.0, 1e-10);
+
+    // displace the centre mass by +0.5 in y (tests/grid_2d_test.cpp:70)
+    state[4 * 4 + 1] += 0.5;
+    auto d = system.computeDerivatives(0.0, state);
+    // vertical neighbours: k * extension along y; horizontal ones stretch to sqrt(1.25)
+    ASSERT_TRUE(d[1 * 4 + 3] == 5.0);
+    ASSERT_TRUE(d[4 * 4 + 3] == -11.05572809000084);
+    double sum_fx = 0.0, sum_fy = 0.0;
+    for (size_t i = 0; i < 9; ++i) { sum_fx += d[i * 4 + 2]; sum_fy += d[i * 4 + 3]; }
+    ASSERT_NEAR(sum_fx, 0.0, 1e-10);       // Newton's third law (verify_grid_physics.cpp:116)
+    ASSERT_NEAR(sum_fy, 0.0, 1e-10);
+
+    // 2 s at dt = 1e-3 through RK4Solver::solve with the reference's wrapper lambda
+    auto derivs = [&system](double t, StateView s) { return system.computeDerivatives(t, std::vector<double>(s.begin(), s.end())); };
+    auto r = createRK4Solver().solve(derivs, system.getStateDimension(), 0.0, 2.0, 1e-3, state);
+    ASSERT_TRUE(r.size() == 2001);
+    const double m4[4] = {1.0, 1.0591398935343284, 9.242763473708605e-15, 0.34510243258588474};
+    const double m0[4] = {-0.020994531627621757, 0.04803146894323672, 0.0060584375046768705, 0.02911491181820517};
+    for (int j = 0; j < 4; ++j) {
+        ASSERT_TRUE(r.states.back()[4 * 4 + j] == m4[j]);
+        ASSERT_TRUE(r.states.back()[j] == m0[j]);
+    }
+    // bulk entry point == stored-trajectory path
+    auto bulk = state;
+    system.integrate(bulk, 1e-3, 2000, b200::FpMode::Strict);
+    ASSERT_TRUE(bulk == r.states.back());
+
+    // 4x4 cloth with diagonals and the triangular variant (different edge orders, grid_2d.hpp:111-139, :274-281)
+    auto cloth = makeGrid2DSystem<double, 4, 4, true>(0.1, 0.5, 50.0, 1.0);
+    auto tri = makeTriangularGridSystem<double, 4, 4>(0.1, 0.5, 50.0, 1.0);
+    auto s = cloth.getInitialState();
+    for (size_t i = 0; i < 16; ++i) s[i * 4 + 3] = -2.0;
+    s[5 * 4] += 0.05;
+    auto s_tri = s;
+    cloth.integrate(s, 5e-4, 400, b200::FpMode::Strict);
+    tri.integrate(s_tri, 5e-4, 400, b200::FpMode::Strict);
+    const double c5[4] = {0.5022594504116984, 0.09959025766244589, -3.914618797161261e-06, -1.996861584618476};
+    const double t5[4] = {0.5022594504116984, 0.09959025766244589, -3.914618797164784e-06, -1.996861584618476};
+    for (int j = 0; j < 4; ++j) { ASSERT_TRUE(s[5 * 4 + j] == c5[j]); ASSERT_TRUE(s_tri[5 * 4 + j] == t5[j]); }
+
+    // runtime-sized twin, far beyond what the templated reference can instantiate; contract mode stays within
+    // 1e-12 per step of strict
+    auto big = makeGrid2DSystem(256, 320, 1.0, 0.5, 50.0, 0.5);
+    auto y = big.getInitialState();
+    y[(128 * 320 + 160) * 4] += 0.1;
+    auto y_fast = y;
+    big.integrate(y, 1e-3, 1, b200::FpMode::Strict);
+    big.integrate(y_fast, 1e-3, 1, b200::FpMode::Contract);
+    double err = 0.0, scale = 0.0;
+    for (size_t i = 0; i < y.size(); ++i) { err = std::max(err, std::abs(y[i] - y_fast[i])); scale = std::max(scale, std::abs(y[i])); }
+    ASSERT_TRUE(err <= 1e-12 * scale);
+    ASSERT_THROWS(makeGrid2DSystem(1, 8, 1.0, 0.5, 50.0), std::invalid_argument);
+    std::puts("grid2d_test: OK");
+    return 0;
+}

@@ -1,0 +1,103 @@
+// 6-DOF rocket through the reference's driver interface (rocket/rocket.hpp:115-303): configure, setup,
+// simulateRocket, statistics.  The reference ships no rocket data files and no ctest touches Rocket<T>
+// (parity unpinned by reference tests), so the known answer below comes from the
+// unmodified reference compiled by oracle/ (Rocket components composed by hand, synthetic engine and mass
+// tables of wasm/wasm_rocket.cpp:385-428, elevation 85 deg, azimuth 0, diameter 0.16 m, 30 s at dt = 0.01).
+// Needs a B200.
+#include <cstdio>
+#include <fstream>
+#include <sopot/rocket/rocket.hpp>
+#include "check.hpp"
+
+using namespace sopot;
+using namespace sopot::rocket;
+
+static std::vector<double> engine_table(int rows = 36, double thrust = 1500.0, double t_flat = 3.0, double t_burn = 3.5) {
+    std::vector<double> tab;
+    for (int i = 0; i < rows; ++i) {
+        const double t = t_burn * double(i) / double(rows - 1);   // numpy.linspace: start + i*step
+        double F = t <= t_flat ? thrust : thrust * (t_burn - t) / (t_burn - t_flat);
+        F = std::max(F, 0.0);
+        const double p_c = 5.0e6, CF = 1.6, eps = 6.0;
+        const double A_throat = F > 0 ? F / (p_c * CF) : 1e-6;
+        const double d_throat = 2.0 * std::sqrt(A_throat / 3.14159265359);
+        const double row[8] = {t, d_throat, d_throat * std::sqrt(eps), p_c, 3000.0, 1.24, 0.024, 0.96};
+        tab.insert(tab.end(), row, row + 8);
+    }
+    return tab;
+}
+static std::vector<double> mass_table(int rows = 36, double m_wet = 20.0, double m_dry = 14.75, double t_burn = 3.5) {
+    std::vector<double> tab;
+    for (int i = 0; i < rows; ++i) {
+        const double t = t_burn * double(i) / double(rows - 1);
+        tab.push_back(t);
+        tab.push_back(m_wet + (m_dry - m_wet) * t / t_burn);
+    }
+    return tab;
+}
+
+int main() {
+    Rocket<double> rocket;
+    ASSERT_THROWS(rocket.getInitialState(), std::runtime_error);     // "Call setupBeforeSimulation() first"
+    rocket.setLauncher(85.0, 0.0);
+    rocket.setDiameter(0.16);
+    rocket.setEngineTable(engine_table());
+    rocket.setMassTable(mass_table());
+    ASSERT_NEAR(rocket.getBurnTime(), 3.5, 1e-15);
+
+    auto result = simulateRocket(rocket, 30.0, 0.01);
+    ASSERT_TRUE(result.size() == 3001);
+    ASSERT_TRUE(rocket.getStateDimension() == 14);
+    const auto& y0 = result.states.front();
+    ASSERT_TRUE(y0[0] == 0.0 && y0[3] == 0.0 && y0[11] == 0.0);
+    ASSERT_NEAR(y0[7] * y0[7] + y0[8] * y0[8] + y0[9] * y0[9] + y0[10] * y0[10], 1.0, 1e-14);
+
+    // final state of the reference run; libm-level differences only (<= 1e-9 relative on the final state)
+    const double ref_final[14] = {30.00000000000189, 4.751621710833997e-13, 473.78546748858656, 1668.16272022101,
+                                  1.3195469879623669e-14, 13.851338727967878, -85.25061288170275,
+                                  0.47771441710826085, -0.4777144171082609, 0.5213338044735968, 0.5213338044735969,
+                                  0.0, 0.0, 0.0};
+    const auto& yN = result.states.back();
+    double scale = 0.0;
+    for (double v : ref_final) scale = std::max(scale, std::abs(v));
+    for (int j = 0; j < 14; ++j) ASSERT_NEAR(yN[j], ref_final[j], 1e-9 * scale);
+    ASSERT_TRUE(result.times.back() == yN[0] || std::abs(result.times.back() - yN[0]) < 1e-9);
+
+    // apogee from the stored trajectory (SimulationResult::computeStatistics semantics: max of state[3])
+    double apogee = 0.0, apogee_t = 0.0;
+    for (size_t i = 0; i < result.size(); ++i)
+        if (result.states[i][3] > apogee) { apogee = result.states[i][3]; apogee_t = result.times[i]; }
+    ASSERT_NEAR(apogee, 2071.874676142213, 1e-9 * 2071.874676142213);
+    ASSERT_NEAR(apogee_t, 20.79, 1e-9);
+    ASSERT_NEAR(rocket.getAltitude(yN), yN[3], 0.0);
+
+    // the same flight inside a Monte-Carlo ensemble: fused running statistics, no trajectory stored
+    const size_t n = 64;
+    std::vector<double> elev(n), az(n);
+    for (size_t i = 0; i < n; ++i) { elev[i] = 85.0 + 2.0 * std::sin(double(i)); az[i] = 360.0 * double(i) / double(n); }
+    elev[0] = 85.0; az[0] = 0.0;
+    RocketEnsemble ens{n, elev, az, 0.16, 9.80665, rocket.tables()};
+    b200::EnsembleOptions opt;
+    opt.fp_mode = b200::FpMode::Strict;
+    auto er = createRK4Solver().solveEnsemble(ens, 0.0, 30.0, 0.01, opt);
+    ASSERT_TRUE(er.stat(Apogee, 0) == apogee);
+    for (int j = 0; j < 14; ++j) ASSERT_TRUE(er.final(j, 0) == yN[j]);
+    auto disp = RocketEnsemble::dispersion(b200::Engine::shared(), er);
+    ASSERT_TRUE(disp[Apogee].count == double(n) && disp[Apogee].min <= apogee && disp[Apogee].max >= apogee);
+    ASSERT_TRUE(disp[Apogee].stddev > 0.0 && disp[Apogee].nonfinite == 0.0);
+
+    // CSV path of the reference (rocket/rocket.hpp:124-133): numeric rows, header cells skipped
+    {
+        std::ofstream e("/tmp/sopot_b200_sim_engine.csv");
+        e << "time,throat_d,exit_d,p_comb,T_comb,gamma,mol_mass,efficiency\n";
+        e.precision(17);
+        const auto tab = engine_table();
+        for (size_t r = 0; r < tab.size() / 8; ++r) { for (int c = 0; c < 8; ++c) e << (c ? "," : "") << tab[r * 8 + c]; e << "\n"; }
+    }
+    Rocket<double> from_csv;
+    from_csv.loadEngineData("/tmp/sopot_b200_");
+    ASSERT_TRUE(from_csv.tables().engine == engine_table());
+    ASSERT_THROWS(from_csv.loadEngineData("/nonexistent/dir/"), std::runtime_error);
+    std::puts("rocket_test: OK");
+    return 0;
+}
