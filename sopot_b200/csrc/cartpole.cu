@@ -105,6 +105,7 @@ struct CartPlant {
 struct CartpoleSys {
     static constexpr int DIM = 4;
     static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
+    static constexpr bool FAST_STEP = false;
     struct DevParams { ParamRef mc, m, L, g, x, th, xd, w, force; };
     template <bool S> struct Inst { CartPlant<1, Real<S>> plant; Real<S> F; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}

@@ -38,6 +38,44 @@ __device__ __forceinline__ int rk4_step(const typename Sys::template Inst<S>& in
     return st;
 }
 
+// FP_CONTRACT form of the same step.  The stage vectors k_i = dt*f_i are never formed: with
+// F = f1 + 2 f2 + 2 f3 + f4 the update is y += (dt/6) F and the stage arguments are y + (dt/2) f, y + dt f, each
+// one FMA per state element (7 FP64 instructions per element and step instead of 12).  Same real-number
+// formula as core/solver.hpp:95-125, different rounding points: differs from the reference by a few ulp of the
+// increment, far inside the 1e-12 relative per step this mode promises (tests/test_gpu_parity.py).
+struct StepConsts { double dt, hdt, dt6; };
+__device__ __forceinline__ StepConsts make_step_consts(double dt) { return StepConsts{dt, 0.5 * dt, dt / 6.0}; }
+
+template <class Sys>
+__device__ __forceinline__ int rk4_step_fast(const typename Sys::template Inst<false>& in,
+                                             Real<false> (&y)[Sys::DIM], const StepConsts& c) {
+    constexpr int D = Sys::DIM;
+    Real<false> f[D], F[D], tmp[D];
+    int st = Sys::template rhs<false>(in, y, f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { F[d] = f[d]; tmp[d].v = fma(c.hdt, f[d].v, y[d].v); }
+    st |= Sys::template rhs<false>(in, tmp, f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { F[d].v = fma(2.0, f[d].v, F[d].v); tmp[d].v = fma(c.hdt, f[d].v, y[d].v); }
+    st |= Sys::template rhs<false>(in, tmp, f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { F[d].v = fma(2.0, f[d].v, F[d].v); tmp[d].v = fma(c.dt, f[d].v, y[d].v); }
+    st |= Sys::template rhs<false>(in, tmp, f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) y[d].v = fma(c.dt6, F[d].v + f[d].v, y[d].v);
+    return st;
+}
+
+// dispatch: FP_STRICT -> reference association; FP_CONTRACT -> the system's own fused step when it has one
+// (Sys::FAST_STEP, e.g. DpendSys shares the trigonometry between the four stages), else rk4_step_fast.
+template <class Sys, bool S>
+__device__ __forceinline__ int rk4_step_any(const typename Sys::template Inst<S>& in, Real<S> (&y)[Sys::DIM],
+                                            const StepConsts& c) {
+    if constexpr (S) return rk4_step<Sys, true>(in, y, Real<true>(c.dt));
+    else if constexpr (Sys::FAST_STEP) return Sys::fast_step(in, y, c);
+    else return rk4_step_fast<Sys>(in, y, c);
+}
+
 // IPT = instances per thread (Sys::IPT): IPT independent instances are advanced in lock-step by one
 // thread, which gives the scheduler IPT independent dependency chains per warp (FP64 latency hiding)
 // while per-system constants held in registers are shared.  Instance j of a thread is
@@ -61,7 +99,7 @@ rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const doubl
         idx[j] = i < n ? i : base;           // a ragged tail re-computes instance `base` and discards it
         Sys::template load<S>(P, idx[j], in[j], y[j]);
     }
-    const Real<S> dt(dt_);
+    const StepConsts sc = make_step_consts(dt_);
     double t = t0;                           // accumulated like the reference: t += dt (core/solver.hpp:127)
 #pragma unroll
     for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);   // initial condition is stored (:87-88)
@@ -71,7 +109,7 @@ rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const doubl
     size_t until_snap = store_every, snap = 0;
     for (size_t step = 0; step < n_steps; ++step) {
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) st[j] |= rk4_step<Sys, S>(in[j], y[j], dt);
+        for (int j = 0; j < IPT; ++j) st[j] |= rk4_step_any<Sys, S>(in[j], y[j], sc);
         t += dt_;
 #pragma unroll
         for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);

@@ -11,6 +11,7 @@
 struct HoSys {
     static constexpr int DIM = 2;
     static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
+    static constexpr bool FAST_STEP = false;
     struct DevParams { ParamRef m, k, c, x0, v0; };
     template <bool S> struct Inst { Real<S> a, b; };   // a = -k/m, b = c/m
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
@@ -100,8 +101,9 @@ SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
 struct DpendSys {
     static constexpr int DIM = 4;
     static constexpr int BLOCK = SB_DPEND_BLOCK, IPT = SB_DPEND_IPT, MIN_BLOCKS = SB_DPEND_MINB;
+    static constexpr bool FAST_STEP = true;
     struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
-    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g; };
+    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, a11L2; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
@@ -111,6 +113,7 @@ struct DpendSys {
         in.m12g = (m1 + m2) * g;
         in.negL1 = -L1;
         in.L1 = L1; in.L2 = L2; in.g = g;
+        in.a11L2 = in.a11 * L2;         // a11*a22, :172
         y[0] = Real<S>(P.th1.at(i)); y[1] = Real<S>(P.th2.at(i));
         y[2] = Real<S>(P.w1.at(i));  y[3] = Real<S>(P.w2.at(i));
     }
@@ -147,6 +150,62 @@ struct DpendSys {
         if constexpr (S) { dy[2] = n1 / det; dy[3] = n2 / det; }
         else { const Real<S> inv(sbtrig::rcp_fast(det.v)); dy[2] = n1 * inv; dy[3] = n2 * inv; }
         return st;
+    }
+    // ---- FP_CONTRACT fast step -------------------------------------------------------------------------------
+    // angular accelerations from sin/cos of both angles and the rates (the Cramer solve of :162-175 with the
+    // parameter-only products pre-multiplied); 24 FP64 instructions + 1 MUFU
+    static __device__ __forceinline__ void accel(const Inst<false>& in, double s1, double c1, double s2, double c2,
+                                                 double w1, double w2, double& a1, double& a2) {
+        const double sd = fma(s1, c2, -(c1 * s2));                  // sin(th1 - th2)
+        const double cd = fma(c1, c2, s1 * s2);                     // cos(th1 - th2)
+        const double b1 = fma(in.m2L2.v * (w2 * w2), sd, -(in.m12g.v * s1));        // :168
+        const double b2 = fma(in.negL1.v * (w1 * w1), sd, -(in.g.v * s2));          // :169
+        const double a12 = in.m2L2.v * cd, a21 = in.L1.v * cd;      // :163-164
+        const double det = fma(-a12, a21, in.a11L2.v);              // :172
+        const double n1 = fma(b1, in.L2.v, -(b2 * a12));            // :174
+        const double n2 = fma(in.a11.v, b2, -(a21 * b1));           // :175
+        const double inv = sbtrig::rcp_fast(det);
+        a1 = n1 * inv; a2 = n2 * inv;
+    }
+    // sin/cos of (base + h) for both angles: rotation by the small increment, full routine when an increment is large
+    static __device__ __forceinline__ void stage_trig(const double th1, const double th2, const double s1, const double c1,
+                                                      const double s2, const double c2, const double h1, const double h2,
+                                                      double& s1o, double& c1o, double& s2o, double& c2o) {
+        if (sbtrig::small_angle(h1) && sbtrig::small_angle(h2)) {
+            sbtrig::rotate_small(s1, c1, h1, s1o, c1o);
+            sbtrig::rotate_small(s2, c2, h2, s2o, c2o);
+        } else {
+            sbtrig::sincos(th1 + h1, s1o, c1o);
+            sbtrig::sincos(th2 + h2, s2o, c2o);
+        }
+    }
+    // One RK4 step, y += (dt/6)(f1 + 2 f2 + 2 f3 + f4) as in rk4_step_fast, with ONE full sincos per angle: the
+    // stage arguments th + (dt/2) w, th + dt w differ from the base angle by a small increment, so their
+    // sin/cos follow from the base pair by the addition theorem (sbtrig::rotate_small).  ~240 FP64 instructions
+    // per instance-step instead of ~310 with four full sincos pairs.
+    static __device__ __forceinline__ int fast_step(const Inst<false>& in, Real<false> (&y)[4], const StepConsts& k) {
+        const double th1 = y[0].v, th2 = y[1].v, w1 = y[2].v, w2 = y[3].v;
+        double s1, c1, s2, c2;
+        sbtrig::sincos(th1, s1, c1);
+        sbtrig::sincos(th2, s2, c2);
+        double a1, a2;
+        accel(in, s1, c1, s2, c2, w1, w2, a1, a2);                                  // f1 = (w1, w2, a1, a2)
+        double F0 = w1, F1 = w2, F2 = a1, F3 = a2;
+        double u1 = fma(k.hdt, a1, w1), u2 = fma(k.hdt, a2, w2);                    // stage-2 rates
+        double s1s, c1s, s2s, c2s;
+        stage_trig(th1, th2, s1, c1, s2, c2, k.hdt * w1, k.hdt * w2, s1s, c1s, s2s, c2s);
+        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f2 = (u1, u2, a1, a2)
+        F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
+        stage_trig(th1, th2, s1, c1, s2, c2, k.hdt * u1, k.hdt * u2, s1s, c1s, s2s, c2s);
+        u1 = fma(k.hdt, a1, w1); u2 = fma(k.hdt, a2, w2);                           // stage-3 rates
+        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f3
+        F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
+        stage_trig(th1, th2, s1, c1, s2, c2, k.dt * u1, k.dt * u2, s1s, c1s, s2s, c2s);
+        u1 = fma(k.dt, a1, w1); u2 = fma(k.dt, a2, w2);                             // stage-4 rates
+        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f4
+        y[0].v = fma(k.dt6, F0 + u1, th1); y[1].v = fma(k.dt6, F1 + u2, th2);
+        y[2].v = fma(k.dt6, F2 + a1, w1);  y[3].v = fma(k.dt6, F3 + a2, w2);
+        return 0;
     }
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
     template <bool S>

@@ -99,6 +99,7 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
 struct RocketSys {
     static constexpr int DIM = 14;
     static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
+    static constexpr bool FAST_STEP = false;
     struct DevParams {
         ParamRef elev, az, diam, g;
         RocketTablesDev tab;

@@ -39,6 +39,11 @@ constexpr double kC1 = 4.16666666666666019037e-02, kC2 = -1.38888888888741095749
                  kC3 = 2.48015872894767294178e-05, kC4 = -2.75573143513906633035e-07,
                  kC5 = 2.08757232129817482790e-09, kC6 = -1.13596475577881948265e-11;
 
+// Taylor coefficients of sin h / cos h for the small-increment rotation (|h| <= kSmallAngle)
+constexpr double kT3 = -1.0 / 6.0, kT5 = 1.0 / 120.0, kT7 = -1.0 / 5040.0;
+constexpr double kU2 = -0.5, kU4 = 1.0 / 24.0, kU6 = -1.0 / 720.0;
+constexpr double kSmallAngle = 0.03125;                  // 2^-5
+
 SB_HD int lo_word(double x) {
 #ifdef __CUDA_ARCH__
     return __double2loint(x);
@@ -61,11 +66,11 @@ SB_HD double flip_sign_if(double x, int neg_mask_bit31) {     // xor bit 31 of t
 // registers cost the third RF read, but a __constant__ table read with STATIC indices is loaded once
 // (LDCU.128) into uniform registers that stay live across the whole time loop and feed DFMA directly.
 #ifdef __CUDACC__
-__constant__ double c_trig[17] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
-                                  kC1, kC2, kC3, kC4, kC5, kC6};
+__constant__ double c_trig[23] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
+                                  kC1, kC2, kC3, kC4, kC5, kC6, kT3, kT5, kT7, kU2, kU4, kU6};
 #endif
-constexpr double h_trig[17] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
-                               kC1, kC2, kC3, kC4, kC5, kC6};
+constexpr double h_trig[23] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, kS1, kS2, kS3, kS4, kS5, kS6,
+                               kC1, kC2, kC3, kC4, kC5, kC6, kT3, kT5, kT7, kU2, kU4, kU6};
 #ifdef __CUDA_ARCH__
 #define SB_TRIG(i) c_trig[i]
 #else
@@ -97,6 +102,29 @@ SB_HD void sincos(double x, double& s, double& c) {
     const double sv = odd ? cr : sr, cv = odd ? sr : cr;
     s = flip_sign_if(sv, (q << 30) & 0x80000000);           // sin < 0 in quadrants 2, 3
     c = flip_sign_if(cv, ((q + 1) << 30) & 0x80000000);     // cos < 0 in quadrants 1, 2
+}
+
+// sin/cos of (x + h) from s = sin x, c = cos x and a small increment h, |h| <= kSmallAngle = 2^-5:
+//   sin h = h + h^3 (T3 + h^2 (T5 + h^2 T7))          truncation h^9/9!  <= 7.8e-20
+//   cos h - 1 = h^2 (U2 + h^2 (U4 + h^2 U6))          truncation h^8/8!  <= 2.2e-17
+//   sin(x+h) = s + (s (cos h - 1) + c sin h),  cos(x+h) = c + (c (cos h - 1) - s sin h)
+// 12 FP64 instructions against 21 for a full sincos; absolute error <= 2 ulp(1).  Used by the RK4 stages 2-4,
+// whose arguments are the step's base angle plus dt/2 or dt times an angular rate.
+SB_HD bool small_angle(double h) {
+#ifdef __CUDA_ARCH__
+    return (__double2hiint(h) & 0x7fffffff) <= 0x3fa00000;    // |h| <= 2^-5, integer compare (ALU pipe, not FP64)
+#else
+    return std::fabs(h) <= kSmallAngle;
+#endif
+}
+SB_HD void rotate_small(double s, double c, double h, double& s_out, double& c_out) {
+    const double h2 = h * h;
+    double p = fma(h2, SB_TRIG(19), SB_TRIG(18)); p = fma(h2, p, SB_TRIG(17));
+    const double sh = fma(h2 * h, p, h);
+    double q = fma(h2, SB_TRIG(22), SB_TRIG(21)); q = fma(h2, q, SB_TRIG(20));
+    const double cm1 = h2 * q;
+    s_out = fma(s, cm1, fma(c, sh, s));
+    c_out = fma(c, cm1, fma(-s, sh, c));
 }
 
 // sin(x) only (both polynomials, one select: cheaper on the RF than selecting 6 coefficient pairs)
