@@ -103,7 +103,7 @@ struct DpendSys {
     static constexpr int BLOCK = SB_DPEND_BLOCK, IPT = SB_DPEND_IPT, MIN_BLOCKS = SB_DPEND_MINB;
     static constexpr bool FAST_STEP = true;
     struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
-    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, a11L2; };
+    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, kap, lam, gL1, gL2; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
@@ -113,7 +113,9 @@ struct DpendSys {
         in.m12g = (m1 + m2) * g;
         in.negL1 = -L1;
         in.L1 = L1; in.L2 = L2; in.g = g;
-        in.a11L2 = in.a11 * L2;         // a11*a22, :172
+        if constexpr (!S) {             // row-scaled coefficients of the fast step (accel)
+            in.kap = in.m2L2 / in.a11; in.lam = L1 / L2; in.gL1 = g / L1; in.gL2 = g / L2;
+        }
         y[0] = Real<S>(P.th1.at(i)); y[1] = Real<S>(P.th2.at(i));
         y[2] = Real<S>(P.w1.at(i));  y[3] = Real<S>(P.w2.at(i));
     }
@@ -152,20 +154,23 @@ struct DpendSys {
         return st;
     }
     // ---- FP_CONTRACT fast step -------------------------------------------------------------------------------
-    // angular accelerations from sin/cos of both angles and the rates (the Cramer solve of :162-175 with the
-    // parameter-only products pre-multiplied); 24 FP64 instructions + 1 MUFU
+    // angular accelerations from sin/cos of both angles and the rates: the Cramer solve of :162-175 with both
+    // equations scaled by their parameter-only leading coefficient (row 1 by 1/a11, row 2 by 1/a22), so that
+    //   B1 = kap P sd - (g/L1) s1,   B2 = -lam Q sd - (g/L2) s2,   P = w2^2, Q = w1^2,
+    //   a1 = (B1 - kap cd B2) / D,   a2 = (B2 - lam cd B1) / D,    D = 1 - kap lam cd^2  in (0, 1]
+    // with kap = m2 L2 / ((m1+m2) L1), lam = L1 / L2.  21 FP64 instructions + 1 MUFU; only 6 of them read
+    // three distinct vector registers.
     static __device__ __forceinline__ void accel(const Inst<false>& in, double s1, double c1, double s2, double c2,
                                                  double w1, double w2, double& a1, double& a2) {
         const double sd = fma(s1, c2, -(c1 * s2));                  // sin(th1 - th2)
         const double cd = fma(c1, c2, s1 * s2);                     // cos(th1 - th2)
-        const double b1 = fma(in.m2L2.v * (w2 * w2), sd, -(in.m12g.v * s1));        // :168
-        const double b2 = fma(in.negL1.v * (w1 * w1), sd, -(in.g.v * s2));          // :169
-        const double a12 = in.m2L2.v * cd, a21 = in.L1.v * cd;      // :163-164
-        const double det = fma(-a12, a21, in.a11L2.v);              // :172
-        const double n1 = fma(b1, in.L2.v, -(b2 * a12));            // :174
-        const double n2 = fma(in.a11.v, b2, -(a21 * b1));           // :175
-        const double inv = sbtrig::rcp_fast(det);
-        a1 = n1 * inv; a2 = n2 * inv;
+        const double B1 = fma(in.kap.v * sd, w2 * w2, -(in.gL1.v * s1));
+        const double B2 = -fma(in.lam.v * sd, w1 * w1, in.gL2.v * s2);
+        const double kc = in.kap.v * cd, lc = in.lam.v * cd;
+        const double D = fma(-kc, lc, 1.0);
+        const double inv = sbtrig::rcp_fast(D);
+        a1 = fma(-kc, B2, B1) * inv;
+        a2 = fma(-lc, B1, B2) * inv;
     }
     // sin/cos of (base + h) for both angles: rotation by the small increment, full routine when an increment is large
     static __device__ __forceinline__ void stage_trig(const double th1, const double th2, const double s1, const double c1,

@@ -1,0 +1,48 @@
+// Host-side accuracy check of csrc/trig.cuh (the header compiles for the host with the same fma() sequence):
+// max error in ulp of sbtrig::sincos against long double libm over |x| <= 1e6 and near multiples of pi/2, and
+// of rotate_small(sin x, cos x, h) against sin/cos(x + h) for |h| <= 2^-5.  Pure CPU; run by tests/test_oracle.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include "../../sopot_b200/csrc/trig.cuh"
+
+static double ulp_err(double got, long double want) {
+    const double w = (double)want;
+    const double u = std::ldexp(1.0, std::ilogb(w == 0.0 ? 1e-300 : w) - 52);
+    return (double)std::fabs(((long double)got - want) / u);
+}
+
+int main(int argc, char** argv) {
+    const long n = argc > 1 ? std::atol(argv[1]) : 400000;
+    std::mt19937_64 rng(7);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    double worst_s = 0, worst_c = 0, worst_rs = 0, worst_rc = 0;
+    for (long i = 0; i < n; ++i) {
+        double x;
+        switch (i & 3) {
+            case 0: x = 3.5 * U(rng); break;
+            case 1: x = 1e3 * U(rng); break;
+            case 2: x = 1e6 * U(rng); break;
+            default: x = std::round(40 * U(rng)) * 1.5707963267948966 + 1e-3 * U(rng); break;
+        }
+        double s, c;
+        sbtrig::sincos(x, s, c);
+        const long double sl = sinl((long double)x), cl = cosl((long double)x);
+        worst_s = std::fmax(worst_s, ulp_err(s, sl));
+        worst_c = std::fmax(worst_c, ulp_err(c, cl));
+        const double h = sbtrig::kSmallAngle * U(rng);
+        if (!sbtrig::small_angle(h)) { std::printf("small_angle rejects %.17g\n", h); return 1; }
+        double rs, rc;
+        sbtrig::rotate_small((double)sl, (double)cl, h, rs, rc);
+        // absolute error in units of ulp(1) = 2^-52: the rotated pair feeds products of magnitude <= 1
+        // (x + h is not representable for large x: the exact pair comes from the addition theorem in long double)
+        const long double shl = sinl((long double)h), chl = cosl((long double)h);
+        worst_rs = std::fmax(worst_rs, (double)std::fabs((long double)rs - (sl * chl + cl * shl)) / 0x1p-52);
+        worst_rc = std::fmax(worst_rc, (double)std::fabs((long double)rc - (cl * chl - sl * shl)) / 0x1p-52);
+    }
+    if (sbtrig::small_angle(0.03126) || !sbtrig::small_angle(-0.03125)) { std::puts("small_angle threshold wrong"); return 1; }
+    std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f\n", worst_s, worst_c,
+                worst_rs, worst_rc);
+    return (worst_s <= 2.0 && worst_c <= 2.0 && worst_rs <= 2.0 && worst_rc <= 2.0) ? 0 : 2;
+}

@@ -7,10 +7,12 @@ bit, (3) where oracle/_ref exists, the reference itself on fresh random inputs, 
 tests/verify_grid_physics.cpp:76,116,
 tests/rocket_flight_test.cpp:194-209, tests/autodiff_test.cpp:516-523).
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import ROOT, golden
 from sopot_b200 import workloads as W
 
 
@@ -161,3 +163,15 @@ def test_rk4_step_count_rule(port):
     assert port.rk4_num_steps(0.0, 30.0, 0.01) == 3000
     assert port.rk4_num_steps(0.0, 0.0, 0.01) == 0
     assert port.rk4_num_steps(0.0, 0.014, 0.01) == 1 and port.rk4_num_steps(0.0, 0.016, 0.01) == 2
+
+
+def test_lean_trig_accuracy(tmp_path):
+    """csrc/trig.cuh (the FP_CONTRACT sincos and the small-increment rotation) against long double libm, on the
+    host: <= 2 ulp for sincos over |x| <= 1e6, <= 2 ulp(1) absolute for the rotation.  Checks the kernel's own
+    header, compiled for the host (same fma() sequence as the device)."""
+    import subprocess
+    exe = tmp_path / "trig_accuracy"
+    src = os.path.join(ROOT, "tests", "cpp", "trig_accuracy.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", src, "-o", str(exe)], check=True)     # fma() is exact with or without -mfma
+    r = subprocess.run([str(exe), "400000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
