@@ -16,8 +16,10 @@
  *    device (SOPOT_B200_MEM_DEVICE) or host (SOPOT_B200_MEM_HOST) addresses; host buffers are
  *    staged through a ctx-owned device arena (H2D before, D2H after, same stream).
  *  - Ensemble data is SoA: element i of component d lives at base[d * n + i].
- *  - Per-instance parameters: a parameter pointer addresses n doubles, or ONE double when its bit
- *    is set in `broadcast` (bit index = position of the field in the params struct).
+ *  - Per-instance parameters: a parameter pointer addresses n doubles in the call's memory space, or --
+ *    when its bit is set in `broadcast` (bit index = position of the field in the params struct) --
+ *    ONE double in HOST memory, whatever `mem` says: it is read at call time and passed to the kernel
+ *    by value.
  *  - fp_mode: SOPOT_B200_FP_CONTRACT lets the compiler fuse a*b+c into DFMA and replaces x/6.0
  *    style divisions by reciprocal multiplies (<= 1e-12 relative per step against the reference);
  *    SOPOT_B200_FP_STRICT evaluates every operation with the reference's association and IEEE

@@ -260,16 +260,18 @@ class Engine:
         for j, (k, v) in enumerate(arrays.items()):
             if isinstance(v, DeviceArray):
                 assert mem == MEM_DEVICE
-                if int(np.prod(v.shape)) == 1 and n != 1:
-                    mask |= 1 << j
-                ptrs[k] = v.ptr
-                continue
+                if int(np.prod(v.shape)) != 1 or n == 1:
+                    ptrs[k] = v.ptr
+                    continue
+                v = v.download()                      # broadcast scalars are host values by contract
             a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
             if a.ndim == 0 or (a.size == 1 and n != 1):
                 a = a.reshape(1)
                 mask |= 1 << j
-            else:
-                assert a.size == n, (k, a.size, n)
+                ptrs[k] = a.ctypes.data               # host scalar, read by the entry point at call time
+                keep.append(a)
+                continue
+            assert a.size == n, (k, a.size, n)
             if mem == MEM_DEVICE:
                 a = self.to_device(a)
                 ptrs[k] = a.ptr

@@ -75,11 +75,12 @@ struct Staging {
 };
 
 // ---- per-instance parameter access -----------------------------------------------------------
-// A parameter is an array of n doubles or (broadcast) a single double.
+// A parameter is an array of n doubles in the call's memory space, or (broadcast) ONE double that the entry point
+// read from HOST memory and passes by value: it then lives in a uniform register for the whole kernel.
 struct ParamRef {
-    const double* p;
-    size_t stride;   // 1 or 0
-    __device__ __forceinline__ double at(size_t i) const { return __ldg(p + i * stride); }
+    const double* p;   // nullptr: broadcast
+    double value;
+    __device__ __forceinline__ double at(size_t i) const { return p ? __ldg(p + i) : value; }
 };
 
 // ---- Real<Strict> ----------------------------------------------------------------------------

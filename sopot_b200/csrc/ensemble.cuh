@@ -189,11 +189,12 @@ inline int sb_stage_params(Staging& sg, const double* const* user, int count, si
     for (int j = 0; j < count; ++j) {
         if (!user[j]) return sb_fail(sg.ctx, SOPOT_B200_EINVAL, "parameter pointer %d is NULL", j);
         const bool bc = (broadcast >> j) & 1u;
+        if (bc) { refs[j].p = nullptr; refs[j].value = *user[j]; continue; }     // host scalar, by value
         const void* dev = nullptr;
-        int rc = sg.in(user[j], (bc ? 1 : n) * sizeof(double), &dev);
+        int rc = sg.in(user[j], n * sizeof(double), &dev);
         if (rc) return rc;
         refs[j].p = static_cast<const double*>(dev);
-        refs[j].stride = bc ? 0 : 1;
+        refs[j].value = 0.0;
     }
     return SOPOT_B200_OK;
 }

@@ -19,6 +19,7 @@
 // block; all lanes of a warp read the same time interval (state[0] advances identically in every
 // instance), so table reads are shared-memory broadcasts.
 #include "ensemble.cuh"
+#include "trig.cuh"
 #include <cmath>
 #include <vector>
 
@@ -34,6 +35,23 @@ constexpr double kAtmP0 = 101325.0, kAtmT0 = 288.15;
 constexpr double kAtmRs = kAtmR / kAtmM;
 constexpr double kEnginePi = 3.14159265358979323846;   // interpolated_engine.hpp:34
 constexpr double kAeroPi = 3.14159265358979;            // axisymmetric_aero.hpp:56 (truncated, literal)
+
+// A divisor used several times: IEEE division per use when Strict (the reference divides each time); otherwise
+// one fast reciprocal (MUFU seed + 3 FMA, <= 1 ulp, trig.cuh) and a multiply per use.
+template <bool S>
+struct Recip {
+    Real<S> d, inv;
+    __device__ __forceinline__ explicit Recip(Real<S> x) : d(x) { if constexpr (!S) inv = Real<S>(sbtrig::rcp_fast(x.v)); }
+    __device__ __forceinline__ Real<S> of(Real<S> a) const { if constexpr (S) return a / d; else return a * inv; }
+};
+
+// pow(base, e) of standard_atmosphere.hpp:64.  Strict: libdevice pow (<= 1 ulp, the reference calls glibc pow).
+// Otherwise exp(e * log(base)): base = T_b / T lies in (0.7, 1.4) and |e| <= 35, so the relative error is
+// |e log(base)| * ulp-level ~ 1e-15, two orders inside the 1e-12 per-step promise, at a quarter of the instructions.
+template <bool S>
+__device__ __forceinline__ Real<S> r_pow(Real<S> base, double e) {
+    if constexpr (S) return Real<S>(pow(base.v, e)); else return Real<S>(exp(e * log(base.v)));
+}
 
 struct RocketTablesDev {
     // one packed device buffer: engine columns time, exit_d, p_comb, press_ratio, engine_force
@@ -56,18 +74,28 @@ struct Lerp {   // io/interpolation.hpp:49-71 on a shared time grid
     }
 };
 
+// `hint` carries the interval of the previous lookup on this table: simulation time only moves forward, so the
+// interval is almost always unchanged or the next one and the binary search is skipped (same index either way).
 template <bool S>
-__device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv) {
+__device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv, int& hint) {
     Lerp<S> L;
     L.t = Real<S>(0.0);
     if (xv <= x[0]) { L.i = -1; return L; }
     if (xv >= x[n - 1]) { L.i = -2; return L; }
-    int lo = 0, hi = n;                       // std::lower_bound: first element >= xv
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < xv) lo = mid + 1; else hi = mid; }
-    const int i = lo > 0 ? lo - 1 : 0;
+    int i = hint;
+    if (!(x[i] < xv && xv <= x[i + 1])) {         // lower_bound semantics: x[i] < xv <= x[i+1]
+        if (i + 2 < n && x[i + 1] < xv && xv <= x[i + 2]) {
+            i = i + 1;
+        } else {
+            int lo = 0, hi = n;                   // std::lower_bound: first element >= xv
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < xv) lo = mid + 1; else hi = mid; }
+            i = lo > 0 ? lo - 1 : 0;
+        }
+        hint = i;
+    }
     const Real<S> x0(x[i]), x1(x[i + 1]);
     L.i = i;
-    L.t = (Real<S>(xv) - x0) / (x1 - x0);
+    L.t = Recip<S>(x1 - x0).of(Real<S>(xv) - x0);
     return L;
 }
 
@@ -84,13 +112,13 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
     if (fabs(l.lapse) < 1e-10) {
         T = Real<S>(l.T_base);
         // P_base * exp(-(g0*M) * (h - h_base) / (R*T_base))                    :62
-        const Real<S> arg = Real<S>(-(kAtmG0 * kAtmM)) * dh / Real<S>(l.exp_den);
+        const Real<S> arg = Recip<S>(Real<S>(l.exp_den)).of(Real<S>(-(kAtmG0 * kAtmM)) * dh);
         P = Real<S>(l.P_base) * Real<S>(exp(arg.v));
     } else {
         const Real<S> Tl = Real<S>(l.T_base) + Real<S>(l.lapse) * dh;           // :50, :63
         T = Tl;
-        const Real<S> ratio = Real<S>(l.T_base) / Tl;
-        P = Real<S>(l.P_base) * Real<S>(pow(ratio.v, l.pow_exp));               // :64
+        const Real<S> ratio = Recip<S>(Tl).of(Real<S>(l.T_base));
+        P = Real<S>(l.P_base) * r_pow<S>(ratio, l.pow_exp);                     // :64
     }
 }
 
@@ -111,6 +139,7 @@ struct RocketSys {
         int er, mr, xr, yr, use_interp;
         double burn;
         double apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd;
+        mutable int h_eng, h_mass, h_ix, h_iyz;   // lerp_locate interval hints
     };
     static size_t smem_bytes(const DevParams& P) {
         return sizeof(double) * (size_t)(5 * P.tab.er + 2 * P.tab.mr + 2 * P.tab.xr + 2 * P.tab.yr);
@@ -131,6 +160,7 @@ struct RocketSys {
         in.g = Real<S>(P.g.at(i));
         in.area = Real<S>(kAeroPi) * Real<S>(d) * Real<S>(d) / Real<S>(4.0);   // axisymmetric_aero.hpp:56
         in.len = Real<S>(d);
+        in.h_eng = in.h_mass = in.h_ix = in.h_iyz = 0;
         in.apogee = 0; in.apogee_t = 0; in.vmax = 0; in.vmax_t = 0; in.bo_alt = 0; in.bo_spd = 0;
 #pragma unroll
         for (int k = 0; k < 14; ++k) y[k] = Real<S>(0.0);
@@ -167,15 +197,18 @@ struct RocketSys {
         const R vbx = R00 * s[4] + R10 * s[5] + R20 * s[6];
         const R vby = R01 * s[4] + R11 * s[5] + R21 * s[6];
         const R vbz = R02 * s[4] + R12 * s[5] + R22 * s[6];
-        const R airspeed = r_sqrt(vbx * vbx + vby * vby + vbz * vbz);
-        const bool aero_on = !(airspeed.v < 1.0);
+        const R v2 = vbx * vbx + vby * vby + vbz * vbz;
+        R airspeed, inv_airspeed;
+        if constexpr (S) airspeed = r_sqrt(v2);
+        else if (v2.v >= 1.0) sbtrig::sqrt_rsqrt_fast(v2.v, airspeed.v, inv_airspeed.v);   // else: aero off, root unused
+        const bool aero_on = S ? !(airspeed.v < 1.0) : (v2.v >= 1.0 && !(airspeed.v < 1.0));
 
         // ---- mass and inertia, rocket_body.hpp:121-179 ----
         R mass(100.0), Ix(10.0), Iyz(100.0);
         if (in.use_interp) {
-            if (in.mr) mass = lerp_locate<S>(mass_t, in.mr, time.v).eval(mass_t + in.mr, in.mr);
-            if (in.xr) Ix = lerp_locate<S>(ix_t, in.xr, time.v).eval(ix_t + in.xr, in.xr);
-            if (in.yr) Iyz = lerp_locate<S>(iyz_t, in.yr, time.v).eval(iyz_t + in.yr, in.yr);
+            if (in.mr) mass = lerp_locate<S>(mass_t, in.mr, time.v, in.h_mass).eval(mass_t + in.mr, in.mr);
+            if (in.xr) Ix = lerp_locate<S>(ix_t, in.xr, time.v, in.h_ix).eval(ix_t + in.xr, in.xr);
+            if (in.yr) Iyz = lerp_locate<S>(iyz_t, in.yr, time.v, in.h_iyz).eval(iyz_t + in.yr, in.yr);
         }
 
         // ---- thrust, interpolated_engine.hpp:103-152 ----
@@ -184,11 +217,11 @@ struct RocketSys {
         if (burning || aero_on) atmosphere<S>(alt, P, T);
         R thrust(0.0);
         if (burning) {
-            const Lerp<S> L = lerp_locate<S>(eng_t, in.er, time.v);
+            const Lerp<S> L = lerp_locate<S>(eng_t, in.er, time.v, in.h_eng);
             const R d_exit = L.eval(eng_t + in.er, in.er);
             const R p_comb = L.eval(eng_t + 2 * in.er, in.er);
             const R press_ratio = L.eval(eng_t + 3 * in.er, in.er);
-            const R exit_area = R(kEnginePi) * d_exit * d_exit / R(4.0);
+            const R exit_area = r_div_const(R(kEnginePi) * d_exit * d_exit, 4.0);
             const R exit_pressure = p_comb * press_ratio;
             const R engine_force = L.eval(eng_t + 4 * in.er, in.er);
             thrust = engine_force + exit_area * (exit_pressure - P);
@@ -197,18 +230,20 @@ struct RocketSys {
         // ---- aerodynamic force (ENU) and damping moment (body) ----
         R Fax(0.0), Fay(0.0), Faz(0.0), Mx(0.0), My(0.0), Mz(0.0);
         if (aero_on) {
-            const R density = P / (R(kAtmRs) * T);                               // standard_atmosphere.hpp:70
+            const R density = Recip<S>(R(kAtmRs) * T).of(P);                      // standard_atmosphere.hpp:70
             const R dynp = R(0.5) * density * airspeed * airspeed;                // :198
             const R qS = dynp * in.area;                                          // :212
             R ux(0.0), uy(0.0), uz(0.0);
-            if (!(airspeed.v < 1e-15)) { ux = vbx / airspeed; uy = vby / airspeed; uz = vbz / airspeed; }
+            if constexpr (S) { if (!(airspeed.v < 1e-15)) { ux = vbx / airspeed; uy = vby / airspeed; uz = vbz / airspeed; } }
+            else { ux = vbx * inv_airspeed; uy = vby * inv_airspeed; uz = vbz * inv_airspeed; }
             const R drag = qS * R(0.3);                                           // Cd default, :142
             const R fbx = (-ux) * drag, fby = (-uy) * drag, fbz = (-uz) * drag;   // :228
             Fax = R00 * fbx + R01 * fby + R02 * fbz;                              // :251-253
             Fay = R10 * fbx + R11 * fby + R12 * fbz;
             Faz = R20 * fbx + R21 * fby + R22 * fbz;
             const R qSd = qS * in.len;                                            // :271
-            const R damping = in.len / airspeed;                                  // :274
+            R damping;                                                            // :274
+            if constexpr (S) damping = in.len / airspeed; else damping = in.len * inv_airspeed;
             const R cq = R(-450.0) * qSd * damping;                               // :275, :283-287
             Mx = cq * wx; My = cq * wy; Mz = cq * wz;
         }
@@ -220,14 +255,16 @@ struct RocketSys {
 
         d[0] = R(1.0);                                                            // simulation_time.hpp:46-54
         d[1] = s[4]; d[2] = s[5]; d[3] = s[6];                                    // translation_kinematics.hpp:46-55
-        d[4] = Fx / mass; d[5] = Fy / mass; d[6] = Fz / mass;                     // translation_dynamics.hpp:35-42
+        const Recip<S> by_mass(mass);
+        d[4] = by_mass.of(Fx); d[5] = by_mass.of(Fy); d[6] = by_mass.of(Fz);      // translation_dynamics.hpp:35-42
         d[7] = ((q4 * wx + q2 * wz) - q3 * wy) * R(0.5);                          // quaternion.hpp:80-90
         d[8] = ((q4 * wy - q1 * wz) + q3 * wx) * R(0.5);
         d[9] = ((q4 * wz + q1 * wy) - q2 * wx) * R(0.5);
         d[10] = (((-(q1 * wx)) - q2 * wy) - q3 * wz) * R(0.5);
-        d[11] = (Mx - (Iyz - Iyz) * wy * wz) / Ix;                                // rotation_dynamics.hpp:42-44
-        d[12] = (My - (Ix - Iyz) * wx * wz) / Iyz;
-        d[13] = (Mz - (Iyz - Ix) * wx * wy) / Iyz;
+        const Recip<S> by_Ix(Ix), by_Iyz(Iyz);
+        d[11] = by_Ix.of(Mx - (Iyz - Iyz) * wy * wz);                             // rotation_dynamics.hpp:42-44
+        d[12] = by_Iyz.of(My - (Ix - Iyz) * wx * wz);
+        d[13] = by_Iyz.of(Mz - (Iyz - Ix) * wx * wy);
         return 0;
     }
 

@@ -69,15 +69,18 @@ dispersion_final_kernel(const Partial* __restrict__ partials, const int nblk, do
 }
 
 // ---- roofline probes ----------------------------------------------------------------------------------
-// 8 independent DFMA chains per thread: pure FP64-pipe issue rate, FMA = 2 flop.
+// 8 independent DFMA chains per thread: pure FP64-pipe issue rate, FMA = 2 flop.  The multiplicand is a per-thread
+// vector register: x = fma(x, y, U) issues every 2.02 cycles per sub-partition, the best of the operand placements
+// measured in tools/microbench/fp64_operands.cu (two uniform operands: 2.22; three distinct vector registers: 3.02).
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, const int iters, const double a, const double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    const double y = a + 1e-12 * threadIdx.x;
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+            x0 = fma(x0, y, b); x1 = fma(x1, y, b); x2 = fma(x2, y, b); x3 = fma(x3, y, b);
+            x4 = fma(x4, y, b); x5 = fma(x5, y, b); x6 = fma(x6, y, b); x7 = fma(x7, y, b);
         }
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;

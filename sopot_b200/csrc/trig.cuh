@@ -156,4 +156,24 @@ SB_HD double rcp_fast(double x) {
 #endif
 }
 
+// sqrt(x) and 1/sqrt(x) together for normal, positive x: MUFU.RSQ64H seed (2^-20) + two Newton steps on the
+// reciprocal root, one residual correction on the root; both <= 1 ulp, no special-case branch.  Replaces an IEEE
+// sqrt (slow-path branch) followed by IEEE divisions by the root.
+SB_HD void sqrt_rsqrt_fast(double x, double& root, double& inv_root) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-(hx * y), y, 0.5);        // (1 - x y^2) / 2
+    y = fma(y, e, y);
+    e = fma(-(hx * y), y, 0.5);
+    y = fma(y, e, y);
+    double r = x * y;
+    r = fma(fma(-r, r, x), 0.5 * y, r);
+    root = r; inv_root = y;
+#else
+    root = std::sqrt(x); inv_root = 1.0 / root;
+#endif
+}
+
 }  // namespace sbtrig

@@ -1,0 +1,48 @@
+"""Time one config's kernel, device-resident, back-to-back launches between CUDA events:
+   python tools/time_cfg.py rocket|ho|lin|grid|grid_strict [n] [steps]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sopot_b200 import workloads as W
+from sopot_b200.capi import FP_CONTRACT, FP_STRICT, MEM_DEVICE, Engine
+cfg = sys.argv[1]
+eng = Engine(0)
+def timed(fn, reps):
+    fn(); eng.sync()
+    eng.event_record(0)
+    for _ in range(reps): fn()
+    eng.event_record(1)
+    return eng.elapsed_ms(0, 1) / reps
+if cfg == "rocket":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3000
+    w = W.rocket_ensemble(n)
+    d = [eng.to_device(w[k]) for k in ("elev", "az", "diam", "g0")]
+    st, stats = eng.empty((14, n)), eng.empty((8, n))
+    ms = timed(lambda: eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, steps, mem=MEM_DEVICE,
+                                      want_status=False, state_out=st, stats_out=stats, sync=False), 2)
+    h = stats.download()
+    print("rocket %d x %d: %.2f ms  %.3e inst-steps/s  apogee mean %.9f" % (n, steps, ms, n * steps / ms * 1e3, h[0].mean()))
+elif cfg == "ho":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
+    w = W.ho_ensemble(n)
+    d = [eng.to_device(w[k]) for k in ("m", "k", "c", "x0", "v0")]
+    st = eng.empty((2, n))
+    ms = timed(lambda: eng.ho_rk4(*d, n, 0.0, 0.01, 1000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, want_status=False, state_out=st, sync=False), 5)
+    print("ho %d x 1000: %.3f ms  %.3e inst-steps/s  checksum %.12e" % (n, ms, n * 1000 / ms * 1e3, float(st.download()[:, ::4097].sum())))
+elif cfg == "lin":
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
+    w = W.cartpole_points(P)
+    dx, du = eng.to_device(w["x"]), eng.to_device(w["u"])
+    A, B = eng.empty((16, P)), eng.empty((4, P))
+    ms = timed(lambda: eng.cartpole_linearize(1.0, 0.1, 0.5, 9.81, dx, du, P, mem=MEM_DEVICE, A=A, B=B, want_status=False, sync=False), 20)
+    print("lin %d: %.4f ms  %.1f GB/s (200 B/point)  checksum %.12e" % (P, ms, 200.0 * P / ms / 1e6, float(A.download()[:, ::4097].sum())))
+elif cfg in ("grid", "grid_strict"):
+    p = W.GRID2D_PARAMS
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
+    mode = FP_STRICT if cfg == "grid_strict" else FP_CONTRACT
+    ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False), 2) / 10
+    print("%s %d^2: %.3f ms/step  %.1f GB/s (544 B/mass-step)" % (cfg, n, ms, 544.0 * n * n / ms / 1e6))
+eng.close()
