@@ -40,6 +40,10 @@ N_PER_GPU = 1 << 22
 N_STEPS = 10000
 DT = 1e-3
 FLOP_PER_INSTANCE_STEP = 204.0
+# FP64 issue cycles per warp and instance-step of rk4_ensemble_kernel<DpendSys,false>, from the kernel's own
+# instruction inventory: ~240 FP64 instructions at 2 cycles + ~50 three-register DFMAs at
+# one extra cycle (profiles/r1_fp64_operand_rule.txt).  Used for roofline.fp64_issue_frac only.
+FP64_ISSUE_CYCLES_PER_STEP = 2.0 * 240 + 50
 METRIC = "RK4 instance-steps/s (FP64)"
 UNIT = "instance-steps/s"
 
@@ -329,6 +333,11 @@ def main():
                          "frac": achieved / fp64_peak, "traffic": None,
                          "kernel": "rk4_ensemble_kernel<DpendSys,false>", "kernel_ms": kernel_ms,
                          "flop_per_unit": FLOP_PER_INSTANCE_STEP,
+                         # share of the FP64 pipe's issue cycles the kernel's own instructions need at this rate
+                         # (148 SMs x 4 sub-partitions, clock = median SM clock sampled during the timed region)
+                         "fp64_issue_frac": (per_gpu_rate / 32.0 * FP64_ISSUE_CYCLES_PER_STEP /
+                                             (148 * 4 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6))
+                         if clocks and clocks.get("sm_mhz") else None,
                          "peak_source": "DFMA issue rate measured in this run (sopot_b200_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm_copy_live_gbs": hbm_peak_live},

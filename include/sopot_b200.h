@@ -51,6 +51,9 @@ enum {
 
 enum { SOPOT_B200_MEM_DEVICE = 0, SOPOT_B200_MEM_HOST = 1 };
 enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
+/* grid2d: run the four RK stages as four kernels with one 1-row halo exchange each (the literal per-stage
+ * schedule) instead of the default fused step kernel with one 4-row halo exchange per step */
+enum { SOPOT_B200_FLAG_GRID_PER_STAGE = 1 };
 enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2,
        SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */ };
 
@@ -102,7 +105,7 @@ typedef struct {
     uint32_t fp_mode;      /* SOPOT_B200_FP_*                                         */
     size_t   store_every;  /* 0: final state only                                     */
     uint32_t broadcast;    /* bit i: i-th params pointer addresses a single double    */
-    uint32_t reserved;
+    uint32_t flags;        /* SOPOT_B200_FLAG_*                                       */
 } sopot_b200_rk4_opts;
 
 /* physics::HarmonicOscillator<double>(mass, k, c, x0, v0), physics/harmonic_oscillator.hpp:44-85 */
@@ -187,7 +190,10 @@ int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* values, size_
  * topology: 0 quad, 1 quad + diagonals (IncludeDiagonals=true), 2 triangular.
  * Multi-GPU: each rank of the ctx owns the contiguous slab rows [row_begin, row_begin + rows_local)
  * of the global grid and `state` addresses only that slab; one boundary row is exchanged with each
- * neighbour before every RK stage (NCCL send/recv over NVLink).
+ * neighbour before every RK stage (NCCL send/recv over NVLink) with SOPOT_B200_FLAG_GRID_PER_STAGE; by
+ * default the whole RK4 step is one kernel (all four stages on a shared-memory tile with a 4-cell halo) and
+ * FOUR boundary rows are exchanged once per step -- same values bit for bit, a quarter of the messages and
+ * 64 instead of 544 bytes of HBM traffic per mass and step.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     size_t rows, cols;            /* GLOBAL grid size                         */

@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
+FLAG_GRID_PER_STAGE = 1
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
 
 _dp = POINTER(c_double)
@@ -31,7 +32,7 @@ class SopotB200Error(RuntimeError):
 
 class RK4Opts(ctypes.Structure):
     _fields_ = [("mem", c_uint32), ("fp_mode", c_uint32), ("store_every", c_size_t),
-                ("broadcast", c_uint32), ("reserved", c_uint32)]
+                ("broadcast", c_uint32), ("flags", c_uint32)]
 
 
 class HoParams(ctypes.Structure):
@@ -423,10 +424,11 @@ class Engine:
         self.sync()
         return st
 
-    def grid2d_rk4(self, g: Grid2DParams, dt, n_steps, state, fp_mode=FP_STRICT, sync=True):
-        """In place on `state` (numpy host array or DeviceArray)."""
+    def grid2d_rk4(self, g: Grid2DParams, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, per_stage=False):
+        """In place on `state` (numpy host array or DeviceArray).  per_stage=True: four stage kernels with a 1-row
+        halo exchange each instead of the fused step kernel (same values)."""
         mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
-        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        opts = RK4Opts(mem, fp_mode, 0, 0, FLAG_GRID_PER_STAGE if per_stage else 0)
         self._ck(self.lib.sopot_b200_grid2d_rk4(self.ctx, byref(g), dt, n_steps, byref(opts), _ptr(state)))
         if sync:
             self.sync()

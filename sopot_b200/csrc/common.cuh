@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/sopot_b200.h"
+#include "ieee.cuh"
 
 #define SB_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -99,9 +100,13 @@ struct Real {
 #ifdef __CUDA_ARCH__
 #define SB_ADD(a, b) __dadd_rn((a), (b))
 #define SB_MUL(a, b) __dmul_rn((a), (b))
+#define SB_DIV(a, b) sb_div_rn((a), (b))
+#define SB_SQRT(a) sb_sqrt_rn((a))
 #else
 #define SB_ADD(a, b) ((a) + (b))
 #define SB_MUL(a, b) ((a) * (b))
+#define SB_DIV(a, b) ((a) / (b))
+#define SB_SQRT(a) sqrt((a))
 #endif
 
 template <bool S> __host__ __device__ __forceinline__ Real<S> operator+(Real<S> a, Real<S> b) {
@@ -114,7 +119,7 @@ template <bool S> __host__ __device__ __forceinline__ Real<S> operator*(Real<S> 
     if constexpr (S) return Real<S>(SB_MUL(a.v, b.v)); else return Real<S>(a.v * b.v);
 }
 template <bool S> __host__ __device__ __forceinline__ Real<S> operator/(Real<S> a, Real<S> b) {
-    return Real<S>(a.v / b.v);   // IEEE division in both modes (-prec-div=true)
+    return Real<S>(SB_DIV(a.v, b.v));   // correctly rounded division in both modes (ieee.cuh)
 }
 template <bool S> __host__ __device__ __forceinline__ Real<S> operator-(Real<S> a) { return Real<S>(-a.v); }
 template <bool S> __host__ __device__ __forceinline__ Real<S>& operator+=(Real<S>& a, Real<S> b) { a = a + b; return a; }
@@ -131,7 +136,7 @@ template <bool S> __host__ __device__ __forceinline__ bool operator>(Real<S> a, 
 template <bool S> __host__ __device__ __forceinline__ bool operator<=(Real<S> a, Real<S> b) { return a.v <= b.v; }
 template <bool S> __host__ __device__ __forceinline__ bool operator>=(Real<S> a, Real<S> b) { return a.v >= b.v; }
 
-template <bool S> __device__ __forceinline__ Real<S> r_sqrt(Real<S> a) { return Real<S>(sqrt(a.v)); }
+template <bool S> __device__ __forceinline__ Real<S> r_sqrt(Real<S> a) { return Real<S>(SB_SQRT(a.v)); }
 template <bool S> __device__ __forceinline__ Real<S> r_sin(Real<S> a) { return Real<S>(sin(a.v)); }
 template <bool S> __device__ __forceinline__ Real<S> r_cos(Real<S> a) { return Real<S>(cos(a.v)); }
 template <bool S> __device__ __forceinline__ void r_sincos(Real<S> a, Real<S>& s, Real<S>& c) {
@@ -139,7 +144,7 @@ template <bool S> __device__ __forceinline__ void r_sincos(Real<S> a, Real<S>& s
 }
 // x / d where the reference divides: IEEE division when Strict, reciprocal multiply otherwise
 template <bool S> __device__ __forceinline__ Real<S> r_div_const(Real<S> a, double d) {
-    if constexpr (S) return Real<S>(a.v / d); else return Real<S>(a.v * (1.0 / d));
+    if constexpr (S) return Real<S>(SB_DIV(a.v, d)); else return Real<S>(a.v * (1.0 / d));
 }
 
 inline unsigned sb_grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }

@@ -24,13 +24,14 @@
 // ncclSend/ncclRecv in one group after the producing stage kernel.
 #include "common.cuh"
 #include "nccl_api.h"
+#include "trig.cuh"
 
 namespace {
 
 struct GridDev {
     size_t rows, cols;        // global
     size_t row_begin, rows_local;
-    double mass, k, c, L_orth, L_diag;
+    double mass, k, c, L_orth, L_diag, inv_mass;
 };
 
 // stencil input: slab rows plus one ghost row on each side (ghosts unused at the global boundary)
@@ -59,11 +60,20 @@ __device__ __forceinline__ void spring_force(const Mass4& pi, const Mass4& pj, c
                                              const double L0, Real<S>& fx, Real<S>& fy) {
     using R = Real<S>;
     const R dx = R(pj.x) - R(pi.x), dy = R(pj.y) - R(pi.y);
-    const R length = r_sqrt(dx * dx + dy * dy);
-    const R length_safe = length.v < 1e-10 ? R(1e-10) : length;            // :125
-    R ux, uy;
-    if constexpr (S) { ux = dx / length_safe; uy = dy / length_safe; }
-    else { const R inv = R(1.0) / length_safe; ux = dx * inv; uy = dy * inv; }
+    R length, ux, uy;
+    if constexpr (S) {
+        length = r_sqrt(dx * dx + dy * dy);
+        const R length_safe = length.v < 1e-10 ? R(1e-10) : length;           // :125
+        ux = dx / length_safe; uy = dy / length_safe;
+    } else {
+        // root and reciprocal root from one MUFU seed, no IEEE slow-path branches; coincident masses (the
+        // len_safe clamp) take the generic route
+        const double l2 = fma(dx.v, dx.v, dy.v * dy.v);
+        double inv;
+        if (l2 > 1e-20) sbtrig::sqrt_rsqrt_fast(l2, length.v, inv);
+        else { length.v = sqrt(l2); inv = 1.0 / (length.v < 1e-10 ? 1e-10 : length.v); }
+        ux = dx * R(inv); uy = dy * R(inv);
+    }
     const R extension = length - R(L0);
     const R dvx = R(pj.vx) - R(pi.vx), dvy = R(pj.vy) - R(pi.vy);
     const R rel = dvx * ux + dvy * uy;
@@ -71,11 +81,38 @@ __device__ __forceinline__ void spring_force(const Mass4& pi, const Mass4& pj, c
     fx = F * ux; fy = F * uy;
 }
 
-// derivative of one mass, gather form (every incident spring evaluated here)
+// derivative of one mass, gather form (every incident spring evaluated here).  nb(dr, dc) returns the state of the
+// neighbour at (row + dr, col + dc); it is only called for neighbours that exist in the global grid.
+template <bool S, int TOPO, class Fetch>
+__device__ __forceinline__ void mass_derivative_from(const GridDev& g, const Mass4& P, const bool has_l, const bool has_r,
+                                                     const bool has_u, const bool has_d, Fetch nb, Real<S> (&d)[4]) {
+    using R = Real<S>;
+    R Fx(0.0), Fy(0.0), fx, fy;
+    // horizontals then verticals (global edge order): left(-), right(+), up(-), down(+)
+    if (has_l) { spring_force<S>(nb(0, -1), P, g.k, g.c, g.L_orth, fx, fy); Fx -= fx; Fy -= fy; }
+    if (has_r) { spring_force<S>(P, nb(0, 1), g.k, g.c, g.L_orth, fx, fy); Fx += fx; Fy += fy; }
+    if (has_u) { spring_force<S>(nb(-1, 0), P, g.k, g.c, g.L_orth, fx, fy); Fx -= fx; Fy -= fy; }
+    if (has_d) { spring_force<S>(P, nb(1, 0), g.k, g.c, g.L_orth, fx, fy); Fx += fx; Fy += fy; }
+    if constexpr (TOPO == 1) {
+        // all main diagonals (r,c)-(r+1,c+1), then all anti-diagonals (r,c)-(r+1,c-1)
+        if (has_u && has_l) { spring_force<S>(nb(-1, -1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
+        if (has_d && has_r) { spring_force<S>(P, nb(1, 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
+        if (has_u && has_r) { spring_force<S>(nb(-1, 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
+        if (has_d && has_l) { spring_force<S>(P, nb(1, -1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
+    } else if constexpr (TOPO == 2) {
+        // per cell, row-major: main (r,c)-(r+1,c+1) then anti (r,c+1)-(r+1,c)
+        if (has_u && has_l) { spring_force<S>(nb(-1, -1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
+        if (has_u && has_r) { spring_force<S>(nb(-1, 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
+        if (has_d && has_l) { spring_force<S>(P, nb(1, -1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
+        if (has_d && has_r) { spring_force<S>(P, nb(1, 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
+    }
+    d[0] = R(P.vx); d[1] = R(P.vy);
+    d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass);
+}
+
 template <bool S, int TOPO>
 __device__ __forceinline__ void mass_derivative(const GridDev& g, const StencilIn& in, const size_t rl,
                                                 const size_t col, Real<S> (&d)[4], Mass4& self_out) {
-    using R = Real<S>;
     const size_t gr = g.row_begin + rl;
     const double* r0 = in.row((long long)rl, g.rows_local, g.cols);
     const Mass4 P = load_mass(r0, col);
@@ -83,27 +120,8 @@ __device__ __forceinline__ void mass_derivative(const GridDev& g, const StencilI
     const bool has_l = col > 0, has_r = col + 1 < g.cols, has_u = gr > 0, has_d = gr + 1 < g.rows;
     const double* ru = has_u ? in.row((long long)rl - 1, g.rows_local, g.cols) : r0;
     const double* rd = has_d ? in.row((long long)rl + 1, g.rows_local, g.cols) : r0;
-    R Fx(0.0), Fy(0.0), fx, fy;
-    // horizontals then verticals (global edge order): left(-), right(+), up(-), down(+)
-    if (has_l) { spring_force<S>(load_mass(r0, col - 1), P, g.k, g.c, g.L_orth, fx, fy); Fx -= fx; Fy -= fy; }
-    if (has_r) { spring_force<S>(P, load_mass(r0, col + 1), g.k, g.c, g.L_orth, fx, fy); Fx += fx; Fy += fy; }
-    if (has_u) { spring_force<S>(load_mass(ru, col), P, g.k, g.c, g.L_orth, fx, fy); Fx -= fx; Fy -= fy; }
-    if (has_d) { spring_force<S>(P, load_mass(rd, col), g.k, g.c, g.L_orth, fx, fy); Fx += fx; Fy += fy; }
-    if constexpr (TOPO == 1) {
-        // all main diagonals (r,c)-(r+1,c+1), then all anti-diagonals (r,c)-(r+1,c-1)
-        if (has_u && has_l) { spring_force<S>(load_mass(ru, col - 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
-        if (has_d && has_r) { spring_force<S>(P, load_mass(rd, col + 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
-        if (has_u && has_r) { spring_force<S>(load_mass(ru, col + 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
-        if (has_d && has_l) { spring_force<S>(P, load_mass(rd, col - 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
-    } else if constexpr (TOPO == 2) {
-        // per cell, row-major: main (r,c)-(r+1,c+1) then anti (r,c+1)-(r+1,c)
-        if (has_u && has_l) { spring_force<S>(load_mass(ru, col - 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
-        if (has_u && has_r) { spring_force<S>(load_mass(ru, col + 1), P, g.k, g.c, g.L_diag, fx, fy); Fx -= fx; Fy -= fy; }
-        if (has_d && has_l) { spring_force<S>(P, load_mass(rd, col - 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
-        if (has_d && has_r) { spring_force<S>(P, load_mass(rd, col + 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
-    }
-    d[0] = R(P.vx); d[1] = R(P.vy);
-    d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass);
+    auto nb = [&](int dr, int dc) { return load_mass(dr < 0 ? ru : (dr > 0 ? rd : r0), col + dc); };
+    mass_derivative_from<S, TOPO>(g, P, has_l, has_r, has_u, has_d, nb, d);
 }
 
 __device__ __forceinline__ void store4(double* p, const double a, const double b, const double c, const double d) {
@@ -157,6 +175,208 @@ grid_stage_gather(const GridDev g, const StencilIn in, const size_t r_lo, const 
     }
 }
 
+// ---- fused RK4 step: all four stages in one kernel on a shared-memory tile -----------------------------------
+// A CTA owns TX x TY interior masses and loads them with a 4-cell halo (one cell per RK stage).  Stage s evaluates
+// the derivative on the region shrunk by s cells, so the stencil input of stage s+1 is complete inside the tile:
+//   Y (halo 4) -> k1 on halo 3 -> A1 = y + k1/2 (halo 3) -> k2 on halo 2 -> A2 (halo 2) -> k3 on halo 1 -> A3 = y + k3
+//   (halo 1) -> k4 on the interior -> y_new = y + (S + k4)/6, S = k1 + 2 k2 + 2 k3 kept in registers.
+// Halo cells are recomputed by the neighbouring CTA with the same operations on the same inputs, so the result is
+// bit-identical to the four-kernel schedule (FP_STRICT: to the reference).  HBM traffic per mass and step: 32 B read
+// (+ halo re-reads, served by L2) and 32 B written, instead of 544 B -- the step becomes FP64-bound, so the FP64
+// work is halved as well: every spring is evaluated ONCE, by its first endpoint (the reference's edge orientation:
+// left->right, up->down, and for the diagonal topologies up-left->down-right, up-right->down-left), and its force
+// goes through shared memory to the second endpoint, which subtracts it -- exactly the reference's
+// "+= on edge.first, -= on edge.second" (force_aggregator_2d.hpp:69-81; negation is exact).
+//
+// Each stage is two phases separated by __syncthreads():
+//   spring phase  cells of margin >= s-1: forces of the cell's right/down (and diagonal) springs -> F planes
+//   update phase  cells of margin >= s  : sum the incident forces in edge-list order, k = dt*f, write the next
+//                 stage input (or, in stage 4, y_new to global memory)
+// Ownership is static: thread t owns interior cell (4 + t/TX, 4 + t%TX) and, for t < #halo cells, ONE halo cell,
+// enumerated ring by ring from the inside out, so "margin >= m" is a prefix of the enumeration and the halo cell's
+// own y stays in registers for all stages.
+// Shared memory: two SoA state buffers (ping-pong stage inputs) and one force buffer of (TX+8) x (TY+8) cells
+// (x 4 planes; 8 planes of forces with diagonals); 64-bit plane accesses are bank-conflict free.
+template <int TX, int TY, int TOPO>
+struct FusedTile {
+    static constexpr int H = 4;
+    static constexpr int W = TX + 2 * H, HT = TY + 2 * H, CELLS = W * HT;
+    static constexpr int THREADS = TX * TY;
+    static constexpr int FPLANES = TOPO == 0 ? 4 : 8;
+    static constexpr size_t SMEM = (size_t)(8 + FPLANES) * CELLS * sizeof(double);
+    // halo cells with margin >= m (margin = distance to the tile edge), m = 0..3; margin 4 = interior
+    static constexpr int ring(int m) { return 2 * (W - 2 * m) + 2 * (HT - 2 * m - 2); }
+    static constexpr int upto(int m) { int n = 0; for (int k = H - 1; k >= m; --k) n += ring(k); return n; }
+    static_assert(upto(0) == CELLS - TX * TY && upto(0) <= THREADS, "one halo cell per thread");
+};
+
+// y of the local slab plus FOUR ghost rows on either side (ghost_top row j = global row row_begin - 4 + j,
+// ghost_bot row j = global row row_begin + rows_local + j)
+struct StepIn {
+    const double* slab;
+    const double* ghost_top;
+    const double* ghost_bot;
+};
+
+template <int CELLS>
+__device__ __forceinline__ Mass4 tile_cell(const double* __restrict__ pl, const int o) {
+    return Mass4{pl[o], pl[CELLS + o], pl[2 * CELLS + o], pl[3 * CELLS + o]};
+}
+
+// spring phase for one cell: forces of the springs whose FIRST endpoint is this cell
+template <bool S, int TOPO, int TX, int TY, bool FULL>
+__device__ __forceinline__ void fused_springs(const GridDev& g, const double* __restrict__ in_pl, double* __restrict__ F,
+                                              const int r, const int c, const long long gr, const long long gc) {
+    using T = FusedTile<TX, TY, TOPO>;
+    const int o = r * T::W + c;
+    const bool here = FULL || (gr >= 0 && gc >= 0 && gr < (long long)g.rows && gc < (long long)g.cols);
+    const bool right = c + 1 < T::W && here && (FULL || gc + 1 < (long long)g.cols);
+    const bool down = r + 1 < T::HT && here && (FULL || gr + 1 < (long long)g.rows);
+    Mass4 P;
+    if (right || down) P = tile_cell<T::CELLS>(in_pl, o);
+    Real<S> fx, fy;
+    if (right) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + 1), g.k, g.c, g.L_orth, fx, fy); F[o] = fx.v; F[T::CELLS + o] = fy.v; }
+    if (down) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W), g.k, g.c, g.L_orth, fx, fy); F[2 * T::CELLS + o] = fx.v; F[3 * T::CELLS + o] = fy.v; }
+    if constexpr (TOPO != 0) {
+        const bool dr = down && c + 1 < T::W && (FULL || gc + 1 < (long long)g.cols);
+        const bool dl = down && c >= 1 && (FULL || gc >= 1);
+        if (dr) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W + 1), g.k, g.c, g.L_diag, fx, fy); F[4 * T::CELLS + o] = fx.v; F[5 * T::CELLS + o] = fy.v; }
+        if (dl) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W - 1), g.k, g.c, g.L_diag, fx, fy); F[6 * T::CELLS + o] = fx.v; F[7 * T::CELLS + o] = fy.v; }
+    }
+}
+
+// update phase for one cell: aggregate in the reference's edge-list order, then the stage arithmetic of rk4_step
+template <bool S, int TOPO, int STAGE, int TX, int TY, bool FULL>
+__device__ __forceinline__ void fused_update(const GridDev& g, const double dt_, const double* __restrict__ in_pl,
+                                             const double* __restrict__ F, double* __restrict__ out_pl, const int r, const int c,
+                                             const long long gr, const long long gc, const Real<S> (&y)[4], Real<S> (&Sacc)[4],
+                                             const bool interior, double* __restrict__ y_out) {
+    using R = Real<S>;
+    using T = FusedTile<TX, TY, TOPO>;
+    if (!FULL && (gr < 0 || gc < 0 || gr >= (long long)g.rows || gc >= (long long)g.cols)) return;
+    const int o = r * T::W + c;
+    const bool has_l = FULL || gc > 0, has_r = FULL || gc + 1 < (long long)g.cols;
+    const bool has_u = FULL || gr > 0, has_d = FULL || gr + 1 < (long long)g.rows;
+    R Fx(0.0), Fy(0.0);
+    // horizontals then verticals: left(-), right(+), up(-), down(+)
+    if (has_l) { Fx -= R(F[o - 1]); Fy -= R(F[T::CELLS + o - 1]); }
+    if (has_r) { Fx += R(F[o]); Fy += R(F[T::CELLS + o]); }
+    if (has_u) { Fx -= R(F[2 * T::CELLS + o - T::W]); Fy -= R(F[3 * T::CELLS + o - T::W]); }
+    if (has_d) { Fx += R(F[2 * T::CELLS + o]); Fy += R(F[3 * T::CELLS + o]); }
+    if constexpr (TOPO == 1) {        // main diagonals, then anti-diagonals
+        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::W - 1]); Fy -= R(F[5 * T::CELLS + o - T::W - 1]); }
+        if (has_d && has_r) { Fx += R(F[4 * T::CELLS + o]); Fy += R(F[5 * T::CELLS + o]); }
+        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::W + 1]); Fy -= R(F[7 * T::CELLS + o - T::W + 1]); }
+        if (has_d && has_l) { Fx += R(F[6 * T::CELLS + o]); Fy += R(F[7 * T::CELLS + o]); }
+    } else if constexpr (TOPO == 2) { // per cell: main then anti
+        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::W - 1]); Fy -= R(F[5 * T::CELLS + o - T::W - 1]); }
+        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::W + 1]); Fy -= R(F[7 * T::CELLS + o - T::W + 1]); }
+        if (has_d && has_l) { Fx += R(F[6 * T::CELLS + o]); Fy += R(F[7 * T::CELLS + o]); }
+        if (has_d && has_r) { Fx += R(F[4 * T::CELLS + o]); Fy += R(F[5 * T::CELLS + o]); }
+    }
+    R d[4];
+    d[0] = R(in_pl[2 * T::CELLS + o]); d[1] = R(in_pl[3 * T::CELLS + o]);           // {vx, vy, Fx/m, Fy/m}
+    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); }
+    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); }
+    const R dt(dt_);
+    R k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = d[j] * dt;
+    if constexpr (STAGE == 4) {
+        const size_t off = (((size_t)gr - g.row_begin) * g.cols + (size_t)gc) * 4;
+        R yn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yn[j] = y[j] + r_div_const(Sacc[j] + k[j], 6.0);
+        store4(y_out + off, yn[0].v, yn[1].v, yn[2].v, yn[3].v);
+    } else {
+        if (interior) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Sacc[j] = (STAGE == 1) ? k[j] : Sacc[j] + 2.0 * k[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out_pl[j * T::CELLS + o] = ((STAGE == 3) ? y[j] + k[j] : y[j] + 0.5 * k[j]).v;
+    }
+}
+
+template <bool S, int TOPO, int TX, int TY, bool FULL>
+__device__ __forceinline__ void fused_step_body(const GridDev& g, const long long r0, const long long c0, const double dt,
+                                                double* __restrict__ A, double* __restrict__ B, double* __restrict__ F,
+                                                double* __restrict__ y_out) {
+    using T = FusedTile<TX, TY, TOPO>;
+    using R = Real<S>;
+    constexpr int H = T::H;
+    const int tid = threadIdx.x;
+    // interior cell of this thread
+    const int ri = H + tid / TX, ci = H + tid % TX;
+    // halo cell of this thread: rings enumerated from margin 3 (innermost) to margin 0
+    int rr = 0, cr = 0, mr = -1;          // mr = margin of the halo cell, -1: none
+    if (tid < T::upto(0)) {
+        int q = tid;
+        mr = H - 1;
+#pragma unroll
+        for (int m = H - 1; m >= 1; --m) if (tid >= T::upto(m)) { mr = m - 1; q = tid - T::upto(m); }
+        const int w = T::W - 2 * mr;
+        if (q < w) { rr = mr; cr = mr + q; }
+        else if (q < 2 * w) { rr = T::HT - 1 - mr; cr = mr + q - w; }
+        else { q -= 2 * w; rr = mr + 1 + (q >> 1); cr = (q & 1) ? T::W - 1 - mr : mr; }
+    }
+    const int oi = ri * T::W + ci, orr = rr * T::W + cr;
+    R yi[4], yr[4], Sacc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { yi[j] = R(A[j * T::CELLS + oi]); yr[j] = R(mr >= 0 ? A[j * T::CELLS + orr] : 0.0); }
+    // rows of the next rank's slab are computed as halo but never written
+    const bool write_i = r0 + ri < (long long)(g.row_begin + g.rows_local);
+
+#define SB_FUSED_STAGE(STAGE, IN, OUT)                                                                                  \
+    fused_springs<S, TOPO, TX, TY, FULL>(g, IN, F, ri, ci, r0 + ri, c0 + ci);                                           \
+    if (mr >= STAGE - 1) fused_springs<S, TOPO, TX, TY, FULL>(g, IN, F, rr, cr, r0 + rr, c0 + cr);                      \
+    __syncthreads();                                                                                                    \
+    if (STAGE < 4 || write_i)                                                                                           \
+        fused_update<S, TOPO, STAGE, TX, TY, FULL>(g, dt, IN, F, OUT, ri, ci, r0 + ri, c0 + ci, yi, Sacc, true, y_out);  \
+    if (STAGE < 4 && mr >= STAGE)                                                                                       \
+        fused_update<S, TOPO, STAGE, TX, TY, FULL>(g, dt, IN, F, OUT, rr, cr, r0 + rr, c0 + cr, yr, Sacc, false, y_out); \
+    if (STAGE < 4) __syncthreads();
+
+    SB_FUSED_STAGE(1, A, B)
+    SB_FUSED_STAGE(2, B, A)
+    SB_FUSED_STAGE(3, A, B)
+    SB_FUSED_STAGE(4, B, A)
+#undef SB_FUSED_STAGE
+}
+
+template <bool S, int TOPO, int TX, int TY>
+__global__ void __launch_bounds__(TX * TY, 2)
+grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __restrict__ y_out) {
+    using T = FusedTile<TX, TY, TOPO>;
+    extern __shared__ double fused_smem[];
+    double* A = fused_smem;
+    double* B = A + 4 * T::CELLS;
+    double* F = B + 4 * T::CELLS;
+    // GLOBAL grid coordinates of cell (0, 0) of the shared-memory tile
+    const long long r0 = (long long)g.row_begin + (long long)blockIdx.y * TY - T::H;
+    const long long c0 = (long long)blockIdx.x * TX - T::H;
+    for (int idx = threadIdx.x; idx < T::CELLS; idx += T::THREADS) {
+        const int r = idx / T::W, c = idx % T::W;
+        const long long gr = r0 + r, gc = c0 + c;
+        double2 a = make_double2(0.0, 0.0), b = a;
+        const long long rl = gr - (long long)g.row_begin;
+        // (only 4 ghost rows exist below the slab: a ragged last tile row must not read past them)
+        if (gr >= 0 && gc >= 0 && gr < (long long)g.rows && gc < (long long)g.cols && rl < (long long)g.rows_local + T::H) {
+            const double* rowp = rl < 0 ? in.ghost_top + (size_t)(rl + T::H) * g.cols * 4
+                               : rl >= (long long)g.rows_local ? in.ghost_bot + (size_t)(rl - (long long)g.rows_local) * g.cols * 4
+                               : in.slab + (size_t)rl * g.cols * 4;
+            a = __ldg(reinterpret_cast<const double2*>(rowp + 4 * gc));
+            b = __ldg(reinterpret_cast<const double2*>(rowp + 4 * gc) + 1);
+        }
+        A[idx] = a.x; A[T::CELLS + idx] = a.y; A[2 * T::CELLS + idx] = b.x; A[3 * T::CELLS + idx] = b.y;
+    }
+    __syncthreads();
+    // tiles that lie entirely inside the global grid (all but the boundary tiles) skip every existence test
+    const bool full = r0 >= 0 && c0 >= 0 && r0 + T::HT <= (long long)g.rows && c0 + T::W <= (long long)g.cols;
+    if (full) fused_step_body<S, TOPO, TX, TY, true>(g, r0, c0, dt, A, B, F, y_out);
+    else fused_step_body<S, TOPO, TX, TY, false>(g, r0, c0, dt, A, B, F, y_out);
+}
+
 __global__ void grid_init_kernel(const size_t rows_local, const size_t cols, const size_t row_begin,
                                  const double spacing, double* __restrict__ state) {
     const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,7 +398,7 @@ int check_grid(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* p, GridDev& 
         return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [%zu, %zu) outside grid of %zu rows", p->row_begin,
                        p->row_begin + p->rows_local, p->rows);
     g.rows = p->rows; g.cols = p->cols; g.row_begin = p->row_begin; g.rows_local = p->rows_local;
-    g.mass = p->mass; g.k = p->stiffness; g.c = p->damping;
+    g.mass = p->mass; g.k = p->stiffness; g.c = p->damping; g.inv_mass = 1.0 / p->mass;
     // rest lengths, connectivity_matrix_2d.hpp:190-192: spacing * sqrt(dx*dx + dy*dy)
     g.L_orth = p->spacing * std::sqrt(1.0 * 1.0 + 0.0 * 0.0);
     g.L_diag = p->spacing * std::sqrt(1.0 * 1.0 + 1.0 * 1.0);
@@ -216,9 +436,10 @@ void launch_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, int
 }
 
 // exchange the first / last slab row of `buf` into the neighbours' ghost rows (and receive ours)
-int halo_exchange(sopot_b200_ctx* ctx, const GridDev& g, const double* buf, double* ghost_top, double* ghost_bot) {
+int halo_exchange(sopot_b200_ctx* ctx, const GridDev& g, const double* buf, double* ghost_top, double* ghost_bot,
+                  const size_t nrows = 1) {
     if (ctx->nranks == 1) return SOPOT_B200_OK;
-    const size_t row_elems = g.cols * 4;
+    const size_t row_elems = g.cols * 4 * nrows;      // nrows boundary rows are contiguous in the row-major slab
     const bool up = g.row_begin > 0, down = g.row_begin + g.rows_local < g.rows;
     const NcclApi* n = ctx->nccl;
     SB_NCCL(ctx, n->GroupStart());
@@ -227,11 +448,55 @@ int halo_exchange(sopot_b200_ctx* ctx, const GridDev& g, const double* buf, doub
         SB_NCCL(ctx, n->Recv(ghost_top, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
     }
     if (down) {
-        SB_NCCL(ctx, n->Send(buf + (g.rows_local - 1) * row_elems, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1,
+        SB_NCCL(ctx, n->Send(buf + (g.rows_local - nrows) * g.cols * 4, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1,
                              ctx->nccl_comm, ctx->stream));
         SB_NCCL(ctx, n->Recv(ghost_bot, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
     }
     SB_NCCL(ctx, n->GroupEnd());
+    return SOPOT_B200_OK;
+}
+
+// fused schedule: per step one 4-row halo exchange (multi-rank) and one kernel, y ping-pongs with a scratch slab
+constexpr int kFusedTX = 32, kFusedTY = 16;
+
+template <bool S, int TOPO>
+int launch_fused(sopot_b200_ctx* ctx, const GridDev& g, const StepIn& in, double dt, double* y_out) {
+    using T = FusedTile<kFusedTX, kFusedTY, TOPO>;
+    auto kern = grid_rk4_fused<S, TOPO, kFusedTX, kFusedTY>;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)((g.cols + kFusedTX - 1) / kFusedTX), (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY));
+    kern<<<grid, T::THREADS, T::SMEM, ctx->stream>>>(g, in, dt, y_out);
+    SB_CHECK_LAUNCH(ctx);
+    return SOPOT_B200_OK;
+}
+
+int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool strict, double dt, size_t n_steps, double* y) {
+    const size_t slab = g.rows_local * g.cols * 4, ghost = 4 * g.cols * 4;
+    if (ctx->nranks > 1 && g.rows_local < 4)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "the fused grid step needs >= 4 rows per rank (use SOPOT_B200_FLAG_GRID_PER_STAGE)");
+    void* scr;
+    int rc = sb_scratch(ctx, (slab + 2 * ghost) * 8 + 1024, &scr);
+    if (rc) return rc;
+    double* alt = static_cast<double*>(scr);
+    double* g_top = alt + slab;
+    double* g_bot = g_top + ghost;
+    double* cur = y;
+    double* nxt = alt;
+    for (size_t step = 0; step < n_steps; ++step) {
+        if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4))) return rc;
+        const StepIn in{cur, g_top, g_bot};
+#define SB_FUSED_CASE(SS, TT) rc = launch_fused<SS, TT>(ctx, g, in, dt, nxt)
+        if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
+        else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
+#undef SB_FUSED_CASE
+        if (rc) return rc;
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, slab * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return SOPOT_B200_OK;
 }
 
@@ -297,6 +562,11 @@ SB_EXPORT int sopot_b200_grid2d_rk4(sopot_b200_ctx* ctx, const sopot_b200_grid2d
         sg.outs.push_back({state, y, slab * 8});
     } else {
         y = state;
+    }
+    if (!(opts->flags & SOPOT_B200_FLAG_GRID_PER_STAGE)) {
+        rc = grid_rk4_fused_run(ctx, g, p->topology, strict, dt, n_steps, y);
+        if (rc) return rc;
+        return sg.finish();
     }
     // scratch: S, A, B slabs + ghost rows for y, A, B (top and bottom each)
     void* scr;

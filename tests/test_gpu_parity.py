@@ -304,3 +304,23 @@ def test_grid2d_large_properties(engine, port):
     crop = np.ascontiguousarray(s0.reshape(n, n, 4)[:512, :512]).reshape(-1, 4)
     ref = port.grid2d_rk4(512, 512, 0, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], 3, crop, nthreads=8).reshape(512, 512, 4)
     assert np.array_equal(out[:64, :64], ref[:64, :64])
+
+
+@pytest.mark.parametrize("rows,cols,topo,steps", [(37, 45, 0, 7), (64, 64, 1, 4), (19, 130, 2, 5), (130, 33, 0, 6)])
+def test_grid2d_fused_step_equals_per_stage_schedule(engine, port, rows, cols, topo, steps):
+    """The fused RK4-step kernel (all four stages on a shared-memory tile with a 4-cell halo, the default) and the
+    four-kernel per-stage schedule produce the same bits in strict mode (== the oracle) and agree to rounding in
+    contract mode.  Ragged
+    sizes exercise partial tiles on both axes, odd step counts the ping-pong copy-back."""
+    p = W.GRID2D_PARAMS
+    s0 = W.grid2d_state(rows, cols, p["spacing"])
+    gp = engine.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"])
+    fused = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT)
+    staged = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT, per_stage=True)
+    assert np.array_equal(fused, staged)
+    # contract mode: the two kernels contract different expressions, so they agree to rounding, not to the bit
+    fused_c = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_CONTRACT)
+    staged_c = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_CONTRACT, per_stage=True)
+    assert rel_err(fused_c.ravel(), fused.ravel()).max() <= FINAL and rel_err(staged_c.ravel(), fused.ravel()).max() <= FINAL
+    ref = port.grid2d_rk4(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], steps, s0, nthreads=4)
+    assert np.array_equal(engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT).ravel(), ref)

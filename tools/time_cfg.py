@@ -43,6 +43,8 @@ elif cfg in ("grid", "grid_strict"):
     gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
     state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
     mode = FP_STRICT if cfg == "grid_strict" else FP_CONTRACT
-    ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False), 2) / 10
-    print("%s %d^2: %.3f ms/step  %.1f GB/s (544 B/mass-step)" % (cfg, n, ms, 544.0 * n * n / ms / 1e6))
+    for per_stage in (False, True):
+        ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False, per_stage=per_stage), 2) / 10
+        print("%s %d^2 %s: %.3f ms/step  %.3e mass-steps/s  %.1f GB/s at 544 B/mass-step" %
+              (cfg, n, "per-stage" if per_stage else "fused", ms, n * n / ms * 1e3, 544.0 * n * n / ms / 1e6))
 eng.close()
