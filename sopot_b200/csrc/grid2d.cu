@@ -563,7 +563,10 @@ SB_EXPORT int sopot_b200_grid2d_rk4(sopot_b200_ctx* ctx, const sopot_b200_grid2d
     } else {
         y = state;
     }
-    if (!(opts->flags & SOPOT_B200_FLAG_GRID_PER_STAGE)) {
+    // The fused step exchanges 4 boundary rows at once, so every rank needs >= 4 rows; all ranks must take the same
+    // branch (the exchanges are collective), hence the test on the GLOBAL size (slabs differ by at most one row).
+    const bool thin_slabs = ctx->nranks > 1 && g.rows / (size_t)ctx->nranks < 4;
+    if (!(opts->flags & SOPOT_B200_FLAG_GRID_PER_STAGE) && !thin_slabs) {
         rc = grid_rk4_fused_run(ctx, g, p->topology, strict, dt, n_steps, y);
         if (rc) return rc;
         return sg.finish();

@@ -1,6 +1,7 @@
 """Worker for tests/test_multigpu.py: run under torchrun with one rank per GPU.
 Checks (1) dispersion statistics all-reduced over NCCL == numpy on the concatenated data,
-(2) slab-decomposed grid2d with per-stage halo exchange == the single-GPU run bit for bit,
+(2) slab-decomposed grid2d (fused step with one 4-row halo exchange, and per-stage 1-row exchanges) == the
+    single-GPU run bit for bit,
 (3) ensemble sharding: concatenated shard results == one-GPU results bit for bit."""
 import os
 import sys
@@ -33,7 +34,7 @@ for r in range(6):
 
 # (2) grid2d slabs vs single domain (computed redundantly on every rank with a private single-rank engine)
 p = W.GRID2D_PARAMS
-for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2, 3), (1024, 1024, 0, 4)):
+for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2, 3), (4 * world + 1, 70, 0, 5), (1024, 1024, 0, 4)):
     s0 = W.grid2d_state(rows, cols, p["spacing"]).reshape(rows, cols, 4)
     solo = Engine(local)
     ref = solo.grid2d_rk4(solo.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], steps,
@@ -41,8 +42,9 @@ for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2,
     solo.close()
     rb, rl = slab(rows, rank, world)
     gp = eng.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], row_begin=rb, rows_local=rl)
-    mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT)
-    assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo)
+    for per_stage in (False, True):       # fused step (one 4-row exchange per step) and per-stage schedule (four 1-row)
+        mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT, per_stage=per_stage)
+        assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo, per_stage)
     dev = eng.to_device(s0[rb:rb + rl].reshape(-1, 4).copy())
     eng.grid2d_rk4(gp, p["dt"], steps, dev, fp_mode=FP_STRICT)
     assert np.array_equal(dev.download().reshape(rl, cols, 4), ref[rb:rb + rl])

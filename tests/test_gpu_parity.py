@@ -324,3 +324,18 @@ def test_grid2d_fused_step_equals_per_stage_schedule(engine, port, rows, cols, t
     assert rel_err(fused_c.ravel(), fused.ravel()).max() <= FINAL and rel_err(staged_c.ravel(), fused.ravel()).max() <= FINAL
     ref = port.grid2d_rk4(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], steps, s0, nthreads=4)
     assert np.array_equal(engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT).ravel(), ref)
+
+
+def test_inline_ieee_division_and_sqrt_are_correctly_rounded(tmp_path):
+    """csrc/ieee.cuh (the branch-light division / sqrt every strict kernel uses) against nvcc's own IEEE operators,
+    bit for bit on 6e8 samples on the device: random mantissas and exponents, exact zeros, quotients next to 1,
+    subnormals / inf / nan through the fallback."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "exact_math_check"
+    src = os.path.join(ROOT, "tests", "cuda", "exact_math_check.cu")
+    subprocess.run(["nvcc", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), src], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 mismatches" in r.stdout
