@@ -199,16 +199,23 @@ def other_configs(eng, hbm_peak, fp64_peak):
                                "apogee_mean_m": disp[0]["mean"], "apogee_std_m": disp[0]["stddev"]}
     for a in (st, stats, *d.values()):
         a.free()
-    # config 5: grid2d 8192^2, 10 RK4 steps (544 B / mass-step)
+    # config 5: grid2d 8192^2, 10 RK4 steps.  Default schedule = fused step kernel (64 B of HBM traffic per mass-step:
+    # FP64/latency bound); per_stage = the four-kernel schedule (544 B per mass-step: HBM bound, the fraction below).
     p = W.GRID2D_PARAMS
     n = 8192
     gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
     state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
     for mode, name in ((FP_STRICT, "strict"), (FP_CONTRACT, "contract")):
-        ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False), 1) / 10.0
-        out[f"grid2d_8192x8192_{name}"] = {"ms_per_step": ms, "mass_steps_per_s": n * n / (ms * 1e-3),
-                                           "GBs": 544.0 * n * n / (ms * 1e-3) / 1e9,
-                                           "hbm_frac": 544.0 * n * n / (ms * 1e-3) / 1e9 / hbm_peak}
+        for per_stage in (False, True):
+            ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False, per_stage=per_stage), 2) / 10.0
+            row = {"ms_per_step": ms, "mass_steps_per_s": n * n / (ms * 1e-3)}
+            if per_stage:
+                row["GBs"] = 544.0 * n * n / (ms * 1e-3) / 1e9
+                row["hbm_frac"] = row["GBs"] / hbm_peak
+            else:
+                row["hbm_bytes_per_mass_step"] = 64
+                row["speedup_vs_hbm_bound_at_544B"] = (544.0 * n * n / (hbm_peak * 1e9)) / (ms * 1e-3)
+            out[f"grid2d_8192x8192_{name}_{'per_stage' if per_stage else 'fused'}"] = row
     state.free()
     return out
 

@@ -55,7 +55,8 @@ enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
  * schedule) instead of the default fused step kernel with one 4-row halo exchange per step */
 enum { SOPOT_B200_FLAG_GRID_PER_STAGE = 1 };
 enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2,
-       SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */ };
+       SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */,
+       SOPOT_B200_ST_NOT_CONVERGED = 8 /* LQR::solve returned false (Riccati iteration diverged) */ };
 
 typedef struct sopot_b200_ctx sopot_b200_ctx;
 
@@ -146,6 +147,34 @@ typedef struct { const double *mc, *m, *L, *g; } sopot_b200_cartpole_plant;
 int sopot_b200_cartpole_linearize(sopot_b200_ctx* ctx, const sopot_b200_cartpole_plant* plant,
                                   const double* x0, const double* u0, size_t P,
                                   const sopot_b200_rk4_opts* opts, double* A, double* B, int32_t* status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched LQR: replaces LQR<4,1>::solve(A, B, Q, R, dt, max_iter, tol) + getGain()
+ * (physics/control/lqr.hpp:260-396) for P linearizations at once -- the consumer of the Jacobians above
+ * ("A/B Jacobians for LQR sweep").  A [16][P], B [4][P] exactly as sopot_b200_cartpole_linearize writes
+ * them; Q16 (row-major 4x4) and R are HOST values shared by the sweep.  K [4][P] (u = -K x); optional
+ * Pric [16][P] (Riccati solution), iters [P] (iterations used).  status[p]: 0 = the reference's solve()
+ * returned true, SOPOT_B200_ST_NOT_CONVERGED = it returned false, SOPOT_B200_ST_SINGULAR = it threw
+ * "LQR solveForGain: ... singular".  The reference's defaults are riccati_dt 0.01, max_iter 1000, tol 1e-8.
+ * ------------------------------------------------------------------------------------------- */
+int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const double* B, size_t P, const double* Q16,
+                         double R, double riccati_dt, size_t max_iter, double tol,
+                         const sopot_b200_rk4_opts* opts, double* K, double* Pric, int32_t* iters, int32_t* status);
+
+/* Closed-loop cart-pole ensemble: StateFeedbackController<4,1>::compute (state_feedback_controller.hpp:88-104,
+ * u = -K (x - x_ref), clamped to [u_min, u_max] when saturate != 0) drives CartNPendulum<1,double> through
+ * setControlForce; the force is evaluated ONCE per RK4 step from the state at the start of the step and held
+ * over the four stages (zero-order hold, as wasm/wasm_inverted_pendulum.cpp:110-135 does), the step itself is
+ * RK4Solver's (core/solver.hpp:95-125).  K [4][n] in the call's memory space (e.g. straight from
+ * sopot_b200_lqr4_gain); x_ref [4][n] or NULL (= 0).  p->force is ignored.  stats_out [2][n] (optional):
+ * max |theta| and max |u| over the run (the quantities tests/inverted_pendulum_test.cpp:241-292 asserts on).
+ * broadcast bits as for sopot_b200_cartpole_rk4.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const double* K; const double* x_ref; double u_min, u_max; int saturate; } sopot_b200_feedback;
+int sopot_b200_cartpole_feedback_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p,
+                                     const sopot_b200_feedback* fb, size_t n, double t0, double dt, size_t n_steps,
+                                     const sopot_b200_rk4_opts* opts, double* state_out, double* traj_out,
+                                     double* stats_out, int32_t* status);
 
 /* ---------------------------------------------------------------------------------------------
  * 6-DOF rocket Monte Carlo: replaces rocket::simulateRocket(rocket, t_end, dt) +

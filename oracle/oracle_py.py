@@ -124,6 +124,27 @@ class Checker:
             n, _p(mc), _p(m), _p(L), _p(g), _p(s0), _p(force), t0, t1, dt, _p(fin), nthreads)
         return fin
 
+    # ---------------- section 8f-1: LQR and closed loop ----------------
+    def lqr4(self, A, B, Q16, R, dt=0.01, max_iter=1000, tol=1e-8, nthreads=1):
+        A = _f64(A); P = A.shape[1]
+        B, Q16 = _f64(B), _f64(Q16).reshape(16)
+        K = np.empty((4, P)); Pric = np.empty((16, P))
+        iters = np.zeros(P, dtype=np.int32); st = np.zeros(P, dtype=np.int32)
+        self._fn("lqr4", [_sz, _dp, _dp, _dp, _d, _d, _sz, _d, _dp, _dp, _ip, _ip, _i])(
+            P, _p(A), _p(B), _p(Q16), R, dt, max_iter, tol, _p(K), _p(Pric), iters.ctypes.data_as(_ip),
+            st.ctypes.data_as(_ip), nthreads)
+        return K, Pric, iters, st
+
+    def cartpole_feedback_rk4(self, mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, nthreads=1):
+        s0 = _f64(s0); n = s0.shape[1]
+        mc, m, L, g = (_f64(a, n) for a in (mc, m, L, g))
+        K = _f64(K); xref = None if xref is None else _f64(xref)
+        fin = np.empty((4, n)); stats = np.empty((2, n))
+        self._fn("cartpole_feedback_rk4", [_sz] + [_dp] * 7 + [_d, _d, _i, _d, _d, _sz, _dp, _dp, _i])(
+            n, _p(mc), _p(m), _p(L), _p(g), _p(s0), _p(K), _p(xref), umin, umax, int(saturate), t0, dt, n_steps,
+            _p(fin), _p(stats), nthreads)
+        return fin, stats
+
     # ---------------- config 4 ----------------
     @staticmethod
     def _tab(t, cols):

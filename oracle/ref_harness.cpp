@@ -17,6 +17,8 @@
 #include "physics/harmonic_oscillator.hpp"
 #include "physics/pendulum/double_pendulum.hpp"
 #include "physics/control/cart_n_pendulum.hpp"
+#include "physics/control/lqr.hpp"
+#include "physics/control/state_feedback_controller.hpp"
 #include "physics/connected_masses/connectivity_matrix_2d.hpp"
 #include "rocket/rocket.hpp"
 
@@ -162,6 +164,67 @@ int ref_cartpole_rk4(size_t n, const double* mc, const double* m, const double* 
         sys.template getComponent<0>().setControlForce(force[i]);
         auto r = solve_system(sys, t0, t1, dt);
         scatter_result(r, 4, i, n, 0, final_out, nullptr, nullptr);
+    });
+    return 0;
+}
+
+// ---- section 8f-1: LQR<4,1>::solve and the closed loop ----
+// The reference's own LQR class on A, B as the linearizer produced them; status 0 = solve() true, 8 = false,
+// 2 = solveForGain threw.
+int ref_lqr4(size_t P, const double* A /*[16][P]*/, const double* B /*[4][P]*/, const double* Q16, double R, double dt,
+             size_t max_iter, double tol, double* K /*[4][P]*/, double* Pric, int* iters_unused, int* status, int nthreads) {
+    (void)iters_unused;
+    parallel_for(P, nthreads, [&](size_t p) {
+        control::LQR<4, 1>::StateMatrix Am, Qm;
+        control::LQR<4, 1>::InputMatrix Bm;
+        for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 4; ++j) { Am[i][j] = A[(i * 4 + j) * P + p]; Qm[i][j] = Q16[i * 4 + j]; }
+            Bm[i][0] = B[i * P + p];
+        }
+        control::LQR<4, 1>::InputWeightMatrix Rm{};
+        Rm[0][0] = R;
+        control::LQR<4, 1> lqr;
+        int st = 0;
+        try { st = lqr.solve(Am, Bm, Qm, Rm, dt, max_iter, tol) ? 0 : 8; } catch (const std::runtime_error&) { st = 2; }
+        for (int j = 0; j < 4; ++j) K[j * P + p] = st ? NAN : lqr.getGain()[0][j];
+        if (Pric) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Pric[(i * 4 + j) * P + p] = lqr.getRiccatiSolution()[i][j];
+        if (status) status[p] = st;
+    });
+    return 0;
+}
+
+// StateFeedbackController<4,1>::compute -> setControlForce -> ONE RK4Solver::solve step with the force held,
+// repeated n_steps times (the stepping pattern of wasm/wasm_inverted_pendulum.cpp:110-135 with core/solver.hpp's RK4).
+int ref_cartpole_feedback_rk4(size_t n, const double* mc, const double* m, const double* L, const double* g,
+                              const double* s0, const double* K, const double* xref, double umin, double umax, int saturate,
+                              double t0, double dt, size_t n_steps, double* final_out, double* stats, int nthreads) {
+    parallel_for(n, nthreads, [&](size_t i) {
+        control::StateFeedbackController<4, 1>::GainMatrix Km{};
+        std::array<double, 4> ref{};
+        for (int q = 0; q < 4; ++q) { Km[0][q] = K[q * n + i]; ref[q] = xref ? xref[q * n + i] : 0.0; }
+        control::StateFeedbackController<4, 1> ctl(Km);
+        ctl.setReference(ref);
+        if (saturate) ctl.setSaturationLimits({umin}, {umax});
+        control::CartNPendulum<1, double> plant(mc[i], {m[i]}, {L[i]}, g[i]);
+        auto sys = makeTypedODESystem<double>(std::move(plant));
+        auto solver = createRK4Solver();
+        std::vector<double> y = {s0[i], s0[n + i], s0[2 * n + i], s0[3 * n + i]};
+        double t = t0, max_th = std::abs(y[1]), max_u = 0.0;
+        auto derivs = [&sys](double tt, StateView sv) {
+            std::vector<double> v(sv.begin(), sv.end());
+            return sys.computeDerivatives(tt, v);
+        };
+        for (size_t step = 0; step < n_steps; ++step) {
+            const double u = ctl.compute({y[0], y[1], y[2], y[3]})[0];
+            max_u = std::max(max_u, std::abs(u));
+            sys.template getComponent<0>().setControlForce(u);
+            auto r = solver.solve(derivs, 4, t, t + dt, dt, y);
+            y = r.states.back();
+            t += dt;
+            max_th = std::max(max_th, std::abs(y[1]));
+        }
+        for (int q = 0; q < 4; ++q) final_out[q * n + i] = y[q];
+        if (stats) { stats[i] = max_th; stats[n + i] = max_u; }
     });
     return 0;
 }

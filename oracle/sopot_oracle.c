@@ -406,6 +406,133 @@ ORC_API int orc_cartpole_rk4(size_t n, const double* mc, const double* m, const 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Section 8f-1 -- LQR<4,1>::solve (physics/control/lqr.hpp:260-396) and the closed loop
+ * StateFeedbackController<4,1>::compute (state_feedback_controller.hpp:88-104) -> setControlForce ->
+ * one RK4Solver step with the force held (zero-order hold).
+ * ------------------------------------------------------------------------------------------ */
+#define LN 4
+static double orc_frob(const double A[LN][LN]) {                     /* lqr.hpp:140-148 */
+    double sum = 0.0;
+    for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) sum += A[i][j] * A[i][j];
+    return sqrt(sum);
+}
+static void orc_mm(const double A[LN][LN], const double B[LN][LN], double C[LN][LN]) {   /* multiply, :74-85 */
+    for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) {
+        C[i][j] = 0.0;
+        for (int k = 0; k < LN; ++k) C[i][j] += A[i][k] * B[k][j];
+    }
+}
+/* returns 0 solved, 8 not converged (solve() == false), 2 singular (solveForGain throws) */
+static int orc_lqr4_one(const double A[LN][LN], const double B[LN], const double Q[LN][LN], double R, double dt,
+                        size_t max_iter, double tol, double K[LN], double P[LN][LN], int* iters) {
+    double Adt[LN][LN], Adt2[LN][LN], Ad[LN][LN], AdT[LN][LN], Bcoef[LN][LN], Bd[LN], Qd[LN][LN];
+    for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) Adt[i][j] = A[i][j] * dt;
+    orc_mm(Adt, Adt, Adt2);
+    for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) {
+        const double id = i == j ? 1.0 : 0.0;
+        Ad[i][j] = (id + Adt[i][j]) + Adt2[i][j] * 0.5;               /* :274-275 */
+        Bcoef[i][j] = id * dt + Adt[i][j] * (dt * 0.5);               /* :278 */
+        Qd[i][j] = Q[i][j] * dt;                                      /* :282 */
+        P[i][j] = Q[i][j] * 1.0;                                      /* :285 */
+    }
+    for (int i = 0; i < LN; ++i) { Bd[i] = 0.0; for (int k = 0; k < LN; ++k) Bd[i] += Bcoef[i][k] * B[k]; }
+    for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) AdT[i][j] = Ad[j][i];
+    *iters = 0;
+    int converged = 0;
+    for (size_t it = 0; it < max_iter; ++it) {
+        double AdTP[LN][LN], BdTP[LN], g[LN], Kd[LN], AdTPAd[LN][LN], Pn[LN][LN], diff[LN][LN];
+        orc_mm(AdT, P, AdTP);
+        for (int j = 0; j < LN; ++j) { BdTP[j] = 0.0; for (int k = 0; k < LN; ++k) BdTP[j] += Bd[k] * P[k][j]; }
+        double bpb = 0.0;
+        for (int k = 0; k < LN; ++k) bpb += BdTP[k] * Bd[k];
+        const double sden = R * dt + bpb;
+        for (int j = 0; j < LN; ++j) { g[j] = 0.0; for (int k = 0; k < LN; ++k) g[j] += BdTP[k] * Ad[k][j]; }
+        if (fabs(sden) < 1e-12) return 2;
+        for (int j = 0; j < LN; ++j) Kd[j] = g[j] / sden;
+        orc_mm(AdTP, Ad, AdTPAd);
+        for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) {
+            double ktrk = 0.0; ktrk += Kd[i] * g[j];
+            Pn[i][j] = (AdTPAd[i][j] - ktrk) + Qd[i][j];
+        }
+        for (int i = 0; i < LN; ++i) for (int j = i + 1; j < LN; ++j) {
+            const double avg = 0.5 * (Pn[i][j] + Pn[j][i]);
+            Pn[i][j] = avg; Pn[j][i] = avg;
+        }
+        for (int i = 0; i < LN; ++i) for (int j = 0; j < LN; ++j) diff[i][j] = Pn[i][j] - P[i][j];
+        const double change = orc_frob(diff), p_norm = orc_frob(Pn);
+        const double rel = (p_norm > 1e-10) ? change / p_norm : change;
+        memcpy(P, Pn, sizeof Pn);
+        *iters = (int)it + 1;
+        if (rel < tol || change < tol) { converged = 1; break; }
+        if (p_norm > 1e15 || isnan(change)) break;
+    }
+    if (!converged) {
+        const double fn = orc_frob(P);
+        if (!(fn < 1e10) || isnan(fn)) return 8;
+    }
+    if (fabs(R) < 1e-12) return 2;
+    for (int j = 0; j < LN; ++j) { double s = 0.0; for (int k = 0; k < LN; ++k) s += B[k] * P[k][j]; K[j] = s / R; }
+    return 0;
+}
+
+typedef struct { size_t P; const double *A, *B, *Q; double R, dt; size_t max_iter; double tol; double *K, *Pric; int *iters, *status; } orc_lqr_job_t;
+static void orc_lqr_range(void* user, size_t b, size_t e) {
+    const orc_lqr_job_t* j = (const orc_lqr_job_t*)user;
+    const size_t P = j->P;
+    for (size_t p = b; p < e; ++p) {
+        double A[LN][LN], B[LN], Q[LN][LN], K[LN] = {NAN, NAN, NAN, NAN}, Pm[LN][LN];
+        int it = 0;
+        for (int r = 0; r < LN; ++r) { for (int c = 0; c < LN; ++c) { A[r][c] = j->A[(r * LN + c) * P + p]; Q[r][c] = j->Q[r * LN + c]; } B[r] = j->B[r * P + p]; }
+        const int st = orc_lqr4_one(A, B, Q, j->R, j->dt, j->max_iter, j->tol, K, Pm, &it);
+        for (int c = 0; c < LN; ++c) j->K[c * P + p] = st ? NAN : K[c];
+        if (j->Pric) for (int r = 0; r < LN; ++r) for (int c = 0; c < LN; ++c) j->Pric[(r * LN + c) * P + p] = Pm[r][c];
+        if (j->iters) j->iters[p] = it;
+        if (j->status) j->status[p] = st;
+    }
+}
+ORC_API int orc_lqr4(size_t P, const double* A /*[16][P]*/, const double* B /*[4][P]*/, const double* Q16, double R,
+                     double dt, size_t max_iter, double tol, double* K /*[4][P]*/, double* Pric, int* iters, int* status,
+                     int nthreads) {
+    orc_lqr_job_t j = {P, A, B, Q16, R, dt, max_iter, tol, K, Pric, iters, status};
+    orc_parallel_for(P, 4, nthreads, orc_lqr_range, &j);
+    return 0;
+}
+
+typedef struct {
+    size_t n; const double *mc, *m, *L, *g, *s0, *K, *xref; double umin, umax; int saturate;
+    double t0, dt; size_t n_steps; double *final_out, *stats;
+} orc_fb_job_t;
+static void orc_fb_range(void* user, size_t b, size_t e) {
+    const orc_fb_job_t* j = (const orc_fb_job_t*)user;
+    const size_t n = j->n;
+    for (size_t i = b; i < e; ++i) {
+        orc_cp_t p = {j->mc[i], j->m[i], j->L[i], j->g[i], 0.0, 0};
+        double y[4] = {j->s0[i], j->s0[n + i], j->s0[2 * n + i], j->s0[3 * n + i]}, work[20];
+        double t = j->t0, max_th = fabs(y[1]), max_u = 0.0;
+        for (size_t step = 0; step < j->n_steps; ++step) {
+            double u = 0.0;                                            /* state_feedback_controller.hpp:91-95 */
+            for (int q = 0; q < 4; ++q) u -= j->K[q * n + i] * (y[q] - (j->xref ? j->xref[q * n + i] : 0.0));
+            if (j->saturate) u = u < j->umin ? j->umin : (j->umax < u ? j->umax : u);   /* std::clamp, :98-100 */
+            p.F = u;
+            if (fabs(u) > max_u) max_u = fabs(u);
+            orc_rk4(orc_cartpole_rhs_fn, &p, 4, t, t + j->dt, j->dt, y, work, NULL, NULL, NULL);   /* exactly one step */
+            t += j->dt;
+            if (fabs(y[1]) > max_th) max_th = fabs(y[1]);
+        }
+        for (int q = 0; q < 4; ++q) j->final_out[q * n + i] = y[q];
+        if (j->stats) { j->stats[i] = max_th; j->stats[n + i] = max_u; }
+    }
+}
+ORC_API int orc_cartpole_feedback_rk4(size_t n, const double* mc, const double* m, const double* L, const double* g,
+                                      const double* s0, const double* K, const double* xref, double umin, double umax,
+                                      int saturate, double t0, double dt, size_t n_steps, double* final_out,
+                                      double* stats, int nthreads) {
+    orc_fb_job_t j = {n, mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, final_out, stats};
+    orc_parallel_for(n, 16, nthreads, orc_fb_range, &j);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Config 4 -- 6-DOF rocket.
  * ------------------------------------------------------------------------------------------ */
 /* LinearInterpolator::interpolate, io/interpolation.hpp:49-71 */

@@ -51,6 +51,10 @@ class CartpolePlant(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in ("mc", "m", "L", "g")]
 
 
+class Feedback(ctypes.Structure):
+    _fields_ = [("K", c_void_p), ("x_ref", c_void_p), ("u_min", c_double), ("u_max", c_double), ("saturate", c_int)]
+
+
 class RocketParams(ctypes.Structure):
     _fields_ = [("elevation_deg", c_void_p), ("azimuth_deg", c_void_p), ("diameter", c_void_p),
                 ("gravity", c_void_p),
@@ -96,6 +100,11 @@ SYMBOLS = {
                                   POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
     "sopot_b200_ho_rhs": (c_int, [_ctx, POINTER(HoParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_cartpole_rhs": (c_int, [_ctx, POINTER(CartpoleParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
+    "sopot_b200_lqr4_gain": (c_int, [_ctx, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
+                                     POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sopot_b200_cartpole_feedback_rk4": (c_int, [_ctx, POINTER(CartpoleParams), POINTER(Feedback), c_size_t, c_double,
+                                                 c_double, c_size_t, POINTER(RK4Opts), c_void_p, c_void_p, c_void_p,
+                                                 c_void_p]),
     "sopot_b200_dpend_rk4": (c_int, [_ctx, POINTER(DpendParams), c_size_t, c_double, c_double, c_size_t,
                                      POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
     "sopot_b200_dpend_rhs": (c_int, [_ctx, POINTER(DpendParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
@@ -362,6 +371,50 @@ class Engine:
         if sync:
             self.sync()
         return A, B, status
+
+    def lqr4_gain(self, A, B, P, Q, R, riccati_dt=0.01, max_iter=1000, tol=1e-8, mem=MEM_HOST, fp_mode=FP_CONTRACT,
+                  K=None, want_riccati=False, want_iters=True, sync=True):
+        """Batched LQR<4,1>::solve on linearizer output A [16][P], B [4][P] -> K [4][P], (Pric, iters, status)."""
+        Q = np.ascontiguousarray(np.asarray(Q, dtype=np.float64).reshape(16))
+        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        if mem == MEM_HOST:
+            A = np.ascontiguousarray(A, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
+            K = np.empty((4, P)) if K is None else K
+            Pric = np.empty((16, P)) if want_riccati else None
+            iters = np.zeros(P, dtype=np.int32) if want_iters else None
+            status = np.zeros(P, dtype=np.int32)
+        else:
+            K = self.empty((4, P)) if K is None else K
+            Pric = self.empty((16, P)) if want_riccati else None
+            iters = self.empty((P,), np.int32) if want_iters else None
+            status = self.empty((P,), np.int32)
+        self._ck(self.lib.sopot_b200_lqr4_gain(self.ctx, _ptr(A), _ptr(B), P, Q.ctypes.data, R, riccati_dt, max_iter, tol,
+                                               byref(opts), _ptr(K), _ptr(Pric), _ptr(iters), _ptr(status)))
+        if sync:
+            self.sync()
+        return K, Pric, iters, status
+
+    def cartpole_feedback_rk4(self, mc, m, L, g, x, th, xd, w, K, n, t0, dt, n_steps, x_ref=None, u_min=0.0, u_max=0.0,
+                              saturate=False, mem=MEM_HOST, fp_mode=FP_CONTRACT, store_every=0, want_status=True,
+                              want_stats=True, sync=True):
+        """Closed-loop cart-pole ensemble: u = clamp(-K (x - x_ref)) held over each RK4 step."""
+        ptrs, mask, keep = self._prep(dict(mc=mc, m=m, L=L, g=g, x=x, th=th, xd=xd, w=w), n, mem)
+        params = CartpoleParams(force=None, **ptrs)
+        if mem == MEM_HOST:
+            K = np.ascontiguousarray(K, dtype=np.float64)
+            x_ref = None if x_ref is None else np.ascontiguousarray(x_ref, dtype=np.float64)
+        fb = Feedback(_ptr(K), _ptr(x_ref), u_min, u_max, int(bool(saturate)))
+        opts = RK4Opts(mem, fp_mode, store_every, mask, 0)
+        state, traj, status = self._outs(4, n, n_steps, store_every, mem, want_status, None, None)
+        stats = None
+        if want_stats:
+            stats = np.empty((2, n)) if mem == MEM_HOST else self.empty((2, n))
+        self._ck(self.lib.sopot_b200_cartpole_feedback_rk4(self.ctx, byref(params), byref(fb), n, t0, dt, n_steps,
+                                                           byref(opts), _ptr(state), _ptr(traj), _ptr(stats), _ptr(status)))
+        self._keep = keep
+        if sync:
+            self.sync()
+        return state, stats, traj, status
 
     def _rocket_params(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, mem):
         ptrs, mask, keep = self._prep(dict(elevation_deg=elev, azimuth_deg=az, diameter=diam, gravity=g0), n, mem)

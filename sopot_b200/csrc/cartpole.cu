@@ -167,6 +167,91 @@ SB_EXPORT int sopot_b200_cartpole_rhs(sopot_b200_ctx* ctx, const sopot_b200_cart
     return sg.finish();
 }
 
+// ---- K1 closed loop: state feedback with zero-order hold ----------------------------------------------------
+// StateFeedbackController<4,1>::compute (state_feedback_controller.hpp:88-104): u = 0; u -= K[j]*(x[j] - ref[j]) for
+// j = 0..3 in order; std::clamp(u, u_min, u_max) when saturation is on.  Evaluated in begin_step from the state at
+// the start of the step, held over the four stages.
+struct CartpoleFbSys {
+    static constexpr int DIM = 4;
+    static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
+    static constexpr bool FAST_STEP = false;
+    static constexpr bool HAS_BEGIN_STEP = true;
+    struct DevParams {
+        ParamRef mc, m, L, g, x, th, xd, w;
+        const double* K;       // [4][n]
+        const double* x_ref;   // [4][n] or nullptr
+        double u_min, u_max;
+        int saturate;
+        size_t n;
+        double* stats_out;     // [2][n] or nullptr
+    };
+    template <bool S> struct Inst {
+        CartPlant<1, Real<S>> plant;
+        Real<S> F, K[4], ref[4];
+        double u_min, u_max, max_theta, max_u;
+        int saturate;
+    };
+    template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
+    template <bool S>
+    static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
+        in.plant.mc = P.mc.at(i); in.plant.m[0] = P.m.at(i); in.plant.L[0] = P.L.at(i); in.plant.g = P.g.at(i);
+        y[0] = Real<S>(P.x.at(i)); y[1] = Real<S>(P.th.at(i)); y[2] = Real<S>(P.xd.at(i)); y[3] = Real<S>(P.w.at(i));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            in.K[j] = Real<S>(__ldg(P.K + (size_t)j * P.n + i));
+            in.ref[j] = Real<S>(P.x_ref ? __ldg(P.x_ref + (size_t)j * P.n + i) : 0.0);
+        }
+        in.u_min = P.u_min; in.u_max = P.u_max; in.saturate = P.saturate;
+        in.F = Real<S>(0.0); in.max_theta = 0.0; in.max_u = 0.0;
+    }
+    template <bool S>
+    static __device__ __forceinline__ void begin_step(Inst<S>& in, const Real<S> (&y)[4]) {
+        Real<S> u(0.0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u = u - in.K[j] * (y[j] - in.ref[j]);
+        if (in.saturate) u = Real<S>(u.v < in.u_min ? in.u_min : (in.u_max < u.v ? in.u_max : u.v));   // std::clamp
+        in.F = u;
+        in.max_u = fmax(in.max_u, fabs(u.v));
+    }
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
+        return in.plant.derivatives(y, in.F, dy);
+    }
+    template <bool S> static __device__ __forceinline__ void observe(Inst<S>& in, double, const Real<S> (&y)[4]) {
+        in.max_theta = fmax(in.max_theta, fabs(y[1].v));
+    }
+    template <bool S>
+    static __device__ __forceinline__ int finish(const DevParams& P, const Inst<S>& in, size_t i, size_t n, const Real<S> (&)[4]) {
+        if (P.stats_out) { P.stats_out[i] = in.max_theta; P.stats_out[n + i] = in.max_u; }
+        return 0;
+    }
+};
+
+SB_EXPORT int sopot_b200_cartpole_feedback_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartpole_params* p,
+                                               const sopot_b200_feedback* fb, size_t n, double t0, double dt,
+                                               size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out,
+                                               double* traj_out, double* stats_out, int32_t* status) {
+    EnsembleArgs a{ctx, n, t0, dt, n_steps, opts, state_out, traj_out, status};
+    int rc = sb_check_ensemble(a, p);
+    if (rc) return rc;
+    if (!fb || !fb->K) return sb_fail(ctx, SOPOT_B200_EINVAL, "feedback gain K must be given");
+    if (fb->saturate && !(fb->u_min <= fb->u_max)) return sb_fail(ctx, SOPOT_B200_EINVAL, "u_min must not exceed u_max");
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_ensemble_arena_bytes(8, 4, n, n_steps, opts, traj_out, status,
+                                                                     2 * sb_align(4 * n * 8) + sb_align(2 * n * 8)))))
+        return rc;
+    const double* user[8] = {p->mc, p->m, p->L, p->g, p->x, p->th, p->xd, p->w};
+    ParamRef r[8];
+    if ((rc = sb_stage_params(sg, user, 8, n, opts->broadcast, r))) return rc;
+    const void *d_K, *d_ref; void* d_stats;
+    if ((rc = sg.in(fb->K, 4 * n * 8, &d_K))) return rc;
+    if ((rc = sg.in(fb->x_ref, 4 * n * 8, &d_ref))) return rc;
+    if ((rc = sg.out(stats_out, 2 * n * 8, &d_stats))) return rc;
+    CartpoleFbSys::DevParams P{r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], (const double*)d_K, (const double*)d_ref,
+                               fb->u_min, fb->u_max, fb->saturate, n, (double*)d_stats};
+    return sb_launch_ensemble<CartpoleFbSys>(a, P, sg);
+}
+
 // ---- K2: batched linearization, one operating point per thread ------------------------------------
 // Dual<double,5> = 6 doubles per scalar, the whole 2x2 solve stays in registers.  Inputs and the 20
 // Jacobian entries are SoA, so every load and store of a warp is one fully coalesced 256 B segment:

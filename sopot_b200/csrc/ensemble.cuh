@@ -76,6 +76,11 @@ __device__ __forceinline__ int rk4_step_any(const typename Sys::template Inst<S>
     else return rk4_step_fast<Sys>(in, y, c);
 }
 
+// optional hook: Sys::begin_step<S>(Inst&, y) runs once before every step (e.g. a sampled-data controller that
+// evaluates its output from the state at the start of the step and holds it over the four stages)
+template <class Sys, class = void> struct sb_has_begin_step : std::false_type {};
+template <class Sys> struct sb_has_begin_step<Sys, std::void_t<decltype(Sys::HAS_BEGIN_STEP)>> : std::true_type {};
+
 // IPT = instances per thread (Sys::IPT): IPT independent instances are advanced in lock-step by one
 // thread, which gives the scheduler IPT independent dependency chains per warp (FP64 latency hiding)
 // while per-system constants held in registers are shared.  Instance j of a thread is
@@ -108,6 +113,10 @@ rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const doubl
     for (int j = 0; j < IPT; ++j) st[j] = 0;
     size_t until_snap = store_every, snap = 0;
     for (size_t step = 0; step < n_steps; ++step) {
+        if constexpr (sb_has_begin_step<Sys>::value) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) Sys::template begin_step<S>(in[j], y[j]);
+        }
 #pragma unroll
         for (int j = 0; j < IPT; ++j) st[j] |= rk4_step_any<Sys, S>(in[j], y[j], sc);
         t += dt_;

@@ -124,9 +124,15 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
 
 }  // namespace
 
+#ifndef SB_ROCKET_BLOCK
+#define SB_ROCKET_BLOCK 128
+#endif
+#ifndef SB_ROCKET_MINB
+#define SB_ROCKET_MINB 1
+#endif
 struct RocketSys {
     static constexpr int DIM = 14;
-    static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
+    static constexpr int BLOCK = SB_ROCKET_BLOCK, IPT = 1, MIN_BLOCKS = SB_ROCKET_MINB;
     static constexpr bool FAST_STEP = false;
     struct DevParams {
         ParamRef elev, az, diam, g;

@@ -87,9 +87,43 @@ def main():
     out["g3x3t0_degenerate_state"] = s
     out["g3x3t0_degenerate_rhs"] = R.grid2d_rhs(3, 3, 0, 1.0, 0.5, 50.0, 0.5, s)
     np.savez(os.path.join(OUT, "grid2d.npz"), **out)
+    control_golden(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def control_golden(R):
+    """Section 8f-1: the reference's LQR<4,1>::solve on its own linearizer output, and the closed loop
+    StateFeedbackController<4,1> -> CartNPendulum<1> -> RK4Solver (one step per controller sample)."""
+    P = 48
+    w = W.cartpole_points(P, seed=31)
+    x = w["x"].copy()
+    x[1] *= 0.15                                   # near upright: stabilisable
+    x[:, 0] = 0.0                                  # the upright equilibrium itself first
+    mc = 1.0 + 0.2 * np.linspace(-1, 1, P); m = 0.1 * (1 + 0.3 * np.cos(np.arange(P))); L = 0.5 * (1 + 0.2 * np.sin(np.arange(P)))
+    g = np.full(P, 9.81)
+    A, B = R.cartpole_linearize(x, w["u"], mc, m, L, g)
+    Q = np.diag([10.0, 100.0, 1.0, 10.0]) + 0.1     # full (non-diagonal) weight matrix
+    Q = 0.5 * (Q + Q.T)
+    out = dict(x=x, u=w["u"], mc=mc, m=m, L=L, g=g, A=A, B=B, Q=Q)
+    for tag, r, dt, mi, tol in (("a", 0.01, 0.01, 1000, 1e-8), ("b", 0.5, 0.002, 300, 1e-10)):
+        K, Pr, _, st = R.lqr4(A, B, Q, r, dt, mi, tol)
+        out["K_" + tag], out["P_" + tag], out["st_" + tag] = K, Pr, st
+    # degenerate problems: B = 0 with R = 0 -> "singular" throw; unstable + uncontrollable -> diverges
+    A2 = np.zeros((16, 2)); B2 = np.zeros((4, 2))
+    A2[0 * 4 + 0, 1] = 500.0
+    K2, P2, _, st2 = R.lqr4(A2, B2, np.eye(4), 0.0, 0.01, 1000, 1e-8)
+    K3, P3, _, st3 = R.lqr4(A2, B2, np.eye(4), 1.0, 0.01, 1000, 1e-8)
+    out.update(A2=A2, B2=B2, st_sing=st2, st_div=st3, K_div=K3)
+    n = 40
+    s0 = np.zeros((4, n)); s0[0] = 0.2 * np.sin(np.arange(n)); s0[1] = 0.08 * np.linspace(-1, 1, n); s0[3] = 0.1 * np.cos(np.arange(n))
+    Kc = out["K_a"][:, :n].copy()
+    xref = np.zeros((4, n)); xref[0] = 0.05
+    fin, stats = R.cartpole_feedback_rk4(mc[:n], m[:n], L[:n], g[:n], s0, Kc, xref, -15.0, 15.0, 1, 0.0, 0.002, 1500)
+    fin_ns, stats_ns = R.cartpole_feedback_rk4(mc[:n], m[:n], L[:n], g[:n], s0, Kc, None, 0.0, 0.0, 0, 0.0, 0.002, 700)
+    out.update(cl_s0=s0, cl_K=Kc, cl_xref=xref, cl_final=fin, cl_stats=stats, cl_final_ns=fin_ns, cl_stats_ns=stats_ns)
+    np.savez(os.path.join(OUT, "control.npz"), **out)
 
 
 if __name__ == "__main__":

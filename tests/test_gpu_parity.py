@@ -339,3 +339,63 @@ def test_inline_ieee_division_and_sqrt_are_correctly_rounded(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 mismatches" in r.stdout
+
+
+# ---------------------------------------------------------------- section 8f-1: LQR sweep and closed loop
+def test_lqr_golden_bit_exact_strict(engine):
+    """Batched LQR<4,1>::solve: strict mode == the reference's class bit for bit (gains, Riccati solution, status),
+    including the 'singular' throw and the diverging iteration; contract mode within 1e-9 of it."""
+    g = golden("control")
+    P = g["A"].shape[1]
+    for tag, r, dt, mi, tol in (("a", 0.01, 0.01, 1000, 1e-8), ("b", 0.5, 0.002, 300, 1e-10)):
+        K, Pr, it, st = engine.lqr4_gain(g["A"], g["B"], P, g["Q"], r, dt, mi, tol, fp_mode=FP_STRICT, want_riccati=True)
+        assert np.array_equal(K, g["K_" + tag]) and np.array_equal(Pr, g["P_" + tag]) and np.array_equal(st, g["st_" + tag])
+        Kc, _, _, stc = engine.lqr4_gain(g["A"], g["B"], P, g["Q"], r, dt, mi, tol, fp_mode=FP_CONTRACT)
+        assert not stc.any() and rel_err(Kc, g["K_" + tag]).max() <= 1e-6     # gain of an iteration stopped at tol 1e-8
+    _, _, _, st = engine.lqr4_gain(g["A2"], g["B2"], 2, np.eye(4), 0.0, fp_mode=FP_STRICT)
+    assert list(st) == [2, 2]
+    K, _, _, st = engine.lqr4_gain(g["A2"], g["B2"], 2, np.eye(4), 1.0, fp_mode=FP_STRICT)
+    assert np.array_equal(st, g["st_div"]) and np.array_equal(K, g["K_div"], equal_nan=True)
+
+
+def test_closed_loop_golden_bit_exact_strict(engine):
+    g = golden("control")
+    n = g["cl_s0"].shape[1]
+    pl = [g[k][:n] for k in ("mc", "m", "L", "g")]
+    s0 = g["cl_s0"]
+    fin, stats, _, st = engine.cartpole_feedback_rk4(*pl, s0[0], s0[1], s0[2], s0[3], g["cl_K"], n, 0.0, 0.002, 1500,
+                                                     x_ref=g["cl_xref"], u_min=-15.0, u_max=15.0, saturate=True, fp_mode=FP_STRICT)
+    assert not st.any() and np.abs(fin - g["cl_final"]).max() <= 1e-12      # sin/cos: libm-level differences only
+    assert np.abs(stats - g["cl_stats"]).max() <= 1e-12
+    fin, stats, _, _ = engine.cartpole_feedback_rk4(*pl, s0[0], s0[1], s0[2], s0[3], g["cl_K"], n, 0.0, 0.002, 700, fp_mode=FP_CONTRACT)
+    assert rel_err(fin, g["cl_final_ns"]).max() <= FINAL and rel_err(stats, g["cl_stats_ns"]).max() <= FINAL
+
+
+def test_linearize_lqr_closed_loop_pipeline_on_device(engine, port):
+    """The whole sweep without leaving the GPU: linearize (K2) -> LQR (K5) -> closed-loop ensemble (K1), device
+    pointers throughout, 20 000 plants; a sample is checked against the oracle and every loop must stabilise."""
+    P = 20000
+    rng = np.random.default_rng(11)
+    mc, m, L = rng.uniform(0.8, 1.5, P), rng.uniform(0.05, 0.2, P), rng.uniform(0.4, 0.8, P)
+    g = np.full(P, 9.81)
+    x0 = np.zeros((4, P)); u0 = np.zeros(P)
+    d = {k: engine.to_device(v) for k, v in dict(mc=mc, m=m, L=L, g=g).items()}
+    dx, du = engine.to_device(x0), engine.to_device(u0)
+    A, B, _ = engine.cartpole_linearize(d["mc"], d["m"], d["L"], d["g"], dx, du, P, mem=MEM_DEVICE, fp_mode=FP_STRICT)
+    Q = np.diag([10.0, 100.0, 1.0, 10.0])
+    K, _, it, st = engine.lqr4_gain(A, B, P, Q, 0.01, mem=MEM_DEVICE, fp_mode=FP_STRICT)
+    assert not st.download().any()
+    s0 = np.zeros((4, P)); s0[1] = rng.uniform(-0.1, 0.1, P); s0[0] = rng.uniform(-0.5, 0.5, P)
+    ds = [engine.to_device(np.ascontiguousarray(s0[j])) for j in range(4)]
+    fin, stats, _, st2 = engine.cartpole_feedback_rk4(d["mc"], d["m"], d["L"], d["g"], *ds, K, P, 0.0, 0.002, 2500,
+                                                      u_min=-50.0, u_max=50.0, saturate=True, mem=MEM_DEVICE, fp_mode=FP_STRICT)
+    fin, stats = fin.download(), stats.download()
+    assert not st2.download().any()
+    assert np.abs(fin[1]).max() < 0.01 and stats[0].max() < 0.2 and np.abs(fin[0]).max() < 0.05
+    idx = np.arange(0, P, 997)
+    rA, rB = port.cartpole_linearize(x0[:, idx], u0[idx], mc[idx], m[idx], L[idx], g[idx])
+    assert np.abs(A.download()[:, idx] - rA).max() <= 1e-12
+    rK, _, rit, rst = port.lqr4(A.download()[:, idx], B.download()[:, idx], Q, 0.01)
+    assert np.array_equal(K.download()[:, idx], rK) and np.array_equal(it.download()[idx], rit)
+    rfin, rstats = port.cartpole_feedback_rk4(mc[idx], m[idx], L[idx], g[idx], s0[:, idx], rK, None, -50.0, 50.0, 1, 0.0, 0.002, 2500, nthreads=4)
+    assert np.abs(fin[:, idx] - rfin).max() <= 1e-9 and np.abs(stats[:, idx] - rstats).max() <= 1e-9

@@ -175,3 +175,42 @@ def test_lean_trig_accuracy(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O2", src, "-o", str(exe)], check=True)     # fma() is exact with or without -mfma
     r = subprocess.run([str(exe), "400000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_golden_lqr_and_closed_loop(port):
+    """Section 8f-1: the C restatement of LQR<4,1>::solve and of the sampled-data closed loop against the reference's
+    own classes (golden vectors from oracle/ref_harness.cpp): gains, Riccati solutions, status codes incl. the
+    'singular' throw and the diverging iteration, closed-loop final states and running maxima -- bit for bit."""
+    g = golden("control")
+    for tag, r, dt, mi, tol in (("a", 0.01, 0.01, 1000, 1e-8), ("b", 0.5, 0.002, 300, 1e-10)):
+        K, P, it, st = port.lqr4(g["A"], g["B"], g["Q"], r, dt, mi, tol, nthreads=4)
+        assert np.array_equal(K, g["K_" + tag]) and np.array_equal(P, g["P_" + tag]) and np.array_equal(st, g["st_" + tag])
+        assert it.min() >= 1 and it.max() <= mi
+    _, _, _, st = port.lqr4(g["A2"], g["B2"], np.eye(4), 0.0)
+    assert np.array_equal(st, g["st_sing"]) and list(st) == [2, 2]
+    K, _, _, st = port.lqr4(g["A2"], g["B2"], np.eye(4), 1.0)
+    assert np.array_equal(st, g["st_div"]) and np.array_equal(K, g["K_div"], equal_nan=True)
+    n = g["cl_s0"].shape[1]
+    pl = [g[k][:n] for k in ("mc", "m", "L", "g")]
+    fin, stats = port.cartpole_feedback_rk4(*pl, g["cl_s0"], g["cl_K"], g["cl_xref"], -15.0, 15.0, 1, 0.0, 0.002, 1500, nthreads=4)
+    assert np.array_equal(fin, g["cl_final"]) and np.array_equal(stats, g["cl_stats"])
+    fin, stats = port.cartpole_feedback_rk4(*pl, g["cl_s0"], g["cl_K"], None, 0.0, 0.0, 0, 0.0, 0.002, 700, nthreads=4)
+    assert np.array_equal(fin, g["cl_final_ns"]) and np.array_equal(stats, g["cl_stats_ns"])
+    # the loop is stabilised: every pendulum ends near upright (tests/inverted_pendulum_test.cpp:288-289 style bounds)
+    assert np.abs(g["cl_final"][1]).max() < 0.01 and g["cl_stats"][0].max() < 0.2
+
+
+def test_lqr_port_equals_reference_on_fresh_inputs(port, ref):
+    rng = np.random.default_rng(5)
+    P = 24
+    x = np.stack([rng.uniform(-1, 1, P), rng.uniform(-0.4, 0.4, P), rng.uniform(-1, 1, P), rng.uniform(-1, 1, P)])
+    mc, m, L = rng.uniform(0.5, 2, P), rng.uniform(0.05, 0.3, P), rng.uniform(0.3, 1.0, P)
+    A, B = ref.cartpole_linearize(x, rng.uniform(-3, 3, P), mc, m, L, np.full(P, 9.81))
+    Q = np.diag(rng.uniform(1, 100, 4))
+    a = port.lqr4(A, B, Q, 0.05, 0.005, 800, 1e-9)
+    b = ref.lqr4(A, B, Q, 0.05, 0.005, 800, 1e-9)
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    s0 = np.zeros((4, P)); s0[1] = rng.uniform(-0.1, 0.1, P)
+    fa = port.cartpole_feedback_rk4(mc, m, L, np.full(P, 9.81), s0, a[0], None, -30.0, 30.0, 1, 0.0, 0.001, 400)
+    fb = ref.cartpole_feedback_rk4(mc, m, L, np.full(P, 9.81), s0, a[0], None, -30.0, 30.0, 1, 0.0, 0.001, 400)
+    assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
