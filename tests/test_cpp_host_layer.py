@@ -13,7 +13,7 @@ import pytest
 from conftest import ROOT
 
 CPP = os.path.join(ROOT, "tests", "cpp")
-PROGRAMS = ["compile_time_test", "double_pendulum_test", "linearization_test", "rocket_test", "grid2d_test"]
+PROGRAMS = ["compile_time_test", "double_pendulum_test", "linearization_test", "rocket_test", "grid2d_test", "lqr_test"]
 
 
 @pytest.fixture(scope="module")
