@@ -186,6 +186,28 @@ def other_configs(eng, hbm_peak, fp64_peak):
                 a.free()
     for a in (dx, du, A, B, st, *d.values()):
         a.free()
+    # section 8f-1: the LQR sweep that consumes the Jacobians (64 Ki plants at upright, jittered parameters), then the
+    # closed loop under those gains (64 Ki plants x 2000 steps).  FP64-bound: ~590 Riccati iterations per point.
+    P = 1 << 16
+    rng = np.random.default_rng(3)
+    plant = {k: eng.to_device(v) for k, v in dict(mc=rng.uniform(0.8, 1.5, P), m=rng.uniform(0.05, 0.2, P),
+                                                   L=rng.uniform(0.4, 0.8, P), g=np.full(P, 9.81)).items()}
+    dx, du = eng.to_device(np.zeros((4, P))), eng.to_device(np.zeros(P))
+    A, B, _ = eng.cartpole_linearize(plant["mc"], plant["m"], plant["L"], plant["g"], dx, du, P, mem=MEM_DEVICE, want_status=False)
+    Q = np.diag([10.0, 100.0, 1.0, 10.0])
+    K = eng.empty((4, P))
+    ms = timed(lambda: eng.lqr4_gain(A, B, P, Q, 0.01, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, K=K, want_iters=False, sync=False), 2)
+    _, _, iters, st = eng.lqr4_gain(A, B, P, Q, 0.01, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, K=K)
+    mean_it = float(iters.download().mean())
+    out["lqr4_sweep_64Ki"] = {"ms": ms, "gains_per_s": P / (ms * 1e-3), "mean_riccati_iterations": mean_it,
+                              "failed": int(np.count_nonzero(st.download()))}
+    s0 = [eng.to_device(v) for v in (rng.uniform(-0.5, 0.5, P), rng.uniform(-0.1, 0.1, P), np.zeros(P), np.zeros(P))]
+    ms = timed(lambda: eng.cartpole_feedback_rk4(plant["mc"], plant["m"], plant["L"], plant["g"], *s0, K, P, 0.0, 0.002, 2000,
+                                                 u_min=-50.0, u_max=50.0, saturate=True, mem=MEM_DEVICE, want_status=False,
+                                                 want_stats=False, sync=False), 2)
+    out["cartpole_closed_loop_64Ki_x2000"] = {"ms": ms, "instance_steps_per_s": P * 2000 / (ms * 1e-3)}
+    for a in (dx, du, A, B, K, iters, st, *s0, *plant.values()):
+        a.free()
     # config 4: rocket Monte Carlo 1 Mi x 3000 steps + dispersion reduction
     n = 1 << 20
     w = W.rocket_ensemble(n)
