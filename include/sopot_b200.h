@@ -73,6 +73,10 @@ const char* sopot_b200_last_error(const sopot_b200_ctx* ctx);   /* ctx may be NU
 int  sopot_b200_sync(sopot_b200_ctx* ctx);
 /* adopt an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
 int  sopot_b200_set_stream(sopot_b200_ctx* ctx, void* cuda_stream);
+/* the ctx stream as a cudaStream_t, for kernels a host program instantiates itself from sopot/b200/generic_ensemble.cuh
+ * (user-defined component systems compiled with nvcc); sopot_b200_note_launches adds them to the launch count */
+int  sopot_b200_get_stream(sopot_b200_ctx* ctx, void** cuda_stream);
+int  sopot_b200_note_launches(sopot_b200_ctx* ctx, uint64_t count);
 int  sopot_b200_device_info(sopot_b200_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                             size_t* global_mem_bytes, char* name, size_t name_len);
 

@@ -145,6 +145,15 @@ class Checker:
             _p(fin), _p(stats), nthreads)
         return fin, stats
 
+    # ---------------- plugin-path check: coupled oscillator ----------------
+    def coupled_rk4(self, m1, m2, k, L0, c, x1, x2, t0, t1, dt, nthreads=1):
+        k = _f64(k).reshape(-1); n = k.size
+        m1, m2, L0, c, x1, x2 = (_f64(a, n).reshape(-1) for a in (m1, m2, L0, c, x1, x2))
+        fin = np.empty((4, n)); en = np.empty(n)
+        self._fn("coupled_rk4", [_sz] + [_dp] * 7 + [_d] * 3 + [_dp, _dp, _i])(
+            n, _p(m1), _p(m2), _p(k), _p(L0), _p(c), _p(x1), _p(x2), t0, t1, dt, _p(fin), _p(en), nthreads)
+        return fin, en
+
     # ---------------- config 4 ----------------
     @staticmethod
     def _tab(t, cols):

@@ -18,6 +18,7 @@
 #include "physics/pendulum/double_pendulum.hpp"
 #include "physics/control/cart_n_pendulum.hpp"
 #include "physics/control/lqr.hpp"
+#include "physics/coupled_oscillator/coupled_system.hpp"
 #include "physics/control/state_feedback_controller.hpp"
 #include "physics/connected_masses/connectivity_matrix_2d.hpp"
 #include "rocket/rocket.hpp"
@@ -225,6 +226,19 @@ int ref_cartpole_feedback_rk4(size_t n, const double* mc, const double* m, const
         }
         for (int q = 0; q < 4; ++q) final_out[q * n + i] = y[q];
         if (stats) { stats[i] = max_th; stats[n + i] = max_u; }
+    });
+    return 0;
+}
+
+// ---- plugin-path check: the reference's own multi-component example (physics/coupled_oscillator/) ----
+int ref_coupled_rk4(size_t n, const double* m1, const double* m2, const double* k, const double* L0, const double* c,
+                    const double* x1, const double* x2, double t0, double t1, double dt, double* final_out /*[4][n]*/,
+                    double* energy_out /*[n] total energy of the final state*/, int nthreads) {
+    parallel_for(n, nthreads, [&](size_t i) {
+        auto sys = physics::coupled::createCoupledOscillator<double>(m1[i], x1[i], 0.0, m2[i], x2[i], 0.0, k[i], L0[i], c[i]);
+        auto r = solve_system(sys, t0, t1, dt);
+        scatter_result(r, 4, i, n, 0, final_out, nullptr, nullptr);
+        if (energy_out) energy_out[i] = sys.template computeStateFunction<physics::coupled::system::TotalEnergy>(r.states.back());
     });
     return 0;
 }

@@ -533,6 +533,37 @@ ORC_API int orc_cartpole_feedback_rk4(size_t n, const double* mc, const double* 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Plugin-path check -- the reference's composition example, physics/coupled_oscillator/: two PointMass
+ * (point_mass.hpp:70-84: {v, F/m}), one Spring (spring.hpp:96-131: F1 = -k (x1 - x2 - L0) [+ -c (v1 - v2) when
+ * c > 0], F2 = -F1), state [x1, v1, x2, v2].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { double m1, m2, k, L0, c; } orc_coupled_t;
+static void orc_coupled_rhs(const void* ctx, double t, const double* y, double* dy) {
+    const orc_coupled_t* p = (const orc_coupled_t*)ctx;
+    (void)t;
+    double f1 = -p->k * (y[0] - y[2] - p->L0);
+    if (p->c > 0.0) f1 += -p->c * (y[1] - y[3]);
+    dy[0] = y[1]; dy[1] = f1 / p->m1;
+    dy[2] = y[3]; dy[3] = (-f1) / p->m2;
+}
+ORC_API int orc_coupled_rk4(size_t n, const double* m1, const double* m2, const double* k, const double* L0, const double* c,
+                            const double* x1, const double* x2, double t0, double t1, double dt, double* final_out,
+                            double* energy_out, int nthreads) {
+    (void)nthreads;
+    for (size_t i = 0; i < n; ++i) {
+        orc_coupled_t p = {m1[i], m2[i], k[i], L0[i], c[i]};
+        double y[4] = {x1[i], 0.0, x2[i], 0.0}, work[20];
+        orc_rk4(orc_coupled_rhs, &p, 4, t0, t1, dt, y, work, NULL, NULL, NULL);
+        for (int q = 0; q < 4; ++q) final_out[q * n + i] = y[q];
+        if (energy_out) {                                  /* energy_monitor.hpp: KE1 + KE2 + 0.5 k ext^2 */
+            const double ext = y[0] - y[2] - p.L0;
+            energy_out[i] = 0.5 * p.m1 * y[1] * y[1] + 0.5 * p.m2 * y[3] * y[3] + (0.5 * p.k) * ext * ext;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Config 4 -- 6-DOF rocket.
  * ------------------------------------------------------------------------------------------ */
 /* LinearInterpolator::interpolate, io/interpolation.hpp:49-71 */

@@ -81,6 +81,8 @@ SYMBOLS = {
     "sopot_b200_destroy": (None, [_ctx]),
     "sopot_b200_last_error": (c_char_p, [_ctx]),
     "sopot_b200_sync": (c_int, [_ctx]),
+    "sopot_b200_get_stream": (c_int, [_ctx, POINTER(c_void_p)]),
+    "sopot_b200_note_launches": (c_int, [_ctx, ctypes.c_uint64]),
     "sopot_b200_set_stream": (c_int, [_ctx, c_void_p]),
     "sopot_b200_device_info": (c_int, [_ctx, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                        POINTER(c_size_t), c_char_p, c_size_t]),

@@ -157,6 +157,18 @@ SB_EXPORT int sopot_b200_sync(sopot_b200_ctx* ctx) {
     return SOPOT_B200_OK;
 }
 
+SB_EXPORT int sopot_b200_get_stream(sopot_b200_ctx* ctx, void** cuda_stream) {
+    if (!ctx || !cuda_stream) return SOPOT_B200_EINVAL;
+    *cuda_stream = ctx->stream;
+    return SOPOT_B200_OK;
+}
+
+SB_EXPORT int sopot_b200_note_launches(sopot_b200_ctx* ctx, uint64_t count) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    ctx->launches += count;
+    return SOPOT_B200_OK;
+}
+
 SB_EXPORT int sopot_b200_set_stream(sopot_b200_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SOPOT_B200_EINVAL;
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -60,7 +60,8 @@ public:
     SolutionResult solve(b200::SystemDerivs<System> derivs, size_t state_dim, double t_start, double t_end, double dt,
                          const StateVector& initial_state) const {
         using Binding = typename System::Binding;
-        static_assert(Binding::available, "no B200 binding for this system");
+        static_assert(Binding::available || (System::device_integrable && SOPOT_B200_DEVICE_COMPILER),
+                      "no B200 kernel for this system (see core/typed_component.hpp)");
         const auto wall0 = std::chrono::high_resolution_clock::now();
         if (state_dim != System::getStateDimension() || initial_state.size() != state_dim)
             throw std::invalid_argument("state dimension mismatch");
@@ -68,8 +69,11 @@ public:
         b200::EnsembleOptions opt;
         opt.fp_mode = m_fp_mode;
         opt.store_every = 1;                                  // the reference keeps every step (:130-131)
-        b200::EnsembleResult r = Binding::solve(b200::Engine::shared(), derivs.system->components(), initial_state,
-                                                n_steps, t_start, dt, opt);
+        b200::EnsembleResult r;
+        if constexpr (Binding::available)
+            r = Binding::solve(b200::Engine::shared(), derivs.system->components(), initial_state, n_steps, t_start, dt, opt);
+        else
+            r = b200::generic::solve_one(b200::Engine::shared(), *derivs.system, initial_state, n_steps, t_start, dt, opt);
         r.throwOnFailure();
         SolutionResult out = unpack(r, state_dim, n_steps, t_start, dt, initial_state);
         out.total_time = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - wall0).count();

@@ -1,0 +1,169 @@
+// user_components.cu -- the plugin path end to end: components written against the reference's TypedComponent contract
+// (this is the reference's own composition example, physics/coupled_oscillator/: two point masses, a spring that
+// provides both forces through the registry, an energy monitor that only provides state functions), compiled with nvcc
+// into an RK4 ensemble kernel by sopot/b200/generic_ensemble.cuh.  Checks:
+//   1. the reference's call shapes work unchanged (makeTypedODESystem, computeStateFunction<Tag>, computeDerivatives,
+//      createRK4Solver().solve with the wrapper lambda) and run on the GPU;
+//   2. an ensemble of jittered systems built by a device factory equals instance-by-instance single solves bit for bit;
+//   3. -fmad=false builds reproduce the reference's CPU result of the same system (known answer below, from the
+//      unmodified reference compiled by oracle/ref_harness.cpp) bit for bit; default builds to 1e-12.
+// Build: nvcc -std=c++20 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a [-fmad=false] ... -lsopot_b200
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <sopot/core/solver.hpp>
+#include <sopot/core/typed_component.hpp>
+
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "%s:%d CHECK FAILED: %s\n", __FILE__, __LINE__, #c); std::abort(); } } while (0)
+
+namespace coupled {
+using namespace sopot;
+// tags as in physics/coupled_oscillator/tags.hpp
+namespace mass1 { struct Position : StateFunction {}; struct Velocity : StateFunction {}; struct Force : StateFunction {}; struct Mass : StateFunction {};
+                  struct TagSet { using Position = mass1::Position; using Velocity = mass1::Velocity; using Force = mass1::Force; using Mass = mass1::Mass; }; }
+namespace mass2 { struct Position : StateFunction {}; struct Velocity : StateFunction {}; struct Force : StateFunction {}; struct Mass : StateFunction {};
+                  struct TagSet { using Position = mass2::Position; using Velocity = mass2::Velocity; using Force = mass2::Force; using Mass = mass2::Mass; }; }
+namespace spring { struct Extension : StateFunction {}; struct PotentialEnergy : StateFunction {}; }
+namespace system { struct TotalEnergy : StateFunction {}; struct Momentum : StateFunction {}; struct CenterOfMass : StateFunction {}; }
+
+// physics/coupled_oscillator/point_mass.hpp: state [x, v]; derivative {v, F/m} with F queried from the registry
+template <typename TagSet, Scalar T = double>
+class PointMass final : public TypedComponent<2, T> {
+public:
+    using Base = TypedComponent<2, T>;
+    using typename Base::LocalState;
+    using typename Base::LocalDerivative;
+    SOPOT_HD PointMass(double mass, double x0 = 0.0, double v0 = 0.0) : m_mass(mass), m_x0(x0), m_v0(v0) {}
+    SOPOT_HD LocalState getInitialLocalState() const { return {T(m_x0), T(m_v0)}; }
+    template <typename Registry>
+    SOPOT_HD LocalDerivative derivatives(T, std::span<const T> local, std::span<const T> global, const Registry& registry) const {
+        const T force = registry.template computeFunction<typename TagSet::Force>(global);
+        return {local[1], force / T(m_mass)};
+    }
+    SOPOT_HD T compute(typename TagSet::Position, std::span<const T> s) const { return this->getGlobalState(s, 0); }
+    SOPOT_HD T compute(typename TagSet::Velocity, std::span<const T> s) const { return this->getGlobalState(s, 1); }
+    SOPOT_HD T compute(typename TagSet::Mass, std::span<const T>) const { return T(m_mass); }
+private:
+    double m_mass, m_x0, m_v0;
+};
+
+// physics/coupled_oscillator/spring.hpp: no state; extension = x1 - x2 - L0, F1 = -k ext - c (v1 - v2), F2 = -F1
+template <typename TS1, typename TS2, Scalar T = double>
+class Spring final : public TypedComponent<0, T> {
+public:
+    SOPOT_HD Spring(double k, double L0 = 1.0, double c = 0.0) : m_k(k), m_L0(L0), m_c(c) {}
+    typename TypedComponent<0, T>::LocalState getInitialLocalState() const { return {}; }
+    template <typename Registry>
+    SOPOT_HD T compute(spring::Extension, std::span<const T> s, const Registry& r) const {
+        return r.template computeFunction<typename TS1::Position>(s) - r.template computeFunction<typename TS2::Position>(s) - T(m_L0);
+    }
+    template <typename Registry>
+    SOPOT_HD T compute(typename TS1::Force, std::span<const T> s, const Registry& r) const {
+        const T ext = compute(spring::Extension{}, s, r);
+        const T rel = r.template computeFunction<typename TS1::Velocity>(s) - r.template computeFunction<typename TS2::Velocity>(s);
+        T spring_force = -T(m_k) * ext;                                       // spring.hpp:105-112
+        if (m_c > 0.0) spring_force += -T(m_c) * rel;
+        return spring_force;
+    }
+    template <typename Registry>
+    SOPOT_HD T compute(typename TS2::Force, std::span<const T> s, const Registry& r) const { return -compute(typename TS1::Force{}, s, r); }
+    template <typename Registry>
+    SOPOT_HD T compute(spring::PotentialEnergy, std::span<const T> s, const Registry& r) const {
+        const T ext = compute(spring::Extension{}, s, r);
+        return T(0.5 * m_k) * ext * ext;
+    }
+private:
+    double m_k, m_L0, m_c;
+};
+
+// physics/coupled_oscillator/energy_monitor.hpp: state functions only
+template <Scalar T = double>
+class EnergyMonitor final : public TypedComponent<0, T> {
+public:
+    typename TypedComponent<0, T>::LocalState getInitialLocalState() const { return {}; }
+    template <typename Registry>
+    SOPOT_HD T compute(system::TotalEnergy, std::span<const T> s, const Registry& r) const {
+        const T m1 = r.template computeFunction<mass1::Mass>(s), m2 = r.template computeFunction<mass2::Mass>(s);
+        const T v1 = r.template computeFunction<mass1::Velocity>(s), v2 = r.template computeFunction<mass2::Velocity>(s);
+        return T(0.5) * m1 * v1 * v1 + T(0.5) * m2 * v2 * v2 + r.template computeFunction<spring::PotentialEnergy>(s);
+    }
+    template <typename Registry>
+    SOPOT_HD T compute(system::Momentum, std::span<const T> s, const Registry& r) const {
+        return r.template computeFunction<mass1::Mass>(s) * r.template computeFunction<mass1::Velocity>(s) +
+               r.template computeFunction<mass2::Mass>(s) * r.template computeFunction<mass2::Velocity>(s);
+    }
+};
+
+inline auto make(double m1, double m2, double k, double L0, double c, double x1, double x2) {
+    return makeTypedODESystem<double>(PointMass<mass1::TagSet>(m1, x1, 0.0), PointMass<mass2::TagSet>(m2, x2, 0.0),
+                                      Spring<mass1::TagSet, mass2::TagSet>(k, L0, c), EnergyMonitor<double>());
+}
+using System = decltype(make(1, 1, 1, 1, 0, 0, 0));
+
+// device factory: stiffness and damping jittered per instance
+struct Factory {
+    const double* k;
+    const double* c;
+    __device__ System operator()(size_t i) const {
+        return makeTypedODESystem<double>(PointMass<mass1::TagSet>(1.0, 0.0, 0.0), PointMass<mass2::TagSet>(1.5, 2.0, 0.0),
+                                          Spring<mass1::TagSet, mass2::TagSet>(k[i], 1.0, c[i]), EnergyMonitor<double>());
+    }
+};
+}  // namespace coupled
+
+int main() {
+    using namespace sopot;
+    using namespace coupled;
+    // 1. the reference's call shapes on a user-defined pack
+    auto sys = coupled::make(1.0, 1.5, 4.0, 1.0, 0.0, 0.0, 2.0);
+    static_assert(decltype(sys)::hasFunction<coupled::system::TotalEnergy>() && decltype(sys)::hasFunction<mass2::Force>());
+    static_assert(decltype(sys)::device_integrable && !decltype(sys)::Binding::available);
+    CHECK(sys.getStateDimension() == 4 && sys.getComponentCount() == 4);
+    auto y0 = sys.getInitialState();
+    CHECK(y0[0] == 0.0 && y0[2] == 2.0);
+    CHECK(sys.computeStateFunction<spring::Extension>(y0) == -3.0);
+    CHECK(sys.computeStateFunction<mass1::Force>(y0) == 12.0 && sys.computeStateFunction<mass2::Force>(y0) == -12.0);
+    const double e0 = sys.computeStateFunction<coupled::system::TotalEnergy>(y0);
+    CHECK(e0 == 18.0);
+    auto d = sys.computeDerivatives(0.0, y0);                                  // on the device
+    CHECK(d[0] == 0.0 && d[1] == 12.0 && d[2] == 0.0 && d[3] == -12.0 / 1.5);
+    auto derivs = [&sys](double t, StateView s) { return sys.computeDerivatives(t, std::vector<double>(s.begin(), s.end())); };
+    auto r = createRK4Solver().solve(derivs, sys.getStateDimension(), 0.0, 5.0, 0.01, y0);
+    CHECK(r.size() == 501);
+    const double e1 = sys.computeStateFunction<coupled::system::TotalEnergy>(r.states.back());
+    CHECK(std::abs(e1 - e0) / e0 < 1e-8);                                      // undamped: energy conserved
+    CHECK(std::abs(sys.computeStateFunction<coupled::system::Momentum>(r.states.back())) < 1e-12);
+    // known answer: the reference's createMass1/createMass2/createSpring system, RK4Solver 0..5 s, dt = 0.01 (CPU)
+    const double ref[4] = {0.1051977204129609, 1.5655568262665147, 1.929868186391363, -1.043704550844343};
+    for (int j = 0; j < 4; ++j) {
+#ifdef SOPOT_TEST_STRICT
+        CHECK(r.states.back()[j] == ref[j]);
+#else
+        CHECK(std::abs(r.states.back()[j] - ref[j]) <= 1e-12 * (1.0 + std::abs(ref[j])));
+#endif
+    }
+
+    // 2. ensemble built by a device factory == single solves
+    const size_t n = 4096;
+    std::vector<double> k(n), c(n);
+    for (size_t i = 0; i < n; ++i) { k[i] = 4.0 * (1.0 + 0.3 * std::sin(double(i))); c[i] = 0.05 * (1.0 + std::cos(double(i))); }
+    double *dk, *dc;
+    cudaMalloc(&dk, n * 8); cudaMalloc(&dc, n * 8);
+    cudaMemcpy(dk, k.data(), n * 8, cudaMemcpyHostToDevice); cudaMemcpy(dc, c.data(), n * 8, cudaMemcpyHostToDevice);
+    b200::EnsembleOptions opt;
+    opt.store_every = 100;
+    auto ens = createRK4Solver().solveEnsemble(b200::ensembleOf(n, Factory{dk, dc}), 0.0, 5.0, 0.01, opt);
+    CHECK(ens.snapshots() == 5 && ens.dim == 4 && ens.n == n);
+    for (size_t i : {size_t(0), size_t(1234), n - 1}) {
+        auto one = coupled::make(1.0, 1.5, k[i], 1.0, c[i], 0.0, 2.0);
+        auto r1 = createRK4Solver().solve(one, 0.0, 5.0, 0.01);
+        for (int j = 0; j < 4; ++j) {
+            CHECK(ens.final(j, i) == r1.states.back()[j]);
+            CHECK(ens.at(2, j, i) == r1.states[300][j]);
+        }
+        CHECK(ens.status[i] == 0);
+    }
+    cudaFree(dk); cudaFree(dc);
+    std::puts("user_components: OK");
+    return 0;
+}

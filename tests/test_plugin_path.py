@@ -1,0 +1,70 @@
+"""The plugin path: user-defined components (the reference's TypedComponent contract with SOPOT_HD markers) compiled
+by nvcc into an RK4 ensemble kernel through sopot/b200/generic_ensemble.cuh.
+
+CPU: tests/cuda/user_components.cu -- the reference's own composition example (physics/coupled_oscillator/: two point
+masses, a spring providing both forces through the registry, an energy monitor) -- cross-compiles for sm_100a with and
+without FMA contraction, and the generic kernel keeps its whole state in registers (no local memory).
+GPU: the program runs: reference call shapes on a user pack, ensemble == single solves, and the -fmad=false build
+reproduces the reference's CPU result bit for bit."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SRC = os.path.join(ROOT, "tests", "cuda", "user_components.cu")
+
+
+def _nvcc(out, *extra):
+    cmd = ["nvcc", "-std=c++20", "--expt-relaxed-constexpr", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-Xptxas", "-v",
+           "-I" + os.path.join(ROOT, "sopot_b200", "include"), *extra, "-o", str(out), SRC,
+           "-L" + os.path.join(ROOT, "sopot_b200", "lib"), "-lsopot_b200", "-Xlinker", "-rpath", "-Xlinker",
+           os.path.join(ROOT, "sopot_b200", "lib")]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module")
+def programs(tmp_path_factory):
+    from sopot_b200 import build
+    build.build()
+    d = tmp_path_factory.mktemp("plugin")
+    logs = {}
+    for name, extra in (("contract", ()), ("strict", ("-fmad=false", "-DSOPOT_TEST_STRICT"))):
+        r = _nvcc(d / name, *extra)
+        assert r.returncode == 0, r.stdout + r.stderr
+        logs[name] = r.stdout + r.stderr
+    return d, logs
+
+
+def test_user_components_compile_to_register_resident_kernels(programs):
+    _, logs = programs
+    for log in logs.values():
+        kernels = re.findall(r"Compiling entry function '(\S*rk4_kernel\S*)'.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores", log)
+        assert len(kernels) >= 2                       # the factory ensemble and the single-system instantiation
+        for name, stack, spill in kernels:
+            assert int(stack) == 0 and int(spill) == 0, (name, stack, spill)
+
+
+def test_coupled_oscillator_port_equals_reference(port, ref):
+    """oracle side of the plugin check: C restatement of the coupled oscillator == the reference's components."""
+    rng = np.random.default_rng(2)
+    n = 16
+    args = (rng.uniform(0.5, 2, n), rng.uniform(0.5, 2, n), rng.uniform(1, 10, n), rng.uniform(0.5, 1.5, n),
+            np.where(np.arange(n) % 2, 0.0, rng.uniform(0, 0.3, n)), rng.uniform(-1, 1, n), rng.uniform(1, 3, n))
+    a = port.coupled_rk4(*args, 0.0, 3.0, 0.01)
+    b = ref.coupled_rk4(*args, 0.0, 3.0, 0.01)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    f, e = port.coupled_rk4(1.0, 1.5, np.array([4.0]), 1.0, 0.0, 0.0, 2.0, 0.0, 5.0, 0.01)      # the .cu test's known answer
+    assert f[:, 0].tolist() == [0.1051977204129609, 1.5655568262665147, 1.929868186391363, -1.043704550844343]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["contract", "strict"])
+def test_user_components_run_on_the_gpu(programs, mode):
+    d, _ = programs
+    r = subprocess.run([str(d / mode)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "user_components: OK" in r.stdout
