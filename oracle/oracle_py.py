@@ -145,6 +145,18 @@ class Checker:
             _p(fin), _p(stats), nthreads)
         return fin, stats
 
+    def cartn_rk4(self, n_links, mc, m, L, g, s0, force, t0, t1, dt, nthreads=1):
+        """CartNPendulum<N,double>, constant force: m, L [N][n]; s0 [2(N+1)][n]."""
+        s0 = _f64(s0); n = s0.shape[1]
+        m, L = _f64(m).reshape(n_links, n), _f64(L).reshape(n_links, n)
+        mc, g, force = (_f64(a, n).reshape(-1) for a in (mc, g, force))
+        fin = np.empty_like(s0)
+        rc = self._fn("cartn_rk4", [_i, _sz] + [_dp] * 6 + [_d] * 3 + [_dp, _i])(
+            n_links, n, _p(mc), _p(m), _p(L), _p(g), _p(s0), _p(force), t0, t1, dt, _p(fin), nthreads)
+        if rc:
+            raise KeyError("link count not instantiated")
+        return fin
+
     # ---------------- plugin-path check: coupled oscillator ----------------
     def coupled_rk4(self, m1, m2, k, L0, c, x1, x2, t0, t1, dt, nthreads=1):
         k = _f64(k).reshape(-1); n = k.size

@@ -243,6 +243,37 @@ int ref_coupled_rk4(size_t n, const double* m1, const double* m2, const double* 
     return 0;
 }
 
+// N-link cart pendulum, constant force (the reference's own tests use N = 2 and N = 6, tests/inverted_pendulum_test.cpp)
+extern "C++" {
+template <size_t NL>
+static void cartn_one(const double* mc, const double* m, const double* L, const double* g, const double* s0, const double* force,
+                      size_t n, size_t i, double t0, double t1, double dt, double* final_out) {
+    std::array<double, NL> mm, LL;
+    std::array<double, 2 * (NL + 1)> init;
+    for (size_t q = 0; q < NL; ++q) { mm[q] = m[q * n + i]; LL[q] = L[q * n + i]; }
+    for (size_t q = 0; q < 2 * (NL + 1); ++q) init[q] = s0[q * n + i];
+    control::CartNPendulum<NL, double> plant(mc[i], mm, LL, g[i], init);
+    auto sys = makeTypedODESystem<double>(std::move(plant));
+    sys.template getComponent<0>().setControlForce(force[i]);
+    auto r = solve_system(sys, t0, t1, dt);
+    scatter_result(r, 2 * (NL + 1), i, n, 0, final_out, nullptr, nullptr);
+}
+}  // extern "C++"
+int ref_cartn_rk4(int n_links, size_t n, const double* mc, const double* m /*[N][n]*/, const double* L /*[N][n]*/, const double* g,
+                  const double* s0 /*[2(N+1)][n]*/, const double* force, double t0, double t1, double dt, double* final_out,
+                  int nthreads) {
+    if (n_links != 1 && n_links != 2 && n_links != 3 && n_links != 6) return -1;
+    parallel_for(n, nthreads, [&](size_t i) {
+        switch (n_links) {
+            case 1: cartn_one<1>(mc, m, L, g, s0, force, n, i, t0, t1, dt, final_out); break;
+            case 2: cartn_one<2>(mc, m, L, g, s0, force, n, i, t0, t1, dt, final_out); break;
+            case 3: cartn_one<3>(mc, m, L, g, s0, force, n, i, t0, t1, dt, final_out); break;
+            default: cartn_one<6>(mc, m, L, g, s0, force, n, i, t0, t1, dt, final_out); break;
+        }
+    });
+    return 0;
+}
+
 // ---- config 4: 6-DOF rocket ----
 // The 11 components of Rocket<T>::SystemType (rocket/rocket.hpp:73-85) composed by hand so
 // that gravity can be jittered (Rocket<T> has no gravity setter). Tables reach the reference

@@ -533,6 +533,74 @@ ORC_API int orc_cartpole_feedback_rk4(size_t n, const double* mc, const double* 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * CartNPendulum<N,double> for any N <= 8 (physics/control/cart_n_pendulum.hpp:143-221, :319-359), constant force.
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_MAXL 8
+typedef struct { int N; double mc, m[ORC_MAXL], L[ORC_MAXL], g, F; int status; } orc_cpn_t;
+static void orc_cartn_rhs_fn(const void* ctx, double t, const double* y, double* dy) {
+    orc_cpn_t* p = (orc_cpn_t*)ctx;
+    (void)t;
+    const int N = p->N, ND = N + 1;
+    double s[ORC_MAXL], c[ORC_MAXL], om[ORC_MAXL], Mt[ORC_MAXL], A[ORC_MAXL + 1][ORC_MAXL + 1], b[ORC_MAXL + 1], x[ORC_MAXL + 1];
+    for (int i = 0; i < N; ++i) { s[i] = sin(y[1 + i]); c[i] = cos(y[1 + i]); om[i] = y[ND + 1 + i]; }
+    for (int i = 0; i < N; ++i) { double sum = 0.0; for (int j = i; j < N; ++j) sum += p->m[j]; Mt[i] = sum; }
+    double total = p->mc;
+    for (int i = 0; i < N; ++i) total = total + p->m[i];
+    A[0][0] = total;
+    b[0] = p->F;
+    for (int a = 0; a < N; ++a) {
+        const double coupling = Mt[a] * p->L[a] * c[a];
+        A[0][1 + a] = coupling; A[1 + a][0] = coupling;
+        b[0] = b[0] + Mt[a] * p->L[a] * s[a] * om[a] * om[a];
+    }
+    for (int a = 0; a < N; ++a) {
+        double rhs_a = Mt[a] * p->g * p->L[a] * s[a];
+        for (int bb = 0; bb < N; ++bb) {
+            const int mx = a > bb ? a : bb;
+            const double cab = c[a] * c[bb] + s[a] * s[bb];
+            A[1 + a][1 + bb] = Mt[mx] * p->L[a] * p->L[bb] * cab;
+            if (bb != a) { const double sab = s[a] * c[bb] - c[a] * s[bb]; rhs_a = rhs_a - Mt[mx] * p->L[a] * p->L[bb] * sab * om[bb] * om[bb]; }
+        }
+        b[1 + a] = rhs_a;
+    }
+    for (int col = 0; col < ND; ++col) {
+        int pivot = col; double best = fabs(A[col][col]);
+        for (int row = col + 1; row < ND; ++row) { const double mag = fabs(A[row][col]); if (mag > best) { best = mag; pivot = row; } }
+        if (best < 1e-15) { p->status = 1; for (int i = 0; i < 2 * ND; ++i) dy[i] = NAN; return; }
+        if (pivot != col) {
+            for (int j = 0; j < ND; ++j) { const double tt = A[col][j]; A[col][j] = A[pivot][j]; A[pivot][j] = tt; }
+            const double tt = b[col]; b[col] = b[pivot]; b[pivot] = tt;
+        }
+        for (int row = col + 1; row < ND; ++row) {
+            const double factor = A[row][col] / A[col][col];
+            for (int j = col; j < ND; ++j) A[row][j] = A[row][j] - factor * A[col][j];
+            b[row] = b[row] - factor * b[col];
+        }
+    }
+    for (int i = ND - 1; i >= 0; --i) {
+        double sum = b[i];
+        for (int j = i + 1; j < ND; ++j) sum = sum - A[i][j] * x[j];
+        x[i] = sum / A[i][i];
+    }
+    for (int i = 0; i < ND; ++i) { dy[i] = y[ND + i]; dy[ND + i] = x[i]; }
+}
+ORC_API int orc_cartn_rk4(int n_links, size_t n, const double* mc, const double* m, const double* L, const double* g,
+                          const double* s0, const double* force, double t0, double t1, double dt, double* final_out, int nthreads) {
+    (void)nthreads;
+    if (n_links < 1 || n_links > ORC_MAXL) return -1;
+    const int dim = 2 * (n_links + 1);
+    for (size_t i = 0; i < n; ++i) {
+        orc_cpn_t p; p.N = n_links; p.mc = mc[i]; p.g = g[i]; p.F = force[i]; p.status = 0;
+        for (int q = 0; q < n_links; ++q) { p.m[q] = m[q * n + i]; p.L[q] = L[q * n + i]; }
+        double y[2 * (ORC_MAXL + 1)], work[10 * (ORC_MAXL + 1)];
+        for (int q = 0; q < dim; ++q) y[q] = s0[q * n + i];
+        orc_rk4(orc_cartn_rhs_fn, &p, (size_t)dim, t0, t1, dt, y, work, NULL, NULL, NULL);
+        for (int q = 0; q < dim; ++q) final_out[q * n + i] = y[q];
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Plugin-path check -- the reference's composition example, physics/coupled_oscillator/: two PointMass
  * (point_mass.hpp:70-84: {v, F/m}), one Spring (spring.hpp:96-131: F1 = -k (x1 - x2 - L0) [+ -c (v1 - v2) when
  * c > 0], F2 = -F1), state [x1, v1, x2, v2].

@@ -6,6 +6,8 @@
 //   T = Dual<double, K>  -> sopot_b200_cartpole_linearize        (K2) + chain rule over the caller's seeds
 #pragma once
 #include <array>
+#include <cmath>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include "../../core/typed_component.hpp"
@@ -28,7 +30,7 @@ public:
                   const std::array<double, NLinks>& link_lengths, double gravity = 9.81,
                   const std::array<double, num_state>& initial_state = {})
         : m_cart_mass(cart_mass), m_mass(link_masses), m_length(link_lengths), m_gravity(gravity),
-          m_initial_state(initial_state), m_name("CartNPendulum") {
+          m_initial_state(initial_state) {
         if (cart_mass <= 0.0) throw std::invalid_argument("Cart mass must be positive");
         for (size_t i = 0; i < NLinks; ++i) {
             if (m_mass[i] <= 0.0) throw std::invalid_argument("All link masses must be positive");
@@ -36,17 +38,88 @@ public:
         }
     }
     // control input: const + mutable exactly like the reference (:70, :117) -- not thread-safe there either
-    void setControlForce(T force) const { m_control_force = force; }
-    T getControlForce() const { return m_control_force; }
+    SOPOT_HD void setControlForce(T force) const { m_control_force = force; }
+    SOPOT_HD T getControlForce() const { return m_control_force; }
 
-    LocalState getInitialLocalState() const {
+    SOPOT_HD LocalState getInitialLocalState() const {
         LocalState s;
         for (size_t i = 0; i < num_state; ++i) s[i] = T(m_initial_state[i]);
         return s;
     }
+    // Euler-Lagrange derivative, any number of links (:143-221 with the Gaussian elimination of :319-359): trig cache,
+    // tail masses, (N+1)x(N+1) mass matrix with cos(a-b) = ca cb + sa sb, partial pivoting on the value.  One link runs
+    // on the tuned kernels through its SystemBinding; N >= 2 (the reference's own tests use N = 2 and N = 6) compiles
+    // into a generic kernel under nvcc.  Every loop has constant bounds and the row exchange is a predicated element
+    // swap, so after unrolling all indices are static (register-resident on the device).  Where the reference throws
+    // "mass matrix is singular" the derivative becomes NaN (device code cannot throw): the ensemble status reports it.
+    template <typename Registry>
+    SOPOT_HD LocalDerivative derivatives(T, std::span<const T> local, std::span<const T>, const Registry&) const {
+        using std::sin; using std::cos; using sopot::sin; using sopot::cos;
+        constexpr size_t ND = num_dof;
+        T s[NLinks], c[NLinks], omega[NLinks];
+        double Mtail[NLinks];
+        for (size_t i = 0; i < NLinks; ++i) {
+            const T theta = local[1 + i];
+            s[i] = sin(theta); c[i] = cos(theta);
+            omega[i] = local[ND + 1 + i];
+            Mtail[i] = tailMass(i);
+        }
+        const T g = T(m_gravity);
+        T A[ND][ND], b[ND];
+        T total = T(m_cart_mass);
+        for (size_t i = 0; i < NLinks; ++i) total = total + T(m_mass[i]);
+        A[0][0] = total;
+        b[0] = m_control_force;
+        for (size_t a = 0; a < NLinks; ++a) {
+            const T coupling = T(Mtail[a]) * T(m_length[a]) * c[a];
+            A[0][1 + a] = coupling; A[1 + a][0] = coupling;
+            b[0] = b[0] + T(Mtail[a]) * T(m_length[a]) * s[a] * omega[a] * omega[a];
+        }
+        for (size_t a = 0; a < NLinks; ++a) {
+            T rhs_a = T(Mtail[a]) * g * T(m_length[a]) * s[a];
+            for (size_t bb = 0; bb < NLinks; ++bb) {
+                const size_t mx = a > bb ? a : bb;
+                A[1 + a][1 + bb] = T(Mtail[mx]) * T(m_length[a]) * T(m_length[bb]) * (c[a] * c[bb] + s[a] * s[bb]);
+                if (bb != a)
+                    rhs_a = rhs_a - T(Mtail[mx]) * T(m_length[a]) * T(m_length[bb]) * (s[a] * c[bb] - c[a] * s[bb]) * omega[bb] * omega[bb];
+            }
+            b[1 + a] = rhs_a;
+        }
+        bool singular = false;
+        for (size_t col = 0; col < ND; ++col) {
+            size_t pivot = col;
+            double best = std::abs(value_of(A[col][col]));
+            for (size_t row = col + 1; row < ND; ++row) {
+                const double mag = std::abs(value_of(A[row][col]));
+                if (mag > best) { best = mag; pivot = row; }
+            }
+            singular = singular || best < 1e-15;
+            for (size_t row = col + 1; row < ND; ++row) {
+                if (row == pivot) {
+                    for (size_t j = 0; j < ND; ++j) { const T tmp = A[col][j]; A[col][j] = A[row][j]; A[row][j] = tmp; }
+                    const T tmp = b[col]; b[col] = b[row]; b[row] = tmp;
+                }
+            }
+            for (size_t row = col + 1; row < ND; ++row) {
+                const T factor = A[row][col] / A[col][col];
+                for (size_t j = col; j < ND; ++j) A[row][j] = A[row][j] - factor * A[col][j];
+                b[row] = b[row] - factor * b[col];
+            }
+        }
+        T x[ND];
+        for (size_t i = ND; i-- > 0;) {
+            T sum = b[i];
+            for (size_t j = i + 1; j < ND; ++j) sum = sum - A[i][j] * x[j];
+            x[i] = sum / A[i][i];
+        }
+        constexpr double kNaN = std::numeric_limits<double>::quiet_NaN();
+        LocalDerivative d;
+        for (size_t i = 0; i < ND; ++i) { d[i] = singular ? T(kNaN) : T(local[ND + i]); d[ND + i] = singular ? T(kNaN) : x[i]; }
+        return d;
+    }
     std::string_view getComponentType() const { return "CartNPendulum"; }
-    std::string_view getComponentName() const { return m_name; }
-    double tailMass(size_t link) const {
+    std::string_view getComponentName() const { return "CartNPendulum"; }
+    SOPOT_HD double tailMass(size_t link) const {
         double sum = 0.0;
         for (size_t i = link; i < NLinks; ++i) sum += m_mass[i];
         return sum;
@@ -108,7 +181,6 @@ private:
     double m_gravity;
     std::array<double, num_state> m_initial_state;
     mutable T m_control_force = T(0.0);
-    std::string m_name;
 };
 
 // SoA parameter block of a cart-pole (N = 1) ensemble for RK4Solver::solveEnsemble

@@ -1,8 +1,11 @@
 // physics::HarmonicOscillator<T> -- m x'' + c x' + k x = 0, state [x, v].
-// Constructor, validation, state functions and factories follow physics/harmonic_oscillator.hpp:44-167;
-// the derivative {v, (-k/m) x - (c/m) v} (:75-85) lives in csrc/ho_dpend.cu (HoSys) and runs on the GPU.
+// Constructor, validation, state functions and factories follow physics/harmonic_oscillator.hpp:44-167.
+// A system made of this component alone runs on the hand-tuned kernel (HoSys, csrc/ho_dpend.cu) through its
+// SystemBinding; the SOPOT_HD derivatives() below ({v, (-k/m) x - (c/m) v}, :75-85) exists so that packs which MIX it
+// with user-defined components compile into a generic kernel (b200/generic_ensemble.cuh).  Nothing calls it on the host.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -20,24 +23,29 @@ public:
     HarmonicOscillator(double mass, double spring_constant, double damping = 0.0, double initial_position = 1.0,
                        double initial_velocity = 0.0, std::string name = "harmonic_oscillator")
         : m_mass(mass), m_k(spring_constant), m_c(damping), m_x0(initial_position), m_v0(initial_velocity),
-          m_omega(std::sqrt(spring_constant / mass)), m_name(std::move(name)) {
+          m_omega(std::sqrt(spring_constant / mass)) {
+        std::strncpy(m_name, name.c_str(), sizeof(m_name) - 1);      // fixed storage: the component stays trivially copyable
         if (mass <= 0.0) throw std::invalid_argument("Mass must be positive");
         if (spring_constant <= 0.0) throw std::invalid_argument("Spring constant must be positive");
         if (damping < 0.0) throw std::invalid_argument("Damping must be non-negative");
     }
-    LocalState getInitialLocalState() const { return {T(m_x0), T(m_v0)}; }
+    SOPOT_HD LocalState getInitialLocalState() const { return {T(m_x0), T(m_v0)}; }
+    template <typename Registry>
+    SOPOT_HD LocalDerivative derivatives(T, std::span<const T> local, std::span<const T>, const Registry&) const {
+        return {local[1], T(-m_k / m_mass) * local[0] - T(m_c / m_mass) * local[1]};
+    }
     std::string_view getComponentType() const { return "HarmonicOscillator"; }
     std::string_view getComponentName() const { return m_name; }
 
-    T compute(kinematics::Position, std::span<const T> s) const { return this->getGlobalState(s, 0); }
-    T compute(kinematics::Velocity, std::span<const T> s) const { return this->getGlobalState(s, 1); }
-    T compute(kinematics::Acceleration, std::span<const T> s) const {
+    SOPOT_HD T compute(kinematics::Position, std::span<const T> s) const { return this->getGlobalState(s, 0); }
+    SOPOT_HD T compute(kinematics::Velocity, std::span<const T> s) const { return this->getGlobalState(s, 1); }
+    SOPOT_HD T compute(kinematics::Acceleration, std::span<const T> s) const {
         return T(-m_k / m_mass) * this->getGlobalState(s, 0) - T(m_c / m_mass) * this->getGlobalState(s, 1);
     }
-    T compute(energy::Kinetic, std::span<const T> s) const { const T v = this->getGlobalState(s, 1); return T(0.5 * m_mass) * v * v; }
-    T compute(energy::Potential, std::span<const T> s) const { const T x = this->getGlobalState(s, 0); return T(0.5 * m_k) * x * x; }
-    T compute(energy::Total, std::span<const T> s) const { return compute(energy::Kinetic{}, s) + compute(energy::Potential{}, s); }
-    T compute(dynamics::Mass, std::span<const T>) const { return T(m_mass); }
+    SOPOT_HD T compute(energy::Kinetic, std::span<const T> s) const { const T v = this->getGlobalState(s, 1); return T(0.5 * m_mass) * v * v; }
+    SOPOT_HD T compute(energy::Potential, std::span<const T> s) const { const T x = this->getGlobalState(s, 0); return T(0.5 * m_k) * x * x; }
+    SOPOT_HD T compute(energy::Total, std::span<const T> s) const { return compute(energy::Kinetic{}, s) + compute(energy::Potential{}, s); }
+    SOPOT_HD T compute(dynamics::Mass, std::span<const T>) const { return T(m_mass); }
 
     double getMass() const noexcept { return m_mass; }
     double getSpringConstant() const noexcept { return m_k; }
@@ -53,7 +61,7 @@ public:
     }
 private:
     double m_mass, m_k, m_c, m_x0, m_v0, m_omega;
-    std::string m_name;
+    char m_name[24] = {};
 };
 
 template <Scalar T = double>

@@ -26,40 +26,55 @@ public:
         };
         need(mass1, "Mass 1"); need(mass2, "Mass 2"); need(length1, "Length 1"); need(length2, "Length 2");
     }
-    LocalState getInitialLocalState() const { return {T(m_ic[0]), T(m_ic[1]), T(m_ic[2]), T(m_ic[3])}; }
+    SOPOT_HD LocalState getInitialLocalState() const { return {T(m_ic[0]), T(m_ic[1]), T(m_ic[2]), T(m_ic[3])}; }
+    // :126-179, for packs that mix this component with user-defined ones (generic kernel); the single-component
+    // system runs on the tuned DpendSys kernel through its SystemBinding
+    template <typename Registry>
+    SOPOT_HD LocalDerivative derivatives(T, std::span<const T> local, std::span<const T>, const Registry&) const {
+        using std::sin; using std::cos; using sopot::sin; using sopot::cos;
+        const T th1 = local[0], th2 = local[1], w1 = local[2], w2 = local[3];
+        const T delta = th1 - th2;
+        const T sd = sin(delta), cd = cos(delta), s1 = sin(th1), s2 = sin(th2);
+        const T m1(m_m1), m2(m_m2), L1(m_L1), L2(m_L2), g(m_g);
+        const T a11 = (m1 + m2) * L1, a12 = m2 * L2 * cd, a21 = L1 * cd, a22 = L2;
+        const T b1 = m2 * L2 * w2 * w2 * sd - (m1 + m2) * g * s1;
+        const T b2 = -L1 * w1 * w1 * sd - g * s2;
+        const T det = a11 * a22 - a12 * a21;
+        return {w1, w2, (b1 * a22 - b2 * a12) / det, (a11 * b2 - a21 * b1) / det};
+    }
     std::string_view getComponentType() const { return "DoublePendulum"; }
     std::string_view getComponentName() const { return "DoublePendulum"; }
 
-    T compute(mass1::Angle, std::span<const T> s) const { return this->getGlobalState(s, 0); }
-    T compute(mass1::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 2); }
-    T compute(mass2::Angle, std::span<const T> s) const { return this->getGlobalState(s, 1); }
-    T compute(mass2::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 3); }
-    T compute(mass1::Mass, std::span<const T>) const { return T(m_m1); }
-    T compute(mass2::Mass, std::span<const T>) const { return T(m_m2); }
-    T compute(system::Length1, std::span<const T>) const { return T(m_L1); }
-    T compute(system::Length2, std::span<const T>) const { return T(m_L2); }
-    std::array<T, 2> compute(mass1::CartesianPosition, std::span<const T> s) const {
+    SOPOT_HD T compute(mass1::Angle, std::span<const T> s) const { return this->getGlobalState(s, 0); }
+    SOPOT_HD T compute(mass1::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 2); }
+    SOPOT_HD T compute(mass2::Angle, std::span<const T> s) const { return this->getGlobalState(s, 1); }
+    SOPOT_HD T compute(mass2::AngularVelocity, std::span<const T> s) const { return this->getGlobalState(s, 3); }
+    SOPOT_HD T compute(mass1::Mass, std::span<const T>) const { return T(m_m1); }
+    SOPOT_HD T compute(mass2::Mass, std::span<const T>) const { return T(m_m2); }
+    SOPOT_HD T compute(system::Length1, std::span<const T>) const { return T(m_L1); }
+    SOPOT_HD T compute(system::Length2, std::span<const T>) const { return T(m_L2); }
+    SOPOT_HD std::array<T, 2> compute(mass1::CartesianPosition, std::span<const T> s) const {
         using std::sin; using std::cos;
         const T th1 = this->getGlobalState(s, 0);
         return {T(m_L1) * sin(th1), -T(m_L1) * cos(th1)};
     }
-    std::array<T, 2> compute(mass1::CartesianVelocity, std::span<const T> s) const {
+    SOPOT_HD std::array<T, 2> compute(mass1::CartesianVelocity, std::span<const T> s) const {
         using std::sin; using std::cos;
         const T th1 = this->getGlobalState(s, 0), w1 = this->getGlobalState(s, 2);
         return {T(m_L1) * cos(th1) * w1, T(m_L1) * sin(th1) * w1};
     }
-    std::array<T, 2> compute(mass2::CartesianPosition, std::span<const T> s) const {
+    SOPOT_HD std::array<T, 2> compute(mass2::CartesianPosition, std::span<const T> s) const {
         using std::sin; using std::cos;
         const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
         return {T(m_L1) * sin(th1) + T(m_L2) * sin(th2), -T(m_L1) * cos(th1) - T(m_L2) * cos(th2)};
     }
-    std::array<T, 2> compute(mass2::CartesianVelocity, std::span<const T> s) const {
+    SOPOT_HD std::array<T, 2> compute(mass2::CartesianVelocity, std::span<const T> s) const {
         using std::sin; using std::cos;
         const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
         const T w1 = this->getGlobalState(s, 2), w2 = this->getGlobalState(s, 3);
         return {T(m_L1) * cos(th1) * w1 + T(m_L2) * cos(th2) * w2, T(m_L1) * sin(th1) * w1 + T(m_L2) * sin(th2) * w2};
     }
-    T compute(system::KineticEnergy, std::span<const T> s) const {
+    SOPOT_HD T compute(system::KineticEnergy, std::span<const T> s) const {
         using std::cos;
         const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
         const T w1 = this->getGlobalState(s, 2), w2 = this->getGlobalState(s, 3);
@@ -68,12 +83,12 @@ public:
         const T v2 = L1 * L1 * w1 * w1 + L2 * L2 * w2 * w2 + T(2.0) * L1 * L2 * w1 * w2 * cos(th1 - th2);
         return T(0.5) * T(m_m1) * v1 + T(0.5) * T(m_m2) * v2;
     }
-    T compute(system::PotentialEnergy, std::span<const T> s) const {
+    SOPOT_HD T compute(system::PotentialEnergy, std::span<const T> s) const {
         using std::cos;
         const T th1 = this->getGlobalState(s, 0), th2 = this->getGlobalState(s, 1);
         return -T(m_g) * ((T(m_m1) + T(m_m2)) * T(m_L1) * cos(th1) + T(m_m2) * T(m_L2) * cos(th2));
     }
-    T compute(system::TotalEnergy, std::span<const T> s) const {
+    SOPOT_HD T compute(system::TotalEnergy, std::span<const T> s) const {
         return compute(system::KineticEnergy{}, s) + compute(system::PotentialEnergy{}, s);
     }
     double getMass1() const { return m_m1; }

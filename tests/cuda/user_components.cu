@@ -13,6 +13,9 @@
 #include <cmath>
 #include <sopot/core/solver.hpp>
 #include <sopot/core/typed_component.hpp>
+#include <sopot/physics/control/cart_n_pendulum.hpp>
+#include <sopot/physics/harmonic_oscillator.hpp>
+#include <sopot/physics/pendulum/double_pendulum.hpp>
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "%s:%d CHECK FAILED: %s\n", __FILE__, __LINE__, #c); std::abort(); } } while (0)
 
@@ -164,6 +167,56 @@ int main() {
         CHECK(ens.status[i] == 0);
     }
     cudaFree(dk); cudaFree(dc);
+
+    // 3. shipped components inside a larger pack: HarmonicOscillator + DoublePendulum side by side (6 states) -- no
+    //    tuned kernel exists for this pack, nvcc instantiates the generic one; each part evolves as it does alone
+    {
+        const double pi = 3.14159265358979323846;
+        auto pack = makeTypedODESystem<double>(physics::createDampedOscillator<double>(2.0, 9.0, 0.1, 1.5),
+                                               pendulum::DoublePendulum<double>(1.0, 1.0, 1.0, 1.0, 9.81, pi / 4, pi / 6, 0.0, 0.0));
+        static_assert(!decltype(pack)::Binding::available && decltype(pack)::device_integrable);
+        CHECK(pack.getStateDimension() == 6);
+        auto rp = createRK4Solver().solve(pack, 0.0, 10.0, 0.01);
+        CHECK(rp.size() == 1001);
+        auto ho = makeTypedODESystem<double>(physics::createDampedOscillator<double>(2.0, 9.0, 0.1, 1.5));   // tuned kernel, strict
+        auto rh = createRK4Solver().solve(ho, 0.0, 10.0, 0.01);
+        for (int j = 0; j < 2; ++j) {
+#ifdef SOPOT_TEST_STRICT
+            CHECK(rp.states.back()[j] == rh.states.back()[j]);             // == the reference's -0.8212904505639914, -1.741913057783819
+#else
+            CHECK(std::abs(rp.states.back()[j] - rh.states.back()[j]) <= 1e-12 * 2.0);
+#endif
+        }
+        auto dp = makeTypedODESystem<double>(pendulum::DoublePendulum<double>(1.0, 1.0, 1.0, 1.0, 9.81, pi / 4, pi / 6, 0.0, 0.0));
+        auto rd = createRK4Solver().solve(dp, 0.0, 10.0, 0.01);
+        for (int j = 0; j < 4; ++j) CHECK(std::abs(rp.states.back()[2 + j] - rd.states.back()[j]) <= 1e-9 * 10.0);
+        CHECK(pack.computeStateFunction<energy::Total>(rp.states.back()) > 0.0);          // oscillator's tag, found in the pack
+        CHECK(std::isfinite(pack.computeStateFunction<pendulum::system::TotalEnergy>(rp.states.back())));
+    }
+
+    // 4. N-link cart pendulum (the reference's tests use N = 2 and N = 6): generic kernel, constant force; known answers
+    //    from the unmodified reference (oracle/ref_harness.cpp, 0..0.5 s, dt = 1e-3)
+    {
+        control::CartNPendulum<2, double> p2(1.0, {0.1, 0.2}, {0.5, 0.3}, 9.81, {0.0, -0.03, -0.06, 0.0, 0.0, 0.0});
+        p2.setControlForce(0.4);
+        auto s2 = makeTypedODESystem<double>(control::CartNPendulum<2, double>(p2));    // (lvalues are rejected, as in the reference)
+        static_assert(!decltype(s2)::Binding::available && decltype(s2)::device_integrable);
+        auto r2 = createRK4Solver().solve(s2, 0.0, 0.5, 0.001);
+        const double ref2[6] = {0.05772152317547522, 0.1607029210223462, -1.260629618377168, 0.21007074548257548, 0.37351030122614226, -7.011211112024978};
+        for (int j = 0; j < 6; ++j) CHECK(std::abs(r2.states.back()[j] - ref2[j]) <= 1e-10 * 8.0);
+        control::CartNPendulum<6, double> p6(1.0, {0.1, 0.12000000000000001, 0.14, 0.16, 0.18, 0.2},
+                                             {0.5, 0.46, 0.42, 0.38, 0.33999999999999997, 0.3}, 9.81,
+                                             {0.0, -0.03, -0.06, -0.09, -0.12, -0.15, -0.18, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0});
+        p6.setControlForce(0.4);
+        auto s6 = makeTypedODESystem<double>(control::CartNPendulum<6, double>(p6));
+        auto r6 = createRK4Solver().solve(s6, 0.0, 0.5, 0.001);
+        const double ref6[14] = {0.04636578083826137, 0.8964738324552634, -1.288132050948551, -0.15209224959668097, -0.26008585952299235,
+                                 -0.2880802460174711, -0.327630208430215, 0.1396841594166301, 3.034633113175984, -4.439563119100859,
+                                 -1.2399832070583412, -0.25932876407463595, -0.33246554222609737, -0.3465573887257405};
+        for (int j = 0; j < 14; ++j) CHECK(std::abs(r6.states.back()[j] - ref6[j]) <= 1e-9 * 5.0);
+        // energy bookkeeping of the plant's own state queries on the device-integrated trajectory
+        CHECK(std::isfinite(p6.totalEnergy(std::span<const double>(r6.states.back()))));
+    }
     std::puts("user_components: OK");
     return 0;
 }
