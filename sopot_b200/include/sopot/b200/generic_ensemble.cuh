@@ -16,8 +16,9 @@
 // rounding level, <= 1e-12 relative per step); -fmad=false evaluates every operation separately and reproduces the
 // reference's g++ -O3 result bit for bit wherever the components use + - * / sqrt only.
 //
-// Per-instance parameters come from a FACTORY: a trivially copyable functor with
-//     __device__ System operator()(size_t i) const
+// Per-instance parameters come from a FACTORY: a functor passed to the kernel by value with
+//     SOPOT_HD System operator()(size_t i) const      (__device__ alone works when the return type is spelled out:
+//                                                      nvcc's host pass cannot deduce `auto` of a __device__ function)
 // that builds the i-th system (typically from device arrays it holds pointers to).  The integration starts from the
 // components' own initial states unless an explicit y0 array is given.
 #pragma once

@@ -26,16 +26,18 @@ public:
     using typename Base::LocalState;
     using typename Base::LocalDerivative;
 
-    CartNPendulum(double cart_mass, const std::array<double, NLinks>& link_masses,
-                  const std::array<double, NLinks>& link_lengths, double gravity = 9.81,
-                  const std::array<double, num_state>& initial_state = {})
+    SOPOT_HD CartNPendulum(double cart_mass, const std::array<double, NLinks>& link_masses,
+                           const std::array<double, NLinks>& link_lengths, double gravity = 9.81,
+                           const std::array<double, num_state>& initial_state = {})
         : m_cart_mass(cart_mass), m_mass(link_masses), m_length(link_lengths), m_gravity(gravity),
           m_initial_state(initial_state) {
+#ifndef __CUDA_ARCH__        // validation throws on the host (reference :99-110); device factories skip it
         if (cart_mass <= 0.0) throw std::invalid_argument("Cart mass must be positive");
         for (size_t i = 0; i < NLinks; ++i) {
             if (m_mass[i] <= 0.0) throw std::invalid_argument("All link masses must be positive");
             if (m_length[i] <= 0.0) throw std::invalid_argument("All link lengths must be positive");
         }
+#endif
     }
     // control input: const + mutable exactly like the reference (:70, :117) -- not thread-safe there either
     SOPOT_HD void setControlForce(T force) const { m_control_force = force; }

@@ -18,13 +18,17 @@ public:
     using typename Base::LocalState;
     using typename Base::LocalDerivative;
 
-    explicit DoublePendulum(double mass1, double mass2, double length1, double length2, double gravity = 9.81,
-                            double theta1_0 = 0.0, double theta2_0 = 0.0, double omega1_0 = 0.0, double omega2_0 = 0.0)
+    // SOPOT_HD so that a device factory can build per-instance pendulums; argument validation (std::invalid_argument,
+    // reference :86-97) happens on the host side only -- device code cannot throw
+    SOPOT_HD explicit DoublePendulum(double mass1, double mass2, double length1, double length2, double gravity = 9.81,
+                                     double theta1_0 = 0.0, double theta2_0 = 0.0, double omega1_0 = 0.0, double omega2_0 = 0.0)
         : m_m1(mass1), m_m2(mass2), m_L1(length1), m_L2(length2), m_g(gravity), m_ic{theta1_0, theta2_0, omega1_0, omega2_0} {
+#ifndef __CUDA_ARCH__
         auto need = [](double v, const char* what) {
             if (v <= 0.0) throw std::invalid_argument(std::string(what) + " must be positive (got " + std::to_string(v) + ")");
         };
         need(mass1, "Mass 1"); need(mass2, "Mass 2"); need(length1, "Length 1"); need(length2, "Length 2");
+#endif
     }
     SOPOT_HD LocalState getInitialLocalState() const { return {T(m_ic[0]), T(m_ic[1]), T(m_ic[2]), T(m_ic[3])}; }
     // :126-179, for packs that mix this component with user-defined ones (generic kernel); the single-component
@@ -98,7 +102,7 @@ public:
     double getGravity() const { return m_g; }
 private:
     double m_m1, m_m2, m_L1, m_L2, m_g;
-    std::array<double, 4> m_ic;
+    double m_ic[4];
 };
 
 struct DoublePendulumEnsemble {
