@@ -40,10 +40,13 @@ N_PER_GPU = 1 << 22
 N_STEPS = 10000
 DT = 1e-3
 FLOP_PER_INSTANCE_STEP = 204.0
-# FP64 issue cycles per warp and instance-step of rk4_ensemble_kernel<DpendSys,false>, from the kernel's own
-# instruction inventory: ~240 FP64 instructions at 2 cycles + ~50 three-register DFMAs at
-# one extra cycle (profiles/r1_fp64_operand_rule.txt).  Used for roofline.fp64_issue_frac only.
-FP64_ISSUE_CYCLES_PER_STEP = 2.0 * 240 + 50
+# From the ncu --set full capture of this very command (profiles/r1_final_dpend_bench.txt, one launch = 4 Mi x 10 000):
+#   226 FP64-pipe instructions per instance-step (142 DFMA, 80 DMUL, 4 DADD) at 2 issue cycles each, FP64 pipe 85.2 %
+#   busy; the remaining issue cycles are three-register DFMAs at 3 cycles (profiles/r1_fp64_operand_rule.txt): ~79.
+#   DRAM traffic per launch 320.8 MB read + 113.0 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
+FP64_INSTR_PER_STEP = 226.0
+FP64_ISSUE_CYCLES_PER_STEP = 2.0 * FP64_INSTR_PER_STEP + 79.0
+NCU_DRAM_BYTES_PER_LAUNCH_4MI = 320796672 + 113023744
 METRIC = "RK4 instance-steps/s (FP64)"
 UNIT = "instance-steps/s"
 
@@ -359,7 +362,11 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, same command); only valid
+                         # for the BASELINE batch size the capture was taken at
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_4MI if n == N_PER_GPU else None,
+                         "fp64_instr_per_unit": FP64_INSTR_PER_STEP,
                          "kernel": "rk4_ensemble_kernel<DpendSys,false>", "kernel_ms": kernel_ms,
                          "flop_per_unit": FLOP_PER_INSTANCE_STEP,
                          # share of the FP64 pipe's issue cycles the kernel's own instructions need at this rate

@@ -41,12 +41,21 @@ elif cfg == "rocket":
     for _ in range(reps):
         eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, 600, mem=MEM_DEVICE, want_status=False,
                        state_out=st, stats_out=stats)
+elif cfg == "lqr":
+    P = 1 << 14
+    rng = np.random.default_rng(3)
+    A, B, _ = eng.cartpole_linearize(eng.to_device(rng.uniform(0.8, 1.5, P)), eng.to_device(rng.uniform(0.05, 0.2, P)),
+                                     eng.to_device(rng.uniform(0.4, 0.8, P)), eng.to_device(np.full(P, 9.81)),
+                                     eng.to_device(np.zeros((4, P))), eng.to_device(np.zeros(P)), P, mem=MEM_DEVICE, want_status=False)
+    for _ in range(reps):
+        eng.lqr4_gain(A, B, P, np.diag([10.0, 100.0, 1.0, 10.0]), 0.01, mem=MEM_DEVICE, fp_mode=FP_CONTRACT)
 elif cfg in ("grid", "grid_strict"):
     p = W.GRID2D_PARAMS
     n = 8192
     gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
     state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
-    eng.grid2d_rk4(gp, p["dt"], reps, state, fp_mode=FP_STRICT if cfg == "grid_strict" else FP_CONTRACT)
+    eng.grid2d_rk4(gp, p["dt"], reps, state, fp_mode=FP_STRICT if cfg == "grid_strict" else FP_CONTRACT,
+                   per_stage=len(sys.argv) > 3 and sys.argv[3] == "per_stage")
 else:
     raise SystemExit("unknown config " + cfg)
 eng.sync()
