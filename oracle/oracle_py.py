@@ -157,6 +157,19 @@ class Checker:
             raise KeyError("link count not instantiated")
         return fin
 
+    def cartn_linearize(self, n_links, mc, m, L, g, x, u, nthreads=1):
+        """makeLinearizer<2(N+1),1> around CartNPendulum<N,Dual>: A [(2N+2)^2][P], B [2N+2][P] (reference only)."""
+        assert self.kind == "reference"
+        x = _f64(x); P = x.shape[1]; ns = 2 * (n_links + 1)
+        m, L = _f64(m).reshape(n_links, P), _f64(L).reshape(n_links, P)
+        mc, g, u = (_f64(a, P).reshape(-1) for a in (mc, g, u))
+        A = np.empty((ns * ns, P)); B = np.empty((ns, P))
+        rc = self._fn("cartn_linearize", [_i, _sz] + [_dp] * 8 + [_i])(n_links, P, _p(mc), _p(m), _p(L), _p(g), _p(x), _p(u),
+                                                                       _p(A), _p(B), nthreads)
+        if rc:
+            raise KeyError("link count not instantiated")
+        return A, B
+
     # ---------------- plugin-path check: coupled oscillator ----------------
     def coupled_rk4(self, m1, m2, k, L0, c, x1, x2, t0, t1, dt, nthreads=1):
         k = _f64(k).reshape(-1); n = k.size

@@ -274,6 +274,49 @@ int ref_cartn_rk4(int n_links, size_t n, const double* mc, const double* m /*[N]
     return 0;
 }
 
+// N-link linearization: makeLinearizer<2(N+1),1> around CartNPendulum<N, Dual<double, 2N+3>> (the pattern of
+// ref_cartpole_linearize), A [(2N+2)^2][P], B [2N+2][P]
+extern "C++" {
+template <size_t NL>
+static void cartn_lin_one(const double* mc, const double* m, const double* L, const double* g, const double* x, const double* u,
+                          size_t P, size_t p, double* A, double* B) {
+    constexpr size_t NS = 2 * (NL + 1);
+    using Lin = SystemLinearizer<NS, 1>;
+    using D = typename Lin::DualT;
+    std::array<double, NL> mm, LL;
+    for (size_t q = 0; q < NL; ++q) { mm[q] = m[q * P + p]; LL[q] = L[q * P + p]; }
+    control::CartNPendulum<NL, D> plant(mc[p], mm, LL, g[p]);
+    auto sys = makeTypedODESystem<D>(std::move(plant));
+    auto lin = makeLinearizer<NS, 1>([&sys](D t, const typename Lin::DualState& xs, const typename Lin::DualInput& us) {
+        sys.template getComponent<0>().setControlForce(us[0]);
+        std::vector<D> sv(xs.begin(), xs.end());
+        auto d = sys.computeDerivatives(t, sv);
+        typename Lin::DualDerivative out;
+        for (size_t i = 0; i < NS; ++i) out[i] = d[i];
+        return out;
+    });
+    Vector<NS> x0;
+    for (size_t i = 0; i < NS; ++i) x0[i] = x[i * P + p];
+    auto r = lin.linearize(0.0, x0, {u[p]});
+    for (size_t i = 0; i < NS; ++i) {
+        for (size_t j = 0; j < NS; ++j) A[(i * NS + j) * P + p] = r.A[i][j];
+        B[i * P + p] = r.B[i][0];
+    }
+}
+}  // extern "C++"
+int ref_cartn_linearize(int n_links, size_t P, const double* mc, const double* m, const double* L, const double* g,
+                        const double* x, const double* u, double* A, double* B, int nthreads) {
+    if (n_links != 1 && n_links != 2 && n_links != 6) return -1;
+    parallel_for(P, nthreads, [&](size_t p) {
+        switch (n_links) {
+            case 1: cartn_lin_one<1>(mc, m, L, g, x, u, P, p, A, B); break;
+            case 2: cartn_lin_one<2>(mc, m, L, g, x, u, P, p, A, B); break;
+            default: cartn_lin_one<6>(mc, m, L, g, x, u, P, p, A, B); break;
+        }
+    });
+    return 0;
+}
+
 // ---- config 4: 6-DOF rocket ----
 // The 11 components of Rocket<T>::SystemType (rocket/rocket.hpp:73-85) composed by hand so
 // that gravity can be jittered (Rocket<T> has no gravity setter). Tables reach the reference

@@ -8,6 +8,7 @@
 #include <cstddef>
 #include <ostream>
 #include <type_traits>
+#include "macros.hpp"
 
 namespace sopot {
 
@@ -88,36 +89,36 @@ template <typename T, size_t N> constexpr Dual<T, N> operator*(T s, const Dual<T
 template <typename T, size_t N> constexpr Dual<T, N> operator/(T s, const Dual<T, N>& d) noexcept { return Dual<T, N>::constant(s) / d; }
 
 // chain rule: f(u) with scalar factor f'(u)
-template <typename T, size_t N> Dual<T, N> dual_chain(const Dual<T, N>& x, T value, T factor) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> dual_chain(const Dual<T, N>& x, T value, T factor) {
     return Dual<T, N>::make(value, [&](size_t i) { return factor * x.derivative(i); });
 }
-template <typename T, size_t N> Dual<T, N> sin(const Dual<T, N>& x) { return dual_chain(x, std::sin(x.value()), std::cos(x.value())); }
-template <typename T, size_t N> Dual<T, N> cos(const Dual<T, N>& x) { return dual_chain(x, std::cos(x.value()), -std::sin(x.value())); }
-template <typename T, size_t N> Dual<T, N> tan(const Dual<T, N>& x) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> sin(const Dual<T, N>& x) { return dual_chain(x, std::sin(x.value()), std::cos(x.value())); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> cos(const Dual<T, N>& x) { return dual_chain(x, std::cos(x.value()), -std::sin(x.value())); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> tan(const Dual<T, N>& x) {
     const T c = std::cos(x.value());
     return dual_chain(x, std::tan(x.value()), T{1} / (c * c));
 }
-template <typename T, size_t N> Dual<T, N> asin(const Dual<T, N>& x) { return dual_chain(x, std::asin(x.value()), T{1} / std::sqrt(T{1} - x.value() * x.value())); }
-template <typename T, size_t N> Dual<T, N> acos(const Dual<T, N>& x) { return dual_chain(x, std::acos(x.value()), T{-1} / std::sqrt(T{1} - x.value() * x.value())); }
-template <typename T, size_t N> Dual<T, N> atan(const Dual<T, N>& x) { return dual_chain(x, std::atan(x.value()), T{1} / (T{1} + x.value() * x.value())); }
-template <typename T, size_t N> Dual<T, N> atan2(const Dual<T, N>& y, const Dual<T, N>& x) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> asin(const Dual<T, N>& x) { return dual_chain(x, std::asin(x.value()), T{1} / std::sqrt(T{1} - x.value() * x.value())); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> acos(const Dual<T, N>& x) { return dual_chain(x, std::acos(x.value()), T{-1} / std::sqrt(T{1} - x.value() * x.value())); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> atan(const Dual<T, N>& x) { return dual_chain(x, std::atan(x.value()), T{1} / (T{1} + x.value() * x.value())); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> atan2(const Dual<T, N>& y, const Dual<T, N>& x) {
     const T inv = T{1} / (x.value() * x.value() + y.value() * y.value());
     return Dual<T, N>::make(std::atan2(y.value(), x.value()),
                             [&](size_t i) { return (x.value() * y.derivative(i) - y.value() * x.derivative(i)) * inv; });
 }
-template <typename T, size_t N> Dual<T, N> exp(const Dual<T, N>& x) { const T e = std::exp(x.value()); return dual_chain(x, e, e); }
-template <typename T, size_t N> Dual<T, N> log(const Dual<T, N>& x) { return dual_chain(x, std::log(x.value()), T{1} / x.value()); }
-template <typename T, size_t N> Dual<T, N> sqrt(const Dual<T, N>& x) { const T s = std::sqrt(x.value()); return dual_chain(x, s, T{0.5} / s); }
-template <typename T, size_t N> Dual<T, N> abs(const Dual<T, N>& x) { return dual_chain(x, std::abs(x.value()), x.value() >= T{0} ? T{1} : T{-1}); }
-template <typename T, size_t N> Dual<T, N> tanh(const Dual<T, N>& x) { const T t = std::tanh(x.value()); return dual_chain(x, t, T{1} - t * t); }
-template <typename T, size_t N> Dual<T, N> pow(const Dual<T, N>& b, T e) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> exp(const Dual<T, N>& x) { const T e = std::exp(x.value()); return dual_chain(x, e, e); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> log(const Dual<T, N>& x) { return dual_chain(x, std::log(x.value()), T{1} / x.value()); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> sqrt(const Dual<T, N>& x) { const T s = std::sqrt(x.value()); return dual_chain(x, s, T{0.5} / s); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> abs(const Dual<T, N>& x) { return dual_chain(x, std::abs(x.value()), x.value() >= T{0} ? T{1} : T{-1}); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> tanh(const Dual<T, N>& x) { const T t = std::tanh(x.value()); return dual_chain(x, t, T{1} - t * t); }
+template <typename T, size_t N> SOPOT_HD Dual<T, N> pow(const Dual<T, N>& b, T e) {
     return dual_chain(b, std::pow(b.value(), e), e * std::pow(b.value(), e - T{1}));
 }
-template <typename T, size_t N> Dual<T, N> pow(const Dual<T, N>& b, const Dual<T, N>& e) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> pow(const Dual<T, N>& b, const Dual<T, N>& e) {
     const T p = std::pow(b.value(), e.value()), lb = std::log(b.value()), ib = T{1} / b.value();
     return Dual<T, N>::make(p, [&](size_t i) { return p * (e.derivative(i) * lb + e.value() * b.derivative(i) * ib); });
 }
-template <typename T, size_t N> Dual<T, N> sign(const Dual<T, N>& x) {
+template <typename T, size_t N> SOPOT_HD Dual<T, N> sign(const Dual<T, N>& x) {
     return Dual<T, N>((x.value() > T{0}) ? T{1} : ((x.value() < T{0}) ? T{-1} : T{0}));
 }
 template <typename T, size_t N> std::ostream& operator<<(std::ostream& os, const Dual<T, N>& d) {

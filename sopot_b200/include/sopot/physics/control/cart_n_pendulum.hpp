@@ -60,7 +60,7 @@ public:
         constexpr size_t ND = num_dof;
         T s[NLinks], c[NLinks], omega[NLinks];
         double Mtail[NLinks];
-        for (size_t i = 0; i < NLinks; ++i) {
+        SOPOT_UNROLL for (size_t i = 0; i < NLinks; ++i) {
             const T theta = local[1 + i];
             s[i] = sin(theta); c[i] = cos(theta);
             omega[i] = local[ND + 1 + i];
@@ -69,17 +69,17 @@ public:
         const T g = T(m_gravity);
         T A[ND][ND], b[ND];
         T total = T(m_cart_mass);
-        for (size_t i = 0; i < NLinks; ++i) total = total + T(m_mass[i]);
+        SOPOT_UNROLL for (size_t i = 0; i < NLinks; ++i) total = total + T(m_mass[i]);
         A[0][0] = total;
         b[0] = m_control_force;
-        for (size_t a = 0; a < NLinks; ++a) {
+        SOPOT_UNROLL for (size_t a = 0; a < NLinks; ++a) {
             const T coupling = T(Mtail[a]) * T(m_length[a]) * c[a];
             A[0][1 + a] = coupling; A[1 + a][0] = coupling;
             b[0] = b[0] + T(Mtail[a]) * T(m_length[a]) * s[a] * omega[a] * omega[a];
         }
-        for (size_t a = 0; a < NLinks; ++a) {
+        SOPOT_UNROLL for (size_t a = 0; a < NLinks; ++a) {
             T rhs_a = T(Mtail[a]) * g * T(m_length[a]) * s[a];
-            for (size_t bb = 0; bb < NLinks; ++bb) {
+            SOPOT_UNROLL for (size_t bb = 0; bb < NLinks; ++bb) {
                 const size_t mx = a > bb ? a : bb;
                 A[1 + a][1 + bb] = T(Mtail[mx]) * T(m_length[a]) * T(m_length[bb]) * (c[a] * c[bb] + s[a] * s[bb]);
                 if (bb != a)
@@ -88,42 +88,42 @@ public:
             b[1 + a] = rhs_a;
         }
         bool singular = false;
-        for (size_t col = 0; col < ND; ++col) {
+        SOPOT_UNROLL for (size_t col = 0; col < ND; ++col) {
             size_t pivot = col;
             double best = std::abs(value_of(A[col][col]));
-            for (size_t row = col + 1; row < ND; ++row) {
+            SOPOT_UNROLL for (size_t row = col + 1; row < ND; ++row) {
                 const double mag = std::abs(value_of(A[row][col]));
                 if (mag > best) { best = mag; pivot = row; }
             }
             singular = singular || best < 1e-15;
-            for (size_t row = col + 1; row < ND; ++row) {
+            SOPOT_UNROLL for (size_t row = col + 1; row < ND; ++row) {
                 if (row == pivot) {
-                    for (size_t j = 0; j < ND; ++j) { const T tmp = A[col][j]; A[col][j] = A[row][j]; A[row][j] = tmp; }
+                    SOPOT_UNROLL for (size_t j = 0; j < ND; ++j) { const T tmp = A[col][j]; A[col][j] = A[row][j]; A[row][j] = tmp; }
                     const T tmp = b[col]; b[col] = b[row]; b[row] = tmp;
                 }
             }
-            for (size_t row = col + 1; row < ND; ++row) {
+            SOPOT_UNROLL for (size_t row = col + 1; row < ND; ++row) {
                 const T factor = A[row][col] / A[col][col];
-                for (size_t j = col; j < ND; ++j) A[row][j] = A[row][j] - factor * A[col][j];
+                SOPOT_UNROLL for (size_t j = col; j < ND; ++j) A[row][j] = A[row][j] - factor * A[col][j];
                 b[row] = b[row] - factor * b[col];
             }
         }
         T x[ND];
-        for (size_t i = ND; i-- > 0;) {
+        SOPOT_UNROLL for (size_t i = ND; i-- > 0;) {
             T sum = b[i];
-            for (size_t j = i + 1; j < ND; ++j) sum = sum - A[i][j] * x[j];
+            SOPOT_UNROLL for (size_t j = i + 1; j < ND; ++j) sum = sum - A[i][j] * x[j];
             x[i] = sum / A[i][i];
         }
         constexpr double kNaN = std::numeric_limits<double>::quiet_NaN();
         LocalDerivative d;
-        for (size_t i = 0; i < ND; ++i) { d[i] = singular ? T(kNaN) : T(local[ND + i]); d[ND + i] = singular ? T(kNaN) : x[i]; }
+        SOPOT_UNROLL for (size_t i = 0; i < ND; ++i) { d[i] = singular ? T(kNaN) : T(local[ND + i]); d[ND + i] = singular ? T(kNaN) : x[i]; }
         return d;
     }
     std::string_view getComponentType() const { return "CartNPendulum"; }
     std::string_view getComponentName() const { return "CartNPendulum"; }
     SOPOT_HD double tailMass(size_t link) const {
         double sum = 0.0;
-        for (size_t i = link; i < NLinks; ++i) sum += m_mass[i];
+        SOPOT_UNROLL for (size_t i = 0; i < NLinks; ++i) if (i >= link) sum += m_mass[i];    // (same order, constant bounds)
         return sum;
     }
 

@@ -88,6 +88,7 @@ def main():
     out["g3x3t0_degenerate_rhs"] = R.grid2d_rhs(3, 3, 0, 1.0, 0.5, 50.0, 0.5, s)
     np.savez(os.path.join(OUT, "grid2d.npz"), **out)
     control_golden(R)
+    cartn_linearize_golden(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
@@ -128,3 +129,16 @@ def control_golden(R):
 
 if __name__ == "__main__":
     main()
+
+
+def cartn_linearize_golden(R):
+    """N-link linearization (makeLinearizer<2(N+1),1> around CartNPendulum<N,Dual<double,2N+3>>), N = 1, 2, 6."""
+    out = {}
+    rng = np.random.default_rng(17)
+    for N, P in ((1, 37), (2, 21), (6, 9)):
+        ns = 2 * (N + 1)
+        m = rng.uniform(0.05, 0.3, (N, P)); L = rng.uniform(0.3, 0.8, (N, P)); mc = rng.uniform(0.5, 2.0, P); g = np.full(P, 9.81)
+        x = rng.uniform(-0.5, 0.5, (ns, P)); x[:, 0] = 0.0; u = rng.uniform(-2, 2, P)
+        A, B = R.cartn_linearize(N, mc, m, L, g, x, u)
+        out.update({f"n{N}_mc": mc, f"n{N}_m": m, f"n{N}_L": L, f"n{N}_g": g, f"n{N}_x": x, f"n{N}_u": u, f"n{N}_A": A, f"n{N}_B": B})
+    np.savez(os.path.join(OUT, "cartn_linearize.npz"), **out)

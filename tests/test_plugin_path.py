@@ -74,3 +74,54 @@ def test_user_components_run_on_the_gpu(programs, mode):
     r = subprocess.run([str(d / mode)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "user_components: OK" in r.stdout
+
+
+# ---------------------------------------------------------------- lane-parallel Dual linearization, any number of links
+LIN_SRC = os.path.join(ROOT, "tests", "cuda", "cartn_linearize.cu")
+
+
+@pytest.fixture(scope="module")
+def lin_program(tmp_path_factory):
+    from sopot_b200 import build
+    build.build()
+    exe = tmp_path_factory.mktemp("cartn") / "cartn_linearize"
+    cmd = ["nvcc", "-std=c++20", "--expt-relaxed-constexpr", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-I" + os.path.join(ROOT, "sopot_b200", "include"), "-o", str(exe), LIN_SRC,
+           "-L" + os.path.join(ROOT, "sopot_b200", "lib"), "-lsopot_b200", "-Xlinker", "-rpath", "-Xlinker",
+           os.path.join(ROOT, "sopot_b200", "lib")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return exe
+
+
+def test_lane_parallel_linearization_compiles(lin_program):
+    assert os.path.exists(lin_program)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_links", [1, 2, 6])
+def test_lane_parallel_linearization_matches_reference(lin_program, tmp_path, n_links):
+    """Dual partials spread over the lanes of a warp (Dual<double,1> per lane, component code unchanged) == the
+    reference's makeLinearizer<2(N+1),1> around CartNPendulum<N, Dual<double,2N+3>> on the CPU (golden vectors),
+    for 1, 2 and 6 links; per-point plant parameters."""
+    from conftest import golden
+    g = golden("cartn_linearize")
+    k = f"n{n_links}_"
+    P = g[k + "u"].size
+    ns = 2 * (n_links + 1)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.array([n_links, P], dtype=np.int32).tobytes())
+        for name in ("mc", "m", "L", "g", "x", "u"):
+            f.write(np.ascontiguousarray(g[k + name], dtype=np.float64).tobytes())
+    r = subprocess.run([str(lin_program), str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = np.fromfile(out, dtype=np.float64)
+    A, B = res[:ns * ns * P].reshape(ns * ns, P), res[ns * ns * P:].reshape(ns, P)
+    scale = max(np.abs(g[k + "A"]).max(), 1.0)
+    assert np.abs(A - g[k + "A"]).max() <= 1e-11 * scale
+    assert np.abs(B - g[k + "B"]).max() <= 1e-11 * max(np.abs(g[k + "B"]).max(), 1.0)
+    # structure: d(position rates)/d(velocities) = identity block, exactly
+    for i in range(ns // 2):
+        for j in range(ns):
+            assert np.all(A[i * ns + j] == (1.0 if j == ns // 2 + i else 0.0))
