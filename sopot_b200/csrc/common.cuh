@@ -68,7 +68,8 @@ struct Staging {
     bool host;
     struct Out { void* user; void* dev; size_t bytes; };
     std::vector<Out> outs;
-    Staging(sopot_b200_ctx* c, uint32_t mem) : ctx(c), host(mem == SOPOT_B200_MEM_HOST) {}
+    // every entry point builds a Staging first: make the ctx's device current (a process may hold contexts on several GPUs)
+    Staging(sopot_b200_ctx* c, uint32_t mem) : ctx(c), host(mem == SOPOT_B200_MEM_HOST) { if (c) cudaSetDevice(c->device); }
     // returns the device address to read from (nullptr stays nullptr)
     int in(const void* user, size_t bytes, const void** dev);
     int out(void* user, size_t bytes, void** dev);

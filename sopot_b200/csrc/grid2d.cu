@@ -463,11 +463,9 @@ template <bool S, int TOPO>
 int launch_fused(sopot_b200_ctx* ctx, const GridDev& g, const StepIn& in, double dt, double* y_out) {
     using T = FusedTile<kFusedTX, kFusedTY, TOPO>;
     auto kern = grid_rk4_fused<S, TOPO, kFusedTX, kFusedTY>;
-    static bool attr_set = false;       // per instantiation
-    if (!attr_set) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-        attr_set = true;
-    }
+    // (a function attribute belongs to the current device: set it on every launch rather than caching a flag that a
+    // second context on another GPU of the same process would inherit)
+    SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     const dim3 grid((unsigned)((g.cols + kFusedTX - 1) / kFusedTX), (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY));
     kern<<<grid, T::THREADS, T::SMEM, ctx->stream>>>(g, in, dt, y_out);
     SB_CHECK_LAUNCH(ctx);
