@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SOPOT_B200_ABI_VERSION 1
+#define SOPOT_B200_ABI_VERSION 2
 
 enum {
     SOPOT_B200_OK = 0,
@@ -194,12 +194,23 @@ int sopot_b200_cartpole_feedback_rk4(sopot_b200_ctx* ctx, const sopot_b200_cartp
  * state_out [14][n]; stats_out [8][n] (optional): apogee, apogee_time, max_speed, max_speed_time,
  * burnout_altitude, burnout_speed, final East, final North.
  * ------------------------------------------------------------------------------------------- */
+/* 2-D coefficient table of io::BilinearInterpolator (io/interpolation.hpp:77-181): row_vals[rows], col_vals[cols],
+ * data[rows][cols] row-major, all HOST pointers; rows == 0 means "not loaded".  Aerodynamic tables are laid out as the
+ * reference reads them: rows = Mach, columns = angle of attack / sideslip in degrees for Cd, Cl, Cs
+ * (rocket/axisymmetric_aero.hpp:133-167, interpolate(mach, angle_deg)); rows = signed angle of attack in degrees,
+ * columns = Mach for the damping coefficient cmq_yz (:276-281, interpolate(aoa_deg, mach)). */
+typedef struct { size_t rows, cols; const double *row_vals, *col_vals, *data; } sopot_b200_table2d;
+typedef struct {
+    sopot_b200_table2d cd_power_on, cd_power_off, cl_power_on, cl_power_off, cs_power_on, cs_power_off, cmq_yz;
+    int engine_on;      /* AxisymmetricAerodynamics::setEngineOn; the reference's default (never changed by Rocket<T>) is 1 */
+} sopot_b200_aero_tables;
 typedef struct {
     const double *elevation_deg, *azimuth_deg, *diameter, *gravity;
     size_t engine_rows; const double* engine;
     size_t mass_rows;   const double* mass;
     size_t ix_rows;     const double* ix;
     size_t iyz_rows;    const double* iyz;
+    const sopot_b200_aero_tables* aero;   /* NULL: no coefficient tables (Cd 0.3, Cl = Cs = 0, cmq -450) */
 } sopot_b200_rocket_params;
 int sopot_b200_rocket_rk4(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n, double dt,
                           size_t n_steps, const sopot_b200_rk4_opts* opts, double* state_out,

@@ -188,8 +188,25 @@ class Checker:
         assert t.ndim == 2 and t.shape[1] == cols
         return t.shape[0], t
 
+    @staticmethod
+    def aero_blob(tables: dict | None, engine_on: bool = True):
+        """{name: (row_vals, col_vals, data)} -> flat array: engine_on, then 7 x (rows, cols, row_vals, col_vals, data)."""
+        if tables is None:
+            return None
+        names = ("cd_power_on", "cd_power_off", "cl_power_on", "cl_power_off", "cs_power_on", "cs_power_off", "cmq_yz")
+        assert set(tables) <= set(names), tables.keys()
+        out = [np.array([1.0 if engine_on else 0.0])]
+        for k in names:
+            if k in tables:
+                rv, cv, data = (np.asarray(x, dtype=np.float64) for x in tables[k])
+                assert data.shape == (rv.size, cv.size)
+                out += [np.array([rv.size, cv.size], dtype=np.float64), rv, cv, data.ravel()]
+            else:
+                out.append(np.zeros(2))
+        return np.ascontiguousarray(np.concatenate(out))
+
     def rocket_rk4(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, t_end, dt,
-                   store_every=0, n_snap=0, want_stats=True, nthreads=1):
+                   store_every=0, n_snap=0, want_stats=True, nthreads=1, aero=None, engine_on=True):
         elev = _f64(elev); n = elev.size
         az, diam, g0 = (_f64(a, n) for a in (az, diam, g0))
         er, engine = self._tab(engine, 8)
@@ -199,19 +216,21 @@ class Checker:
         fin = np.empty((14, n))
         stats = np.empty((8, n)) if want_stats else None
         traj = np.full((n_snap, 14, n), np.nan) if store_every else None
-        rc = self._fn("rocket_rk4", [_sz] + [_dp] * 4 + [_sz, _dp] * 4 + [_d, _d, _sz, _dp, _dp, _dp, _i])(
+        blob = self.aero_blob(aero, engine_on)
+        rc = self._fn("rocket_rk4_aero", [_sz] + [_dp] * 4 + [_sz, _dp] * 4 + [_d, _d, _sz, _dp, _dp, _dp, _i, _dp])(
             n, _p(elev), _p(az), _p(diam), _p(g0), er, _p(engine), mr, _p(mass_tab), xr, _p(ix_tab),
-            yr, _p(iyz_tab), t_end, dt, store_every, _p(fin), _p(traj), _p(stats), nthreads)
+            yr, _p(iyz_tab), t_end, dt, store_every, _p(fin), _p(traj), _p(stats), nthreads, _p(blob))
         assert rc == 0
         return fin, stats, traj
 
-    def rocket_rhs(self, elev, az, diam, g0, engine, mass_tab, state):
+    def rocket_rhs(self, elev, az, diam, g0, engine, mass_tab, state, aero=None, engine_on=True):
         state = _f64(state); n = state.shape[1]
         er, engine = self._tab(engine, 8)
         mr, mass_tab = self._tab(mass_tab, 2)
         out = np.empty((14, n))
-        rc = self._fn("rocket_rhs", [_sz, _d, _d, _d, _d, _sz, _dp, _sz, _dp, _dp, _dp])(
-            n, elev, az, diam, g0, er, _p(engine), mr, _p(mass_tab), _p(state), _p(out))
+        blob = self.aero_blob(aero, engine_on)
+        rc = self._fn("rocket_rhs_aero", [_sz, _d, _d, _d, _d, _sz, _dp, _sz, _dp, _dp, _dp, _dp])(
+            n, elev, az, diam, g0, er, _p(engine), mr, _p(mass_tab), _p(state), _p(out), _p(blob))
         assert rc == 0
         return out
 

@@ -336,6 +336,44 @@ static std::string write_csv(const std::string& dir, const char* name, size_t ro
     return path;
 }
 
+// aero blob (same layout as the port): engine_on, then 7 x (rows, cols, row_vals, col_vals, data) in the order cd_on, cd_off,
+// cl_on, cl_off, cs_on, cs_off, cmq_yz.  Tables reach AxisymmetricAerodynamics only through its CSV loaders
+// (rocket/axisymmetric_aero.hpp:73-111): first line = column headers behind a placeholder cell, then one line per row.
+static void apply_aero_blob(sopot::rocket::AxisymmetricAerodynamics<double>& aero, const double* blob, const std::string& dir,
+                            std::vector<std::string>& files) {
+    if (!blob) return;
+    aero.setEngineOn(blob[0] != 0.0);
+    const double* q = blob + 1;
+    for (int k = 0; k < 7; ++k) {
+        const size_t rows = (size_t)q[0], cols = (size_t)q[1];
+        q += 2;
+        const double *rv = q, *cv = q + rows, *data = q + rows + cols;
+        q += rows + cols + rows * cols;
+        if (!rows) continue;
+        const std::string path = dir + "/aero" + std::to_string(k) + ".csv";
+        FILE* f = std::fopen(path.c_str(), "w");
+        std::fprintf(f, "0");
+        for (size_t c = 0; c < cols; ++c) std::fprintf(f, ",%.17g", cv[c]);
+        std::fprintf(f, "\n");
+        for (size_t r = 0; r < rows; ++r) {
+            std::fprintf(f, "%.17g", rv[r]);
+            for (size_t c = 0; c < cols; ++c) std::fprintf(f, ",%.17g", data[r * cols + c]);
+            std::fprintf(f, "\n");
+        }
+        std::fclose(f);
+        files.push_back(path);
+        switch (k) {
+            case 0: aero.loadCdPowerOn(path); break;
+            case 1: aero.loadCdPowerOff(path); break;
+            case 2: aero.loadClPowerOn(path); break;
+            case 3: aero.loadClPowerOff(path); break;
+            case 4: aero.loadCsPowerOn(path); break;
+            case 5: aero.loadCsPowerOff(path); break;
+            default: aero.loadDampingYZ(path); break;
+        }
+    }
+}
+
 struct RocketTables {
     std::string dir;
     std::string engine, mass, ix, iyz;
@@ -343,12 +381,12 @@ struct RocketTables {
 
 // stats layout [8][n]: apogee, apogee_t, max_speed, max_speed_t, burnout_alt, burnout_speed,
 // downrange_E (final state[1]), downrange_N (final state[2])   (rocket/simulation_result.hpp:151-189)
-int ref_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg, const double* diameter,
+int ref_rocket_rk4_aero(size_t n, const double* elev_deg, const double* az_deg, const double* diameter,
                    const double* g0, size_t engine_rows, const double* engine /*[rows][8]*/,
                    size_t mass_rows, const double* mass_tab /*[rows][2]*/,
                    size_t ix_rows, const double* ix_tab, size_t iyz_rows, const double* iyz_tab,
                    double t_end, double dt, size_t store_every, double* final_out /*[14][n]*/,
-                   double* traj_out, double* stats_out /*[8][n] or null*/, int nthreads) {
+                   double* traj_out, double* stats_out /*[8][n] or null*/, int nthreads, const double* aero_blob) {
     using namespace sopot::rocket;
     char tmpl[] = "/tmp/sopot_ref_XXXXXX";
     char* d = mkdtemp(tmpl);
@@ -367,15 +405,20 @@ int ref_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg, const
     if (ix_rows) body0.loadInertiaX(f_ix);
     if (iyz_rows) body0.loadInertiaYZ(f_iyz);
     const double burn = engine0.getBurnTime();
+    AxisymmetricAerodynamics<double> aero0;
+    std::vector<std::string> aero_files;
+    apply_aero_blob(aero0, aero_blob, dir, aero_files);
 
     parallel_for(n, nthreads, [&](size_t i) {
         RotationKinematics<double> att;
         att.setInitialFromLauncherAngles(elev_deg[i], az_deg[i]);
+        AxisymmetricAerodynamics<double> aero_i(aero0);
+        aero_i.setReferenceDiameter(diameter[i]);
         auto sys = makeTypedODESystem<double>(
             SimulationTime<double>(), TranslationKinematics<double>(), TranslationDynamics<double>(),
             std::move(att), RotationDynamics<double>(), StandardAtmosphere<double>(),
             Gravity<double>(g0[i]), RocketBody<double>(body0), InterpolatedEngine<double>(engine0),
-            AxisymmetricAerodynamics<double>(diameter[i]), ForceAggregator<double>());
+            std::move(aero_i), ForceAggregator<double>());
         auto r = solve_system(sys, 0.0, t_end, dt);
         scatter_result(r, 14, i, n, store_every, final_out, traj_out, nullptr);
         if (stats_out) {
@@ -396,14 +439,22 @@ int ref_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg, const
         }
     });
     for (auto* p : {&f_eng, &f_mass, &f_ix, &f_iyz}) if (!p->empty()) unlink(p->c_str());
+    for (auto& f : aero_files) unlink(f.c_str());
     rmdir(dir.c_str());
     return 0;
 }
+int ref_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg, const double* diameter, const double* g0,
+                   size_t engine_rows, const double* engine, size_t mass_rows, const double* mass_tab, size_t ix_rows,
+                   const double* ix_tab, size_t iyz_rows, const double* iyz_tab, double t_end, double dt, size_t store_every,
+                   double* final_out, double* traj_out, double* stats_out, int nthreads) {
+    return ref_rocket_rk4_aero(n, elev_deg, az_deg, diameter, g0, engine_rows, engine, mass_rows, mass_tab, ix_rows, ix_tab,
+                               iyz_rows, iyz_tab, t_end, dt, store_every, final_out, traj_out, stats_out, nthreads, nullptr);
+}
 
 // single RHS evaluation of the full rocket at given states [14][n] (shared config)
-int ref_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0,
+int ref_rocket_rhs_aero(size_t n, double elev_deg, double az_deg, double diameter, double g0,
                    size_t engine_rows, const double* engine, size_t mass_rows, const double* mass_tab,
-                   const double* state, double* out) {
+                   const double* state, double* out, const double* aero_blob) {
     using namespace sopot::rocket;
     char tmpl[] = "/tmp/sopot_ref_XXXXXX";
     char* d = mkdtemp(tmpl);
@@ -414,19 +465,28 @@ int ref_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, do
     InterpolatedEngine<double> engine0; engine0.loadFromFile(f_eng);
     RocketBody<double> body0; body0.loadMass(f_mass);
     RotationKinematics<double> att; att.setInitialFromLauncherAngles(elev_deg, az_deg);
+    AxisymmetricAerodynamics<double> aero0(diameter);
+    std::vector<std::string> aero_files;
+    apply_aero_blob(aero0, aero_blob, dir, aero_files);
     auto sys = makeTypedODESystem<double>(
         SimulationTime<double>(), TranslationKinematics<double>(), TranslationDynamics<double>(),
         std::move(att), RotationDynamics<double>(), StandardAtmosphere<double>(),
         Gravity<double>(g0), std::move(body0), std::move(engine0),
-        AxisymmetricAerodynamics<double>(diameter), ForceAggregator<double>());
+        std::move(aero0), ForceAggregator<double>());
     for (size_t i = 0; i < n; ++i) {
         std::vector<double> s(14);
         for (int j = 0; j < 14; ++j) s[j] = state[j * n + i];
         auto dv = sys.computeDerivatives(0.0, s);
         for (int j = 0; j < 14; ++j) out[j * n + i] = dv[j];
     }
-    unlink(f_eng.c_str()); unlink(f_mass.c_str()); rmdir(dir.c_str());
+    unlink(f_eng.c_str()); unlink(f_mass.c_str());
+    for (auto& f : aero_files) unlink(f.c_str());
+    rmdir(dir.c_str());
     return 0;
+}
+int ref_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0, size_t engine_rows, const double* engine,
+                   size_t mass_rows, const double* mass_tab, const double* state, double* out) {
+    return ref_rocket_rhs_aero(n, elev_deg, az_deg, diameter, g0, engine_rows, engine, mass_rows, mass_tab, state, out, nullptr);
 }
 
 // engine precompute columns (pressure ratio, mass flow, engine force) as the reference derives

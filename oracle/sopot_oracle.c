@@ -761,9 +761,54 @@ typedef struct {
     /* body */
     orc_lerp_t mass, ix, iyz; int use_interp;
     double const_mass, const_ix, const_iyz;
+    /* aerodynamic coefficient tables (axisymmetric_aero.hpp:38-44), rows == 0: not loaded */
+    struct orc_tab2d { size_t rows, cols; const double *rv, *cv, *data; } cd_on, cd_off, cl_on, cl_off, cs_on, cs_off, cmq_yz;
+    int engine_on;
     /* per trajectory */
     double g, ref_area, ref_len;
 } orc_rocket_t;
+
+/* BilinearInterpolator::interpolate, io/interpolation.hpp:137-181 */
+static double orc_bilinear(const struct orc_tab2d* t, double row, double col) {
+    if (t->rows == 0) return 0.0;
+    if (row <= t->rv[0]) row = t->rv[0]; else if (row >= t->rv[t->rows - 1]) row = t->rv[t->rows - 1];
+    if (col <= t->cv[0]) col = t->cv[0]; else if (col >= t->cv[t->cols - 1]) col = t->cv[t->cols - 1];
+    size_t ri = 0, ci = 0;
+    { size_t lo = 0, hi = t->rows; while (lo < hi) { size_t mid = (lo + hi) / 2; if (t->rv[mid] < row) lo = mid + 1; else hi = mid; } ri = lo; }
+    if (ri > 0) --ri;
+    if (ri >= t->rows - 1) ri = t->rows - 2;
+    { size_t lo = 0, hi = t->cols; while (lo < hi) { size_t mid = (lo + hi) / 2; if (t->cv[mid] < col) lo = mid + 1; else hi = mid; } ci = lo; }
+    if (ci > 0) --ci;
+    if (ci >= t->cols - 1) ci = t->cols - 2;
+    const double r0 = t->rv[ri], r1 = t->rv[ri + 1], c0 = t->cv[ci], c1 = t->cv[ci + 1];
+    const double tr = (row - r0) / (r1 - r0), tc = (col - c0) / (c1 - c0);
+    const double v00 = t->data[ri * t->cols + ci], v01 = t->data[ri * t->cols + ci + 1];
+    const double v10 = t->data[(ri + 1) * t->cols + ci], v11 = t->data[(ri + 1) * t->cols + ci + 1];
+    const double v0 = v00 + tc * (v01 - v00), v1 = v10 + tc * (v11 - v10);
+    return v0 + tr * (v1 - v0);
+}
+/* getCd / getCl / getCs, axisymmetric_aero.hpp:133-167 */
+static double orc_coeff(const orc_rocket_t* p, const struct orc_tab2d* on, const struct orc_tab2d* off, double angle_deg,
+                        double mach, double dflt) {
+    if (p->engine_on && on->rows) return orc_bilinear(on, mach, angle_deg);
+    if (off->rows) return orc_bilinear(off, mach, angle_deg);
+    return dflt;
+}
+/* aero blob: engine_on, then 7 x (rows, cols, row_vals[rows], col_vals[cols], data[rows*cols]) in the order
+ * cd_on, cd_off, cl_on, cl_off, cs_on, cs_off, cmq_yz */
+static void orc_rocket_set_aero(orc_rocket_t* p, const double* blob) {
+    p->engine_on = 1;
+    if (!blob) return;
+    p->engine_on = blob[0] != 0.0;
+    const double* q = blob + 1;
+    struct orc_tab2d* t[7] = {&p->cd_on, &p->cd_off, &p->cl_on, &p->cl_off, &p->cs_on, &p->cs_off, &p->cmq_yz};
+    for (int k = 0; k < 7; ++k) {
+        t[k]->rows = (size_t)q[0]; t[k]->cols = (size_t)q[1]; q += 2;
+        t[k]->rv = q; q += t[k]->rows;
+        t[k]->cv = q; q += t[k]->cols;
+        t[k]->data = q; q += t[k]->rows * t[k]->cols;
+    }
+}
 
 typedef struct { double x, y, z; } v3;
 
@@ -824,11 +869,15 @@ static v3 orc_aero_force_body(const orc_rocket_t* p, const double* s) {
     double alt = s[3];
     double density = orc_atm_density(alt);
     double sos = orc_atm_sos(alt);
-    double mach = airspeed / sos; (void)mach;
+    double mach = airspeed / sos;
     double dynp = 0.5 * density * airspeed * airspeed;
     double aoa = (vb.x * vb.x + vb.z * vb.z) < 1e-10 ? 0.0 : atan2(-vb.z, vb.x);   /* :116-122 */
     double aoss = (vb.x * vb.x + vb.y * vb.y) < 1e-10 ? 0.0 : atan2(vb.y, vb.x);  /* :125-131 */
-    double cd = 0.3, cl = 0.0, cs = 0.0;
+    const double rad2deg = 180.0 / 3.14159265358979;                                /* :175 */
+    double aoa_deg = fabs(aoa * rad2deg), aoss_deg = fabs(aoss * rad2deg);          /* :203-204 */
+    double cd = orc_coeff(p, &p->cd_on, &p->cd_off, aoa_deg, mach, 0.3);
+    double cl = orc_coeff(p, &p->cl_on, &p->cl_off, aoa_deg, mach, 0.0);
+    double cs = orc_coeff(p, &p->cs_on, &p->cs_off, aoss_deg, mach, 0.0);
     double qS = dynp * p->ref_area;
     double n = orc_norm(vb);
     v3 vu = zero;
@@ -857,6 +906,12 @@ static v3 orc_aero_moment_body(const orc_rocket_t* p, const double* s) {
     double qSd = dynp * p->ref_area * p->ref_len;
     double damping = p->ref_len / airspeed;
     double cmq = -450.0;
+    if (p->cmq_yz.rows) {                                                           /* :276-281 */
+        double mach = airspeed / orc_atm_sos(s[3]);
+        double aoa = (vb.x * vb.x + vb.z * vb.z) < 1e-10 ? 0.0 : atan2(-vb.z, vb.x);
+        double aoa_deg = aoa * 180.0 / 3.14159265358979;
+        cmq = orc_bilinear(&p->cmq_yz, aoa_deg, mach);
+    }
     v3 r = {cmq * qSd * damping * s[11], cmq * qSd * damping * s[12], cmq * qSd * damping * s[13]};
     return r;
 }
@@ -978,13 +1033,13 @@ static void orc_rocket_range(void* user, size_t b, size_t e) {
     }
 }
 
-ORC_API int orc_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg,
+ORC_API int orc_rocket_rk4_aero(size_t n, const double* elev_deg, const double* az_deg,
                            const double* diameter, const double* g0, size_t engine_rows,
                            const double* engine /*[rows][8]*/, size_t mass_rows,
                            const double* mass_tab /*[rows][2]*/, size_t ix_rows, const double* ix_tab,
                            size_t iyz_rows, const double* iyz_tab, double t_end, double dt,
                            size_t store_every, double* final_out /*[14][n]*/, double* traj_out,
-                           double* stats_out /*[8][n]*/, int nthreads) {
+                           double* stats_out /*[8][n]*/, int nthreads, const double* aero_blob) {
     double* eng_cols = orc_transpose(engine_rows, 8, engine);
     double* derived = (double*)malloc(sizeof(double) * (3 * engine_rows + 1));
     orc_engine_precompute(engine_rows, engine, derived);
@@ -994,6 +1049,7 @@ ORC_API int orc_rocket_rk4(size_t n, const double* elev_deg, const double* az_de
     orc_rocket_t base;
     orc_rocket_setup(&base, engine_rows, eng_cols, derived, mass_rows, mass_cols, ix_rows, ix_cols,
                      iyz_rows, iyz_cols);
+    orc_rocket_set_aero(&base, aero_blob);
     orc_rk_job_t j = {n, elev_deg, az_deg, diameter, g0, &base, t_end, dt, store_every,
                       final_out, traj_out, stats_out};
     orc_parallel_for(n, 4, nthreads, orc_rocket_range, &j);
@@ -1001,9 +1057,18 @@ ORC_API int orc_rocket_rk4(size_t n, const double* elev_deg, const double* az_de
     return 0;
 }
 
-ORC_API int orc_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0,
+ORC_API int orc_rocket_rk4(size_t n, const double* elev_deg, const double* az_deg,
+                           const double* diameter, const double* g0, size_t engine_rows,
+                           const double* engine, size_t mass_rows, const double* mass_tab, size_t ix_rows, const double* ix_tab,
+                           size_t iyz_rows, const double* iyz_tab, double t_end, double dt,
+                           size_t store_every, double* final_out, double* traj_out, double* stats_out, int nthreads) {
+    return orc_rocket_rk4_aero(n, elev_deg, az_deg, diameter, g0, engine_rows, engine, mass_rows, mass_tab, ix_rows, ix_tab,
+                               iyz_rows, iyz_tab, t_end, dt, store_every, final_out, traj_out, stats_out, nthreads, NULL);
+}
+
+ORC_API int orc_rocket_rhs_aero(size_t n, double elev_deg, double az_deg, double diameter, double g0,
                            size_t engine_rows, const double* engine, size_t mass_rows,
-                           const double* mass_tab, const double* state /*[14][n]*/, double* out) {
+                           const double* mass_tab, const double* state /*[14][n]*/, double* out, const double* aero_blob) {
     (void)elev_deg; (void)az_deg;
     double* eng_cols = orc_transpose(engine_rows, 8, engine);
     double* derived = (double*)malloc(sizeof(double) * (3 * engine_rows + 1));
@@ -1011,6 +1076,7 @@ ORC_API int orc_rocket_rhs(size_t n, double elev_deg, double az_deg, double diam
     double* mass_cols = orc_transpose(mass_rows, 2, mass_tab);
     orc_rocket_t p;
     orc_rocket_setup(&p, engine_rows, eng_cols, derived, mass_rows, mass_cols, 0, NULL, 0, NULL);
+    orc_rocket_set_aero(&p, aero_blob);
     p.g = g0; p.ref_area = 3.14159265358979 * diameter * diameter / 4.0; p.ref_len = diameter;
     for (size_t i = 0; i < n; ++i) {
         double s[14], d[14];
@@ -1020,6 +1086,11 @@ ORC_API int orc_rocket_rhs(size_t n, double elev_deg, double az_deg, double diam
     }
     free(eng_cols); free(derived); free(mass_cols);
     return 0;
+}
+
+ORC_API int orc_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0, size_t engine_rows,
+                           const double* engine, size_t mass_rows, const double* mass_tab, const double* state, double* out) {
+    return orc_rocket_rhs_aero(n, elev_deg, az_deg, diameter, g0, engine_rows, engine, mass_rows, mass_tab, state, out, NULL);
 }
 
 ORC_API int orc_engine_thrust(size_t engine_rows, const double* engine, size_t nq, const double* tq,

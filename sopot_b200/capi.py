@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
+ABI_VERSION = 2          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
 
 _dp = POINTER(c_double)
@@ -55,11 +56,23 @@ class Feedback(ctypes.Structure):
     _fields_ = [("K", c_void_p), ("x_ref", c_void_p), ("u_min", c_double), ("u_max", c_double), ("saturate", c_int)]
 
 
+class Table2D(ctypes.Structure):
+    _fields_ = [("rows", c_size_t), ("cols", c_size_t), ("row_vals", c_void_p), ("col_vals", c_void_p), ("data", c_void_p)]
+
+
+AERO_TABLE_NAMES = ("cd_power_on", "cd_power_off", "cl_power_on", "cl_power_off", "cs_power_on", "cs_power_off", "cmq_yz")
+
+
+class AeroTables(ctypes.Structure):
+    _fields_ = [(k, Table2D) for k in AERO_TABLE_NAMES] + [("engine_on", c_int)]
+
+
 class RocketParams(ctypes.Structure):
     _fields_ = [("elevation_deg", c_void_p), ("azimuth_deg", c_void_p), ("diameter", c_void_p),
                 ("gravity", c_void_p),
                 ("engine_rows", c_size_t), ("engine", c_void_p), ("mass_rows", c_size_t), ("mass", c_void_p),
-                ("ix_rows", c_size_t), ("ix", c_void_p), ("iyz_rows", c_size_t), ("iyz", c_void_p)]
+                ("ix_rows", c_size_t), ("ix", c_void_p), ("iyz_rows", c_size_t), ("iyz", c_void_p),
+                ("aero", POINTER(AeroTables))]
 
 
 class Dispersion(ctypes.Structure):
@@ -140,7 +153,7 @@ def load_library() -> ctypes.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
-    if lib.sopot_b200_abi_version() != 1:
+    if lib.sopot_b200_abi_version() != ABI_VERSION:
         raise SopotB200Error("ABI version mismatch")
     _lib = lib
     return lib
@@ -418,7 +431,20 @@ class Engine:
             self.sync()
         return state, stats, traj, status
 
-    def _rocket_params(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, mem):
+    @staticmethod
+    def aero_tables(tables: dict, engine_on: bool = True):
+        """{name: (row_vals, col_vals, data[rows][cols])} for names in AERO_TABLE_NAMES -> (AeroTables, keep-alive)."""
+        a, keep = AeroTables(), []
+        a.engine_on = int(bool(engine_on))
+        for name, (rv, cv, data) in tables.items():
+            assert name in AERO_TABLE_NAMES, name
+            rv, cv, data = (np.ascontiguousarray(x, dtype=np.float64) for x in (rv, cv, data))
+            assert data.shape == (rv.size, cv.size)
+            keep += [rv, cv, data]
+            setattr(a, name, Table2D(rv.size, cv.size, rv.ctypes.data, cv.ctypes.data, data.ctypes.data))
+        return a, keep
+
+    def _rocket_params(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, mem, aero=None):
         ptrs, mask, keep = self._prep(dict(elevation_deg=elev, azimuth_deg=az, diameter=diam, gravity=g0), n, mem)
         tabs = {}
         for name, t, cols in (("engine", engine, 8), ("mass", mass_tab, 2), ("ix", ix_tab, 2), ("iyz", iyz_tab, 2)):
@@ -429,12 +455,17 @@ class Engine:
                 assert t.ndim == 2 and t.shape[1] == cols
                 keep.append(t)
                 tabs[name + "_rows"], tabs[name] = t.shape[0], t.ctypes.data
-        return RocketParams(**ptrs, **tabs), mask, keep
+        p = RocketParams(**ptrs, **tabs)
+        if aero is not None:
+            a, k2 = aero if isinstance(aero, tuple) else self.aero_tables(aero)
+            keep += k2 + [a]
+            p.aero = ctypes.pointer(a)
+        return p, mask, keep
 
     def rocket_rk4(self, elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, dt, n_steps, mem=MEM_HOST,
                    fp_mode=FP_CONTRACT, store_every=0, want_status=True, want_stats=True, state_out=None,
-                   stats_out=None, sync=True):
-        p, mask, keep = self._rocket_params(elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, mem)
+                   stats_out=None, sync=True, aero=None):
+        p, mask, keep = self._rocket_params(elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, mem, aero)
         opts = RK4Opts(mem, fp_mode, store_every, mask, 0)
         state, traj, status = self._outs(14, n, n_steps, store_every, mem, want_status, state_out, None)
         stats = None
@@ -447,10 +478,10 @@ class Engine:
             self.sync()
         return state, stats, traj, status
 
-    def rocket_rhs(self, elev, az, diam, g0, engine, mass_tab, state, fp_mode=FP_CONTRACT, ix_tab=None, iyz_tab=None):
+    def rocket_rhs(self, elev, az, diam, g0, engine, mass_tab, state, fp_mode=FP_CONTRACT, ix_tab=None, iyz_tab=None, aero=None):
         state = np.ascontiguousarray(state, dtype=np.float64)
         n = state.shape[1]
-        p, mask, keep = self._rocket_params(elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, MEM_HOST)
+        p, mask, keep = self._rocket_params(elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, MEM_HOST, aero)
         opts = RK4Opts(MEM_HOST, fp_mode, 0, mask, 0)
         out = np.empty((14, n))
         self._ck(self.lib.sopot_b200_rocket_rhs(self.ctx, byref(p), n, byref(opts), _ptr(state), _ptr(out)))

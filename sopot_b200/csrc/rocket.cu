@@ -53,10 +53,16 @@ __device__ __forceinline__ Real<S> r_pow(Real<S> base, double e) {
     if constexpr (S) return Real<S>(pow(base.v, e)); else return Real<S>(exp(e * log(base.v)));
 }
 
+// one effective coefficient table inside the packed buffer: row_vals[rows], col_vals[cols], data[rows][cols] from `off`
+struct Table2D { int rows, cols, off; };
+
 struct RocketTablesDev {
     // one packed device buffer: engine columns time, exit_d, p_comb, press_ratio, engine_force
-    // (5 * er), then mass time/value (2 * mr), ix (2 * xr), iyz (2 * yr)
+    // (5 * er), then mass time/value (2 * mr), ix (2 * xr), iyz (2 * yr), then the effective aero tables
     const double* packed;
+    int total;                     // doubles in the packed buffer
+    Table2D cd, cl, cs, cmq;       // rows == 0: reference default (host-side copy of the descriptors)
+    int desc_off;                  // the same 4 descriptors as 12 doubles (rows, cols, off) inside the packed buffer
     int er, mr, xr, yr;
     double burn_time;
     int use_interp;
@@ -99,6 +105,32 @@ __device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv
     return L;
 }
 
+// BilinearInterpolator::interpolate, io/interpolation.hpp:137-181: clamp both coordinates to the table, lower_bound
+// interval (index clamped to size-2), tc along the columns first, then tr along the rows.
+__device__ __forceinline__ int interval_of(const double* x, int n, double v) {
+    int lo = 0, hi = n;                                   // std::lower_bound
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < v) lo = mid + 1; else hi = mid; }
+    int i = lo > 0 ? lo - 1 : 0;
+    if (i >= n - 1) i = n - 2;
+    return i;
+}
+template <bool S>
+__device__ __forceinline__ Real<S> bilinear(const double* tb, const Table2D& t, double row, double col) {
+    using R = Real<S>;
+    const double* rv = tb + t.off;
+    const double* cv = rv + t.rows;
+    const double* data = cv + t.cols;
+    if (row <= rv[0]) row = rv[0]; else if (row >= rv[t.rows - 1]) row = rv[t.rows - 1];
+    if (col <= cv[0]) col = cv[0]; else if (col >= cv[t.cols - 1]) col = cv[t.cols - 1];
+    const int ri = interval_of(rv, t.rows, row), ci = interval_of(cv, t.cols, col);
+    const R tr = (R(row) - R(rv[ri])) / (R(rv[ri + 1]) - R(rv[ri]));
+    const R tc = (R(col) - R(cv[ci])) / (R(cv[ci + 1]) - R(cv[ci]));
+    const R v00(data[ri * t.cols + ci]), v01(data[ri * t.cols + ci + 1]);
+    const R v10(data[(ri + 1) * t.cols + ci]), v11(data[(ri + 1) * t.cols + ci + 1]);
+    const R v0 = v00 + tc * (v01 - v00), v1 = v10 + tc * (v11 - v10);
+    return v0 + tr * (v1 - v0);
+}
+
 template <bool S>
 __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S>& T) {
     const double h = alt.v;
@@ -130,30 +162,35 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
 #ifndef SB_ROCKET_MINB
 #define SB_ROCKET_MINB 1
 #endif
-struct RocketSys {
+struct RocketDevParams {
+    ParamRef elev, az, diam, g;
+    RocketTablesDev tab;
+    double* stats_out;   // [8][n] or nullptr
+};
+
+// AT: coefficient tables present (a separate instantiation: the table path needs atan2 / sincos / bilinear lookups and
+// ~60 more registers, which would cost the default configuration one resident block per SM)
+template <bool AT>
+struct RocketSysT {
     static constexpr int DIM = 14;
     static constexpr int BLOCK = SB_ROCKET_BLOCK, IPT = 1, MIN_BLOCKS = SB_ROCKET_MINB;
     static constexpr bool FAST_STEP = false;
-    struct DevParams {
-        ParamRef elev, az, diam, g;
-        RocketTablesDev tab;
-        double* stats_out;   // [8][n] or nullptr
-    };
+    using DevParams = RocketDevParams;
     template <bool S> struct Inst {
         Real<S> g, area, len;
         const double* tb;          // shared-memory copy of the packed tables
         int er, mr, xr, yr, use_interp;
+        int desc;                  // offset of the aero table descriptors in the shared-memory tables (AT only)
         double burn;
         double apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd;
         mutable int h_eng, h_mass, h_ix, h_iyz;   // lerp_locate interval hints
     };
     static size_t smem_bytes(const DevParams& P) {
-        return sizeof(double) * (size_t)(5 * P.tab.er + 2 * P.tab.mr + 2 * P.tab.xr + 2 * P.tab.yr);
+        return sizeof(double) * (size_t)P.tab.total;
     }
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams& P) {
         extern __shared__ double s_tab[];
-        const int total = 5 * P.tab.er + 2 * P.tab.mr + 2 * P.tab.xr + 2 * P.tab.yr;
-        for (int j = threadIdx.x; j < total; j += blockDim.x) s_tab[j] = P.tab.packed[j];
+        for (int j = threadIdx.x; j < P.tab.total; j += blockDim.x) s_tab[j] = P.tab.packed[j];
         __syncthreads();
     }
     template <bool S>
@@ -162,6 +199,7 @@ struct RocketSys {
         in.tb = s_tab;
         in.er = P.tab.er; in.mr = P.tab.mr; in.xr = P.tab.xr; in.yr = P.tab.yr;
         in.use_interp = P.tab.use_interp; in.burn = P.tab.burn_time;
+        in.desc = P.tab.desc_off;
         const double d = P.diam.at(i);
         in.g = Real<S>(P.g.at(i));
         in.area = Real<S>(kAeroPi) * Real<S>(d) * Real<S>(d) / Real<S>(4.0);   // axisymmetric_aero.hpp:56
@@ -242,15 +280,47 @@ struct RocketSys {
             R ux(0.0), uy(0.0), uz(0.0);
             if constexpr (S) { if (!(airspeed.v < 1e-15)) { ux = vbx / airspeed; uy = vby / airspeed; uz = vbz / airspeed; } }
             else { ux = vbx * inv_airspeed; uy = vby * inv_airspeed; uz = vbz * inv_airspeed; }
-            const R drag = qS * R(0.3);                                           // Cd default, :142
-            const R fbx = (-ux) * drag, fby = (-uy) * drag, fbz = (-uz) * drag;   // :228
+            R cd(0.3), cmq(-450.0);                                               // defaults :142, :275
+            R fbx, fby, fbz;
+            if constexpr (!AT) {
+                // Cl = Cs = 0 (:154,:166): lift and side force are +-0, the angles that only feed them are skipped
+                const R drag = qS * cd;
+                fbx = (-ux) * drag; fby = (-uy) * drag; fbz = (-uz) * drag;       // :228
+            } else {
+                // table-driven coefficients (:133-167): speed of sound, Mach, angles of attack / sideslip
+                const R sos = r_sqrt(R(kAtmGamma * kAtmRs) * T);                  // standard_atmosphere.hpp:71
+                const R mach = airspeed / sos;                                    // :197
+                const R rad2deg = R(180.0) / R(kAeroPi);                          // :175
+                const R aoa = (vbx * vbx + vbz * vbz).v < 1e-10 ? R(0.0) : R(atan2(-vbz.v, vbx.v));    // :116-122
+                const R aoss = (vbx * vbx + vby * vby).v < 1e-10 ? R(0.0) : R(atan2(vby.v, vbx.v));   // :125-131
+                const double aoa_deg = fabs((aoa * rad2deg).v), aoss_deg = fabs((aoss * rad2deg).v);  // :203-204
+                auto desc = [&](int k) { const double* q = tb + in.desc + 3 * k; return Table2D{(int)q[0], (int)q[1], (int)q[2]}; };
+                const Table2D t_cd = desc(0), t_cl = desc(1), t_cs = desc(2), t_cmq = desc(3);
+                if (t_cd.rows) cd = bilinear<S>(tb, t_cd, mach.v, aoa_deg);
+                const R cl = t_cl.rows ? bilinear<S>(tb, t_cl, mach.v, aoa_deg) : R(0.0);
+                const R cs = t_cs.rows ? bilinear<S>(tb, t_cs, mach.v, aoss_deg) : R(0.0);
+                const R drag = qS * cd, lift = qS * cl, side = qS * cs;
+                R sa, ca, ss, cs_unused;
+                r_sincos(aoa, sa, ca);
+                r_sincos(aoss, ss, cs_unused);
+                const R ldx = -sa, ldz = aoa.v < 0 ? -ca : ca;                    // :232-233
+                const R sdy = aoss.v < 0 ? -(-ss) : -ss;                          // :237-238
+                // F_drag + F_lift + F_side, component by component (:240)
+                fbx = ((-ux) * drag + ldx * lift) + R(0.0) * side;
+                fby = ((-uy) * drag + R(0.0) * lift) + sdy * side;
+                fbz = ((-uz) * drag + ldz * lift) + R(0.0) * side;
+                if (t_cmq.rows) {                                                 // :276-281, signed angle, arguments swapped
+                    const R aoa_signed_deg = aoa * R(180.0) / R(kAeroPi);
+                    cmq = bilinear<S>(tb, t_cmq, aoa_signed_deg.v, mach.v);
+                }
+            }
             Fax = R00 * fbx + R01 * fby + R02 * fbz;                              // :251-253
             Fay = R10 * fbx + R11 * fby + R12 * fbz;
             Faz = R20 * fbx + R21 * fby + R22 * fbz;
             const R qSd = qS * in.len;                                            // :271
             R damping;                                                            // :274
             if constexpr (S) damping = in.len / airspeed; else damping = in.len * inv_airspeed;
-            const R cq = R(-450.0) * qSd * damping;                               // :275, :283-287
+            const R cq = cmq * qSd * damping;                                     // :283-287
             Mx = cq * wx; My = cq * wy; Mz = cq * wz;
         }
 
@@ -294,6 +364,9 @@ struct RocketSys {
         return 0;
     }
 };
+
+using RocketSys = RocketSysT<false>;
+using RocketSysTables = RocketSysT<true>;
 
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
@@ -371,6 +444,31 @@ void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, Ro
     tab.er = (int)er; tab.mr = (int)mr; tab.xr = (int)xr; tab.yr = (int)yr;
     tab.burn_time = er ? p->engine[(er - 1) * 8] : 0.0;
     tab.use_interp = (mr || xr || yr) ? 1 : 0;
+    // effective aero tables (getCd/getCl/getCs, axisymmetric_aero.hpp:133-167): power-on table when the engine flag is
+    // set and the table is loaded, else the power-off table, else the default coefficient
+    tab.cd = tab.cl = tab.cs = tab.cmq = Table2D{0, 0, 0};
+    if (p->aero) {
+        const sopot_b200_aero_tables& a = *p->aero;
+        auto pick = [&](const sopot_b200_table2d& on, const sopot_b200_table2d& off) -> const sopot_b200_table2d* {
+            if (a.engine_on && on.rows) return &on;
+            if (off.rows) return &off;
+            return nullptr;
+        };
+        auto put = [&](const sopot_b200_table2d* t, Table2D& dst) {
+            if (!t) return;
+            dst = Table2D{(int)t->rows, (int)t->cols, (int)out.size()};
+            out.insert(out.end(), t->row_vals, t->row_vals + t->rows);
+            out.insert(out.end(), t->col_vals, t->col_vals + t->cols);
+            out.insert(out.end(), t->data, t->data + t->rows * t->cols);
+        };
+        put(pick(a.cd_power_on, a.cd_power_off), tab.cd);
+        put(pick(a.cl_power_on, a.cl_power_off), tab.cl);
+        put(pick(a.cs_power_on, a.cs_power_off), tab.cs);
+        put(a.cmq_yz.rows ? &a.cmq_yz : nullptr, tab.cmq);
+    }
+    tab.desc_off = (int)out.size();
+    for (const Table2D* t : {&tab.cd, &tab.cl, &tab.cs, &tab.cmq}) { out.push_back(t->rows); out.push_back(t->cols); out.push_back(t->off); }
+    tab.total = (int)out.size();
 }
 
 int upload_atmosphere(sopot_b200_ctx* ctx) {
@@ -395,6 +493,15 @@ int rocket_prepare(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_
         return sb_fail(ctx, SOPOT_B200_EINVAL, "table pointer is NULL with rows > 0");
     if (p->engine_rows == 1 || p->mass_rows == 1 || p->ix_rows == 1 || p->iyz_rows == 1)
         return sb_fail(ctx, SOPOT_B200_EINVAL, "interpolation tables need at least 2 rows");
+    if (p->aero) {
+        const sopot_b200_table2d* t[7] = {&p->aero->cd_power_on, &p->aero->cd_power_off, &p->aero->cl_power_on, &p->aero->cl_power_off,
+                                          &p->aero->cs_power_on, &p->aero->cs_power_off, &p->aero->cmq_yz};
+        for (const sopot_b200_table2d* q : t) {
+            if (q->rows == 0) continue;
+            if (q->rows < 2 || q->cols < 2 || !q->row_vals || !q->col_vals || !q->data)
+                return sb_fail(ctx, SOPOT_B200_EINVAL, "a loaded coefficient table needs >= 2 rows and columns and non-NULL arrays");
+        }
+    }
     int rc;
     if ((rc = upload_atmosphere(ctx))) return rc;
     std::vector<double> packed;
@@ -417,14 +524,31 @@ int rocket_prepare(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_
     return SOPOT_B200_OK;
 }
 
-template <bool S>
+template <class Sys, bool S>
 int rocket_set_smem(sopot_b200_ctx* ctx, size_t bytes) {
     if (bytes > 48 * 1024) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(rk4_ensemble_kernel<RocketSys, S>,
+        SB_CUDA(ctx, cudaFuncSetAttribute(rk4_ensemble_kernel<Sys, S>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        SB_CUDA(ctx, cudaFuncSetAttribute(rhs_ensemble_kernel<RocketSys, S>,
+        SB_CUDA(ctx, cudaFuncSetAttribute(rhs_ensemble_kernel<Sys, S>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     }
+    return SOPOT_B200_OK;
+}
+
+template <class Sys, bool S>
+int rocket_launch_rk4(sopot_b200_ctx* ctx, const RocketSys::DevParams& P, size_t n, double dt, size_t n_steps, size_t store_every,
+                      size_t smem, double* d_state, double* d_traj, int32_t* d_status) {
+    int rc = rocket_set_smem<Sys, S>(ctx, smem);
+    if (rc) return rc;
+    rk4_ensemble_kernel<Sys, S><<<sb_grid_for(n, Sys::BLOCK), Sys::BLOCK, smem, ctx->stream>>>(
+        P, n, 0.0, dt, n_steps, store_every, d_state, d_traj, d_status);
+    return SOPOT_B200_OK;
+}
+template <class Sys, bool S>
+int rocket_launch_rhs(sopot_b200_ctx* ctx, const RocketSys::DevParams& P, size_t n, size_t smem, const double* d_state, double* d_out) {
+    int rc = rocket_set_smem<Sys, S>(ctx, smem);
+    if (rc) return rc;
+    rhs_ensemble_kernel<Sys, S><<<sb_grid_for(n, Sys::BLOCK), Sys::BLOCK, smem, ctx->stream>>>(P, n, d_state, d_out);
     return SOPOT_B200_OK;
 }
 
@@ -453,16 +577,14 @@ SB_EXPORT int sopot_b200_rocket_rk4(sopot_b200_ctx* ctx, const sopot_b200_rocket
     if ((rc = sg.out(traj_out, snaps * 14 * n * 8, &d_traj))) return rc;
     if ((rc = sg.out(status, n * 4, &d_status))) return rc;
     if (n) {
-        const unsigned grid = sb_grid_for(n, RocketSys::BLOCK);
-        if (opts->fp_mode == SOPOT_B200_FP_STRICT) {
-            if ((rc = rocket_set_smem<true>(ctx, smem))) return rc;
-            rk4_ensemble_kernel<RocketSys, true><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(
-                P, n, 0.0, dt, n_steps, opts->store_every, (double*)d_state, (double*)d_traj, (int32_t*)d_status);
-        } else {
-            if ((rc = rocket_set_smem<false>(ctx, smem))) return rc;
-            rk4_ensemble_kernel<RocketSys, false><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(
-                P, n, 0.0, dt, n_steps, opts->store_every, (double*)d_state, (double*)d_traj, (int32_t*)d_status);
-        }
+        const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
+        const bool tables = P.tab.cd.rows || P.tab.cl.rows || P.tab.cs.rows || P.tab.cmq.rows;
+        double* ds = (double*)d_state; double* dt_ = (double*)d_traj; int32_t* dst = (int32_t*)d_status;
+        if (tables) rc = strict ? rocket_launch_rk4<RocketSysTables, true>(ctx, P, n, dt, n_steps, opts->store_every, smem, ds, dt_, dst)
+                                : rocket_launch_rk4<RocketSysTables, false>(ctx, P, n, dt, n_steps, opts->store_every, smem, ds, dt_, dst);
+        else rc = strict ? rocket_launch_rk4<RocketSys, true>(ctx, P, n, dt, n_steps, opts->store_every, smem, ds, dt_, dst)
+                         : rocket_launch_rk4<RocketSys, false>(ctx, P, n, dt, n_steps, opts->store_every, smem, ds, dt_, dst);
+        if (rc) return rc;
         SB_CHECK_LAUNCH(ctx);
     }
     return sg.finish();
@@ -482,14 +604,13 @@ SB_EXPORT int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket
     if ((rc = sg.out(out, 14 * n * 8, &d_out))) return rc;
     const size_t smem = RocketSys::smem_bytes(P);
     if (n) {
-        const unsigned grid = sb_grid_for(n, RocketSys::BLOCK);
-        if (opts->fp_mode == SOPOT_B200_FP_STRICT) {
-            if ((rc = rocket_set_smem<true>(ctx, smem))) return rc;
-            rhs_ensemble_kernel<RocketSys, true><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
-        } else {
-            if ((rc = rocket_set_smem<false>(ctx, smem))) return rc;
-            rhs_ensemble_kernel<RocketSys, false><<<grid, RocketSys::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
-        }
+        const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
+        const bool tables = P.tab.cd.rows || P.tab.cl.rows || P.tab.cs.rows || P.tab.cmq.rows;
+        if (tables) rc = strict ? rocket_launch_rhs<RocketSysTables, true>(ctx, P, n, smem, (const double*)d_state, (double*)d_out)
+                                : rocket_launch_rhs<RocketSysTables, false>(ctx, P, n, smem, (const double*)d_state, (double*)d_out);
+        else rc = strict ? rocket_launch_rhs<RocketSys, true>(ctx, P, n, smem, (const double*)d_state, (double*)d_out)
+                         : rocket_launch_rhs<RocketSys, false>(ctx, P, n, smem, (const double*)d_state, (double*)d_out);
+        if (rc) return rc;
         SB_CHECK_LAUNCH(ctx);
     }
     return sg.finish();

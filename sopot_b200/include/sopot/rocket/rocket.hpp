@@ -5,8 +5,8 @@
 // The 11-component right-hand side is RocketSys in csrc/rocket.cu; this
 // header only carries configuration to sopot_b200_rocket_rk4 / _rhs.  Tables can be given as arrays
 // (setEngineTable ...) or read from the reference's CSV files (numeric rows, '#' comments, header cells
-// skipped: io/csv_parser.hpp:44-83).  Aerodynamic coefficient tables are not loaded by this build: the
-// reference defaults (Cd 0.3, Cl = Cs = 0, cmq = -450; rocket/axisymmetric_aero.hpp:142-166, :275) apply.
+// skipped: io/csv_parser.hpp:44-83).  Aerodynamic coefficient tables (loadAeroData / loadDampingData / aero()) feed the
+// bilinear lookups of the kernel; without them the reference defaults apply (Cd 0.3, Cl = Cs = 0, cmq = -450).
 #pragma once
 #include <array>
 #include <cmath>
@@ -52,15 +52,73 @@ inline std::vector<double> flatten(const std::vector<std::vector<double>>& rows,
 }
 }  // namespace detail
 
+// io::BilinearInterpolator's table (io/interpolation.hpp:77-133): first CSV line = column headers behind a placeholder
+// cell, then one line per row: row header, data...
+struct CoefficientTable {
+    std::vector<double> rows, cols, data;      // data[rows][cols]
+    bool empty() const { return data.empty(); }
+    void setup(std::vector<double> r, std::vector<double> c, std::vector<double> d) {
+        if (d.size() != r.size() * c.size() || r.size() < 2 || c.size() < 2)
+            throw std::invalid_argument("coefficient table needs >= 2 rows and columns and rows*cols values");
+        rows = std::move(r); cols = std::move(c); data = std::move(d);
+    }
+    void setupFromTable(const std::vector<std::vector<double>>& table) {
+        if (table.empty() || table[0].empty()) throw std::runtime_error("BilinearInterpolator: empty table");
+        std::vector<double> r, c(table[0].begin() + 1, table[0].end()), d;
+        for (size_t i = 1; i < table.size(); ++i) {
+            if (table[i].empty()) continue;
+            r.push_back(table[i][0]);
+            if (table[i].size() != c.size() + 1) throw std::invalid_argument("coefficient table: ragged row");
+            d.insert(d.end(), table[i].begin() + 1, table[i].end());
+        }
+        setup(std::move(r), std::move(c), std::move(d));
+    }
+    void loadFromFile(const std::string& filename) { setupFromTable(detail::parse_csv(filename)); }
+    sopot_b200_table2d view() const {
+        return empty() ? sopot_b200_table2d{0, 0, nullptr, nullptr, nullptr}
+                       : sopot_b200_table2d{rows.size(), cols.size(), rows.data(), cols.data(), data.data()};
+    }
+};
+
+// configuration surface of AxisymmetricAerodynamics (rocket/axisymmetric_aero.hpp:52-111): coefficient tables and the
+// power-on switch; the force / moment model itself is RocketSysT<true> in csrc/rocket.cu
+class AerodynamicsConfig {
+public:
+    void setEngineOn(bool on) { m_engine_on = on; }
+    void loadCdPowerOff(const std::string& f) { cd_power_off.loadFromFile(f); }
+    void loadCdPowerOn(const std::string& f) { cd_power_on.loadFromFile(f); }
+    void loadClPowerOff(const std::string& f) { cl_power_off.loadFromFile(f); }
+    void loadClPowerOn(const std::string& f) { cl_power_on.loadFromFile(f); }
+    void loadCsPowerOff(const std::string& f) { cs_power_off.loadFromFile(f); }
+    void loadCsPowerOn(const std::string& f) { cs_power_on.loadFromFile(f); }
+    void loadDampingX(const std::string& f) { cmq_x.loadFromFile(f); }       // loaded and, as in the reference, never used
+    void loadDampingYZ(const std::string& f) { cmq_yz.loadFromFile(f); }
+    bool any() const {
+        return !(cd_power_on.empty() && cd_power_off.empty() && cl_power_on.empty() && cl_power_off.empty() &&
+                 cs_power_on.empty() && cs_power_off.empty() && cmq_yz.empty());
+    }
+    sopot_b200_aero_tables view() const {
+        return {cd_power_on.view(), cd_power_off.view(), cl_power_on.view(), cl_power_off.view(), cs_power_on.view(),
+                cs_power_off.view(), cmq_yz.view(), m_engine_on ? 1 : 0};
+    }
+    CoefficientTable cd_power_on, cd_power_off, cl_power_on, cl_power_off, cs_power_on, cs_power_off, cmq_x, cmq_yz;
+private:
+    bool m_engine_on = true;
+};
+
 // tables shared by every trajectory of a call (row-major, see include/sopot_b200.h)
 struct RocketTables {
     std::vector<double> engine;   // [rows][8] time, throat_d, exit_d, p_comb, T_comb, gamma, mol_mass, efficiency
     std::vector<double> mass, ix, iyz;   // [rows][2] time, value
-    void fill(sopot_b200_rocket_params& p) const {
+    AerodynamicsConfig aero;
+    // `view` must outlive the call that uses p (it is what p.aero points to)
+    void fill(sopot_b200_rocket_params& p, sopot_b200_aero_tables& view) const {
         p.engine_rows = engine.size() / 8; p.engine = engine.empty() ? nullptr : engine.data();
         p.mass_rows = mass.size() / 2;     p.mass = mass.empty() ? nullptr : mass.data();
         p.ix_rows = ix.size() / 2;         p.ix = ix.empty() ? nullptr : ix.data();
         p.iyz_rows = iyz.size() / 2;       p.iyz = iyz.empty() ? nullptr : iyz.data();
+        p.aero = nullptr;
+        if (aero.any()) { view = aero.view(); p.aero = &view; }
     }
 };
 
@@ -78,19 +136,20 @@ struct RocketEnsemble {
     size_t n;
     b200::Param elevation_deg, azimuth_deg, diameter, gravity;
     RocketTables tables;
-    sopot_b200_rocket_params params(uint32_t& bc) const {
+    sopot_b200_rocket_params params(uint32_t& bc, sopot_b200_aero_tables& aero_view) const {
         const b200::Param* f[4] = {&elevation_deg, &azimuth_deg, &diameter, &gravity};
         bc = 0;
         for (int j = 0; j < 4; ++j) bc |= (f[j]->broadcast(n) ? 1u : 0u) << j;
         sopot_b200_rocket_params p{};
         p.elevation_deg = f[0]->data(); p.azimuth_deg = f[1]->data(); p.diameter = f[2]->data(); p.gravity = f[3]->data();
-        tables.fill(p);
+        tables.fill(p, aero_view);
         return p;
     }
     RocketEnsembleResult integrate(b200::Engine& eng, size_t n_steps, double /*t0: the rocket carries its own clock, state[0]*/,
                                    double dt, const b200::EnsembleOptions& o) const {
         uint32_t bc;
-        const auto p = params(bc);
+        sopot_b200_aero_tables aero_view;
+        const auto p = params(bc, aero_view);
         const auto opts = b200::make_opts(o, bc);
         RocketEnsembleResult r;
         r.n = n; r.dim = 14; r.n_steps = n_steps; r.store_every = o.store_every;
@@ -132,6 +191,18 @@ public:
         m_tables.engine = detail::flatten(detail::parse_csv(path + "sim_engine.csv"), 8, "sim_engine.csv");
         m_ready = false;
     }
+    void loadAeroData(const std::string& path) {                             // :135-142
+        m_tables.aero.loadCdPowerOff(path + "cd_power_off_rocket.csv"); m_tables.aero.loadCdPowerOn(path + "cd_power_on_rocket.csv");
+        m_tables.aero.loadClPowerOff(path + "cl_power_off_rocket.csv"); m_tables.aero.loadClPowerOn(path + "cl_power_on_rocket.csv");
+        m_tables.aero.loadCsPowerOff(path + "cs_power_off_rocket.csv"); m_tables.aero.loadCsPowerOn(path + "cs_power_on_rocket.csv");
+        m_ready = false;
+    }
+    void loadDampingData(const std::string& path) {                          // :144-147
+        m_tables.aero.loadDampingX(path + "cmq_x_power_on_rocket.csv"); m_tables.aero.loadDampingYZ(path + "cmq_yz_power_on_rocket.csv");
+        m_ready = false;
+    }
+    AerodynamicsConfig& aero() { m_ready = false; return m_tables.aero; }     // :152-153
+    const AerodynamicsConfig& aero() const { return m_tables.aero; }
     void setEngineTable(std::vector<double> rows_by_8) { m_tables.engine = std::move(rows_by_8); m_ready = false; }
     void setMassTable(std::vector<double> rows_by_2) { m_tables.mass = std::move(rows_by_2); m_ready = false; }
     void setInertiaTables(std::vector<double> ix, std::vector<double> iyz) { m_tables.ix = std::move(ix); m_tables.iyz = std::move(iyz); m_ready = false; }
@@ -152,7 +223,8 @@ public:
         b200::Engine& eng = b200::Engine::shared();
         const auto e = ensemble();
         uint32_t bc;
-        const auto p = e.params(bc);
+        sopot_b200_aero_tables aero_view;
+        const auto p = e.params(bc, aero_view);
         const auto opts = b200::make_opts(strictOpts(), bc);
         std::vector<double> out(14);
         eng.check(sopot_b200_rocket_rhs(eng.ctx(), &p, 1, &opts, state.data(), out.data()));

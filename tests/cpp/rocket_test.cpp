@@ -98,6 +98,33 @@ int main() {
     from_csv.loadEngineData("/tmp/sopot_b200_");
     ASSERT_TRUE(from_csv.tables().engine == engine_table());
     ASSERT_THROWS(from_csv.loadEngineData("/nonexistent/dir/"), std::runtime_error);
+    // coefficient tables through the reference's loaders (rocket/rocket.hpp:135-147): lift and a drag rise change the flight
+    {
+        auto write = [](const char* path, const std::vector<double>& cols, const std::vector<double>& rows, auto f) {
+            std::ofstream o(path);
+            o.precision(17);
+            o << "0";                                            // placeholder cell in front of the column headers
+            for (double c : cols) o << "," << c;
+            o << "\n";
+            for (double r : rows) { o << r; for (double c : cols) o << "," << f(r, c); o << "\n"; }
+        };
+        const std::vector<double> mach{0.0, 0.3, 0.6, 0.9, 1.2}, ang{0.0, 2.0, 5.0, 10.0, 20.0};
+        write("/tmp/sopot_b200_cd_on.csv", ang, mach, [](double m, double a) { return 0.25 + 0.1 * m + 0.004 * a; });
+        write("/tmp/sopot_b200_cl_on.csv", ang, mach, [](double m, double a) { return 0.02 * a * (1 + 0.2 * m); });
+        Rocket<double> tabled;
+        tabled.setLauncher(85.0, 0.0);
+        tabled.setDiameter(0.16);
+        tabled.setEngineTable(engine_table());
+        tabled.setMassTable(mass_table());
+        tabled.aero().loadCdPowerOn("/tmp/sopot_b200_cd_on.csv");
+        tabled.aero().loadClPowerOn("/tmp/sopot_b200_cl_on.csv");
+        ASSERT_TRUE(tabled.aero().cd_power_on.rows.size() == 5 && tabled.aero().cd_power_on.cols.size() == 5);
+        auto rt = simulateRocket(tabled, 30.0, 0.01);
+        double apogee_t = 0.0;
+        for (const auto& st : rt.states) apogee_t = std::max(apogee_t, st[3]);
+        ASSERT_TRUE(std::isfinite(apogee_t) && std::abs(apogee_t - apogee) > 1.0);     // Cd(M, alpha) != 0.3: a different flight
+        ASSERT_THROWS(tabled.aero().loadCsPowerOn("/nonexistent.csv"), std::runtime_error);
+    }
     std::puts("rocket_test: OK");
     return 0;
 }

@@ -89,6 +89,7 @@ def main():
     np.savez(os.path.join(OUT, "grid2d.npz"), **out)
     control_golden(R)
     cartn_linearize_golden(R)
+    rocket_aero_golden(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
@@ -142,3 +143,33 @@ def cartn_linearize_golden(R):
         A, B = R.cartn_linearize(N, mc, m, L, g, x, u)
         out.update({f"n{N}_mc": mc, f"n{N}_m": m, f"n{N}_L": L, f"n{N}_g": g, f"n{N}_x": x, f"n{N}_u": u, f"n{N}_A": A, f"n{N}_B": B})
     np.savez(os.path.join(OUT, "cartn_linearize.npz"), **out)
+
+
+def rocket_aero_tables():
+    """Synthetic coefficient tables in the reference's layouts (rocket/axisymmetric_aero.hpp:133-167, :276-281)."""
+    mach = np.array([0.0, 0.3, 0.6, 0.9, 1.2]); ang = np.array([0.0, 2.0, 5.0, 10.0, 20.0])
+    cd = 0.25 + 0.1 * mach[:, None] + 0.004 * ang[None, :]
+    cl = 0.02 * ang[None, :] * (1 + 0.2 * mach[:, None])
+    cs = 0.015 * ang[None, :] * (1 + 0.1 * mach[:, None])
+    aoa_signed = np.array([-20.0, -5.0, 0.0, 5.0, 20.0])
+    cmq = -400.0 - 5.0 * np.abs(aoa_signed)[:, None] - 30.0 * mach[None, :]
+    return dict(cd_power_on=(mach, ang, cd), cd_power_off=(mach, ang, cd + 0.05), cl_power_on=(mach, ang, cl),
+                cs_power_off=(mach, ang, cs), cmq_yz=(aoa_signed, mach, cmq))
+
+
+def rocket_aero_golden(R):
+    """Table-driven aerodynamics: full Rocket component system with Cd/Cl/Cs/cmq tables loaded through the CSV loaders."""
+    aero = rocket_aero_tables()
+    n = 12
+    w = W.rocket_ensemble(n, seed=44)
+    out = dict(elev=w["elev"], az=w["az"], diam=w["diam"], g0=w["g0"], engine=w["engine"], mass_tab=w["mass_tab"])
+    for tag, on in (("on", True), ("off", False)):
+        fin, stats, _ = R.rocket_rk4(w["elev"], w["az"], w["diam"], w["g0"], w["engine"], w["mass_tab"], None, None, 10.0, 0.01,
+                                     aero=aero, engine_on=on)
+        out["final_" + tag], out["stats_" + tag] = fin, stats
+    st = out["final_on"].copy()
+    st[11:] = np.array([0.05, -0.03, 0.02])[:, None]            # tumbling: exercises the damping table
+    st[0] = 2.0                                                   # powered flight
+    out["rhs_state"] = st
+    out["rhs"] = R.rocket_rhs(84.0, 30.0, 0.16, 9.80665, w["engine"], w["mass_tab"], st, aero=aero)
+    np.savez(os.path.join(OUT, "rocket_aero.npz"), **out)

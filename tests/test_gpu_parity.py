@@ -399,3 +399,25 @@ def test_linearize_lqr_closed_loop_pipeline_on_device(engine, port):
     assert np.array_equal(K.download()[:, idx], rK) and np.array_equal(it.download()[idx], rit)
     rfin, rstats = port.cartpole_feedback_rk4(mc[idx], m[idx], L[idx], g[idx], s0[:, idx], rK, None, -50.0, 50.0, 1, 0.0, 0.002, 2500, nthreads=4)
     assert np.abs(fin[:, idx] - rfin).max() <= 1e-9 and np.abs(stats[:, idx] - rstats).max() <= 1e-9
+
+
+def test_rocket_aero_tables_golden(engine):
+    """Rocket with bilinear Cd/Cl/Cs and damping tables in shared memory (RocketSysT<true>): trajectories, statistics and
+    one derivative evaluation of a tumbling rocket against the reference's components (golden vectors)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    aero = mg.rocket_aero_tables()
+    g = golden("rocket_aero")
+    n = g["elev"].size
+    for mode in (FP_STRICT, FP_CONTRACT):
+        for tag, on in (("on", True), ("off", False)):
+            st, stats, _, status = engine.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None, None, n,
+                                                     0.01, 1000, fp_mode=mode, aero=engine.aero_tables(aero, engine_on=on))
+            assert not status.any()
+            assert rel_err(st, g["final_" + tag]).max() <= FINAL
+            assert rel_err(stats[[0, 2, 4, 5]], g["stats_" + tag][[0, 2, 4, 5]]).max() <= FINAL
+        rhs = engine.rocket_rhs(84.0, 30.0, 0.16, 9.80665, g["engine"], g["mass_tab"], g["rhs_state"], fp_mode=mode, aero=aero)
+        assert rel_err(rhs, g["rhs"]).max() <= 1e-12

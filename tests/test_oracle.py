@@ -214,3 +214,20 @@ def test_lqr_port_equals_reference_on_fresh_inputs(port, ref):
     fa = port.cartpole_feedback_rk4(mc, m, L, np.full(P, 9.81), s0, a[0], None, -30.0, 30.0, 1, 0.0, 0.001, 400)
     fb = ref.cartpole_feedback_rk4(mc, m, L, np.full(P, 9.81), s0, a[0], None, -30.0, 30.0, 1, 0.0, 0.001, 400)
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
+
+
+def test_golden_rocket_aero_tables(port):
+    """Table-driven aerodynamics (bilinear Cd/Cl/Cs/cmq tables, io/interpolation.hpp:137-181 through
+    rocket/axisymmetric_aero.hpp:133-167,276-281): C restatement == the reference's components, bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    aero = mg.rocket_aero_tables()
+    g = golden("rocket_aero")
+    for tag, on in (("on", True), ("off", False)):
+        fin, stats, _ = port.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None, None, 10.0, 0.01,
+                                        aero=aero, engine_on=on, nthreads=4)
+        assert np.array_equal(fin, g["final_" + tag]) and np.array_equal(stats, g["stats_" + tag])
+    assert not np.array_equal(g["final_on"], g["final_off"])          # the power-on / power-off tables are both used
+    rhs = port.rocket_rhs(84.0, 30.0, 0.16, 9.80665, g["engine"], g["mass_tab"], g["rhs_state"], aero=aero)
+    assert np.array_equal(rhs, g["rhs"])
