@@ -6,7 +6,7 @@
 // Needs a B200.
 #include <cstdio>
 #include <fstream>
-#include <sopot/rocket/rocket.hpp>
+#include <sopot/rocket/simulation_result.hpp>
 #include "check.hpp"
 
 using namespace sopot;
@@ -85,6 +85,22 @@ int main() {
     auto disp = RocketEnsemble::dispersion(b200::Engine::shared(), er);
     ASSERT_TRUE(disp[Apogee].count == double(n) && disp[Apogee].min <= apogee && disp[Apogee].max >= apogee);
     ASSERT_TRUE(disp[Apogee].stddev > 0.0 && disp[Apogee].nonfinite == 0.0);
+
+    // SimulationResult (rocket/simulation_result.hpp): statistics of the stored trajectory == the kernel's running ones,
+    // time-indexed queries interpolate between stored steps
+    {
+        auto sim = simulate(rocket, 30.0, 0.01);
+        ASSERT_TRUE(sim.size() == 3001 && sim.startTime() == 0.0);
+        ASSERT_TRUE(sim.apogee() == er.stat(Apogee, 0) && sim.apogeeTime() == er.stat(ApogeeTime, 0));
+        ASSERT_TRUE(sim.maxSpeed() == er.stat(MaxSpeed, 0) && sim.maxSpeedTime() == er.stat(MaxSpeedTime, 0));
+        ASSERT_TRUE(sim.burnoutAltitude() == er.stat(BurnoutAltitude, 0) && sim.burnoutSpeed() == er.stat(BurnoutSpeed, 0));
+        const auto [i, alpha] = sim.findIndex(12.3456);
+        ASSERT_TRUE(i == 1234 && alpha > 0.55 && alpha < 0.57);
+        const double a0 = sim.stateAt(1234)[3], a1 = sim.stateAt(1235)[3];
+        ASSERT_NEAR(sim.altitude(12.3456), a0 + alpha * (a1 - a0), 1e-9);
+        ASSERT_TRUE(sim.altitude(-1.0) == 0.0 && sim.altitude(99.0) == sim.stateAt(3000)[3]);
+        ASSERT_TRUE(sim.altitudeProfile().size() == 3001 && sim.speed(3.0) > 100.0);
+    }
 
     // CSV path of the reference (rocket/rocket.hpp:124-133): numeric rows, header cells skipped
     {
