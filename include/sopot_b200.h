@@ -165,6 +165,13 @@ int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const double* B, 
                          double R, double riccati_dt, size_t max_iter, double tol,
                          const sopot_b200_rk4_opts* opts, double* K, double* Pric, int32_t* iters, int32_t* status);
 
+/* The same for LQR<state_dim,1> with state_dim 4, 6 or 14 (cart + 1, 2 or 6 links; the reference's own tests use
+ * LQR<14,1>): A [state_dim^2][P], B [state_dim][P], Q [state_dim^2] host row-major, K [state_dim][P].  state_dim 4 runs
+ * one point per thread, 6 and 14 one CTA of state_dim^2 threads per point with the matrices in shared memory. */
+int sopot_b200_lqr_gain(sopot_b200_ctx* ctx, int state_dim, const double* A, const double* B, size_t P, const double* Q,
+                        double R, double riccati_dt, size_t max_iter, double tol, const sopot_b200_rk4_opts* opts,
+                        double* K, double* Pric, int32_t* iters, int32_t* status);
+
 /* Closed-loop cart-pole ensemble: StateFeedbackController<4,1>::compute (state_feedback_controller.hpp:88-104,
  * u = -K (x - x_ref), clamped to [u_min, u_max] when saturate != 0) drives CartNPendulum<1,double> through
  * setControlForce; the force is evaluated ONCE per RK4 step from the state at the start of the step and held

@@ -170,6 +170,28 @@ class Checker:
             raise KeyError("link count not instantiated")
         return A, B
 
+    def lqr_n(self, ns, A, B, Q, R, dt=0.01, max_iter=1000, tol=1e-8, nthreads=1):
+        A = _f64(A); P = A.shape[1]
+        B, Q = _f64(B), _f64(Q).reshape(ns * ns)
+        K = np.empty((ns, P)); Pric = np.empty((ns * ns, P))
+        iters = np.zeros(P, dtype=np.int32); st = np.zeros(P, dtype=np.int32)
+        rc = self._fn("lqr_n", [_i, _sz, _dp, _dp, _dp, _d, _d, _sz, _d, _dp, _dp, _ip, _ip, _i])(
+            ns, P, _p(A), _p(B), _p(Q), R, dt, max_iter, tol, _p(K), _p(Pric), iters.ctypes.data_as(_ip), st.ctypes.data_as(_ip), nthreads)
+        assert rc == 0
+        return K, Pric, iters, st
+
+    def cartn_feedback_rk4(self, n_links, mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, nthreads=1):
+        s0 = _f64(s0); n = s0.shape[1]
+        m, L = _f64(m).reshape(n_links, n), _f64(L).reshape(n_links, n)
+        mc, g = (_f64(a, n).reshape(-1) for a in (mc, g))
+        K = _f64(K); xref = None if xref is None else _f64(xref)
+        fin = np.empty_like(s0); stats = np.empty((2, n))
+        rc = self._fn("cartn_feedback_rk4", [_i, _sz] + [_dp] * 7 + [_d, _d, _i, _d, _d, _sz, _dp, _dp, _i])(
+            n_links, n, _p(mc), _p(m), _p(L), _p(g), _p(s0), _p(K), _p(xref), umin, umax, int(saturate), t0, dt, n_steps,
+            _p(fin), _p(stats), nthreads)
+        assert rc == 0
+        return fin, stats
+
     # ---------------- plugin-path check: coupled oscillator ----------------
     def coupled_rk4(self, m1, m2, k, L0, c, x1, x2, t0, t1, dt, nthreads=1):
         k = _f64(k).reshape(-1); n = k.size

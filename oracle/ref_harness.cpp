@@ -317,6 +317,86 @@ int ref_cartn_linearize(int n_links, size_t P, const double* mc, const double* m
     return 0;
 }
 
+// LQR<NS,1>::solve for NS = 4, 6, 14 and the N-link closed loop (CartNPendulumController-style state feedback, force held
+// over one RK4Solver step)
+extern "C++" {
+template <size_t NS>
+static void lqr_one(const double* A, const double* B, const double* Q, double R, double dt, size_t max_iter, double tol, size_t P,
+                    size_t p, double* K, double* Pric, int* status) {
+    typename control::LQR<NS, 1>::StateMatrix Am, Qm;
+    typename control::LQR<NS, 1>::InputMatrix Bm;
+    for (size_t i = 0; i < NS; ++i) {
+        for (size_t j = 0; j < NS; ++j) { Am[i][j] = A[(i * NS + j) * P + p]; Qm[i][j] = Q[i * NS + j]; }
+        Bm[i][0] = B[i * P + p];
+    }
+    typename control::LQR<NS, 1>::InputWeightMatrix Rm{};
+    Rm[0][0] = R;
+    control::LQR<NS, 1> lqr;
+    int st = 0;
+    try { st = lqr.solve(Am, Bm, Qm, Rm, dt, max_iter, tol) ? 0 : 8; } catch (const std::runtime_error&) { st = 2; }
+    for (size_t j = 0; j < NS; ++j) K[j * P + p] = st ? NAN : lqr.getGain()[0][j];
+    if (Pric) for (size_t i = 0; i < NS; ++i) for (size_t j = 0; j < NS; ++j) Pric[(i * NS + j) * P + p] = lqr.getRiccatiSolution()[i][j];
+    if (status) status[p] = st;
+}
+template <size_t NL>
+static void cartn_feedback_one(const double* mc, const double* m, const double* L, const double* g, const double* s0, const double* K,
+                               const double* xref, double umin, double umax, int saturate, double t0, double dt, size_t n_steps,
+                               size_t n, size_t i, double* final_out, double* stats) {
+    constexpr size_t NS = 2 * (NL + 1);
+    typename control::StateFeedbackController<NS, 1>::GainMatrix Km{};
+    std::array<double, NS> ref{};
+    for (size_t q = 0; q < NS; ++q) { Km[0][q] = K[q * n + i]; ref[q] = xref ? xref[q * n + i] : 0.0; }
+    control::StateFeedbackController<NS, 1> ctl(Km);
+    ctl.setReference(ref);
+    if (saturate) ctl.setSaturationLimits({umin}, {umax});
+    std::array<double, NL> mm, LL;
+    for (size_t q = 0; q < NL; ++q) { mm[q] = m[q * n + i]; LL[q] = L[q * n + i]; }
+    control::CartNPendulum<NL, double> plant(mc[i], mm, LL, g[i]);
+    auto sys = makeTypedODESystem<double>(std::move(plant));
+    auto solver = createRK4Solver();
+    std::vector<double> y(NS);
+    for (size_t q = 0; q < NS; ++q) y[q] = s0[q * n + i];
+    double t = t0, max_th = 0.0, max_u = 0.0;
+    for (size_t q = 1; q <= NL; ++q) max_th = std::max(max_th, std::abs(y[q]));
+    auto derivs = [&sys](double tt, StateView sv) { std::vector<double> v(sv.begin(), sv.end()); return sys.computeDerivatives(tt, v); };
+    for (size_t step = 0; step < n_steps; ++step) {
+        std::array<double, NS> ya;
+        for (size_t q = 0; q < NS; ++q) ya[q] = y[q];
+        const double u = ctl.compute(ya)[0];
+        max_u = std::max(max_u, std::abs(u));
+        sys.template getComponent<0>().setControlForce(u);
+        auto r = solver.solve(derivs, NS, t, t + dt, dt, y);
+        y = r.states.back();
+        t += dt;
+        for (size_t q = 1; q <= NL; ++q) max_th = std::max(max_th, std::abs(y[q]));
+    }
+    for (size_t q = 0; q < NS; ++q) final_out[q * n + i] = y[q];
+    if (stats) { stats[i] = max_th; stats[n + i] = max_u; }
+}
+}  // extern "C++"
+int ref_lqr_n(int ns, size_t P, const double* A, const double* B, const double* Q, double R, double dt, size_t max_iter, double tol,
+              double* K, double* Pric, int* iters_unused, int* status, int nthreads) {
+    (void)iters_unused;
+    if (ns != 4 && ns != 6 && ns != 14) return -1;
+    parallel_for(P, nthreads, [&](size_t p) {
+        if (ns == 4) lqr_one<4>(A, B, Q, R, dt, max_iter, tol, P, p, K, Pric, status);
+        else if (ns == 6) lqr_one<6>(A, B, Q, R, dt, max_iter, tol, P, p, K, Pric, status);
+        else lqr_one<14>(A, B, Q, R, dt, max_iter, tol, P, p, K, Pric, status);
+    });
+    return 0;
+}
+int ref_cartn_feedback_rk4(int n_links, size_t n, const double* mc, const double* m, const double* L, const double* g, const double* s0,
+                           const double* K, const double* xref, double umin, double umax, int saturate, double t0, double dt,
+                           size_t n_steps, double* final_out, double* stats, int nthreads) {
+    if (n_links != 1 && n_links != 2 && n_links != 6) return -1;
+    parallel_for(n, nthreads, [&](size_t i) {
+        if (n_links == 1) cartn_feedback_one<1>(mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, n, i, final_out, stats);
+        else if (n_links == 2) cartn_feedback_one<2>(mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, n, i, final_out, stats);
+        else cartn_feedback_one<6>(mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, n, i, final_out, stats);
+    });
+    return 0;
+}
+
 // ---- config 4: 6-DOF rocket ----
 // The 11 components of Rocket<T>::SystemType (rocket/rocket.hpp:73-85) composed by hand so
 // that gravity can be jittered (Rocket<T> has no gravity setter). Tables reach the reference

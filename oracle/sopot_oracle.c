@@ -498,6 +498,89 @@ ORC_API int orc_lqr4(size_t P, const double* A /*[16][P]*/, const double* B /*[4
     return 0;
 }
 
+/* LQR<NS,1>::solve for any NS <= 14 (same statements as orc_lqr4_one with runtime bounds) */
+#define LMAX 14
+static double orc_frob_n(int ns, double A[LMAX][LMAX]) {
+    double sum = 0.0;
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) sum += A[i][j] * A[i][j];
+    return sqrt(sum);
+}
+static void orc_mm_n(int ns, double A[LMAX][LMAX], double B[LMAX][LMAX], double C[LMAX][LMAX]) {
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) {
+        C[i][j] = 0.0;
+        for (int k = 0; k < ns; ++k) C[i][j] += A[i][k] * B[k][j];
+    }
+}
+static int orc_lqr_one(int ns, double A[LMAX][LMAX], const double* B, double Q[LMAX][LMAX], double R, double dt, size_t max_iter,
+                       double tol, double* K, double P[LMAX][LMAX], int* iters) {
+    static __thread double Adt[LMAX][LMAX], Adt2[LMAX][LMAX], Ad[LMAX][LMAX], AdT[LMAX][LMAX], Bcoef[LMAX][LMAX], Qd[LMAX][LMAX],
+        AdTP[LMAX][LMAX], AdTPAd[LMAX][LMAX], Pn[LMAX][LMAX], diff[LMAX][LMAX];
+    double Bd[LMAX], BdTP[LMAX], g[LMAX], Kd[LMAX];
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) Adt[i][j] = A[i][j] * dt;
+    orc_mm_n(ns, Adt, Adt, Adt2);
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) {
+        const double id = i == j ? 1.0 : 0.0;
+        Ad[i][j] = (id + Adt[i][j]) + Adt2[i][j] * 0.5;
+        Bcoef[i][j] = id * dt + Adt[i][j] * (dt * 0.5);
+        Qd[i][j] = Q[i][j] * dt;
+        P[i][j] = Q[i][j] * 1.0;
+    }
+    for (int i = 0; i < ns; ++i) { Bd[i] = 0.0; for (int k = 0; k < ns; ++k) Bd[i] += Bcoef[i][k] * B[k]; }
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) AdT[i][j] = Ad[j][i];
+    *iters = 0;
+    int converged = 0;
+    for (size_t it = 0; it < max_iter; ++it) {
+        orc_mm_n(ns, AdT, P, AdTP);
+        for (int j = 0; j < ns; ++j) { BdTP[j] = 0.0; for (int k = 0; k < ns; ++k) BdTP[j] += Bd[k] * P[k][j]; }
+        double bpb = 0.0;
+        for (int k = 0; k < ns; ++k) bpb += BdTP[k] * Bd[k];
+        const double sden = R * dt + bpb;
+        for (int j = 0; j < ns; ++j) { g[j] = 0.0; for (int k = 0; k < ns; ++k) g[j] += BdTP[k] * Ad[k][j]; }
+        if (fabs(sden) < 1e-12) return 2;
+        for (int j = 0; j < ns; ++j) Kd[j] = g[j] / sden;
+        orc_mm_n(ns, AdTP, Ad, AdTPAd);
+        for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) {
+            double ktrk = 0.0; ktrk += Kd[i] * g[j];
+            Pn[i][j] = (AdTPAd[i][j] - ktrk) + Qd[i][j];
+        }
+        for (int i = 0; i < ns; ++i) for (int j = i + 1; j < ns; ++j) {
+            const double avg = 0.5 * (Pn[i][j] + Pn[j][i]);
+            Pn[i][j] = avg; Pn[j][i] = avg;
+        }
+        for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) diff[i][j] = Pn[i][j] - P[i][j];
+        const double change = orc_frob_n(ns, diff), p_norm = orc_frob_n(ns, Pn);
+        const double rel = (p_norm > 1e-10) ? change / p_norm : change;
+        for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) P[i][j] = Pn[i][j];
+        *iters = (int)it + 1;
+        if (rel < tol || change < tol) { converged = 1; break; }
+        if (p_norm > 1e15 || isnan(change)) break;
+    }
+    if (!converged) {
+        const double fn = orc_frob_n(ns, P);
+        if (!(fn < 1e10) || isnan(fn)) return 8;
+    }
+    if (fabs(R) < 1e-12) return 2;
+    for (int j = 0; j < ns; ++j) { double s = 0.0; for (int k = 0; k < ns; ++k) s += B[k] * P[k][j]; K[j] = s / R; }
+    return 0;
+}
+ORC_API int orc_lqr_n(int ns, size_t P, const double* A, const double* B, const double* Q, double R, double dt, size_t max_iter,
+                      double tol, double* K, double* Pric, int* iters, int* status, int nthreads) {
+    (void)nthreads;
+    if (ns < 1 || ns > LMAX) return -1;
+    for (size_t p = 0; p < P; ++p) {
+        static __thread double Am[LMAX][LMAX], Qm[LMAX][LMAX], Pm[LMAX][LMAX];
+        double Bv[LMAX], Kv[LMAX];
+        int it = 0;
+        for (int r = 0; r < ns; ++r) { for (int c = 0; c < ns; ++c) { Am[r][c] = A[(r * ns + c) * P + p]; Qm[r][c] = Q[r * ns + c]; } Bv[r] = B[r * P + p]; }
+        const int st = orc_lqr_one(ns, Am, Bv, Qm, R, dt, max_iter, tol, Kv, Pm, &it);
+        for (int c = 0; c < ns; ++c) K[c * P + p] = st ? NAN : Kv[c];
+        if (Pric) for (int r = 0; r < ns; ++r) for (int c = 0; c < ns; ++c) Pric[(r * ns + c) * P + p] = Pm[r][c];
+        if (iters) iters[p] = it;
+        if (status) status[p] = st;
+    }
+    return 0;
+}
+
 typedef struct {
     size_t n; const double *mc, *m, *L, *g, *s0, *K, *xref; double umin, umax; int saturate;
     double t0, dt; size_t n_steps; double *final_out, *stats;
@@ -599,6 +682,36 @@ ORC_API int orc_cartn_rk4(int n_links, size_t n, const double* mc, const double*
     }
     return 0;
 }
+
+/* closed loop for the N-link plant: controller sample -> force held over one RK4 step (as orc_cartpole_feedback_rk4) */
+ORC_API int orc_cartn_feedback_rk4(int n_links, size_t n, const double* mc, const double* m, const double* L, const double* g,
+                                   const double* s0, const double* K /*[2(N+1)][n]*/, const double* xref, double umin, double umax,
+                                   int saturate, double t0, double dt, size_t n_steps, double* final_out, double* stats, int nthreads) {
+    (void)nthreads;
+    if (n_links < 1 || n_links > ORC_MAXL) return -1;
+    const int dim = 2 * (n_links + 1);
+    for (size_t i = 0; i < n; ++i) {
+        orc_cpn_t p; p.N = n_links; p.mc = mc[i]; p.g = g[i]; p.F = 0.0; p.status = 0;
+        for (int q = 0; q < n_links; ++q) { p.m[q] = m[q * n + i]; p.L[q] = L[q * n + i]; }
+        double y[2 * (ORC_MAXL + 1)], work[10 * (ORC_MAXL + 1)], t = t0, max_th = 0.0, max_u = 0.0;
+        for (int q = 0; q < dim; ++q) y[q] = s0[q * n + i];
+        for (int q = 1; q <= n_links; ++q) if (fabs(y[q]) > max_th) max_th = fabs(y[q]);
+        for (size_t step = 0; step < n_steps; ++step) {
+            double u = 0.0;
+            for (int q = 0; q < dim; ++q) u -= K[q * n + i] * (y[q] - (xref ? xref[q * n + i] : 0.0));
+            if (saturate) u = u < umin ? umin : (umax < u ? umax : u);
+            p.F = u;
+            if (fabs(u) > max_u) max_u = fabs(u);
+            orc_rk4(orc_cartn_rhs_fn, &p, (size_t)dim, t, t + dt, dt, y, work, NULL, NULL, NULL);
+            t += dt;
+            for (int q = 1; q <= n_links; ++q) if (fabs(y[q]) > max_th) max_th = fabs(y[q]);
+        }
+        for (int q = 0; q < dim; ++q) final_out[q * n + i] = y[q];
+        if (stats) { stats[i] = max_th; stats[n + i] = max_u; }
+    }
+    return 0;
+}
+
 
 /* ------------------------------------------------------------------------------------------
  * Plugin-path check -- the reference's composition example, physics/coupled_oscillator/: two PointMass

@@ -117,6 +117,8 @@ SYMBOLS = {
     "sopot_b200_cartpole_rhs": (c_int, [_ctx, POINTER(CartpoleParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_lqr4_gain": (c_int, [_ctx, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
                                      POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sopot_b200_lqr_gain": (c_int, [_ctx, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
+                                    POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sopot_b200_cartpole_feedback_rk4": (c_int, [_ctx, POINTER(CartpoleParams), POINTER(Feedback), c_size_t, c_double,
                                                  c_double, c_size_t, POINTER(RK4Opts), c_void_p, c_void_p, c_void_p,
                                                  c_void_p]),
@@ -405,6 +407,24 @@ class Engine:
             status = self.empty((P,), np.int32)
         self._ck(self.lib.sopot_b200_lqr4_gain(self.ctx, _ptr(A), _ptr(B), P, Q.ctypes.data, R, riccati_dt, max_iter, tol,
                                                byref(opts), _ptr(K), _ptr(Pric), _ptr(iters), _ptr(status)))
+        if sync:
+            self.sync()
+        return K, Pric, iters, status
+
+    def lqr_gain(self, state_dim, A, B, P, Q, R, riccati_dt=0.01, max_iter=1000, tol=1e-8, mem=MEM_HOST, fp_mode=FP_CONTRACT,
+                 want_riccati=False, sync=True):
+        """Batched LQR<state_dim,1>::solve (state_dim 4, 6, 14): A [sd^2][P], B [sd][P] -> K [sd][P], Pric, iters, status."""
+        Q = np.ascontiguousarray(np.asarray(Q, dtype=np.float64).reshape(state_dim * state_dim))
+        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        if mem == MEM_HOST:
+            A = np.ascontiguousarray(A, dtype=np.float64); B = np.ascontiguousarray(B, dtype=np.float64)
+            K = np.empty((state_dim, P)); Pric = np.empty((state_dim * state_dim, P)) if want_riccati else None
+            iters = np.zeros(P, dtype=np.int32); status = np.zeros(P, dtype=np.int32)
+        else:
+            K = self.empty((state_dim, P)); Pric = self.empty((state_dim * state_dim, P)) if want_riccati else None
+            iters = self.empty((P,), np.int32); status = self.empty((P,), np.int32)
+        self._ck(self.lib.sopot_b200_lqr_gain(self.ctx, state_dim, _ptr(A), _ptr(B), P, Q.ctypes.data, R, riccati_dt, max_iter, tol,
+                                              byref(opts), _ptr(K), _ptr(Pric), _ptr(iters), _ptr(status)))
         if sync:
             self.sync()
         return K, Pric, iters, status

@@ -186,6 +186,148 @@ lqr4_kernel(const double* __restrict__ Ain, const double* __restrict__ Bin, cons
     if (status) status[p] = st;
 }
 
+// ---- LQR<NS,1>::solve for larger plants: one CTA of NS x NS threads per operating point --------------------------
+// Thread (i, j) owns element (i, j) of every NS x NS matrix; the matrices live in shared memory.  Each dot product
+// runs over k = 0..NS-1 starting from 0.0 and the two Frobenius norms are summed by one thread in row-major order, so
+// the Strict instantiation is bit-identical to the reference class for any NS (the reference's own tests use the
+// 6-link plant: LQR<14,1>, tests/inverted_pendulum_test.cpp:208-232).
+template <int NS, bool S>
+__global__ void __launch_bounds__(NS * NS)
+lqr_block_kernel(const double* __restrict__ Ain, const double* __restrict__ Bin, const size_t P, const double* __restrict__ Qin,
+                 const double R_, const double dt_, const int max_iter, const double tol, double* __restrict__ K,
+                 double* __restrict__ Pric, int32_t* __restrict__ iters_out, int32_t* __restrict__ status) {
+    using T = Real<S>;
+    __shared__ double Ad[NS][NS], Pm[NS][NS], W1[NS][NS], Pn[NS][NS], W2[NS][NS];
+    __shared__ double Bd[NS], BdTP[NS], g[NS], Kd[NS], Bv[NS];
+    __shared__ double s_sden;
+    __shared__ int s_state;          // -1 iterating, 0 converged, -2 diverged, SOPOT_B200_ST_SINGULAR
+    const size_t p = blockIdx.x;
+    const int i = threadIdx.x / NS, j = threadIdx.x % NS, tid = threadIdx.x;
+    const T dt(dt_), R(R_);
+    W1[i][j] = (T(Ain[(size_t)(i * NS + j) * P + p]) * dt).v;                  // Adt = scale(A, dt)
+    if (j == 0) Bv[i] = Bin[(size_t)i * P + p];
+    if (tid == 0) s_state = -1;
+    __syncthreads();
+    const T q(Qin[i * NS + j]);
+    const T Qd = q * dt;                                                       // scale(Q, dt)
+    {
+        T s2(0.0);
+        for (int k = 0; k < NS; ++k) s2 = s2 + T(W1[i][k]) * T(W1[k][j]);      // multiply(Adt, Adt)
+        const T id(i == j ? 1.0 : 0.0);
+        Ad[i][j] = ((id + T(W1[i][j])) + s2 * T(0.5)).v;
+        W2[i][j] = (id * dt + T(W1[i][j]) * (dt * T(0.5))).v;                  // Bcoef
+        Pm[i][j] = (q * T(1.0)).v;                                             // P0 = scale(Q, 1.0)
+    }
+    __syncthreads();
+    if (j == 0) {
+        T s(0.0);
+        for (int k = 0; k < NS; ++k) s = s + T(W2[i][k]) * T(Bv[k]);           // Bd = Bcoef B
+        Bd[i] = s.v;
+    }
+    __syncthreads();
+    const T Rdt = R * dt;
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        {
+            T s(0.0);
+            for (int k = 0; k < NS; ++k) s = s + T(Ad[k][i]) * T(Pm[k][j]);    // AdTP = Ad' P
+            W1[i][j] = s.v;
+        }
+        if (i == 0) {
+            T s(0.0);
+            for (int k = 0; k < NS; ++k) s = s + T(Bd[k]) * T(Pm[k][j]);       // BdTP = Bd' P
+            BdTP[j] = s.v;
+        }
+        __syncthreads();
+        if (i == 0) {
+            T s(0.0);
+            for (int k = 0; k < NS; ++k) s = s + T(BdTP[k]) * T(Ad[k][j]);     // g = Bd'P Ad
+            g[j] = s.v;
+        }
+        if (tid == NS) {                                                       // (a thread of another row: runs beside g)
+            T bpb(0.0);
+            for (int k = 0; k < NS; ++k) bpb = bpb + T(BdTP[k]) * T(Bd[k]);
+            const T sden = Rdt + bpb;
+            s_sden = sden.v;
+            if (fabs(sden.v) < 1e-12) s_state = SOPOT_B200_ST_SINGULAR;
+        }
+        __syncthreads();
+        if (s_state == SOPOT_B200_ST_SINGULAR) break;
+        if (i == 0) Kd[j] = (T(g[j]) / T(s_sden)).v;
+        __syncthreads();
+        {
+            T s(0.0);
+            for (int k = 0; k < NS; ++k) s = s + T(W1[i][k]) * T(Ad[k][j]);    // AdTP Ad
+            const T ktrk = T(0.0) + T(Kd[i]) * T(g[j]);
+            Pn[i][j] = ((s - ktrk) + Qd).v;
+        }
+        __syncthreads();
+        if (i < j) {                                                           // symmetrise: one thread per pair
+            const T avg = T(0.5) * (T(Pn[i][j]) + T(Pn[j][i]));
+            Pn[i][j] = avg.v; Pn[j][i] = avg.v;
+        }
+        __syncthreads();
+        W2[i][j] = (T(Pn[i][j]) - T(Pm[i][j])).v;                              // diff
+        __syncthreads();
+        if (tid == 0 || tid == 32) {                                           // the two norms, each summed in order by one thread
+            const double (*M)[NS] = tid == 0 ? W2 : Pn;
+            T sum(0.0);
+            for (int a = 0; a < NS; ++a)
+                for (int b = 0; b < NS; ++b) sum = sum + T(M[a][b]) * T(M[a][b]);
+            (tid == 0 ? Bv[0] : Bv[1]) = r_sqrt(sum).v;                        // Bv is free after the set-up
+        }
+        Pm[i][j] = Pn[i][j];                                                   // m_P = P_new
+        __syncthreads();
+        if (tid == 0) {
+            const double change = Bv[0], p_norm = Bv[1];
+            const double rel = (p_norm > 1e-10) ? (T(change) / T(p_norm)).v : change;
+            if (rel < tol || change < tol) s_state = 0;
+            else if (p_norm > 1e15 || change != change) s_state = -2;
+        }
+        __syncthreads();
+        if (s_state != -1) { ++it; break; }
+    }
+    int st = s_state;
+    if (st != SOPOT_B200_ST_SINGULAR) {
+        if (st != 0) {                                                         // not converged cleanly (:388-397)
+            if (tid == 0) {
+                T sum(0.0);
+                for (int a = 0; a < NS; ++a)
+                    for (int b = 0; b < NS; ++b) sum = sum + T(Pm[a][b]) * T(Pm[a][b]);
+                const double fn = r_sqrt(sum).v;
+                s_state = (!(fn < 1e10) || fn != fn) ? SOPOT_B200_ST_NOT_CONVERGED : 0;
+            }
+            __syncthreads();
+            st = s_state;
+        }
+        if (st == 0 && fabs(R_) < 1e-12) st = SOPOT_B200_ST_SINGULAR;
+    }
+    const double bad = __longlong_as_double(0x7ff8000000000000LL);
+    if (i == 0) {
+        double kv = bad;
+        if (st == 0) {
+            T s(0.0);
+            for (int k = 0; k < NS; ++k) s = s + T(Bin[(size_t)k * P + p]) * T(Pm[k][j]);   // K = (B'P) / R
+            kv = (s / R).v;
+        }
+        K[(size_t)j * P + p] = kv;
+    }
+    if (Pric) Pric[(size_t)(i * NS + j) * P + p] = Pm[i][j];
+    if (tid == 0) {
+        if (iters_out) iters_out[p] = it;
+        if (status) status[p] = st;
+    }
+}
+
+template <int NS>
+int lqr_block_launch(sopot_b200_ctx* ctx, bool strict, const double* A, const double* B, size_t P, const double* dQ, double R,
+                     double dt, int max_iter, double tol, double* K, double* Pric, int32_t* iters, int32_t* status) {
+    if (strict) lqr_block_kernel<NS, true><<<(unsigned)P, NS * NS, 0, ctx->stream>>>(A, B, P, dQ, R, dt, max_iter, tol, K, Pric, iters, status);
+    else lqr_block_kernel<NS, false><<<(unsigned)P, NS * NS, 0, ctx->stream>>>(A, B, P, dQ, R, dt, max_iter, tol, K, Pric, iters, status);
+    SB_CHECK_LAUNCH(ctx);
+    return SOPOT_B200_OK;
+}
+
 }  // namespace
 
 SB_EXPORT int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const double* B, size_t P, const double* Q16,
@@ -219,6 +361,43 @@ SB_EXPORT int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const d
             lqr4_kernel<false><<<grid, 128, 0, ctx->stream>>>((const double*)d_A, (const double*)d_B, P, qr, riccati_dt, (int)max_iter,
                                                               tol, (double*)d_K, (double*)d_P, (int32_t*)d_it, (int32_t*)d_st);
         SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}
+
+SB_EXPORT int sopot_b200_lqr_gain(sopot_b200_ctx* ctx, int state_dim, const double* A, const double* B, size_t P, const double* Q,
+                                  double R, double riccati_dt, size_t max_iter, double tol, const sopot_b200_rk4_opts* opts,
+                                  double* K, double* Pric, int32_t* iters, int32_t* status) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (state_dim == 4) return sopot_b200_lqr4_gain(ctx, A, B, P, Q, R, riccati_dt, max_iter, tol, opts, K, Pric, iters, status);
+    if (state_dim != 6 && state_dim != 14)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "LQR kernels exist for state dimensions 4, 6 and 14 (1, 2 and 6 links)");
+    if (!A || !B || !Q || !opts || !K) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
+    if (!(riccati_dt > 0.0) || max_iter > 0x7fffffff || P > 0x7fffffff) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad riccati_dt / max_iter / P");
+    const size_t ns = (size_t)state_dim, nn = ns * ns;
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 2 * sb_align(nn * P * 8) + 2 * sb_align(ns * P * 8) + 2 * sb_align(P * 4) + 4096)))
+        return rc;
+    const void *d_A, *d_B; void *d_K, *d_P, *d_it, *d_st;
+    if ((rc = sg.in(A, nn * P * 8, &d_A))) return rc;
+    if ((rc = sg.in(B, ns * P * 8, &d_B))) return rc;
+    if ((rc = sg.out(K, ns * P * 8, &d_K))) return rc;
+    if ((rc = sg.out(Pric, nn * P * 8, &d_P))) return rc;
+    if ((rc = sg.out(iters, P * 4, &d_it))) return rc;
+    if ((rc = sg.out(status, P * 4, &d_st))) return rc;
+    void* d_Q;                                             // the weights are HOST values; they travel through the scratch
+    if ((rc = sb_scratch(ctx, nn * 8 + 256, &d_Q))) return rc;
+    SB_CUDA(ctx, cudaMemcpyAsync(d_Q, Q, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // Q may be a temporary of the caller
+    if (P) {
+        const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
+        if (state_dim == 6) rc = lqr_block_launch<6>(ctx, strict, (const double*)d_A, (const double*)d_B, P, (const double*)d_Q, R, riccati_dt,
+                                                     (int)max_iter, tol, (double*)d_K, (double*)d_P, (int32_t*)d_it, (int32_t*)d_st);
+        else rc = lqr_block_launch<14>(ctx, strict, (const double*)d_A, (const double*)d_B, P, (const double*)d_Q, R, riccati_dt,
+                                       (int)max_iter, tol, (double*)d_K, (double*)d_P, (int32_t*)d_it, (int32_t*)d_st);
+        if (rc) return rc;
     }
     return sg.finish();
 }

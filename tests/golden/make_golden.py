@@ -90,6 +90,7 @@ def main():
     control_golden(R)
     cartn_linearize_golden(R)
     rocket_aero_golden(R)
+    control_n_golden(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
@@ -173,3 +174,20 @@ def rocket_aero_golden(R):
     out["rhs_state"] = st
     out["rhs"] = R.rocket_rhs(84.0, 30.0, 0.16, 9.80665, w["engine"], w["mass_tab"], st, aero=aero)
     np.savez(os.path.join(OUT, "rocket_aero.npz"), **out)
+
+
+def control_n_golden(R):
+    """LQR<6,1> / LQR<14,1> on the N-link linearizations at upright and the N-link closed loop (the reference's
+    inverted-pendulum test configuration for 6 links: mc 2, m 0.1, L 0.3, Q = diag(1, 200.., 1, 10..), R 1e-3, dt 5e-3)."""
+    out = {}
+    for N, P in ((2, 5), (6, 4)):
+        ns = 2 * (N + 1)
+        m = np.full((N, P), 0.1) * (1 + 0.1 * np.arange(P))[None, :]; L = np.full((N, P), 0.3); mc = np.full(P, 2.0); g = np.full(P, 9.81)
+        A, B = R.cartn_linearize(N, mc, m, L, g, np.zeros((ns, P)), np.zeros(P))
+        Q = np.diag(np.array([1.0] + [200.0] * N + [1.0] + [10.0] * N))
+        K, Pr, _, st = R.lqr_n(ns, A, B, Q, 0.001, 0.005, 1000, 1e-8)
+        s0 = np.zeros((ns, P)); s0[1:N + 1] = 0.03
+        fin, stats = R.cartn_feedback_rk4(N, mc, m, L, g, s0, K, None, -500.0, 500.0, 1, 0.0, 0.001, 1500)
+        out.update({f"n{N}_mc": mc, f"n{N}_m": m, f"n{N}_L": L, f"n{N}_g": g, f"n{N}_A": A, f"n{N}_B": B, f"n{N}_Q": Q, f"n{N}_K": K,
+                    f"n{N}_P": Pr, f"n{N}_st": st, f"n{N}_s0": s0, f"n{N}_final": fin, f"n{N}_stats": stats})
+    np.savez(os.path.join(OUT, "control_n.npz"), **out)

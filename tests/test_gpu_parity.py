@@ -421,3 +421,20 @@ def test_rocket_aero_tables_golden(engine):
             assert rel_err(stats[[0, 2, 4, 5]], g["stats_" + tag][[0, 2, 4, 5]]).max() <= FINAL
         rhs = engine.rocket_rhs(84.0, 30.0, 0.16, 9.80665, g["engine"], g["mass_tab"], g["rhs_state"], fp_mode=mode, aero=aero)
         assert rel_err(rhs, g["rhs"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("n_links", [2, 6])
+def test_lqr_block_kernel_golden_bit_exact_strict(engine, n_links):
+    """LQR<6,1> / LQR<14,1> (one CTA per operating point, matrices in shared memory): strict mode == the reference class
+    bit for bit on the 2- and 6-link upright linearizations (the reference's own 6-link test configuration)."""
+    g = golden("control_n")
+    k, ns = f"n{n_links}_", 2 * (n_links + 1)
+    P = g[k + "A"].shape[1]
+    K, Pr, it, st = engine.lqr_gain(ns, g[k + "A"], g[k + "B"], P, g[k + "Q"], 0.001, 0.005, 1000, 1e-8, fp_mode=FP_STRICT, want_riccati=True)
+    assert np.array_equal(st, g[k + "st"]) and np.array_equal(K, g[k + "K"]) and np.array_equal(Pr, g[k + "P"])
+    Kc, _, _, stc = engine.lqr_gain(ns, g[k + "A"], g[k + "B"], P, g[k + "Q"], 0.001, 0.005, 1000, 1e-8, fp_mode=FP_CONTRACT)
+    assert not stc.any() and rel_err(Kc, g[k + "K"]).max() <= 1e-6
+    # state_dim 4 routes to the thread-per-point kernel
+    c = golden("control")
+    K4, _, _, st4 = engine.lqr_gain(4, c["A"], c["B"], c["A"].shape[1], c["Q"], 0.01, 0.01, 1000, 1e-8, fp_mode=FP_STRICT)
+    assert np.array_equal(K4, c["K_a"])

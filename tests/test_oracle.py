@@ -231,3 +231,16 @@ def test_golden_rocket_aero_tables(port):
     assert not np.array_equal(g["final_on"], g["final_off"])          # the power-on / power-off tables are both used
     rhs = port.rocket_rhs(84.0, 30.0, 0.16, 9.80665, g["engine"], g["mass_tab"], g["rhs_state"], aero=aero)
     assert np.array_equal(rhs, g["rhs"])
+
+
+def test_golden_lqr_and_closed_loop_n_links(port):
+    """LQR<6,1>, LQR<14,1> and the 2- and 6-link closed loops: C restatement == the reference classes, bit for bit."""
+    g = golden("control_n")
+    for N in (2, 6):
+        k, ns = f"n{N}_", 2 * (N + 1)
+        K, P, it, st = port.lqr_n(ns, g[k + "A"], g[k + "B"], g[k + "Q"], 0.001, 0.005, 1000, 1e-8)
+        assert np.array_equal(K, g[k + "K"]) and np.array_equal(P, g[k + "P"]) and np.array_equal(st, g[k + "st"])
+        fin, stats = port.cartn_feedback_rk4(N, g[k + "mc"], g[k + "m"], g[k + "L"], g[k + "g"], g[k + "s0"], g[k + "K"], None,
+                                             -500.0, 500.0, 1, 0.0, 0.001, 1500)
+        assert np.array_equal(fin, g[k + "final"]) and np.array_equal(stats, g[k + "stats"])
+        assert g[k + "stats"][0].max() < 0.2            # never falls (tests/inverted_pendulum_test.cpp:288)
