@@ -31,6 +31,7 @@
 #include <type_traits>
 #include <vector>
 #include "engine.hpp"
+#include "../core/macros.hpp"
 
 namespace sopot::b200::generic {
 
@@ -48,10 +49,18 @@ struct CopyFactory {
     __device__ System operator()(size_t) const { return sys; }
 };
 
-template <typename Factory>
+// A CONTROLLER is an optional functor  SOPOT_HD void operator()(size_t i, double t, const double (&y)[D], System& sys) const
+// that runs once before every RK4 step and may reconfigure the instance's system from the state at the start of the step
+// (a sampled-data control law: e.g. sys.getComponent<0>().setControlForce(-K x), held over the four stages).
+struct NoController {
+    template <typename System, size_t D>
+    SOPOT_HD void operator()(size_t, double, const double (&)[D], System&) const {}
+};
+
+template <typename Factory, typename Controller>
 __global__ void __launch_bounds__(128)
-rk4_kernel(const Factory make, const size_t n, const double t0, const double dt, const size_t n_steps, const size_t store_every,
-           const double* __restrict__ y0, double* __restrict__ state_out, double* __restrict__ traj_out,
+rk4_kernel(const Factory make, const Controller control, const size_t n, const double t0, const double dt, const size_t n_steps,
+           const size_t store_every, const double* __restrict__ y0, double* __restrict__ state_out, double* __restrict__ traj_out,
            int32_t* __restrict__ status) {
     using System = system_of_t<Factory>;
     constexpr size_t D = System::getStateDimension();
@@ -69,6 +78,7 @@ rk4_kernel(const Factory make, const size_t n, const double t0, const double dt,
     double t = t0;
     size_t until_snap = store_every, snap = 0;
     for (size_t step = 0; step < n_steps; ++step) {
+        control(i, t, y, sys);
         sys.computeDerivativesInto(t, y, k);
 #pragma unroll
         for (size_t d = 0; d < D; ++d) { k[d] = k[d] * dt; acc[d] = k[d]; tmp[d] = y[d] + 0.5 * k[d]; }
@@ -131,9 +141,9 @@ inline cudaStream_t stream_of(Engine& eng) {
 }
 
 // Integrate n instances built by `make`; results come back as host SoA vectors like every other ensemble entry point.
-template <typename Factory>
+template <typename Factory, typename Controller = NoController>
 EnsembleResult integrate(Engine& eng, const Factory& make, size_t n, size_t n_steps, double t0, double dt,
-                         const EnsembleOptions& o, const double* y0_host = nullptr) {
+                         const EnsembleOptions& o, const double* y0_host = nullptr, const Controller& control = Controller{}) {
     using System = system_of_t<Factory>;
     static_assert(System::device_integrable, "every stateful component needs SOPOT_HD derivatives() and must be trivially copyable");
     // (the factory travels to the kernel by value: std::tuple is not formally trivially copyable in libstdc++, its
@@ -151,8 +161,8 @@ EnsembleResult integrate(Engine& eng, const Factory& make, size_t n, size_t n_st
     DeviceBuffer<double> d_state(D * n), d_traj(r.trajectory.size()), d_y0(y0_host ? D * n : 0);
     DeviceBuffer<int32_t> d_status(o.want_status ? n : 0);
     if (y0_host) cuda_check(cudaMemcpyAsync(d_y0.p, y0_host, D * n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D y0");
-    rk4_kernel<Factory><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(make, n, t0, dt, n_steps, o.store_every, d_y0.p, d_state.p,
-                                                                      d_traj.p, d_status.p);
+    rk4_kernel<Factory, Controller><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(make, control, n, t0, dt, n_steps, o.store_every,
+                                                                                  d_y0.p, d_state.p, d_traj.p, d_status.p);
     cuda_check(cudaGetLastError(), "generic rk4 kernel launch");
     eng.check(sopot_b200_note_launches(eng.ctx(), 1));
     cuda_check(cudaMemcpyAsync(r.state.data(), d_state.p, D * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H state");
@@ -191,13 +201,19 @@ EnsembleResult solve_one(Engine& eng, const System& sys, const std::vector<doubl
 namespace sopot::b200 {
 
 // what RK4Solver::solveEnsemble takes for a user-defined system: n instances, built on the device by `make(i)`
-template <typename Factory>
+template <typename Factory, typename Controller = generic::NoController>
 struct GenericEnsemble {
     size_t n;
     Factory make;
+    Controller control{};
+    std::vector<double> y0{};          // optional explicit initial states [D][n]; empty: the components' own
     EnsembleResult integrate(Engine& eng, size_t n_steps, double t0, double dt, const EnsembleOptions& o) const {
-        return generic::integrate(eng, make, n, n_steps, t0, dt, o);
+        return generic::integrate(eng, make, n, n_steps, t0, dt, o, y0.empty() ? nullptr : y0.data(), control);
     }
+    // the same ensemble under a sampled-data controller (see generic::NoController for the functor contract)
+    template <typename C>
+    GenericEnsemble<Factory, C> withController(C c) const { return GenericEnsemble<Factory, C>{n, make, c, y0}; }
+    GenericEnsemble withInitialStates(std::vector<double> states) const { GenericEnsemble e = *this; e.y0 = std::move(states); return e; }
 };
 template <typename Factory>
 GenericEnsemble<Factory> ensembleOf(size_t n, Factory make) { return GenericEnsemble<Factory>{n, make}; }

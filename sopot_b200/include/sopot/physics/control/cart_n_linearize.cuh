@@ -112,4 +112,38 @@ CartNJacobians<NLinks> linearizeCartNPendulumBatch(b200::Engine& eng, const std:
     return r;
 }
 
+// ---- closed loop for the N-link plant ------------------------------------------------------------------------------------
+// Device factory (per-instance plant parameters from arrays) and the state-feedback controller of
+// state_feedback_controller.hpp:88-104 as a generic-kernel controller: u = -K (x - x_ref), clamped when saturate is set,
+// evaluated from the state at the start of every RK4 step and held over its four stages.
+template <size_t NL>
+struct CartNFactory {
+    const double* mc;      // [n] device
+    const double* m;       // [NL][n]
+    const double* L;       // [NL][n]
+    const double* g;       // [n]
+    size_t n;
+    SOPOT_HD TypedODESystem<double, CartNPendulum<NL, double>> operator()(size_t i) const {
+        std::array<double, NL> mm{}, LL{};
+        for (size_t a = 0; a < NL; ++a) { mm[a] = m[a * n + i]; LL[a] = L[a * n + i]; }
+        return makeTypedODESystem<double>(CartNPendulum<NL, double>(mc[i], mm, LL, g[i]));
+    }
+};
+template <size_t NL>
+struct CartNStateFeedback {
+    static constexpr size_t NS = 2 * (NL + 1);
+    const double* K;       // [NS][n] device (e.g. straight from sopot_b200_lqr_gain)
+    const double* x_ref;   // [NS][n] or nullptr
+    size_t n;
+    double u_min, u_max;
+    int saturate;
+    template <typename System>
+    SOPOT_HD void operator()(size_t i, double, const double (&y)[NS], System& sys) const {
+        double u = 0.0;
+        for (size_t j = 0; j < NS; ++j) u -= K[j * n + i] * (y[j] - (x_ref ? x_ref[j * n + i] : 0.0));
+        if (saturate) u = u < u_min ? u_min : (u_max < u ? u_max : u);
+        sys.template getComponent<0>().setControlForce(u);
+    }
+};
+
 }  // namespace sopot::control

@@ -13,7 +13,7 @@
 #include <cmath>
 #include <sopot/core/solver.hpp>
 #include <sopot/core/typed_component.hpp>
-#include <sopot/physics/control/cart_n_pendulum.hpp>
+#include <sopot/physics/control/cart_n_linearize.cuh>
 #include <sopot/physics/harmonic_oscillator.hpp>
 #include <sopot/physics/pendulum/double_pendulum.hpp>
 
@@ -216,6 +216,64 @@ int main() {
         for (int j = 0; j < 14; ++j) CHECK(std::abs(r6.states.back()[j] - ref6[j]) <= 1e-9 * 5.0);
         // energy bookkeeping of the plant's own state queries on the device-integrated trajectory
         CHECK(std::isfinite(p6.totalEnergy(std::span<const double>(r6.states.back()))));
+    }
+    // 5. the reference's 6-link inverted-pendulum test on the GPU (tests/inverted_pendulum_test.cpp:208-292, configuration
+    //    mc 2, m 0.1, L 0.3, Q = diag(1, 200 x6, 1, 10 x6), R 1e-3, Riccati dt 5e-3): lane-parallel Dual linearization at
+    //    upright -> LQR<14,1> kernel -> closed loop of an ensemble through the generic kernel with a state-feedback controller
+    {
+        constexpr size_t NL = 6, NS = 14;
+        const size_t n = 256;
+        auto& eng = b200::Engine::shared();
+        auto J = control::linearizeCartNPendulumBatch<NL>(eng, {2.0}, std::vector<double>(NL, 0.1), std::vector<double>(NL, 0.3), {9.81},
+                                                         std::vector<double>(NS, 0.0), {0.0});
+        double Q[NS * NS] = {};
+        for (size_t i2 = 0; i2 < NS; ++i2) Q[i2 * NS + i2] = (i2 == 0 || i2 == NL + 1) ? 1.0 : (i2 <= NL ? 200.0 : 10.0);
+        double K[NS];
+        int32_t lqr_status = -1, lqr_iters = 0;
+        b200::EnsembleOptions so; so.fp_mode = b200::FpMode::Strict;
+        const auto lopts = b200::make_opts(so, 0);
+        eng.check(sopot_b200_lqr_gain(eng.ctx(), NS, J.A.data(), J.B.data(), 1, Q, 0.001, 0.005, 1000, 1e-8, &lopts, K, nullptr, &lqr_iters, &lqr_status));
+        eng.sync();
+        CHECK(lqr_status == 0 && lqr_iters == 1000);
+        // the reference's gain for this plant (LQR<14,1> on its analytic linearization; ours comes from the Dual Jacobians)
+        const double Kref[NS] = {40.14077817166795, -24057.84045932211, 336162.24090843205, -1570953.7183741203, 3242784.7159446855,
+                                 -3059859.116319377, 1078813.4568454213, 158.3014983927829, -215.6786313378815, 7627.8837693362075,
+                                 -57888.385091549906, 169862.79596712242, -212059.4876367322, 95135.11617195724};
+        for (size_t j = 0; j < NS; ++j) CHECK(std::abs(K[j] - Kref[j]) <= 1e-6 * std::abs(Kref[j]));
+        // ensemble: every plant starts with all links at 0.03 rad (the reference test); link masses jittered by +-0.2 %
+        // (the nominal gain has entries of 3e6: the six-link balance tolerates very little plant mismatch)
+        std::vector<double> mc(n, 2.0), g(n, 9.81), m(NL * n), L(NL * n, 0.3), Kall(NS * n), y0(NS * n, 0.0);
+        for (size_t i2 = 0; i2 < n; ++i2) {
+            for (size_t a = 0; a < NL; ++a) m[a * n + i2] = 0.1 * (i2 == 0 ? 1.0 : 1.0 + 0.002 * std::sin(double(i2 + a)));
+            for (size_t j = 0; j < NS; ++j) Kall[j * n + i2] = K[j];
+            for (size_t a = 1; a <= NL; ++a) y0[a * n + i2] = 0.03;
+        }
+        using b200::generic::DeviceBuffer;
+        DeviceBuffer<double> d_mc(n), d_g(n), d_m(NL * n), d_L(NL * n), d_K(NS * n);
+        auto up = [](DeviceBuffer<double>& d, const std::vector<double>& h) { cudaMemcpy(d.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice); };
+        up(d_mc, mc); up(d_g, g); up(d_m, m); up(d_L, L); up(d_K, Kall);
+        auto loop = b200::ensembleOf(n, control::CartNFactory<NL>{d_mc.p, d_m.p, d_L.p, d_g.p, n})
+                        .withInitialStates(y0)
+                        .withController(control::CartNStateFeedback<NL>{d_K.p, nullptr, n, -500.0, 500.0, 1});
+        b200::EnsembleOptions opt5;
+        opt5.store_every = 50;
+        auto r5 = createRK4Solver().solveEnsemble(loop, 0.0, 5.0, 0.001, opt5);
+        for (size_t i2 = 0; i2 < n; ++i2) {
+            CHECK(r5.status[i2] == 0);
+            double max_angle = 0.03, final_angle = 0.0;
+            for (size_t sidx = 0; sidx < r5.snapshots(); ++sidx)
+                for (size_t a = 1; a <= NL; ++a) max_angle = std::max(max_angle, std::abs(r5.at(sidx, a, i2)));
+            for (size_t a = 1; a <= NL; ++a) final_angle = std::max(final_angle, std::abs(r5.final(a, i2)));
+            CHECK(max_angle < 0.2);          // never falls        (tests/inverted_pendulum_test.cpp:288)
+            CHECK(final_angle < 0.01);       // converges back     (:289)
+        }
+        // plant 0 is the reference's nominal plant: state after 1.5 s of closed loop (snapshot 29) vs the reference stepping
+        // (oracle/ref_harness.cpp: StateFeedbackController + CartNPendulum<6> + one RK4Solver step per sample, reference gain)
+        const double ref15[NS] = {0.3469131415980191, -0.02512949479775311, -0.02363770986465978, -0.02219834441608054,
+                                  -0.02078362623558745, -0.019390286965434777, -0.018027281622197824, 0.2430708885492833,
+                                  -0.02852029197834663, -0.024081851393495852, -0.022182246865190935, -0.02182091176401473,
+                                  -0.02227360805387352, -0.02304653899042201};
+        for (size_t j = 0; j < NS; ++j) CHECK(std::abs(r5.at(29, j, 0) - ref15[j]) <= 1e-5);    // gains agree to 1e-6 relative
     }
     std::puts("user_components: OK");
     return 0;
