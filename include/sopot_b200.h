@@ -261,6 +261,28 @@ int sopot_b200_grid2d_rhs(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* g
                           const sopot_b200_rk4_opts* opts, const double* state, double* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * "Unified" 6-state grid: PointMass2D [x, y, vx, vy, theta, omega] + Spring2D with attachment points on the rim of each
+ * mass and torque coupling (physics/unified/components.hpp:52-138, 206-291), evaluated like
+ * ValidatedSystem::computeDerivatives (physics/unified/validated_system.hpp:204-301) on makeGridTopology<R,C>
+ * (constexpr_topology.hpp:368-414) -- the system behind the reference's Grid2DSimulator (wasm/wasm_grid2d.cpp:223).
+ * State is AoS [rows][cols][6].  Attachment angles: horizontal springs h_attach0 on the left mass / h_attach1 on the
+ * right one, vertical springs v_attach0 on the upper / v_attach1 on the lower mass (the wasm wrapper uses 0, pi, pi/2,
+ * -pi/2; Spring2D's defaults are 0, pi for every spring).  repulsion_stiffness <= 0 means 10 * stiffness; min_distance
+ * 0 disables the repulsion.  Single GPU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    size_t rows, cols;
+    double mass, radius, spacing;
+    double stiffness, rest_length, damping, min_distance, repulsion_stiffness;
+    double h_attach0, h_attach1, v_attach0, v_attach1;
+} sopot_b200_ugrid_params;
+int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, uint32_t mem, double* state);
+int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, const sopot_b200_rk4_opts* opts,
+                         const double* state, double* out);
+int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, double dt, size_t n_steps,
+                         const sopot_b200_rk4_opts* opts, double* state /* in/out */);
+
+/* ---------------------------------------------------------------------------------------------
  * Roofline denominators measured on this device: dependent-free DFMA issue rate (FP64 TFLOP/s,
  * FMA = 2 flop) and a device copy (GB/s, read + write).  Used by bench.py; MEASURED_PEAKS.json has
  * no FP64 figure.

@@ -192,6 +192,19 @@ class Checker:
         assert rc == 0
         return fin, stats
 
+    # ---------------- section 8f-2: unified 6-state grid ----------------
+    def ugrid(self, rows, cols, prm, state=None, dt=0.0, n_steps=0, mode="rhs"):
+        """prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1."""
+        prm = _f64(prm).reshape(12)
+        n = rows * cols * 6
+        out = np.empty(n)
+        st = None if state is None else _f64(state).reshape(n)
+        rc = self._fn("ugrid", [_sz, _sz, _dp, _d, _sz, _dp, _dp, _i])(rows, cols, _p(prm), dt, n_steps, _p(st), _p(out),
+                                                                        {"rhs": 0, "rk4": 1, "init": 2}[mode])
+        if rc:
+            raise KeyError("grid size not instantiated in the reference harness")
+        return out.reshape(rows * cols, 6)
+
     # ---------------- plugin-path check: coupled oscillator ----------------
     def coupled_rk4(self, m1, m2, k, L0, c, x1, x2, t0, t1, dt, nthreads=1):
         k = _f64(k).reshape(-1); n = k.size

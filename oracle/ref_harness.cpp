@@ -19,6 +19,7 @@
 #include "physics/control/cart_n_pendulum.hpp"
 #include "physics/control/lqr.hpp"
 #include "physics/coupled_oscillator/coupled_system.hpp"
+#include "physics/unified/validated_system.hpp"
 #include "physics/control/state_feedback_controller.hpp"
 #include "physics/connected_masses/connectivity_matrix_2d.hpp"
 #include "rocket/rocket.hpp"
@@ -79,6 +80,49 @@ void scatter_result(const SolutionResult& r, size_t dim, size_t i, size_t n,
 }
 
 } // namespace
+
+// unified 6-state grid (physics/unified/): topologies must be objects with static storage to serve as template arguments
+namespace ugrid_topo {
+constexpr auto t3x3 = sopot::unified::makeGridTopology<3, 3>();
+constexpr auto t4x5 = sopot::unified::makeGridTopology<4, 5>();
+constexpr auto t2x7 = sopot::unified::makeGridTopology<2, 7>();
+constexpr auto t6x6 = sopot::unified::makeGridTopology<6, 6>();
+constexpr auto t10x10 = sopot::unified::makeGridTopology<10, 10>();
+}  // namespace ugrid_topo
+
+// populate exactly as Grid2DSimulator::createQuadSystem does (wasm/wasm_grid2d.cpp:417-462): masses row-major with radius,
+// horizontal springs row-major, then vertical springs; attachment angles per orientation
+template <auto& Topology>
+static int ugrid_run(size_t rows, size_t cols, const double* prm /*12*/, double dt, size_t n_steps, const double* state_in, double* out,
+                     int mode /*0 rhs, 1 rk4, 2 initial state*/) {
+    using namespace sopot::unified;
+    ValidatedSystem<double, Topology, PointMass2D<double>, Spring2D<double>> sys;
+    const double mass = prm[0], radius = prm[1], spacing = prm[2], k = prm[3], L0 = prm[4], c = prm[5], mind = prm[6], krep = prm[7];
+    auto& mb = sys.template getBatch<0>();
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t cc = 0; cc < cols; ++cc) mb.add(PointMass2D<double>(mass, {double(cc) * spacing, double(r) * spacing}, {0.0, 0.0}, radius, 0.0, 0.0));
+    auto& sb = sys.template getBatch<1>();
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t cc = 0; cc + 1 < cols; ++cc) sb.add(Spring2D<double>(k, L0, c, mind, krep, prm[8], prm[9]));
+    for (size_t r = 0; r + 1 < rows; ++r)
+        for (size_t cc = 0; cc < cols; ++cc) sb.add(Spring2D<double>(k, L0, c, mind, krep, prm[10], prm[11]));
+    const size_t n = sys.getStateDimension();
+    if (n != rows * cols * 6) return 3;
+    if (mode == 2) { auto s0 = sys.getInitialState(); std::copy(s0.begin(), s0.end(), out); return 0; }
+    std::vector<double> st(state_in, state_in + n);
+    if (mode == 0) { auto d = sys.computeDerivatives(0.0, st); std::copy(d.begin(), d.end(), out); return 0; }
+    auto solver = createRK4Solver();
+    auto derivs = [&sys](double t, StateView sv) { return sys.computeDerivatives(t, sv); };
+    double t = 0.0;
+    // n_steps explicit steps through RK4Solver::solve (one step per call keeps the step count independent of rounding in t_end)
+    for (size_t sidx = 0; sidx < n_steps; ++sidx) {
+        auto r = solver.solve(derivs, n, t, t + dt, dt, st);
+        st = r.states.back();
+        t += dt;
+    }
+    std::copy(st.begin(), st.end(), out);
+    return 0;
+}
 
 extern "C" {
 
@@ -395,6 +439,14 @@ int ref_cartn_feedback_rk4(int n_links, size_t n, const double* mc, const double
         else cartn_feedback_one<6>(mc, m, L, g, s0, K, xref, umin, umax, saturate, t0, dt, n_steps, n, i, final_out, stats);
     });
     return 0;
+}
+
+// prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0, h_attach1, v_attach0, v_attach1
+int ref_ugrid(size_t rows, size_t cols, const double* prm, double dt, size_t n_steps, const double* state_in, double* out, int mode) {
+#define UG_CASE(R, C, T) if (rows == R && cols == C) return ugrid_run<ugrid_topo::T>(rows, cols, prm, dt, n_steps, state_in, out, mode);
+    UG_CASE(3, 3, t3x3) UG_CASE(4, 5, t4x5) UG_CASE(2, 7, t2x7) UG_CASE(6, 6, t6x6) UG_CASE(10, 10, t10x10)
+#undef UG_CASE
+    return -1;
 }
 
 // ---- config 4: 6-DOF rocket ----

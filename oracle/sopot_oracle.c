@@ -714,6 +714,69 @@ ORC_API int orc_cartn_feedback_rk4(int n_links, size_t n, const double* mc, cons
 
 
 /* ------------------------------------------------------------------------------------------
+ * Section 8f-2 -- unified 6-state grid: PointMass2D + Spring2D with attachment points and torque
+ * (physics/unified/components.hpp:52-138, :206-291) driven as ValidatedSystem::computeDerivatives does
+ * (validated_system.hpp:204-301) on makeGridTopology (constexpr_topology.hpp:368-414), runtime sized.
+ * prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { size_t rows, cols; double mass, radius, k, L0, c, mind, krep, ha0, ha1, va0, va1; } orc_ugrid_t;
+static void orc_uspring(const orc_ugrid_t* g, const double* m0, const double* m1, double a0, double a1, double* F /*[rows*cols][3]*/,
+                        size_t i0, size_t i1) {
+    const double r0 = g->radius, r1 = g->radius;
+    const double wa0 = m0[4] + a0, wa1 = m1[4] + a1;
+    const double o0x = r0 * cos(wa0), o0y = r0 * sin(wa0), o1x = r1 * cos(wa1), o1y = r1 * sin(wa1);
+    const double a0x = m0[0] + o0x, a0y = m0[1] + o0y, a1x = m1[0] + o1x, a1y = m1[1] + o1y;
+    const double v0x = m0[2] - m0[5] * o0y, v0y = m0[3] + m0[5] * o0x, v1x = m1[2] - m1[5] * o1y, v1y = m1[3] + m1[5] * o1x;
+    const double dx = a1x - a0x, dy = a1y - a0y;
+    const double len = sqrt(dx * dx + dy * dy), len_safe = len < 1e-10 ? 1e-10 : len;
+    const double ux = dx / len_safe, uy = dy / len_safe, ext = len - g->L0;
+    const double dvx = v1x - v0x, dvy = v1y - v0y, rel = dvx * ux + dvy * uy;
+    double Fm = g->k * ext + g->c * rel;
+    if (g->mind > 0.0 && len < g->mind) { const double rep = -g->krep * (g->mind / len_safe - 1.0); Fm += rep; }
+    const double f0x = Fm * ux, f0y = Fm * uy, f1x = -Fm * ux, f1y = -Fm * uy;
+    const double t0 = o0x * f0y - o0y * f0x, t1 = o1x * f1y - o1y * f1x;
+    F[3 * i0] += f0x; F[3 * i0 + 1] += f0y; F[3 * i1] += f1x; F[3 * i1 + 1] += f1y;      /* addForce on both ends */
+    F[3 * i0 + 2] += t0; F[3 * i1 + 2] += t1;                                          /* addTorque */
+}
+static void orc_ugrid_rhs_fn(const void* ctx, double t, const double* s, double* d) {
+    const orc_ugrid_t* g = (const orc_ugrid_t*)ctx;
+    (void)t;
+    const size_t n = g->rows * g->cols;
+    double* F = (double*)calloc(3 * n, sizeof(double));
+    for (size_t r = 0; r < g->rows; ++r)                                               /* horizontal springs, row-major */
+        for (size_t c = 0; c + 1 < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + 1), g->ha0, g->ha1, F, i, i + 1); }
+    for (size_t r = 0; r + 1 < g->rows; ++r)                                           /* then vertical springs */
+        for (size_t c = 0; c < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + g->cols), g->va0, g->va1, F, i, i + g->cols); }
+    const double I = 0.5 * g->mass * g->radius * g->radius;                            /* components.hpp:98 */
+    for (size_t i = 0; i < n; ++i) {
+        d[6 * i] = s[6 * i + 2]; d[6 * i + 1] = s[6 * i + 3];
+        d[6 * i + 2] = F[3 * i] / g->mass; d[6 * i + 3] = F[3 * i + 1] / g->mass;
+        d[6 * i + 4] = s[6 * i + 5]; d[6 * i + 5] = F[3 * i + 2] / I;
+    }
+    free(F);
+}
+ORC_API int orc_ugrid(size_t rows, size_t cols, const double* prm, double dt, size_t n_steps, const double* state_in, double* out, int mode) {
+    orc_ugrid_t g = {rows, cols, prm[0], prm[1], prm[3], prm[4], prm[5], prm[6], prm[7] > 0.0 ? prm[7] : 10.0 * prm[3], prm[8], prm[9], prm[10], prm[11]};
+    const size_t n = rows * cols * 6;
+    if (mode == 2) {
+        for (size_t r = 0; r < rows; ++r) for (size_t c = 0; c < cols; ++c) {
+            double* q = out + 6 * (r * cols + c);
+            q[0] = (double)c * prm[2]; q[1] = (double)r * prm[2]; q[2] = q[3] = q[4] = q[5] = 0.0;
+        }
+        return 0;
+    }
+    if (mode == 0) { orc_ugrid_rhs_fn(&g, 0.0, state_in, out); return 0; }
+    double* y = (double*)malloc(n * sizeof(double));
+    double* work = (double*)malloc(5 * n * sizeof(double));
+    memcpy(y, state_in, n * sizeof(double));
+    double t = 0.0;
+    for (size_t s = 0; s < n_steps; ++s) { orc_rk4(orc_ugrid_rhs_fn, &g, n, t, t + dt, dt, y, work, NULL, NULL, NULL); t += dt; }
+    memcpy(out, y, n * sizeof(double));
+    free(y); free(work);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Plugin-path check -- the reference's composition example, physics/coupled_oscillator/: two PointMass
  * (point_mass.hpp:70-84: {v, F/m}), one Spring (spring.hpp:96-131: F1 = -k (x1 - x2 - L0) [+ -c (v1 - v2) when
  * c > 0], F2 = -F1), state [x1, v1, x2, v2].

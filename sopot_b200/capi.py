@@ -79,6 +79,12 @@ class Dispersion(ctypes.Structure):
     _fields_ = [(k, c_double) for k in ("count", "sum", "sumsq", "min", "max", "mean", "stddev", "nonfinite")]
 
 
+class UGridParams(ctypes.Structure):
+    _fields_ = [("rows", c_size_t), ("cols", c_size_t)] + [(k, c_double) for k in (
+        "mass", "radius", "spacing", "stiffness", "rest_length", "damping", "min_distance", "repulsion_stiffness",
+        "h_attach0", "h_attach1", "v_attach0", "v_attach1")]
+
+
 class Grid2DParams(ctypes.Structure):
     _fields_ = [("rows", c_size_t), ("cols", c_size_t), ("row_begin", c_size_t), ("rows_local", c_size_t),
                 ("topology", c_int), ("mass", c_double), ("spacing", c_double), ("stiffness", c_double),
@@ -117,6 +123,9 @@ SYMBOLS = {
     "sopot_b200_cartpole_rhs": (c_int, [_ctx, POINTER(CartpoleParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_lqr4_gain": (c_int, [_ctx, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
                                      POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sopot_b200_ugrid_initial_state": (c_int, [_ctx, POINTER(UGridParams), c_uint32, c_void_p]),
+    "sopot_b200_ugrid_rhs": (c_int, [_ctx, POINTER(UGridParams), POINTER(RK4Opts), c_void_p, c_void_p]),
+    "sopot_b200_ugrid_rk4": (c_int, [_ctx, POINTER(UGridParams), c_double, c_size_t, POINTER(RK4Opts), c_void_p]),
     "sopot_b200_lqr_gain": (c_int, [_ctx, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
                                     POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sopot_b200_cartpole_feedback_rk4": (c_int, [_ctx, POINTER(CartpoleParams), POINTER(Feedback), c_size_t, c_double,
@@ -519,6 +528,34 @@ class Engine:
         out = (Dispersion * rows)()
         self._ck(self.lib.sopot_b200_dispersion_stats(self.ctx, _ptr(values), rows, n_local, mem, out))
         return [{k: getattr(o, k) for k, _ in Dispersion._fields_} for o in out]
+
+    # ---- unified 6-state grid ----
+    @staticmethod
+    def ugrid_params(rows, cols, mass, radius, spacing, k, L0, c, min_distance=0.0, krep=-1.0,
+                     attach=(0.0, 3.14159265358979323846, 3.14159265358979323846 / 2.0, -3.14159265358979323846 / 2.0)):
+        return UGridParams(rows, cols, mass, radius, spacing, k, L0, c, min_distance, krep, *attach)
+
+    def ugrid_initial_state(self, g, mem=MEM_HOST):
+        out = np.empty((g.rows * g.cols, 6)) if mem == MEM_HOST else self.empty((g.rows * g.cols, 6))
+        self._ck(self.lib.sopot_b200_ugrid_initial_state(self.ctx, byref(g), mem, _ptr(out)))
+        self.sync()
+        return out
+
+    def ugrid_rhs(self, g, state, fp_mode=FP_STRICT):
+        mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
+        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        out = np.empty_like(state) if mem == MEM_HOST else self.empty(state.shape)
+        self._ck(self.lib.sopot_b200_ugrid_rhs(self.ctx, byref(g), byref(opts), _ptr(state), _ptr(out)))
+        self.sync()
+        return out
+
+    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True):
+        mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
+        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        self._ck(self.lib.sopot_b200_ugrid_rk4(self.ctx, byref(g), dt, n_steps, byref(opts), _ptr(state)))
+        if sync:
+            self.sync()
+        return state
 
     def grid2d_params(self, rows, cols, topo, mass, spacing, k, c, row_begin=0, rows_local=None):
         return Grid2DParams(rows, cols, row_begin, rows if rows_local is None else rows_local, topo, mass,

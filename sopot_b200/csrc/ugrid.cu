@@ -1,0 +1,224 @@
+// ugrid.cu -- the "unified" 6-state mass-spring grid: physics/unified/components.hpp
+//   PointMass2D   state [x, y, vx, vy, theta, omega], I = 1/2 m r^2, derivative {vx, vy, Fx/m, Fy/m, omega, tau/I}   (:52-138)
+//   Spring2D      attaches at radius r on each mass at (theta + attachment_angle); force along the line between the two
+//                 attachment points, damping on their relative velocity (which includes omega x r), optional steep
+//                 repulsion, torque r x F on both masses                                                              (:206-291)
+// driven the way ValidatedSystem::computeDerivatives does (physics/unified/validated_system.hpp:204-301; this is the system
+// behind the reference's Grid2DSimulator, wasm/wasm_grid2d.cpp:223): springs are visited in node order -- all horizontal
+// springs row-major, then all vertical ones (constexpr_topology.hpp:368-414) -- and each adds its force / torque to both
+// end masses, so a mass receives: left spring (as mass 1), right spring (as mass 0), upper spring (as mass 1), lower
+// spring (as mass 0).  The kernels below are the gather form of that: one thread per mass evaluates its incident springs
+// in exactly this order.  State is AoS [rows][cols][6] (48 B per mass), the reference's node order.
+// One RK4 step = four stage kernels with the running accumulator of ensemble.cuh (1.5x the traffic of the 4-state grid).
+// Single GPU (no slab decomposition yet).
+#include "common.cuh"
+#include "trig.cuh"
+
+namespace {
+
+struct UGridDev {
+    size_t rows, cols;
+    double mass, radius, k, L0, c, min_distance, krep, inertia;
+    double ha0, ha1, va0, va1;      // attachment angles: horizontal spring on its left / right mass, vertical on upper / lower
+};
+
+struct Body { double x, y, vx, vy, th, om; };
+
+__device__ __forceinline__ Body load_body(const double* __restrict__ s, size_t idx) {
+    const double2* p = reinterpret_cast<const double2*>(s + 6 * idx);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    return Body{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ void store6(double* p, const double (&v)[6]) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(v[0], v[1]); q[1] = make_double2(v[2], v[3]); q[2] = make_double2(v[4], v[5]);
+}
+
+// Spring2D::computeForcesAndTorques for the spring (m0 -> m1); returns force and torque on the requested end
+template <bool S>
+__device__ __forceinline__ void spring_ft(const UGridDev& g, const Body& m0, const Body& m1, const double a0, const double a1,
+                                          const int end, Real<S>& fx, Real<S>& fy, Real<S>& tq) {
+    using R = Real<S>;
+    const R r(g.radius);
+    R s0, c0, s1, c1;
+    if constexpr (S) { r_sincos(R(m0.th) + R(a0), s0, c0); r_sincos(R(m1.th) + R(a1), s1, c1); }
+    else { sbtrig::sincos(m0.th + a0, s0.v, c0.v); sbtrig::sincos(m1.th + a1, s1.v, c1.v); }
+    const R o0x = r * c0, o0y = r * s0, o1x = r * c1, o1y = r * s1;                    // offsets to the attachment points
+    const R a0x = R(m0.x) + o0x, a0y = R(m0.y) + o0y, a1x = R(m1.x) + o1x, a1y = R(m1.y) + o1y;
+    const R v0x = R(m0.vx) - R(m0.om) * o0y, v0y = R(m0.vy) + R(m0.om) * o0x;          // v + omega x r
+    const R v1x = R(m1.vx) - R(m1.om) * o1y, v1y = R(m1.vy) + R(m1.om) * o1x;
+    const R dx = a1x - a0x, dy = a1y - a0y;
+    const R len = r_sqrt(dx * dx + dy * dy);
+    const R len_safe = len.v < 1e-10 ? R(1e-10) : len;
+    const R ux = dx / len_safe, uy = dy / len_safe;
+    const R ext = len - R(g.L0);
+    const R dvx = v1x - v0x, dvy = v1y - v0y;
+    const R rel = dvx * ux + dvy * uy;
+    R F = R(g.k) * ext + R(g.c) * rel;
+    if (g.min_distance > 0.0 && len.v < g.min_distance)
+        F = F + (-R(g.krep)) * (R(g.min_distance) / len_safe - R(1.0));
+    if (end == 0) { fx = F * ux; fy = F * uy; tq = o0x * fy - o0y * fx; }
+    else { fx = (-F) * ux; fy = (-F) * uy; tq = o1x * fy - o1y * fx; }
+}
+
+template <bool S>
+__device__ __forceinline__ void body_derivative(const UGridDev& g, const double* __restrict__ in, const size_t row, const size_t col,
+                                                Real<S> (&d)[6], Body& self) {
+    using R = Real<S>;
+    const size_t idx = row * g.cols + col;
+    const Body P = load_body(in, idx);
+    self = P;
+    R Fx(0.0), Fy(0.0), Tq(0.0), fx, fy, tq;
+    if (col > 0) { spring_ft<S>(g, load_body(in, idx - 1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    if (col + 1 < g.cols) { spring_ft<S>(g, P, load_body(in, idx + 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    if (row > 0) { spring_ft<S>(g, load_body(in, idx - g.cols), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    if (row + 1 < g.rows) { spring_ft<S>(g, P, load_body(in, idx + g.cols), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    d[0] = R(P.vx); d[1] = R(P.vy);
+    d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass);
+    d[4] = R(P.om); d[5] = Tq / R(g.inertia);
+}
+
+// STAGE 0: out <- f(in);  1..4: the RK4 stages with S-accumulator (see ensemble.cuh / grid2d.cu)
+template <bool S, int STAGE>
+__global__ void __launch_bounds__(256)
+ugrid_stage(const UGridDev g, const double* __restrict__ in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
+            double* __restrict__ out) {
+    using R = Real<S>;
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (col >= g.cols || row >= g.rows) return;
+    R d[6];
+    Body self;
+    body_derivative<S>(g, in, row, col, d, self);
+    const size_t off = (row * g.cols + col) * 6;
+    double o[6];
+    if constexpr (STAGE == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o[j] = d[j].v;
+        store6(out + off, o);
+        return;
+    }
+    const R dt(dt_);
+    R k[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) k[j] = d[j] * dt;
+    R yv[6], sv[6];
+    if constexpr (STAGE == 1) {
+        yv[0] = R(self.x); yv[1] = R(self.y); yv[2] = R(self.vx); yv[3] = R(self.vy); yv[4] = R(self.th); yv[5] = R(self.om);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { yv[j] = R(y[off + j]); sv[j] = R(acc[off + j]); }
+    }
+    if constexpr (STAGE == 4) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o[j] = (yv[j] + r_div_const(sv[j] + k[j], 6.0)).v;
+        store6(y + off, o);
+    } else {
+        double a[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            a[j] = (STAGE == 1 ? k[j] : sv[j] + 2.0 * k[j]).v;
+            o[j] = (STAGE == 3 ? yv[j] + k[j] : yv[j] + 0.5 * k[j]).v;
+        }
+        store6(acc + off, a);
+        store6(out + off, o);
+    }
+}
+
+__global__ void ugrid_init_kernel(const size_t rows, const size_t cols, const double spacing, double* __restrict__ state) {
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (col >= cols || row >= rows) return;
+    const double v[6] = {(double)col * spacing, (double)row * spacing, 0.0, 0.0, 0.0, 0.0};     // wasm_grid2d.cpp:427-433
+    store6(state + (row * cols + col) * 6, v);
+}
+
+int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev& g) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p) return sb_fail(ctx, SOPOT_B200_EINVAL, "ugrid params NULL");
+    if (p->rows < 1 || p->cols < 1 || p->rows * p->cols < 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "the grid needs at least two masses");
+    if (!(p->mass > 0.0) || !(p->radius > 0.0))
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "mass and radius must be positive (I = m r^2 / 2 divides the torque)");
+    g.rows = p->rows; g.cols = p->cols; g.mass = p->mass; g.radius = p->radius; g.k = p->stiffness; g.L0 = p->rest_length;
+    g.c = p->damping; g.min_distance = p->min_distance;
+    g.krep = p->repulsion_stiffness > 0.0 ? p->repulsion_stiffness : 10.0 * p->stiffness;       // components.hpp:186
+    g.inertia = 0.5 * p->mass * p->radius * p->radius;                                          // :98
+    g.ha0 = p->h_attach0; g.ha1 = p->h_attach1; g.va0 = p->v_attach0; g.va1 = p->v_attach1;
+    return SOPOT_B200_OK;
+}
+
+template <int STAGE>
+void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const double* in, double dt, double* y, double* acc, double* out) {
+    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows + 3) / 4));
+    if (strict) ugrid_stage<true, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
+    else ugrid_stage<false, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
+    ctx->launches++;
+}
+
+}  // namespace
+
+SB_EXPORT int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, uint32_t mem, double* state) {
+    UGridDev g;
+    int rc = check_ugrid(ctx, p, g);
+    if (rc) return rc;
+    if (!state || mem > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad state/mem");
+    const size_t bytes = g.rows * g.cols * 48;
+    Staging sg(ctx, mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_align(bytes) + 4096))) return rc;
+    void* d;
+    if ((rc = sg.out(state, bytes, &d))) return rc;
+    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows + 3) / 4));
+    ugrid_init_kernel<<<grid, block, 0, ctx->stream>>>(g.rows, g.cols, p->spacing, (double*)d);
+    SB_CHECK_LAUNCH(ctx);
+    return sg.finish();
+}
+
+SB_EXPORT int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, const sopot_b200_rk4_opts* opts,
+                                   const double* state, double* out) {
+    UGridDev g;
+    int rc = check_ugrid(ctx, p, g);
+    if (rc) return rc;
+    if (!opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    const size_t bytes = g.rows * g.cols * 48;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, 2 * sb_align(bytes) + 4096))) return rc;
+    const void* d_in; void* d_out;
+    if ((rc = sg.in(state, bytes, &d_in))) return rc;
+    if ((rc = sg.out(out, bytes, &d_out))) return rc;
+    launch_ustage<0>(ctx, opts->fp_mode == SOPOT_B200_FP_STRICT, g, (const double*)d_in, 0.0, nullptr, nullptr, (double*)d_out);
+    SB_CUDA(ctx, cudaGetLastError());
+    return sg.finish();
+}
+
+SB_EXPORT int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, double dt, size_t n_steps,
+                                   const sopot_b200_rk4_opts* opts, double* state) {
+    UGridDev g;
+    int rc = check_ugrid(ctx, p, g);
+    if (rc) return rc;
+    if (!opts || !state) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
+    const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
+    const size_t n = g.rows * g.cols * 6;
+    Staging sg(ctx, opts->mem);
+    if (sg.host && (rc = sb_arena_begin(ctx, sb_align(n * 8) + 4096))) return rc;
+    double* y;
+    if (sg.host) {
+        const void* d_in;
+        if ((rc = sg.in(state, n * 8, &d_in))) return rc;
+        y = const_cast<double*>(static_cast<const double*>(d_in));
+        sg.outs.push_back({state, y, n * 8});
+    } else {
+        y = state;
+    }
+    void* scr;
+    if ((rc = sb_scratch(ctx, 3 * n * 8 + 1024, &scr))) return rc;
+    double* acc = static_cast<double*>(scr);
+    double* A = acc + n;
+    double* B = A + n;
+    for (size_t step = 0; step < n_steps; ++step) {
+        launch_ustage<1>(ctx, strict, g, y, dt, y, acc, A);
+        launch_ustage<2>(ctx, strict, g, A, dt, y, acc, B);
+        launch_ustage<3>(ctx, strict, g, B, dt, y, acc, A);
+        launch_ustage<4>(ctx, strict, g, A, dt, y, acc, nullptr);
+    }
+    SB_CUDA(ctx, cudaGetLastError());
+    return sg.finish();
+}

@@ -91,6 +91,7 @@ def main():
     cartn_linearize_golden(R)
     rocket_aero_golden(R)
     control_n_golden(R)
+    ugrid_golden(R)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
@@ -191,3 +192,27 @@ def control_n_golden(R):
         out.update({f"n{N}_mc": mc, f"n{N}_m": m, f"n{N}_L": L, f"n{N}_g": g, f"n{N}_A": A, f"n{N}_B": B, f"n{N}_Q": Q, f"n{N}_K": K,
                     f"n{N}_P": Pr, f"n{N}_st": st, f"n{N}_s0": s0, f"n{N}_final": fin, f"n{N}_stats": stats})
     np.savez(os.path.join(OUT, "control_n.npz"), **out)
+
+
+UGRID_PI = 3.14159265358979323846
+UGRID_PARAMS = {   # mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1
+    "wasm": [1.0, 0.05, 0.5, 50.0, 0.5, 0.5, 0.0, -1.0, 0.0, UGRID_PI, UGRID_PI / 2, -UGRID_PI / 2],      # Grid2DSimulator's layout
+    "repel": [0.7, 0.08, 0.4, 80.0, 0.3, 0.9, 0.35, -1.0, 0.0, UGRID_PI, 0.0, UGRID_PI],                  # Spring2D defaults + repulsion
+}
+
+
+def ugrid_golden(R):
+    """Unified 6-state grid: ValidatedSystem<double, makeGridTopology<R,C>, PointMass2D, Spring2D> (the wasm Grid2DSimulator's
+    system): initial state, one derivative evaluation of a perturbed state, 50 RK4Solver steps."""
+    out = {}
+    for rows, cols in ((3, 3), (4, 5), (2, 7), (6, 6), (10, 10)):
+        for tag, prm in UGRID_PARAMS.items():
+            key = f"u{rows}x{cols}_{tag}"
+            s0 = R.ugrid(rows, cols, prm, mode="init")
+            rng = np.random.default_rng(rows * 100 + cols)
+            st = s0 + rng.normal(0, 0.03, s0.shape)
+            st[:, 4] = rng.normal(0, 0.3, rows * cols); st[:, 5] = rng.normal(0, 0.5, rows * cols)
+            out[key + "_init"], out[key + "_state"] = s0, st
+            out[key + "_rhs"] = R.ugrid(rows, cols, prm, st)
+            out[key + "_rk4"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
+    np.savez(os.path.join(OUT, "ugrid.npz"), **out)

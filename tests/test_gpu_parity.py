@@ -438,3 +438,51 @@ def test_lqr_block_kernel_golden_bit_exact_strict(engine, n_links):
     c = golden("control")
     K4, _, _, st4 = engine.lqr_gain(4, c["A"], c["B"], c["A"].shape[1], c["Q"], 0.01, 0.01, 1000, 1e-8, fp_mode=FP_STRICT)
     assert np.array_equal(K4, c["K_a"])
+
+
+# ---------------------------------------------------------------- section 8f-2: unified 6-state grid
+def _ugrid_prm():
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg.UGRID_PARAMS
+
+
+@pytest.mark.parametrize("rows,cols", [(3, 3), (4, 5), (2, 7), (6, 6), (10, 10)])
+def test_unified_grid_golden(engine, rows, cols):
+    """Unified 6-state grid (PointMass2D + Spring2D with attachment points and torque) against the reference's ValidatedSystem:
+    initial state exact; derivative and 50 RK4 steps to 1e-12 / 1e-9 (sin/cos of the attachment angles: libm-level)."""
+    g = golden("ugrid")
+    for tag, prm in _ugrid_prm().items():
+        key = f"u{rows}x{cols}_{tag}"
+        gp = engine.ugrid_params(rows, cols, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], prm[7], tuple(prm[8:12]))
+        assert np.array_equal(engine.ugrid_initial_state(gp), g[key + "_init"])
+        for mode in (FP_STRICT, FP_CONTRACT):
+            d = engine.ugrid_rhs(gp, g[key + "_state"].copy(), fp_mode=mode)
+            assert np.abs(d - g[key + "_rhs"]).max() <= 1e-12 * np.abs(g[key + "_rhs"]).max()
+            out = engine.ugrid_rk4(gp, 1e-3, 50, g[key + "_state"].copy(), fp_mode=mode)
+            assert rel_err(out.ravel(), g[key + "_rk4"].ravel()).max() <= FINAL
+
+
+def test_unified_grid_medium_vs_oracle(engine, port):
+    """Sizes the templated reference is not instantiated for: against the runtime-sized oracle; device-pointer path; a rest
+    grid whose rest length equals the attachment distance stays at rest exactly."""
+    prm = _ugrid_prm()["wasm"]
+    for rows, cols in ((33, 70), (129, 64)):
+        gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
+        s0 = engine.ugrid_initial_state(gp)
+        rng = np.random.default_rng(rows)
+        st = s0 + rng.normal(0, 0.02, s0.shape); st[:, 4] = rng.normal(0, 0.2, rows * cols)
+        ref = port.ugrid(rows, cols, prm, st, 1e-3, 10, "rk4")
+        got = engine.ugrid_rk4(gp, 1e-3, 10, st.copy(), fp_mode=FP_STRICT)
+        assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL
+        dev = engine.to_device(st)
+        engine.ugrid_rk4(gp, 1e-3, 10, dev, fp_mode=FP_CONTRACT)
+        assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL
+    rest = list(prm); rest[4] = 0.4                                   # 0.5 spacing - 2 * 0.05 radius
+    gp = engine.ugrid_params(64, 64, *rest[:8], tuple(rest[8:12]))
+    s0 = engine.ugrid_initial_state(gp)
+    out = engine.ugrid_rk4(gp, 1e-3, 5, s0.copy(), fp_mode=FP_STRICT)
+    assert np.abs(out - s0).max() < 1e-13

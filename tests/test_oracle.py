@@ -244,3 +244,28 @@ def test_golden_lqr_and_closed_loop_n_links(port):
                                              -500.0, 500.0, 1, 0.0, 0.001, 1500)
         assert np.array_equal(fin, g[k + "final"]) and np.array_equal(stats, g[k + "stats"])
         assert g[k + "stats"][0].max() < 0.2            # never falls (tests/inverted_pendulum_test.cpp:288)
+
+
+def _ugrid_params():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg.UGRID_PARAMS
+
+
+def test_golden_unified_grid(port):
+    """Section 8f-2: runtime-sized restatement of the unified 6-state grid == the reference's ValidatedSystem on
+    makeGridTopology<R,C> (golden vectors), bit for bit: initial state, derivative with rotation / torque / repulsion, RK4."""
+    g = golden("ugrid")
+    for rows, cols in ((3, 3), (4, 5), (2, 7), (6, 6), (10, 10)):
+        for tag, prm in _ugrid_params().items():
+            key = f"u{rows}x{cols}_{tag}"
+            assert np.array_equal(port.ugrid(rows, cols, prm, mode="init"), g[key + "_init"])
+            assert np.array_equal(port.ugrid(rows, cols, prm, g[key + "_state"]), g[key + "_rhs"])
+            assert np.array_equal(port.ugrid(rows, cols, prm, g[key + "_state"], 1e-3, 50, "rk4"), g[key + "_rk4"])
+    # Newton's third law on forces; a rest grid with rest_length = attachment distance feels nothing
+    prm = [1.0, 0.05, 0.5, 50.0, 0.4, 0.5, 0.0, -1.0, 0.0, 3.14159265358979323846, 3.14159265358979323846 / 2, -3.14159265358979323846 / 2]
+    s0 = port.ugrid(7, 9, prm, mode="init")
+    assert np.abs(port.ugrid(7, 9, prm, s0)).max() < 1e-12           # spacing 0.5 - 2 * radius 0.05 = rest length 0.4
+    d = port.ugrid(4, 5, _ugrid_params()["wasm"], g["u4x5_wasm_state"])
+    assert np.abs(d[:, 2:4].sum(axis=0)).max() < 1e-10
