@@ -242,6 +242,17 @@ def other_configs(eng, hbm_peak, fp64_peak):
                 row["speedup_vs_hbm_bound_at_544B"] = (544.0 * n * n / (hbm_peak * 1e9)) / (ms * 1e-3)
             out[f"grid2d_8192x8192_{name}_{'per_stage' if per_stage else 'fused'}"] = row
     state.free()
+    # section 8f-2: the unified 6-state grid (the system of the reference's Grid2DSimulator), 4096^2 masses, per-stage kernels,
+    # 816 B of HBM traffic per mass-step (1.5x the 4-state grid)
+    n = 4096
+    pi = 3.14159265358979323846
+    ug = eng.ugrid_params(n, n, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5, 0.0, -1.0, (0.0, pi, pi / 2, -pi / 2))
+    ustate = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
+    for mode, name in ((FP_STRICT, "strict"), (FP_CONTRACT, "contract")):
+        ms = timed(lambda: eng.ugrid_rk4(ug, 1e-3, 5, ustate, fp_mode=mode, sync=False), 2) / 5.0
+        out[f"unified_grid_4096x4096_{name}"] = {"ms_per_step": ms, "mass_steps_per_s": n * n / (ms * 1e-3),
+                                                 "GBs": 816.0 * n * n / (ms * 1e-3) / 1e9, "hbm_frac": 816.0 * n * n / (ms * 1e-3) / 1e9 / hbm_peak}
+    ustate.free()
     return out
 
 

@@ -5,6 +5,7 @@
 // is bit-identical to it (no libm call on this path).  Needs a B200.
 #include <cstdio>
 #include <sopot/physics/connected_masses/grid_2d.hpp>
+#include <sopot/physics/unified/grid_system.hpp>
 #include "check.hpp"
 
 using namespace sopot;
@@ -73,6 +74,32 @@ int main() {
     for (size_t i = 0; i < y.size(); ++i) { err = std::max(err, std::abs(y[i] - y_fast[i])); scale = std::max(scale, std::abs(y[i])); }
     ASSERT_TRUE(err <= 1e-12 * scale);
     ASSERT_THROWS(makeGrid2DSystem(1, 8, 1.0, 0.5, 50.0), std::invalid_argument);
+    // unified 6-state grid (the reference's Grid2DSimulator system): known answers of ValidatedSystem on makeGridTopology<3,3>
+    // with the wasm layout (radius 0.05, attachment angles 0 / pi / pi/2 / -pi/2), centre mass displaced and turned
+    {
+        unified::UnifiedGridSystem ug(3, 3);
+        ASSERT_TRUE(ug.getStateDimension() == 54 && ug.getNodeCount() == 21);
+        auto s = ug.getInitialState();
+        ASSERT_TRUE(s[4 * 6 + 0] == 0.5 && s[4 * 6 + 1] == 0.5 && s[8 * 6 + 1] == 1.0);
+        s[4 * 6 + 0] += 0.1; s[4 * 6 + 4] = 0.2;
+        auto d = ug.computeDerivatives(0.0, s);
+        const double d4[6] = {0.0, 0.0, -7.9027668235041935, 0.047077641230074185, 0.0, 163.52234344663196};
+        for (int j = 0; j < 6; ++j) ASSERT_NEAR(d[4 * 6 + j], d4[j], 1e-12 * 164.0);
+        auto derivs_u = [&ug](double t, StateView sv) { return ug.computeDerivatives(t, sv); };      // tests/unified_scalability_test.cpp:105-111
+        auto ru = createRK4Solver().solve(derivs_u, ug.getStateDimension(), 0.0, 0.1, 0.001, s);
+        ASSERT_TRUE(ru.size() == 101);
+        const double m4[6] = {0.5660625774724096, 0.49981725468061716, -0.596435952017727, -0.010561942338296723, 1.3521740056572316, 25.18932655850739};
+        const double m0[6] = {-0.02402791697931773, -0.02349146844165254, -0.4623865235560934, -0.4440399378395715, 0.013163793079625924, 0.5247417179459242};
+        for (int j = 0; j < 6; ++j) { ASSERT_NEAR(ru.states.back()[4 * 6 + j], m4[j], 1e-9 * 26.0); ASSERT_NEAR(ru.states.back()[j], m0[j], 1e-9 * 26.0); }
+        unified::UnifiedGridSystem large(512, 384);
+        auto y = large.getInitialState();
+        y[(256 * 384 + 192) * 6] += 0.1;
+        large.integrate(y, 1e-3, 20);
+        double moved = 0.0;
+        for (size_t i = 0; i < y.size(); i += 6) moved = std::max(moved, std::abs(y[i + 4]));
+        ASSERT_TRUE(std::isfinite(moved) && moved > 0.0);                                       // the disturbance turns the neighbours
+        ASSERT_THROWS(unified::UnifiedGridSystem(1, 1), std::invalid_argument);
+    }
     std::puts("grid2d_test: OK");
     return 0;
 }
