@@ -281,6 +281,12 @@ int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, 
                          const double* state, double* out);
 int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, double dt, size_t n_steps,
                          const sopot_b200_rk4_opts* opts, double* state /* in/out */);
+/* the three integrators of the reference's Grid2DSimulator (wasm/wasm_grid2d.cpp:286-413): RK4 as above; symplectic Euler
+ * (v += dt a(x_n, v_n), then x += dt v_new; one derivative evaluation per step); velocity Verlet (x += dt v + dt^2/2 a_n,
+ * a_{n+1} = a(x_{n+1}, v_n), v += dt/2 (a_n + a_{n+1}); two evaluations per step) */
+enum { SOPOT_B200_INTEGRATOR_RK4 = 0, SOPOT_B200_INTEGRATOR_SYMPLECTIC_EULER = 1, SOPOT_B200_INTEGRATOR_VELOCITY_VERLET = 2 };
+int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, int integrator, double dt,
+                               size_t n_steps, const sopot_b200_rk4_opts* opts, double* state /* in/out */);
 
 /* ---------------------------------------------------------------------------------------------
  * Roofline denominators measured on this device: dependent-free DFMA issue rate (FP64 TFLOP/s,

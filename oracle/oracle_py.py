@@ -200,7 +200,7 @@ class Checker:
         out = np.empty(n)
         st = None if state is None else _f64(state).reshape(n)
         rc = self._fn("ugrid", [_sz, _sz, _dp, _d, _sz, _dp, _dp, _i])(rows, cols, _p(prm), dt, n_steps, _p(st), _p(out),
-                                                                        {"rhs": 0, "rk4": 1, "init": 2}[mode])
+                                                                        {"rhs": 0, "rk4": 1, "init": 2, "symplectic_euler": 3, "velocity_verlet": 4}[mode])
         if rc:
             raise KeyError("grid size not instantiated in the reference harness")
         return out.reshape(rows * cols, 6)

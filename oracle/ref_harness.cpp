@@ -111,6 +111,36 @@ static int ugrid_run(size_t rows, size_t cols, const double* prm /*12*/, double 
     if (mode == 2) { auto s0 = sys.getInitialState(); std::copy(s0.begin(), s0.end(), out); return 0; }
     std::vector<double> st(state_in, state_in + n);
     if (mode == 0) { auto d = sys.computeDerivatives(0.0, st); std::copy(d.begin(), d.end(), out); return 0; }
+    if (mode == 3 || mode == 4) {
+        // the two extra integrators of Grid2DSimulator (wasm/wasm_grid2d.cpp:329-413; that file needs emscripten, so its
+        // three-line update loops are repeated here around the reference's own computeDerivatives)
+        const size_t nm = rows * cols;
+        double t = 0.0;
+        for (size_t sidx = 0; sidx < n_steps; ++sidx) {
+            auto d = sys.computeDerivatives(t, st);
+            if (mode == 3) {                                                       // symplecticEulerStep :329-358
+                for (size_t i = 0; i < nm; ++i) { st[i * 6 + 2] += dt * d[i * 6 + 2]; st[i * 6 + 3] += dt * d[i * 6 + 3]; st[i * 6 + 5] += dt * d[i * 6 + 5]; }
+                for (size_t i = 0; i < nm; ++i) { st[i * 6 + 0] += dt * st[i * 6 + 2]; st[i * 6 + 1] += dt * st[i * 6 + 3]; st[i * 6 + 4] += dt * st[i * 6 + 5]; }
+            } else {                                                               // velocityVerletStep :375-410
+                const double half_dt_sq = 0.5 * dt * dt;
+                for (size_t i = 0; i < nm; ++i) {
+                    st[i * 6 + 0] += dt * st[i * 6 + 2] + half_dt_sq * d[i * 6 + 2];
+                    st[i * 6 + 1] += dt * st[i * 6 + 3] + half_dt_sq * d[i * 6 + 3];
+                    st[i * 6 + 4] += dt * st[i * 6 + 5] + half_dt_sq * d[i * 6 + 5];
+                }
+                auto dn = sys.computeDerivatives(t + dt, st);
+                const double half_dt = 0.5 * dt;
+                for (size_t i = 0; i < nm; ++i) {
+                    st[i * 6 + 2] += half_dt * (d[i * 6 + 2] + dn[i * 6 + 2]);
+                    st[i * 6 + 3] += half_dt * (d[i * 6 + 3] + dn[i * 6 + 3]);
+                    st[i * 6 + 5] += half_dt * (d[i * 6 + 5] + dn[i * 6 + 5]);
+                }
+            }
+            t += dt;
+        }
+        std::copy(st.begin(), st.end(), out);
+        return 0;
+    }
     auto solver = createRK4Solver();
     auto derivs = [&sys](double t, StateView sv) { return sys.computeDerivatives(t, sv); };
     double t = 0.0;

@@ -770,6 +770,34 @@ ORC_API int orc_ugrid(size_t rows, size_t cols, const double* prm, double dt, si
     double* work = (double*)malloc(5 * n * sizeof(double));
     memcpy(y, state_in, n * sizeof(double));
     double t = 0.0;
+    if (mode == 3 || mode == 4) {                    /* wasm/wasm_grid2d.cpp:329-358 (symplectic Euler), :375-410 (velocity Verlet) */
+        const size_t nm = rows * cols;
+        double *d = work, *dn = work + n;
+        for (size_t s = 0; s < n_steps; ++s) {
+            orc_ugrid_rhs_fn(&g, t, y, d);
+            if (mode == 3) {
+                for (size_t i = 0; i < nm; ++i) { y[i * 6 + 2] += dt * d[i * 6 + 2]; y[i * 6 + 3] += dt * d[i * 6 + 3]; y[i * 6 + 5] += dt * d[i * 6 + 5]; }
+                for (size_t i = 0; i < nm; ++i) { y[i * 6 + 0] += dt * y[i * 6 + 2]; y[i * 6 + 1] += dt * y[i * 6 + 3]; y[i * 6 + 4] += dt * y[i * 6 + 5]; }
+            } else {
+                const double half_dt_sq = 0.5 * dt * dt, half_dt = 0.5 * dt;
+                for (size_t i = 0; i < nm; ++i) {
+                    y[i * 6 + 0] += dt * y[i * 6 + 2] + half_dt_sq * d[i * 6 + 2];
+                    y[i * 6 + 1] += dt * y[i * 6 + 3] + half_dt_sq * d[i * 6 + 3];
+                    y[i * 6 + 4] += dt * y[i * 6 + 5] + half_dt_sq * d[i * 6 + 5];
+                }
+                orc_ugrid_rhs_fn(&g, t + dt, y, dn);
+                for (size_t i = 0; i < nm; ++i) {
+                    y[i * 6 + 2] += half_dt * (d[i * 6 + 2] + dn[i * 6 + 2]);
+                    y[i * 6 + 3] += half_dt * (d[i * 6 + 3] + dn[i * 6 + 3]);
+                    y[i * 6 + 5] += half_dt * (d[i * 6 + 5] + dn[i * 6 + 5]);
+                }
+            }
+            t += dt;
+        }
+        memcpy(out, y, n * sizeof(double));
+        free(y); free(work);
+        return 0;
+    }
     for (size_t s = 0; s < n_steps; ++s) { orc_rk4(orc_ugrid_rhs_fn, &g, n, t, t + dt, dt, y, work, NULL, NULL, NULL); t += dt; }
     memcpy(out, y, n * sizeof(double));
     free(y); free(work);

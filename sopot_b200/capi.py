@@ -21,7 +21,9 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
-ABI_VERSION = 2          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
+ABI_VERSION = 2
+INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
+         # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
 
 _dp = POINTER(c_double)
@@ -126,6 +128,7 @@ SYMBOLS = {
     "sopot_b200_ugrid_initial_state": (c_int, [_ctx, POINTER(UGridParams), c_uint32, c_void_p]),
     "sopot_b200_ugrid_rhs": (c_int, [_ctx, POINTER(UGridParams), POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_ugrid_rk4": (c_int, [_ctx, POINTER(UGridParams), c_double, c_size_t, POINTER(RK4Opts), c_void_p]),
+    "sopot_b200_ugrid_integrate": (c_int, [_ctx, POINTER(UGridParams), c_int, c_double, c_size_t, POINTER(RK4Opts), c_void_p]),
     "sopot_b200_lqr_gain": (c_int, [_ctx, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_double, c_double, c_size_t, c_double,
                                     POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sopot_b200_cartpole_feedback_rk4": (c_int, [_ctx, POINTER(CartpoleParams), POINTER(Feedback), c_size_t, c_double,
@@ -549,10 +552,11 @@ class Engine:
         self.sync()
         return out
 
-    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True):
+    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, integrator=0):
+        """integrator: 0 RK4, 1 symplectic Euler, 2 velocity Verlet (the reference Grid2DSimulator's three)."""
         mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
         opts = RK4Opts(mem, fp_mode, 0, 0, 0)
-        self._ck(self.lib.sopot_b200_ugrid_rk4(self.ctx, byref(g), dt, n_steps, byref(opts), _ptr(state)))
+        self._ck(self.lib.sopot_b200_ugrid_integrate(self.ctx, byref(g), integrator, dt, n_steps, byref(opts), _ptr(state)))
         if sync:
             self.sync()
         return state

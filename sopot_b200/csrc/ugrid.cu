@@ -98,6 +98,34 @@ ugrid_stage(const UGridDev g, const double* __restrict__ in, const double dt_, d
         return;
     }
     const R dt(dt_);
+    if constexpr (STAGE == 5) {
+        // symplectic Euler, wasm/wasm_grid2d.cpp:329-358: v += dt*a(x_n, v_n), then x += dt*v_new (likewise omega, theta)
+        const R vx = R(self.vx) + dt * d[2], vy = R(self.vy) + dt * d[3], om = R(self.om) + dt * d[5];
+        o[0] = (R(self.x) + dt * vx).v; o[1] = (R(self.y) + dt * vy).v; o[2] = vx.v; o[3] = vy.v;
+        o[4] = (R(self.th) + dt * om).v; o[5] = om.v;
+        store6(out + off, o);
+        return;
+    }
+    if constexpr (STAGE == 6) {
+        // velocity Verlet, first half (:375-398): x += dt*v + (0.5*dt*dt)*a_n; velocities wait for a_{n+1}; a_n is kept in acc
+        const R hdt2 = R(0.5) * dt * dt;
+        o[0] = (R(self.x) + (dt * R(self.vx) + hdt2 * d[2])).v; o[1] = (R(self.y) + (dt * R(self.vy) + hdt2 * d[3])).v;
+        o[2] = self.vx; o[3] = self.vy;
+        o[4] = (R(self.th) + (dt * R(self.om) + hdt2 * d[5])).v; o[5] = self.om;
+        store6(out + off, o);
+        const double a[6] = {d[2].v, d[3].v, d[5].v, 0.0, 0.0, 0.0};
+        store6(acc + off, a);
+        return;
+    }
+    if constexpr (STAGE == 7) {
+        // velocity Verlet, second half (:400-410): a_{n+1} = a(x_{n+1}, v_n); v += (0.5*dt)*(a_n + a_{n+1})
+        const R hdt = R(0.5) * dt;
+        o[0] = self.x; o[1] = self.y; o[4] = self.th;
+        o[2] = (R(self.vx) + hdt * (R(acc[off]) + d[2])).v; o[3] = (R(self.vy) + hdt * (R(acc[off + 1]) + d[3])).v;
+        o[5] = (R(self.om) + hdt * (R(acc[off + 2]) + d[5])).v;
+        store6(out + off, o);
+        return;
+    }
     R k[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) k[j] = d[j] * dt;
@@ -190,10 +218,16 @@ SB_EXPORT int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_p
 
 SB_EXPORT int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, double dt, size_t n_steps,
                                    const sopot_b200_rk4_opts* opts, double* state) {
+    return sopot_b200_ugrid_integrate(ctx, p, SOPOT_B200_INTEGRATOR_RK4, dt, n_steps, opts, state);
+}
+
+SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, int integrator, double dt,
+                                         size_t n_steps, const sopot_b200_rk4_opts* opts, double* state) {
     UGridDev g;
     int rc = check_ugrid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (integrator < 0 || integrator > 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "integrator must be RK4, SYMPLECTIC_EULER or VELOCITY_VERLET");
     if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
     const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
     const size_t n = g.rows * g.cols * 6;
@@ -213,11 +247,30 @@ SB_EXPORT int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_p
     double* acc = static_cast<double*>(scr);
     double* A = acc + n;
     double* B = A + n;
-    for (size_t step = 0; step < n_steps; ++step) {
-        launch_ustage<1>(ctx, strict, g, y, dt, y, acc, A);
-        launch_ustage<2>(ctx, strict, g, A, dt, y, acc, B);
-        launch_ustage<3>(ctx, strict, g, B, dt, y, acc, A);
-        launch_ustage<4>(ctx, strict, g, A, dt, y, acc, nullptr);
+    if (integrator == SOPOT_B200_INTEGRATOR_RK4) {
+        for (size_t step = 0; step < n_steps; ++step) {
+            launch_ustage<1>(ctx, strict, g, y, dt, y, acc, A);
+            launch_ustage<2>(ctx, strict, g, A, dt, y, acc, B);
+            launch_ustage<3>(ctx, strict, g, B, dt, y, acc, A);
+            launch_ustage<4>(ctx, strict, g, A, dt, y, acc, nullptr);
+        }
+    } else {
+        // one (symplectic Euler) or two (velocity Verlet) derivative evaluations per step; a step cannot update in place
+        // (neighbours still read the old state), so the state ping-pongs between y and A
+        double* cur = y;
+        double* nxt = A;
+        for (size_t step = 0; step < n_steps; ++step) {
+            if (integrator == SOPOT_B200_INTEGRATOR_SYMPLECTIC_EULER) {
+                launch_ustage<5>(ctx, strict, g, cur, dt, nullptr, nullptr, nxt);
+                double* t = cur; cur = nxt; nxt = t;
+            } else {
+                launch_ustage<6>(ctx, strict, g, cur, dt, nullptr, acc, B);
+                launch_ustage<7>(ctx, strict, g, B, dt, nullptr, acc, cur == y ? A : y);
+                cur = cur == y ? A : y;
+                nxt = cur == y ? A : y;
+            }
+        }
+        if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     SB_CUDA(ctx, cudaGetLastError());
     return sg.finish();

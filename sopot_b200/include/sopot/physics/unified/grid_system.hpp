@@ -17,6 +17,10 @@ struct GridConfig {
     double h_attach0 = 0.0, h_attach1 = 3.14159265358979323846, v_attach0 = 3.14159265358979323846 / 2.0, v_attach1 = -3.14159265358979323846 / 2.0;
 };
 
+// the three schemes of the reference's Grid2DSimulator (wasm/wasm_grid2d.cpp:38-42, :286-413)
+enum class Integrator : int { RK4 = SOPOT_B200_INTEGRATOR_RK4, SymplecticEuler = SOPOT_B200_INTEGRATOR_SYMPLECTIC_EULER,
+                              VelocityVerlet = SOPOT_B200_INTEGRATOR_VELOCITY_VERLET };
+
 class UnifiedGridSystem {
 public:
     UnifiedGridSystem(size_t rows, size_t cols, const GridConfig& c = {})
@@ -66,11 +70,16 @@ public:
     std::vector<double> computeDerivatives(double t, const std::vector<double>& state) const { return computeDerivatives(t, std::span<const double>(state)); }
     // advance `state` in place by n_steps RK4 steps
     void integrate(std::vector<double>& state, double dt, size_t n_steps, b200::FpMode fp = b200::FpMode::Contract, b200::Engine* engine = nullptr) const {
+        integrate(state, dt, n_steps, Integrator::RK4, fp, engine);
+    }
+    // ... or by n_steps of one of the simulator's three integrators (wasm/wasm_grid2d.cpp:38-42 IntegratorType)
+    void integrate(std::vector<double>& state, double dt, size_t n_steps, Integrator integrator, b200::FpMode fp = b200::FpMode::Contract,
+                   b200::Engine* engine = nullptr) const {
         if (state.size() != getStateDimension()) throw std::invalid_argument("state has the wrong dimension");
         b200::Engine& eng = engine ? *engine : b200::Engine::shared();
         b200::EnsembleOptions o; o.fp_mode = fp;
         const auto opts = b200::make_opts(o, 0);
-        eng.check(sopot_b200_ugrid_rk4(eng.ctx(), &m_p, dt, n_steps, &opts, state.data()));
+        eng.check(sopot_b200_ugrid_integrate(eng.ctx(), &m_p, static_cast<int>(integrator), dt, n_steps, &opts, state.data()));
         eng.sync();
     }
 private:

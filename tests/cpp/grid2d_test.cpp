@@ -91,6 +91,15 @@ int main() {
         const double m4[6] = {0.5660625774724096, 0.49981725468061716, -0.596435952017727, -0.010561942338296723, 1.3521740056572316, 25.18932655850739};
         const double m0[6] = {-0.02402791697931773, -0.02349146844165254, -0.4623865235560934, -0.4440399378395715, 0.013163793079625924, 0.5247417179459242};
         for (int j = 0; j < 6; ++j) { ASSERT_NEAR(ru.states.back()[4 * 6 + j], m4[j], 1e-9 * 26.0); ASSERT_NEAR(ru.states.back()[j], m0[j], 1e-9 * 26.0); }
+        // the simulator's other two integrators, 100 steps of 1e-3 from the same state (reference loops of wasm_grid2d.cpp:329-413)
+        const double se4[6] = {0.5657439557543504, 0.49981696742827497, -0.5967200284371587, -0.01049069666494754, 1.3655253482151337, 25.20979387132567};
+        const double vv4[6] = {0.566042265060754, 0.49982221093902496, -0.5967051876102133, -0.01049151429179392, 1.3529916086711211, 25.208957483209815};
+        for (auto fp : {b200::FpMode::Strict, b200::FpMode::Contract}) {
+            auto ye = s, yv = s;
+            ug.integrate(ye, 1e-3, 100, unified::Integrator::SymplecticEuler, fp);
+            ug.integrate(yv, 1e-3, 100, unified::Integrator::VelocityVerlet, fp);
+            for (int j = 0; j < 6; ++j) { ASSERT_NEAR(ye[4 * 6 + j], se4[j], 1e-9 * 26.0); ASSERT_NEAR(yv[4 * 6 + j], vv4[j], 1e-9 * 26.0); }
+        }
         unified::UnifiedGridSystem large(512, 384);
         auto y = large.getInitialState();
         y[(256 * 384 + 192) * 6] += 0.1;

@@ -216,3 +216,9 @@ def ugrid_golden(R):
             out[key + "_rhs"] = R.ugrid(rows, cols, prm, st)
             out[key + "_rk4"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
     np.savez(os.path.join(OUT, "ugrid.npz"), **out)
+    # the simulator's two other integrators (wasm/wasm_grid2d.cpp:329-413), 80 steps from the same perturbed states
+    integ = {}
+    for rows, cols in ((4, 5), (10, 10)):
+        for mode in ("symplectic_euler", "velocity_verlet"):
+            integ[f"u{rows}x{cols}_{mode}"] = R.ugrid(rows, cols, UGRID_PARAMS["wasm"], out[f"u{rows}x{cols}_wasm_state"], 1e-3, 80, mode)
+    np.savez(os.path.join(OUT, "ugrid_integrators.npz"), **integ)

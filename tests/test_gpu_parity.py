@@ -466,6 +466,37 @@ def test_unified_grid_golden(engine, rows, cols):
             assert rel_err(out.ravel(), g[key + "_rk4"].ravel()).max() <= FINAL
 
 
+def test_unified_grid_integrators(engine, port):
+    """Grid2DSimulator's other two integrators (wasm/wasm_grid2d.cpp:329-413): symplectic Euler and velocity Verlet on the
+    device against the golden vectors (80 steps) and, on a size the reference is not instantiated for, against the oracle.
+    Odd and even step counts exercise both ends of the ping-pong between the state and the scratch buffer."""
+    from sopot_b200.capi import INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET
+    g, gi = golden("ugrid"), golden("ugrid_integrators")
+    prm = _ugrid_prm()["wasm"]
+    ids = {"symplectic_euler": INTEGRATOR_SYMPLECTIC_EULER, "velocity_verlet": INTEGRATOR_VELOCITY_VERLET}
+    for rows, cols in ((4, 5), (10, 10)):
+        gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
+        for name, integ in ids.items():
+            for mode in (FP_STRICT, FP_CONTRACT):
+                out = engine.ugrid_rk4(gp, 1e-3, 80, g[f"u{rows}x{cols}_wasm_state"].copy(), fp_mode=mode, integrator=integ)
+                assert rel_err(out.ravel(), gi[f"u{rows}x{cols}_{name}"].ravel()).max() <= FINAL
+    rows, cols = 45, 77
+    gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
+    s0 = engine.ugrid_initial_state(gp)
+    rng = np.random.default_rng(5)
+    st = s0 + rng.normal(0, 0.02, s0.shape); st[:, 4] = rng.normal(0, 0.2, rows * cols)
+    for name, integ in ids.items():
+        for n_steps in (1, 7, 12):
+            ref = port.ugrid(rows, cols, prm, st, 2e-3, n_steps, name)
+            got = engine.ugrid_rk4(gp, 2e-3, n_steps, st.copy(), fp_mode=FP_STRICT, integrator=integ)
+            assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL
+            dev = engine.to_device(st)
+            engine.ugrid_rk4(gp, 2e-3, n_steps, dev, fp_mode=FP_CONTRACT, integrator=integ)
+            assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL
+    with pytest.raises(Exception):
+        engine.ugrid_rk4(gp, 1e-3, 1, st.copy(), integrator=9)
+
+
 def test_unified_grid_medium_vs_oracle(engine, port):
     """Sizes the templated reference is not instantiated for: against the runtime-sized oracle; device-pointer path; a rest
     grid whose rest length equals the attachment distance stays at rest exactly."""

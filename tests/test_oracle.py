@@ -269,3 +269,17 @@ def test_golden_unified_grid(port):
     assert np.abs(port.ugrid(7, 9, prm, s0)).max() < 1e-12           # spacing 0.5 - 2 * radius 0.05 = rest length 0.4
     d = port.ugrid(4, 5, _ugrid_params()["wasm"], g["u4x5_wasm_state"])
     assert np.abs(d[:, 2:4].sum(axis=0)).max() < 1e-10
+
+
+def test_golden_unified_grid_integrators(port):
+    """Grid2DSimulator's symplectic Euler and velocity Verlet (wasm/wasm_grid2d.cpp:329-413) around the reference's
+    computeDerivatives: the port repeats them bit for bit; both stay within O(dt) / O(dt^2) of the RK4 trajectory."""
+    g, gi = golden("ugrid"), golden("ugrid_integrators")
+    prm = _ugrid_params()["wasm"]
+    for rows, cols in ((4, 5), (10, 10)):
+        st = g[f"u{rows}x{cols}_wasm_state"]
+        for mode in ("symplectic_euler", "velocity_verlet"):
+            assert np.array_equal(port.ugrid(rows, cols, prm, st, 1e-3, 80, mode), gi[f"u{rows}x{cols}_{mode}"])
+        rk = port.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
+        err = [np.abs(port.ugrid(rows, cols, prm, st, 1e-3, 50, m) - rk).max() for m in ("symplectic_euler", "velocity_verlet")]
+        assert err[0] < 0.05 and err[1] < 0.05
