@@ -43,8 +43,15 @@ __device__ __forceinline__ int rk4_step(const typename Sys::template Inst<S>& in
 // one FMA per state element (7 FP64 instructions per element and step instead of 12).  Same real-number
 // formula as core/solver.hpp:95-125, different rounding points: differs from the reference by a few ulp of the
 // increment, far inside the 1e-12 relative per step this mode promises (tests/test_gpu_parity.py).
-struct StepConsts { double dt, hdt, dt6; };
-__device__ __forceinline__ StepConsts make_step_consts(double dt) { return StepConsts{dt, 0.5 * dt, dt / 6.0}; }
+// Computed on the HOST and passed as a kernel parameter: a kernel parameter is read as a constant-bank / uniform-register
+// operand, so an FMA with one of these and two thread values reads two vector registers (2 issue cycles).  Computed in
+// the kernel (0.5 * dt is a per-thread DMUL) the same values sit in vector registers and every such FMA reads three
+// (3 cycles, profiles/r1_fp64_operand_rule.txt).  rot3/rot5/cot4: the full-precision coefficients of the small-angle
+// rotation (trig.cuh); its remaining coefficients are exact in the high word and become instruction immediates.
+struct StepConsts { double dt, hdt, dt6, hdt2, rot3, rot5, cot4; };
+__host__ __device__ __forceinline__ StepConsts make_step_consts(double dt) {
+    return StepConsts{dt, 0.5 * dt, dt / 6.0, (0.5 * dt) * (0.5 * dt), -1.0 / 6.0, 1.0 / 120.0, 1.0 / 24.0};
+}
 
 template <class Sys>
 __device__ __forceinline__ int rk4_step_fast(const typename Sys::template Inst<false>& in,
@@ -69,10 +76,10 @@ __device__ __forceinline__ int rk4_step_fast(const typename Sys::template Inst<f
 // dispatch: FP_STRICT -> reference association; FP_CONTRACT -> the system's own fused step when it has one
 // (Sys::FAST_STEP, e.g. DpendSys shares the trigonometry between the four stages), else rk4_step_fast.
 template <class Sys, bool S>
-__device__ __forceinline__ int rk4_step_any(const typename Sys::template Inst<S>& in, Real<S> (&y)[Sys::DIM],
-                                            const StepConsts& c) {
+__device__ __forceinline__ int rk4_step_any(typename Sys::template Inst<S>& in, Real<S> (&y)[Sys::DIM],
+                                            const StepConsts& c, const size_t step) {
     if constexpr (S) return rk4_step<Sys, true>(in, y, Real<true>(c.dt));
-    else if constexpr (Sys::FAST_STEP) return Sys::fast_step(in, y, c);
+    else if constexpr (Sys::FAST_STEP) return Sys::fast_step(in, y, c, step);   // may carry values from step to step in `in`
     else return rk4_step_fast<Sys>(in, y, c);
 }
 
@@ -87,7 +94,7 @@ template <class Sys> struct sb_has_begin_step<Sys, std::void_t<decltype(Sys::HAS
 // (blockIdx.x*IPT + j)*blockDim.x + threadIdx.x, so every load and store stays fully coalesced.
 template <class Sys, bool S>
 __global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS)
-rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double t0, const double dt_,
+rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double t0, const StepConsts sc,
                     const size_t n_steps, const size_t store_every, double* __restrict__ state_out,
                     double* __restrict__ traj_out, int32_t* __restrict__ status) {
     constexpr int D = Sys::DIM;
@@ -104,7 +111,7 @@ rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const doubl
         idx[j] = i < n ? i : base;           // a ragged tail re-computes instance `base` and discards it
         Sys::template load<S>(P, idx[j], in[j], y[j]);
     }
-    const StepConsts sc = make_step_consts(dt_);
+    const double dt_ = sc.dt;
     double t = t0;                           // accumulated like the reference: t += dt (core/solver.hpp:127)
 #pragma unroll
     for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);   // initial condition is stored (:87-88)
@@ -118,7 +125,7 @@ rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const doubl
             for (int j = 0; j < IPT; ++j) Sys::template begin_step<S>(in[j], y[j]);
         }
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) st[j] |= rk4_step_any<Sys, S>(in[j], y[j], sc);
+        for (int j = 0; j < IPT; ++j) st[j] |= rk4_step_any<Sys, S>(in[j], y[j], sc, step);
         t += dt_;
 #pragma unroll
         for (int j = 0; j < IPT; ++j) Sys::template observe<S>(in[j], t, y[j]);
@@ -229,11 +236,11 @@ int sb_launch_ensemble(const EnsembleArgs& a, const typename Sys::DevParams& P, 
         const unsigned grid = sb_grid_for(n, Sys::BLOCK * Sys::IPT);
         if (a.opts->fp_mode == SOPOT_B200_FP_STRICT)
             rk4_ensemble_kernel<Sys, true><<<grid, Sys::BLOCK, 0, ctx->stream>>>(
-                P, n, a.t0, a.dt, a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
+                P, n, a.t0, make_step_consts(a.dt), a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
                 (int32_t*)d_status);
         else
             rk4_ensemble_kernel<Sys, false><<<grid, Sys::BLOCK, 0, ctx->stream>>>(
-                P, n, a.t0, a.dt, a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
+                P, n, a.t0, make_step_consts(a.dt), a.n_steps, a.opts->store_every, (double*)d_state, (double*)d_traj,
                 (int32_t*)d_status);
         SB_CHECK_LAUNCH(ctx);
     }

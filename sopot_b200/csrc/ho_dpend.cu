@@ -98,12 +98,16 @@ SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
 #ifndef SB_DPEND_MINB
 #define SB_DPEND_MINB 1
 #endif
+#ifndef SB_DPEND_REFRESH
+#define SB_DPEND_REFRESH 16         // full sincos of the carried pairs every this many steps (power of two)
+#endif
 struct DpendSys {
     static constexpr int DIM = 4;
     static constexpr int BLOCK = SB_DPEND_BLOCK, IPT = SB_DPEND_IPT, MIN_BLOCKS = SB_DPEND_MINB;
     static constexpr bool FAST_STEP = true;
     struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
-    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, kap, lam, gL1, gL2; };
+    // kol .. gL2l: row-scaled coefficients of the fast step; s1 .. cd: sin/cos carried from step to step (fast_step)
+    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, kol, lam, gL1, gL2l; double s1, c1, sd, cd; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
@@ -113,11 +117,14 @@ struct DpendSys {
         in.m12g = (m1 + m2) * g;
         in.negL1 = -L1;
         in.L1 = L1; in.L2 = L2; in.g = g;
-        if constexpr (!S) {             // row-scaled coefficients of the fast step (accel)
-            in.kap = in.m2L2 / in.a11; in.lam = L1 / L2; in.gL1 = g / L1; in.gL2 = g / L2;
-        }
         y[0] = Real<S>(P.th1.at(i)); y[1] = Real<S>(P.th2.at(i));
         y[2] = Real<S>(P.w1.at(i));  y[3] = Real<S>(P.w2.at(i));
+        if constexpr (!S) {
+            in.lam = L1 / L2;                                   // lam = L1/L2, kap = m2 L2 / ((m1+m2) L1)
+            in.kol = (in.m2L2 / in.a11) / in.lam;               // kap / lam
+            in.gL1 = g / L1; in.gL2l = (g / L2) / in.lam;
+            refresh_trig(in, y[0].v, y[1].v);
+        }
     }
     template <bool S>
     static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
@@ -154,62 +161,99 @@ struct DpendSys {
         return st;
     }
     // ---- FP_CONTRACT fast step -------------------------------------------------------------------------------
-    // angular accelerations from sin/cos of both angles and the rates: the Cramer solve of :162-175 with both
-    // equations scaled by their parameter-only leading coefficient (row 1 by 1/a11, row 2 by 1/a22), so that
-    //   B1 = kap P sd - (g/L1) s1,   B2 = -lam Q sd - (g/L2) s2,   P = w2^2, Q = w1^2,
-    //   a1 = (B1 - kap cd B2) / D,   a2 = (B2 - lam cd B1) / D,    D = 1 - kap lam cd^2  in (0, 1]
-    // with kap = m2 L2 / ((m1+m2) L1), lam = L1 / L2.  21 FP64 instructions + 1 MUFU; only 6 of them read
-    // three distinct vector registers.
-    static __device__ __forceinline__ void accel(const Inst<false>& in, double s1, double c1, double s2, double c2,
+    // The Cramer solve of :162-175 with both equations scaled by their parameter-only leading coefficient (row 1 by
+    // 1/a11, row 2 by 1/a22):  with kap = m2 L2 / ((m1+m2) L1), lam = L1 / L2, sd/cd = sin/cos(th1 - th2), P = w2^2, Q = w1^2
+    //   B1 = kap P sd - (g/L1) s1,   B2 = -lam Q sd - (g/L2) s2,
+    //   a1 = (B1 - kap cd B2) / D,   a2 = (B2 - lam cd B1) / D,    D = 1 - kap lam cd^2  in (0, 1].
+    // The step works on s1 = sin th1, c1 = cos th1 and the SCALED pair S = lam sd, C = lam cd (a rotation is linear,
+    // so the scaled pair rotates like the unit one): lam cd and lam sd are then free, kap cd = (kap/lam) C,
+    // kap sd = (kap/lam) S, and lam sin th2 = s1 C - c1 S replaces a third carried pair.
+    // 18 FP64 instructions + 1 MUFU; 5 of them read three distinct vector registers.
+    static __device__ __forceinline__ void accel(const Inst<false>& in, double s1, double c1, double S, double C,
                                                  double w1, double w2, double& a1, double& a2) {
-        const double sd = fma(s1, c2, -(c1 * s2));                  // sin(th1 - th2)
-        const double cd = fma(c1, c2, s1 * s2);                     // cos(th1 - th2)
-        const double B1 = fma(in.kap.v * sd, w2 * w2, -(in.gL1.v * s1));
-        const double B2 = -fma(in.lam.v * sd, w1 * w1, in.gL2.v * s2);
-        const double kc = in.kap.v * cd, lc = in.lam.v * cd;
-        const double D = fma(-kc, lc, 1.0);
+        const double s2l = fma(s1, C, -(c1 * S));                   // lam sin(th2)
+        const double kc = in.kol.v * C;                             // kap cd
+        const double B1 = fma(in.kol.v * S, w2 * w2, -(in.gL1.v * s1));
+        const double B2 = -fma(S, w1 * w1, in.gL2l.v * s2l);
+        const double D = fma(-kc, C, 1.0);
         const double inv = sbtrig::rcp_fast(D);
         a1 = fma(-kc, B2, B1) * inv;
-        a2 = fma(-lc, B1, B2) * inv;
+        a2 = fma(-C, B1, B2) * inv;
     }
-    // sin/cos of (base + h) for both angles: rotation by the small increment, full routine when an increment is large
-    static __device__ __forceinline__ void stage_trig(const double th1, const double th2, const double s1, const double c1,
-                                                      const double s2, const double c2, const double h1, const double h2,
-                                                      double& s1o, double& c1o, double& s2o, double& c2o) {
-        if (sbtrig::small_angle(h1) && sbtrig::small_angle(h2)) {
-            sbtrig::rotate_small(s1, c1, h1, s1o, c1o);
-            sbtrig::rotate_small(s2, c2, h2, s2o, c2o);
-        } else {
-            sbtrig::sincos(th1 + h1, s1o, c1o);
-            sbtrig::sincos(th2 + h2, s2o, c2o);
-        }
+    // full evaluation of the carried values from the angles (start of the run, every 8th step, after a large increment)
+    static __device__ __forceinline__ void trig_of(const Inst<false>& in, double th1, double delta, double& s1, double& c1,
+                                                   double& S, double& C) {
+        sbtrig::sincos<true>(th1, s1, c1);                          // cold call sites: constants loaded on use
+        double sd, cd;
+        sbtrig::sincos<true>(delta, sd, cd);
+        S = in.lam.v * sd; C = in.lam.v * cd;
     }
-    // One RK4 step, y += (dt/6)(f1 + 2 f2 + 2 f3 + f4) as in rk4_step_fast, with ONE full sincos per angle: the
-    // stage arguments th + (dt/2) w, th + dt w differ from the base angle by a small increment, so their
-    // sin/cos follow from the base pair by the addition theorem (sbtrig::rotate_small).  ~240 FP64 instructions
-    // per instance-step instead of ~310 with four full sincos pairs.
-    static __device__ __forceinline__ int fast_step(const Inst<false>& in, Real<false> (&y)[4], const StepConsts& k) {
+    static __device__ __forceinline__ void refresh_trig(Inst<false>& in, double th1, double th2) {
+        trig_of(in, th1, th1 - th2, in.s1, in.c1, in.sd, in.cd);     // delta rounded as in the reference (:145)
+    }
+    // sin/cos of (th1 + h1) and lam sin/cos of (delta + hd) from the base values: rotation by the small increments; the
+    // full routine replaces the result when an increment is large.  The rotation is computed unconditionally so that the
+    // common path is straight-line code and the guard a rarely taken forward branch.
+    static __device__ __forceinline__ void stage_trig(const Inst<false>& in, const StepConsts& k, const double th1, const double th2,
+                                                      const double s1, const double c1, const double S, const double C,
+                                                      const double h1, const double hd,
+                                                      double& s1o, double& c1o, double& So, double& Co) {
+        sbtrig::rotate_small_k(s1, c1, h1, k.rot3, k.rot5, k.cot4, s1o, c1o);
+        sbtrig::rotate_small_k(S, C, hd, k.rot3, k.rot5, k.cot4, So, Co);
+        if (!(sbtrig::small_angle(h1) && sbtrig::small_angle(hd))) trig_of(in, th1 + h1, (th1 - th2) + hd, s1o, c1o, So, Co);
+    }
+    // One RK4 step, y += (dt/6)(f1 + 2 f2 + 2 f3 + f4) as in rk4_step_fast, with the trigonometry shared between the
+    // stages and the steps.  Every argument of sin/cos in the step is the base angle plus a small increment:
+    //   stage 2: th + (dt/2) w            -> rotate the base pair (sbtrig::rotate_small, |h| <= 2^-5)
+    //   stage 3: stage 2 + (dt/2)^2 a_1   -> rotate the stage-2 pair by a tiny increment (rotate_tiny, |d| <= 2^-13)
+    //   stage 4: th + dt u_3              -> rotate the base pair
+    //   next step: th_new - th            -> rotate the base pair; full sincos every 8th step bounds the accumulated
+    //                                        rounding of the carried pair to a few 1e-16
+    // Every shortcut has an integer-compare guard on its increment and falls back to the full routine.
+    // 196 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
+    static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
         const double th1 = y[0].v, th2 = y[1].v, w1 = y[2].v, w2 = y[3].v;
-        double s1, c1, s2, c2;
-        sbtrig::sincos(th1, s1, c1);
-        sbtrig::sincos(th2, s2, c2);
+        const double s1 = in.s1, c1 = in.c1, S = in.sd, C = in.cd;
         double a1, a2;
-        accel(in, s1, c1, s2, c2, w1, w2, a1, a2);                                  // f1 = (w1, w2, a1, a2)
+        accel(in, s1, c1, S, C, w1, w2, a1, a2);                                    // f1 = (w1, w2, a1, a2)
         double F0 = w1, F1 = w2, F2 = a1, F3 = a2;
         double u1 = fma(k.hdt, a1, w1), u2 = fma(k.hdt, a2, w2);                    // stage-2 rates
-        double s1s, c1s, s2s, c2s;
-        stage_trig(th1, th2, s1, c1, s2, c2, k.hdt * w1, k.hdt * w2, s1s, c1s, s2s, c2s);
-        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f2 = (u1, u2, a1, a2)
+        const double d1 = k.hdt2 * a1, dd = k.hdt2 * (a1 - a2);                     // stage 3 - stage 2 angles
+        double s1s, c1s, Ss, Cs;
+        stage_trig(in, k, th1, th2, s1, c1, S, C, k.hdt * w1, k.hdt * (w1 - w2), s1s, c1s, Ss, Cs);
+        accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f2 = (u1, u2, a1, a2)
         F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
-        stage_trig(th1, th2, s1, c1, s2, c2, k.hdt * u1, k.hdt * u2, s1s, c1s, s2s, c2s);
+        {
+            const double s1p = s1s, c1p = c1s, Sp = Ss, Cp = Cs;
+            sbtrig::rotate_tiny_k(s1p, c1p, d1, k.rot3, s1s, c1s);
+            sbtrig::rotate_tiny_k(Sp, Cp, dd, k.rot3, Ss, Cs);
+            if (!(sbtrig::tiny_angle(d1) && sbtrig::tiny_angle(dd)))
+                stage_trig(in, k, th1, th2, s1, c1, S, C, k.hdt * u1, k.hdt * (u1 - u2), s1s, c1s, Ss, Cs);
+        }
         u1 = fma(k.hdt, a1, w1); u2 = fma(k.hdt, a2, w2);                           // stage-3 rates
-        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f3
+        accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f3
         F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
-        stage_trig(th1, th2, s1, c1, s2, c2, k.dt * u1, k.dt * u2, s1s, c1s, s2s, c2s);
+        const double h41 = k.dt * u1, h4d = k.dt * (u1 - u2);
+        stage_trig(in, k, th1, th2, s1, c1, S, C, h41, h4d, s1s, c1s, Ss, Cs);
         u1 = fma(k.dt, a1, w1); u2 = fma(k.dt, a2, w2);                             // stage-4 rates
-        accel(in, s1s, c1s, s2s, c2s, u1, u2, a1, a2);                              // f4
-        y[0].v = fma(k.dt6, F0 + u1, th1); y[1].v = fma(k.dt6, F1 + u2, th2);
+        accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f4
+        const double n1 = fma(k.dt6, F0 + u1, th1), n2 = fma(k.dt6, F1 + u2, th2);
+        y[0].v = n1; y[1].v = n2;
         y[2].v = fma(k.dt6, F2 + a1, w1);  y[3].v = fma(k.dt6, F3 + a2, w2);
+        const double g1 = n1 - th1, gd = g1 - (n2 - th2);
+        // the new base angle differs from the stage-4 angle by dt (F/6 - u_3) = O(dt^2 a): tiny rotation of the stage-4 pair
+        const double e1 = g1 - h41, ed = gd - h4d;
+        sbtrig::rotate_tiny_k(s1s, c1s, e1, k.rot3, in.s1, in.c1);
+        sbtrig::rotate_tiny_k(Ss, Cs, ed, k.rot3, in.sd, in.cd);
+        const bool refresh = ((step + 1) & (SB_DPEND_REFRESH - 1)) == 0;
+        if (refresh || !(sbtrig::tiny_angle(e1) && sbtrig::tiny_angle(ed))) {
+            if (!refresh && sbtrig::small_angle(g1) && sbtrig::small_angle(gd)) {
+                sbtrig::rotate_small_k(s1, c1, g1, k.rot3, k.rot5, k.cot4, in.s1, in.c1);
+                sbtrig::rotate_small_k(S, C, gd, k.rot3, k.rot5, k.cot4, in.sd, in.cd);
+            } else {
+                refresh_trig(in, n1, n2);
+            }
+        }
         return 0;
     }
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}

@@ -541,7 +541,7 @@ int rocket_launch_rk4(sopot_b200_ctx* ctx, const RocketSys::DevParams& P, size_t
     int rc = rocket_set_smem<Sys, S>(ctx, smem);
     if (rc) return rc;
     rk4_ensemble_kernel<Sys, S><<<sb_grid_for(n, Sys::BLOCK), Sys::BLOCK, smem, ctx->stream>>>(
-        P, n, 0.0, dt, n_steps, store_every, d_state, d_traj, d_status);
+        P, n, 0.0, make_step_consts(dt), n_steps, store_every, d_state, d_traj, d_status);
     return SOPOT_B200_OK;
 }
 template <class Sys, bool S>

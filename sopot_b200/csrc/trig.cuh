@@ -77,25 +77,47 @@ constexpr double h_trig[23] = {kTwoOverPi, kMagic, kPio2Hi, kPio2Mid, kPio2Lo, k
 #define SB_TRIG(i) h_trig[i]
 #endif
 
+// COLD = true: for a call site on a rarely taken path inside a hot loop.  The 17 constants of the full routine are then
+// fetched where they are used (a volatile constant-bank load that the compiler cannot hoist) instead of being kept in
+// uniform registers across the loop: with them resident (34 of the 63 uniform registers) ptxas moved the loop's own
+// coefficients and step constants to vector registers, which turns their FMAs into three-register ones (3 issue cycles).
+template <bool COLD>
+SB_HD double trig_const(int i) {
+#ifdef __CUDA_ARCH__
+    if constexpr (COLD) {
+        double v;
+        asm volatile("{ .reg .u64 a; cvta.to.const.u64 a, %1; ld.const.f64 %0, [a]; }" : "=d"(v) : "l"(&c_trig[i]));
+        return v;
+    } else {
+        return c_trig[i];
+    }
+#else
+    return h_trig[i];
+#endif
+}
+
 // x = q*(pi/2) + r, |r| <= pi/4 (+ rounding), q returned modulo 2^32 (only its low 2 bits matter)
+template <bool COLD = false>
 SB_HD void reduce(double x, double& r, int& q) {
-    double j = fma(x, SB_TRIG(0), SB_TRIG(1));
+    const double magic = trig_const<COLD>(1);
+    double j = fma(x, trig_const<COLD>(0), magic);
     q = lo_word(j);
-    j -= SB_TRIG(1);
-    r = fma(-j, SB_TRIG(2), x);
-    r = fma(-j, SB_TRIG(3), r);
-    r = fma(-j, SB_TRIG(4), r);
+    j -= magic;
+    r = fma(-j, trig_const<COLD>(2), x);
+    r = fma(-j, trig_const<COLD>(3), r);
+    r = fma(-j, trig_const<COLD>(4), r);
 }
 
 // both sin and cos of x (two polynomials, quadrant swap and sign fix)
+template <bool COLD = false>
 SB_HD void sincos(double x, double& s, double& c) {
     double r; int q;
-    reduce(x, r, q);
+    reduce<COLD>(x, r, q);
     const double z = r * r;
-    double ps = fma(z, SB_TRIG(10), SB_TRIG(9)); ps = fma(z, ps, SB_TRIG(8)); ps = fma(z, ps, SB_TRIG(7));
-    ps = fma(z, ps, SB_TRIG(6)); ps = fma(z, ps, SB_TRIG(5));
-    double pc = fma(z, SB_TRIG(16), SB_TRIG(15)); pc = fma(z, pc, SB_TRIG(14)); pc = fma(z, pc, SB_TRIG(13));
-    pc = fma(z, pc, SB_TRIG(12)); pc = fma(z, pc, SB_TRIG(11));
+    double ps = fma(z, trig_const<COLD>(10), trig_const<COLD>(9)); ps = fma(z, ps, trig_const<COLD>(8)); ps = fma(z, ps, trig_const<COLD>(7));
+    ps = fma(z, ps, trig_const<COLD>(6)); ps = fma(z, ps, trig_const<COLD>(5));
+    double pc = fma(z, trig_const<COLD>(16), trig_const<COLD>(15)); pc = fma(z, pc, trig_const<COLD>(14)); pc = fma(z, pc, trig_const<COLD>(13));
+    pc = fma(z, pc, trig_const<COLD>(12)); pc = fma(z, pc, trig_const<COLD>(11));
     // sin(r) = r (1 + z ps), cos(r) = 1 + z (-1/2 + z pc): Horner forms whose FMAs read at most two distinct
     // vector registers (2-cycle issue; the fdlibm forms fma(z*r, ps, r) / fma(z*z, pc, 1 - z/2) need 3-register
     // FMAs at 3 cycles).  Measured <= 1.7 ulp (tests/test_oracle.py::test_lean_trig_accuracy).
@@ -131,6 +153,46 @@ SB_HD void rotate_small(double s, double c, double h, double& s_out, double& c_o
     const double ch = fma(h2, q, 1.0);                      // cos h
     s_out = fma(s, ch, c * sh);
     c_out = fma(c, ch, -(s * sh));
+}
+
+// The same for a tiny increment, |d| <= kTinyAngle = 2^-13:  sin d = d (1 + T3 d^2) (next term d^5/120: relative 2^-52/120),
+// cos d = 1 - d^2/2 (next term d^4/24 <= 9.3e-18 absolute): 8 FP64 instructions.  RK4 stage 3 differs from stage 2
+// by (dt/2)^2 times an acceleration, which is such an increment for any sensible step.
+constexpr double kTinyAngle = 0x1p-13;
+SB_HD bool tiny_angle(double d) {
+#ifdef __CUDA_ARCH__
+    return (__double2hiint(d) & 0x7fffffff) <= 0x3f200000;    // |d| <= 2^-13
+#else
+    return std::fabs(d) <= kTinyAngle;
+#endif
+}
+SB_HD void rotate_tiny(double s, double c, double d, double& s_out, double& c_out) {
+    const double d2 = d * d;
+    const double sd = d * fma(d2, SB_TRIG(17), 1.0);        // sin d
+    const double cd = fma(d2, SB_TRIG(20), 1.0);            // cos d
+    s_out = fma(s, cd, c * sd);
+    c_out = fma(c, cd, -(s * sd));
+}
+
+// The two rotations with the coefficients as arguments (for a caller that holds T3, T5, U4 in kernel parameters, i.e.
+// constant-bank operands).  T7, U6 truncated to their high word (relative 6e-8 on terms <= 2^-42 of the result) and
+// U2 = -1/2 are instruction immediates, so no FMA of the two polynomials reads more than two vector registers.
+constexpr double kT7hi = -0x1.a01a000000000p-13, kU6hi = -0x1.6c16c00000000p-10;
+SB_HD void rotate_small_k(double s, double c, double h, double T3, double T5, double U4, double& s_out, double& c_out) {
+    const double h2 = h * h;
+    double p = fma(h2, kT7hi, T5); p = fma(h2, p, T3);
+    const double sh = h * fma(h2, p, 1.0);
+    double q = fma(h2, kU6hi, U4); q = fma(h2, q, -0.5);
+    const double ch = fma(h2, q, 1.0);
+    s_out = fma(s, ch, c * sh);
+    c_out = fma(c, ch, -(s * sh));
+}
+SB_HD void rotate_tiny_k(double s, double c, double d, double T3, double& s_out, double& c_out) {
+    const double d2 = d * d;
+    const double sd = d * fma(d2, T3, 1.0);
+    const double cd = fma(d2, -0.5, 1.0);
+    s_out = fma(s, cd, c * sd);
+    c_out = fma(c, cd, -(s * sd));
 }
 
 // sin(x) only (both polynomials, one select: cheaper on the RF than selecting 6 coefficient pairs)
