@@ -40,13 +40,15 @@ N_PER_GPU = 1 << 22
 N_STEPS = 10000
 DT = 1e-3
 FLOP_PER_INSTANCE_STEP = 204.0
-# From the ncu --set full capture of this very command (profiles/r1_final_dpend_bench.txt, one launch = 4 Mi x 10 000):
-#   226 FP64-pipe instructions per instance-step (142 DFMA, 80 DMUL, 4 DADD) at 2 issue cycles each, FP64 pipe 85.2 %
-#   busy; the remaining issue cycles are three-register DFMAs at 3 cycles (profiles/r1_fp64_operand_rule.txt): ~79.
-#   DRAM traffic per launch 320.8 MB read + 113.0 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
-FP64_INSTR_PER_STEP = 226.0
-FP64_ISSUE_CYCLES_PER_STEP = 2.0 * FP64_INSTR_PER_STEP + 79.0
-NCU_DRAM_BYTES_PER_LAUNCH_4MI = 320796672 + 113023744
+# From the ncu capture of this very command (profiles/r1_final_dpend_bench.txt, one launch = 4 Mi x 10 000) and the per-opcode
+# operand analysis of its source page (tools/ncu_fp64_operands.py, profiles/r1_final_dpend_fp64_operands.txt):
+#   187.6 FP64-pipe instructions per instance-step (105.7 DFMA, 71.9 DMUL, 10 DADD) at 2 issue cycles each, of which 41.8
+#   DFMAs read three distinct vector registers and take 3 (profiles/r1_fp64_operand_rule.txt): 417 FP64 issue cycles per
+#   warp-step.
+#   DRAM traffic per launch 319.2 MB read + 113.4 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
+FP64_INSTR_PER_STEP = 187.6
+FP64_ISSUE_CYCLES_PER_STEP = 2.0 * FP64_INSTR_PER_STEP + 41.8
+NCU_DRAM_BYTES_PER_LAUNCH_4MI = 319181568 + 113387520
 METRIC = "RK4 instance-steps/s (FP64)"
 UNIT = "instance-steps/s"
 

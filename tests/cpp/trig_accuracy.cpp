@@ -1,6 +1,7 @@
 // Host-side accuracy check of csrc/trig.cuh (the header compiles for the host with the same fma() sequence):
 // max error in ulp of sbtrig::sincos against long double libm over |x| <= 1e6 and near multiples of pi/2, and
-// of rotate_small(sin x, cos x, h) against sin/cos(x + h) for |h| <= 2^-5.  Pure CPU; run by tests/test_oracle.py.
+// of rotate_small / rotate_small_k (sin x, cos x, h) against sin/cos(x + h) for |h| <= 2^-5 and rotate_tiny / rotate_tiny_k
+// for |d| <= 2^-13 (the variants the double-pendulum step uses).  Pure CPU; run by tests/test_oracle.py.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,7 +18,7 @@ int main(int argc, char** argv) {
     const long n = argc > 1 ? std::atol(argv[1]) : 400000;
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-1.0, 1.0);
-    double worst_s = 0, worst_c = 0, worst_rs = 0, worst_rc = 0;
+    double worst_s = 0, worst_c = 0, worst_rs = 0, worst_rc = 0, worst_k = 0, worst_t = 0;
     for (long i = 0; i < n; ++i) {
         double x;
         switch (i & 3) {
@@ -40,9 +41,24 @@ int main(int argc, char** argv) {
         const long double shl = sinl((long double)h), chl = cosl((long double)h);
         worst_rs = std::fmax(worst_rs, (double)std::fabs((long double)rs - (sl * chl + cl * shl)) / 0x1p-52);
         worst_rc = std::fmax(worst_rc, (double)std::fabs((long double)rc - (cl * chl - sl * shl)) / 0x1p-52);
+        // the same rotation with the coefficients as arguments (T7, U6 truncated to instruction immediates)
+        sbtrig::rotate_small_k((double)sl, (double)cl, h, -1.0 / 6.0, 1.0 / 120.0, 1.0 / 24.0, rs, rc);
+        worst_k = std::fmax(worst_k, (double)std::fabs((long double)rs - (sl * chl + cl * shl)) / 0x1p-52);
+        worst_k = std::fmax(worst_k, (double)std::fabs((long double)rc - (cl * chl - sl * shl)) / 0x1p-52);
+        // tiny increments
+        const double d = sbtrig::kTinyAngle * U(rng);
+        if (!sbtrig::tiny_angle(d)) { std::printf("tiny_angle rejects %.17g\n", d); return 1; }
+        const long double sdl = sinl((long double)d), cdl = cosl((long double)d);
+        double ts, tc, ts2, tc2;
+        sbtrig::rotate_tiny((double)sl, (double)cl, d, ts, tc);
+        sbtrig::rotate_tiny_k((double)sl, (double)cl, d, -1.0 / 6.0, ts2, tc2);
+        if (ts != ts2 || tc != tc2) { std::puts("rotate_tiny and rotate_tiny_k differ"); return 1; }
+        worst_t = std::fmax(worst_t, (double)std::fabs((long double)ts - (sl * cdl + cl * sdl)) / 0x1p-52);
+        worst_t = std::fmax(worst_t, (double)std::fabs((long double)tc - (cl * cdl - sl * sdl)) / 0x1p-52);
     }
     if (sbtrig::small_angle(0.03126) || !sbtrig::small_angle(-0.03125)) { std::puts("small_angle threshold wrong"); return 1; }
-    std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f\n", worst_s, worst_c,
-                worst_rs, worst_rc);
-    return (worst_s <= 2.0 && worst_c <= 2.0 && worst_rs <= 2.0 && worst_rc <= 2.0) ? 0 : 2;
+    if (sbtrig::tiny_angle(0x1.0001p-13) || !sbtrig::tiny_angle(-0x1p-13)) { std::puts("tiny_angle threshold wrong"); return 1; }
+    std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f, _k %.3f, tiny %.3f\n",
+                worst_s, worst_c, worst_rs, worst_rc, worst_k, worst_t);
+    return (worst_s <= 2.0 && worst_c <= 2.0 && worst_rs <= 2.0 && worst_rc <= 2.0 && worst_k <= 2.0 && worst_t <= 2.0) ? 0 : 2;
 }
