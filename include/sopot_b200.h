@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SOPOT_B200_ABI_VERSION 2
+#define SOPOT_B200_ABI_VERSION 3
 
 enum {
     SOPOT_B200_OK = 0,
@@ -268,13 +268,15 @@ int sopot_b200_grid2d_rhs(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* g
  * State is AoS [rows][cols][6].  Attachment angles: horizontal springs h_attach0 on the left mass / h_attach1 on the
  * right one, vertical springs v_attach0 on the upper / v_attach1 on the lower mass (the wasm wrapper uses 0, pi, pi/2,
  * -pi/2; Spring2D's defaults are 0, pi for every spring).  repulsion_stiffness <= 0 means 10 * stiffness; min_distance
- * 0 disables the repulsion.  Single GPU.
+ * 0 disables the repulsion.  Multi-GPU like grid2d: each rank passes its slab of rows (row_begin, rows_local) and its
+ * local state [rows_local][cols][6]; boundary rows travel over NCCL after every kernel that produces a stencil input.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     size_t rows, cols;
     double mass, radius, spacing;
     double stiffness, rest_length, damping, min_distance, repulsion_stiffness;
     double h_attach0, h_attach1, v_attach0, v_attach1;
+    size_t row_begin, rows_local;   /* this rank's slab of rows; rows_local == 0: the whole grid (single rank) */
 } sopot_b200_ugrid_params;
 int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, uint32_t mem, double* state);
 int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, const sopot_b200_rk4_opts* opts,

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
@@ -84,7 +84,7 @@ class Dispersion(ctypes.Structure):
 class UGridParams(ctypes.Structure):
     _fields_ = [("rows", c_size_t), ("cols", c_size_t)] + [(k, c_double) for k in (
         "mass", "radius", "spacing", "stiffness", "rest_length", "damping", "min_distance", "repulsion_stiffness",
-        "h_attach0", "h_attach1", "v_attach0", "v_attach1")]
+        "h_attach0", "h_attach1", "v_attach0", "v_attach1")] + [("row_begin", c_size_t), ("rows_local", c_size_t)]
 
 
 class Grid2DParams(ctypes.Structure):
@@ -535,11 +535,14 @@ class Engine:
     # ---- unified 6-state grid ----
     @staticmethod
     def ugrid_params(rows, cols, mass, radius, spacing, k, L0, c, min_distance=0.0, krep=-1.0,
-                     attach=(0.0, 3.14159265358979323846, 3.14159265358979323846 / 2.0, -3.14159265358979323846 / 2.0)):
-        return UGridParams(rows, cols, mass, radius, spacing, k, L0, c, min_distance, krep, *attach)
+                     attach=(0.0, 3.14159265358979323846, 3.14159265358979323846 / 2.0, -3.14159265358979323846 / 2.0),
+                     row_begin=0, rows_local=0):
+        """rows_local = 0: the whole grid on this rank; else this rank's slab of rows (multi-GPU, like grid2d)."""
+        return UGridParams(rows, cols, mass, radius, spacing, k, L0, c, min_distance, krep, *attach, row_begin, rows_local)
 
     def ugrid_initial_state(self, g, mem=MEM_HOST):
-        out = np.empty((g.rows * g.cols, 6)) if mem == MEM_HOST else self.empty((g.rows * g.cols, 6))
+        nm = (g.rows_local or g.rows) * g.cols
+        out = np.empty((nm, 6)) if mem == MEM_HOST else self.empty((nm, 6))
         self._ck(self.lib.sopot_b200_ugrid_initial_state(self.ctx, byref(g), mem, _ptr(out)))
         self.sync()
         return out

@@ -10,24 +10,37 @@
 // spring (as mass 0).  The kernels below are the gather form of that: one thread per mass evaluates its incident springs
 // in exactly this order.  State is AoS [rows][cols][6] (48 B per mass), the reference's node order.
 // One RK4 step = four stage kernels with the running accumulator of ensemble.cuh (1.5x the traffic of the 4-state grid).
-// Single GPU (no slab decomposition yet).
+// Multi-GPU: contiguous slabs of rows per rank (params row_begin / rows_local), one ghost row above and below each
+// stencil input, refreshed from the neighbouring ranks with ncclSend/ncclRecv after the kernel that produced the buffer.
+#include <cmath>
 #include "common.cuh"
+#include "nccl_api.h"
 #include "trig.cuh"
 
 namespace {
 
 struct UGridDev {
-    size_t rows, cols;
-    double mass, radius, k, L0, c, min_distance, krep, inertia;
+    size_t rows, cols;              // the GLOBAL grid
+    size_t row_begin, rows_local;   // rows [row_begin, row_begin + rows_local) live on this rank
+    double mass, radius, k, L0, c, min_distance, krep, inertia, inv_mass, inv_inertia;
     double ha0, ha1, va0, va1;      // attachment angles: horizontal spring on its left / right mass, vertical on upper / lower
+    double cha0, sha0, cha1, sha1, cva0, sva0, cva1, sva1;      // their cos / sin (contract mode: addition theorem)
 };
 
-struct Body { double x, y, vx, vy, th, om; };
+struct Body { double x, y, vx, vy, th, om; double s, c; };      // s, c = sin / cos(th), filled in contract mode only
+struct UIn { const double* slab; const double* top; const double* bot; };     // local rows + ghost row above / below
 
 __device__ __forceinline__ Body load_body(const double* __restrict__ s, size_t idx) {
     const double2* p = reinterpret_cast<const double2*>(s + 6 * idx);
     const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    return Body{a.x, a.y, b.x, b.y, c.x, c.y};
+    return Body{a.x, a.y, b.x, b.y, c.x, c.y, 0.0, 0.0};
+}
+// contract mode: sin/cos of the body angle ONCE per body; the four attachment directions follow by the addition theorem
+template <bool S>
+__device__ __forceinline__ Body load_body_t(const double* __restrict__ s, size_t idx) {
+    Body b = load_body(s, idx);
+    if constexpr (!S) sbtrig::sincos(b.th, b.s, b.c);
+    return b;
 }
 __device__ __forceinline__ void store6(double* p, const double (&v)[6]) {
     double2* q = reinterpret_cast<double2*>(p);
@@ -35,14 +48,34 @@ __device__ __forceinline__ void store6(double* p, const double (&v)[6]) {
 }
 
 // Spring2D::computeForcesAndTorques for the spring (m0 -> m1); returns force and torque on the requested end
+// contract mode: the same with sin/cos(theta + attachment angle) from the bodies' own sin/cos and the constant
+// cos/sin of the attachment angle, the spring length and its reciprocal from one rsqrt seed (no IEEE division)
+__device__ __forceinline__ void spring_ft_fast(const UGridDev& g, const Body& m0, const Body& m1, const double ca0, const double sa0,
+                                               const double ca1, const double sa1, const int end, double& fx, double& fy, double& tq) {
+    const double r = g.radius;
+    const double c0 = fma(m0.c, ca0, -(m0.s * sa0)), s0 = fma(m0.s, ca0, m0.c * sa0);
+    const double c1 = fma(m1.c, ca1, -(m1.s * sa1)), s1 = fma(m1.s, ca1, m1.c * sa1);
+    const double o0x = r * c0, o0y = r * s0, o1x = r * c1, o1y = r * s1;
+    const double dx = (m1.x + o1x) - (m0.x + o0x), dy = (m1.y + o1y) - (m0.y + o0y);
+    const double dvx = fma(-m1.om, o1y, m1.vx) - fma(-m0.om, o0y, m0.vx), dvy = fma(m1.om, o1x, m1.vy) - fma(m0.om, o0x, m0.vy);
+    const double len2 = fma(dx, dx, dy * dy);
+    double len, inv;
+    if (len2 >= 1e-20) { sbtrig::sqrt_rsqrt_fast(len2, len, inv); }            // components.hpp:246-247: len_safe = max(len, 1e-10)
+    else { len = sqrt(len2); inv = 1e10; }
+    const double ux = dx * inv, uy = dy * inv;
+    double F = fma(g.k, len - g.L0, g.c * fma(dvx, ux, dvy * uy));
+    if (g.min_distance > 0.0 && len < g.min_distance) F = fma(-g.krep, fma(g.min_distance, inv, -1.0), F);
+    if (end == 0) { fx = F * ux; fy = F * uy; tq = fma(o0x, fy, -(o0y * fx)); }
+    else { fx = -F * ux; fy = -F * uy; tq = fma(o1x, fy, -(o1y * fx)); }
+}
+
 template <bool S>
 __device__ __forceinline__ void spring_ft(const UGridDev& g, const Body& m0, const Body& m1, const double a0, const double a1,
                                           const int end, Real<S>& fx, Real<S>& fy, Real<S>& tq) {
     using R = Real<S>;
     const R r(g.radius);
     R s0, c0, s1, c1;
-    if constexpr (S) { r_sincos(R(m0.th) + R(a0), s0, c0); r_sincos(R(m1.th) + R(a1), s1, c1); }
-    else { sbtrig::sincos(m0.th + a0, s0.v, c0.v); sbtrig::sincos(m1.th + a1, s1.v, c1.v); }
+    r_sincos(R(m0.th) + R(a0), s0, c0); r_sincos(R(m1.th) + R(a1), s1, c1);
     const R o0x = r * c0, o0y = r * s0, o1x = r * c1, o1y = r * s1;                    // offsets to the attachment points
     const R a0x = R(m0.x) + o0x, a0y = R(m0.y) + o0y, a1x = R(m1.x) + o1x, a1y = R(m1.y) + o1y;
     const R v0x = R(m0.vx) - R(m0.om) * o0y, v0y = R(m0.vy) + R(m0.om) * o0x;          // v + omega x r
@@ -61,31 +94,48 @@ __device__ __forceinline__ void spring_ft(const UGridDev& g, const Body& m0, con
     else { fx = (-F) * ux; fy = (-F) * uy; tq = o1x * fy - o1y * fx; }
 }
 
+// body at local row lrow in [-1, rows_local] (ghost rows at the two ends), column col
 template <bool S>
-__device__ __forceinline__ void body_derivative(const UGridDev& g, const double* __restrict__ in, const size_t row, const size_t col,
+__device__ __forceinline__ Body body_at(const UGridDev& g, const UIn& in, const long lrow, const size_t col) {
+    if (lrow < 0) return load_body_t<S>(in.top, col);
+    if ((size_t)lrow >= g.rows_local) return load_body_t<S>(in.bot, col);
+    return load_body_t<S>(in.slab, (size_t)lrow * g.cols + col);
+}
+
+template <bool S>
+__device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in, const size_t row /*local*/, const size_t col,
                                                 Real<S> (&d)[6], Body& self) {
     using R = Real<S>;
-    const size_t idx = row * g.cols + col;
-    const Body P = load_body(in, idx);
+    const size_t grow = g.row_begin + row;
+    const long lr = (long)row;
+    const Body P = body_at<S>(g, in, lr, col);
     self = P;
     R Fx(0.0), Fy(0.0), Tq(0.0), fx, fy, tq;
-    if (col > 0) { spring_ft<S>(g, load_body(in, idx - 1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-    if (col + 1 < g.cols) { spring_ft<S>(g, P, load_body(in, idx + 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-    if (row > 0) { spring_ft<S>(g, load_body(in, idx - g.cols), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-    if (row + 1 < g.rows) { spring_ft<S>(g, P, load_body(in, idx + g.cols), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    if constexpr (S) {
+        if (col > 0) { spring_ft<S>(g, body_at<S>(g, in, lr, col - 1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (col + 1 < g.cols) { spring_ft<S>(g, P, body_at<S>(g, in, lr, col + 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow > 0) { spring_ft<S>(g, body_at<S>(g, in, lr - 1, col), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow + 1 < g.rows) { spring_ft<S>(g, P, body_at<S>(g, in, lr + 1, col), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+    } else {
+        if (col > 0) { spring_ft_fast(g, body_at<S>(g, in, lr, col - 1), P, g.cha0, g.sha0, g.cha1, g.sha1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (col + 1 < g.cols) { spring_ft_fast(g, P, body_at<S>(g, in, lr, col + 1), g.cha0, g.sha0, g.cha1, g.sha1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow > 0) { spring_ft_fast(g, body_at<S>(g, in, lr - 1, col), P, g.cva0, g.sva0, g.cva1, g.sva1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow + 1 < g.rows) { spring_ft_fast(g, P, body_at<S>(g, in, lr + 1, col), g.cva0, g.sva0, g.cva1, g.sva1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+    }
     d[0] = R(P.vx); d[1] = R(P.vy);
-    d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass);
-    d[4] = R(P.om); d[5] = Tq / R(g.inertia);
+    d[4] = R(P.om);
+    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); d[5] = Tq / R(g.inertia); }
+    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); d[5] = Tq * R(g.inv_inertia); }
 }
 
 // STAGE 0: out <- f(in);  1..4: the RK4 stages with S-accumulator (see ensemble.cuh / grid2d.cu)
 template <bool S, int STAGE>
 __global__ void __launch_bounds__(256)
-ugrid_stage(const UGridDev g, const double* __restrict__ in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
+ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
             double* __restrict__ out) {
     using R = Real<S>;
     const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
-    if (col >= g.cols || row >= g.rows) return;
+    if (col >= g.cols || row >= g.rows_local) return;
     R d[6];
     Body self;
     body_derivative<S>(g, in, row, col, d, self);
@@ -152,10 +202,11 @@ ugrid_stage(const UGridDev g, const double* __restrict__ in, const double dt_, d
     }
 }
 
-__global__ void ugrid_init_kernel(const size_t rows, const size_t cols, const double spacing, double* __restrict__ state) {
+__global__ void ugrid_init_kernel(const size_t rows, const size_t cols, const size_t row_begin, const double spacing,
+                                  double* __restrict__ state) {
     const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
     if (col >= cols || row >= rows) return;
-    const double v[6] = {(double)col * spacing, (double)row * spacing, 0.0, 0.0, 0.0, 0.0};     // wasm_grid2d.cpp:427-433
+    const double v[6] = {(double)col * spacing, (double)(row_begin + row) * spacing, 0.0, 0.0, 0.0, 0.0};     // wasm_grid2d.cpp:427-433
     store6(state + (row * cols + col) * 6, v);
 }
 
@@ -165,20 +216,45 @@ int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev&
     if (p->rows < 1 || p->cols < 1 || p->rows * p->cols < 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "the grid needs at least two masses");
     if (!(p->mass > 0.0) || !(p->radius > 0.0))
         return sb_fail(ctx, SOPOT_B200_EINVAL, "mass and radius must be positive (I = m r^2 / 2 divides the torque)");
+    g.row_begin = p->rows_local ? p->row_begin : 0;
+    g.rows_local = p->rows_local ? p->rows_local : p->rows;
+    if (g.row_begin + g.rows_local > p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [row_begin, row_begin + rows_local) exceeds the grid");
+    if (ctx->nranks == 1 && g.rows_local != p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "a single-rank ctx must own the whole grid");
     g.rows = p->rows; g.cols = p->cols; g.mass = p->mass; g.radius = p->radius; g.k = p->stiffness; g.L0 = p->rest_length;
     g.c = p->damping; g.min_distance = p->min_distance;
     g.krep = p->repulsion_stiffness > 0.0 ? p->repulsion_stiffness : 10.0 * p->stiffness;       // components.hpp:186
     g.inertia = 0.5 * p->mass * p->radius * p->radius;                                          // :98
     g.ha0 = p->h_attach0; g.ha1 = p->h_attach1; g.va0 = p->v_attach0; g.va1 = p->v_attach1;
+    g.inv_mass = 1.0 / g.mass; g.inv_inertia = 1.0 / g.inertia;
+    g.cha0 = std::cos(g.ha0); g.sha0 = std::sin(g.ha0); g.cha1 = std::cos(g.ha1); g.sha1 = std::sin(g.ha1);
+    g.cva0 = std::cos(g.va0); g.sva0 = std::sin(g.va0); g.cva1 = std::cos(g.va1); g.sva1 = std::sin(g.va1);
     return SOPOT_B200_OK;
 }
 
 template <int STAGE>
-void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const double* in, double dt, double* y, double* acc, double* out) {
-    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows + 3) / 4));
+void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const UIn& in, double dt, double* y, double* acc, double* out) {
+    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows_local + 3) / 4));
     if (strict) ugrid_stage<true, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
     else ugrid_stage<false, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
     ctx->launches++;
+}
+
+// send this slab's first / last row of `in.slab` to the rank above / below and receive their boundary rows into the ghosts
+int ugrid_halo(sopot_b200_ctx* ctx, const UGridDev& g, const UIn& in) {
+    if (ctx->nranks == 1) return SOPOT_B200_OK;
+    const size_t row_elems = g.cols * 6;
+    const NcclApi* n = ctx->nccl;
+    SB_NCCL(ctx, n->GroupStart());
+    if (g.row_begin > 0) {
+        SB_NCCL(ctx, n->Send(in.slab, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+        SB_NCCL(ctx, n->Recv(const_cast<double*>(in.top), row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+    }
+    if (g.row_begin + g.rows_local < g.rows) {
+        SB_NCCL(ctx, n->Send(in.slab + (g.rows_local - 1) * row_elems, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+        SB_NCCL(ctx, n->Recv(const_cast<double*>(in.bot), row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+    }
+    SB_NCCL(ctx, n->GroupEnd());
+    return SOPOT_B200_OK;
 }
 
 }  // namespace
@@ -188,13 +264,13 @@ SB_EXPORT int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b2
     int rc = check_ugrid(ctx, p, g);
     if (rc) return rc;
     if (!state || mem > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad state/mem");
-    const size_t bytes = g.rows * g.cols * 48;
+    const size_t bytes = g.rows_local * g.cols * 48;
     Staging sg(ctx, mem);
     if (sg.host && (rc = sb_arena_begin(ctx, sb_align(bytes) + 4096))) return rc;
     void* d;
     if ((rc = sg.out(state, bytes, &d))) return rc;
-    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows + 3) / 4));
-    ugrid_init_kernel<<<grid, block, 0, ctx->stream>>>(g.rows, g.cols, p->spacing, (double*)d);
+    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows_local + 3) / 4));
+    ugrid_init_kernel<<<grid, block, 0, ctx->stream>>>(g.rows_local, g.cols, g.row_begin, p->spacing, (double*)d);
     SB_CHECK_LAUNCH(ctx);
     return sg.finish();
 }
@@ -205,13 +281,15 @@ SB_EXPORT int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_p
     int rc = check_ugrid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (g.rows_local != g.rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "ugrid_rhs evaluates a whole grid (no slab)");
     const size_t bytes = g.rows * g.cols * 48;
     Staging sg(ctx, opts->mem);
     if (sg.host && (rc = sb_arena_begin(ctx, 2 * sb_align(bytes) + 4096))) return rc;
     const void* d_in; void* d_out;
     if ((rc = sg.in(state, bytes, &d_in))) return rc;
     if ((rc = sg.out(out, bytes, &d_out))) return rc;
-    launch_ustage<0>(ctx, opts->fp_mode == SOPOT_B200_FP_STRICT, g, (const double*)d_in, 0.0, nullptr, nullptr, (double*)d_out);
+    launch_ustage<0>(ctx, opts->fp_mode == SOPOT_B200_FP_STRICT, g, UIn{(const double*)d_in, nullptr, nullptr}, 0.0, nullptr, nullptr,
+                     (double*)d_out);
     SB_CUDA(ctx, cudaGetLastError());
     return sg.finish();
 }
@@ -230,7 +308,7 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
     if (integrator < 0 || integrator > 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "integrator must be RK4, SYMPLECTIC_EULER or VELOCITY_VERLET");
     if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
     const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
-    const size_t n = g.rows * g.cols * 6;
+    const size_t n = g.rows_local * g.cols * 6, row_elems = g.cols * 6;
     Staging sg(ctx, opts->mem);
     if (sg.host && (rc = sb_arena_begin(ctx, sb_align(n * 8) + 4096))) return rc;
     double* y;
@@ -243,34 +321,42 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
         y = state;
     }
     void* scr;
-    if ((rc = sb_scratch(ctx, 3 * n * 8 + 1024, &scr))) return rc;
+    if ((rc = sb_scratch(ctx, (3 * n + 6 * row_elems) * 8 + 1024, &scr))) return rc;
     double* acc = static_cast<double*>(scr);
     double* A = acc + n;
     double* B = A + n;
+    double* gh = B + n;                           // ghost rows: above / below for each of the three stencil inputs
+    const UIn in_y{y, gh, gh + row_elems}, in_A{A, gh + 2 * row_elems, gh + 3 * row_elems}, in_B{B, gh + 4 * row_elems, gh + 5 * row_elems};
+    if ((rc = ugrid_halo(ctx, g, in_y))) return rc;
     if (integrator == SOPOT_B200_INTEGRATOR_RK4) {
         for (size_t step = 0; step < n_steps; ++step) {
-            launch_ustage<1>(ctx, strict, g, y, dt, y, acc, A);
-            launch_ustage<2>(ctx, strict, g, A, dt, y, acc, B);
-            launch_ustage<3>(ctx, strict, g, B, dt, y, acc, A);
-            launch_ustage<4>(ctx, strict, g, A, dt, y, acc, nullptr);
+            launch_ustage<1>(ctx, strict, g, in_y, dt, y, acc, A);
+            if ((rc = ugrid_halo(ctx, g, in_A))) return rc;
+            launch_ustage<2>(ctx, strict, g, in_A, dt, y, acc, B);
+            if ((rc = ugrid_halo(ctx, g, in_B))) return rc;
+            launch_ustage<3>(ctx, strict, g, in_B, dt, y, acc, A);
+            if ((rc = ugrid_halo(ctx, g, in_A))) return rc;
+            launch_ustage<4>(ctx, strict, g, in_A, dt, y, acc, nullptr);
+            if (step + 1 < n_steps && (rc = ugrid_halo(ctx, g, in_y))) return rc;
         }
     } else {
         // one (symplectic Euler) or two (velocity Verlet) derivative evaluations per step; a step cannot update in place
         // (neighbours still read the old state), so the state ping-pongs between y and A
-        double* cur = y;
-        double* nxt = A;
+        const UIn* cur = &in_y;
+        const UIn* nxt = &in_A;
         for (size_t step = 0; step < n_steps; ++step) {
+            double* nxt_slab = const_cast<double*>(nxt->slab);
             if (integrator == SOPOT_B200_INTEGRATOR_SYMPLECTIC_EULER) {
-                launch_ustage<5>(ctx, strict, g, cur, dt, nullptr, nullptr, nxt);
-                double* t = cur; cur = nxt; nxt = t;
+                launch_ustage<5>(ctx, strict, g, *cur, dt, nullptr, nullptr, nxt_slab);
             } else {
-                launch_ustage<6>(ctx, strict, g, cur, dt, nullptr, acc, B);
-                launch_ustage<7>(ctx, strict, g, B, dt, nullptr, acc, cur == y ? A : y);
-                cur = cur == y ? A : y;
-                nxt = cur == y ? A : y;
+                launch_ustage<6>(ctx, strict, g, *cur, dt, nullptr, acc, B);
+                if ((rc = ugrid_halo(ctx, g, in_B))) return rc;
+                launch_ustage<7>(ctx, strict, g, in_B, dt, nullptr, acc, nxt_slab);
             }
+            const UIn* t = cur; cur = nxt; nxt = t;
+            if (step + 1 < n_steps && (rc = ugrid_halo(ctx, g, *cur))) return rc;
         }
-        if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (cur->slab != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur->slab, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     SB_CUDA(ctx, cudaGetLastError());
     return sg.finish();

@@ -2,7 +2,8 @@
 Checks (1) dispersion statistics all-reduced over NCCL == numpy on the concatenated data,
 (2) slab-decomposed grid2d (fused step with one 4-row halo exchange, and per-stage 1-row exchanges) == the
     single-GPU run bit for bit,
-(3) ensemble sharding: concatenated shard results == one-GPU results bit for bit."""
+(3) ensemble sharding: concatenated shard results == one-GPU results bit for bit,
+(4) slab-decomposed unified 6-state grid, all three integrators == the single-GPU run bit for bit."""
 import os
 import sys
 
@@ -61,6 +62,26 @@ solo = Engine(local)
 whole, _, _ = solo.dpend_rk4(*[w[k] for k in keys], n, 0.0, 1e-3, 300, fp_mode=FP_CONTRACT)
 solo.close()
 assert np.array_equal(part, whole[:, b:e])
+
+# (4) unified 6-state grid: slabs + 1-row halo per stencil input vs single domain, RK4 / symplectic Euler / velocity Verlet
+PI = 3.14159265358979323846
+uprm = (1.0, 0.05, 0.5, 50.0, 0.5, 0.5, 0.0, -1.0)
+for rows, cols, steps in ((world, 40, 3), (4 * world + 1, 70, 5), (257, 129, 4)):
+    solo = Engine(local)
+    ug = solo.ugrid_params(rows, cols, *uprm)
+    s0 = solo.ugrid_initial_state(ug).reshape(rows, cols, 6)
+    rng = np.random.default_rng(rows)
+    s0 = s0 + rng.normal(0, 0.02, s0.shape); s0[..., 4] = rng.normal(0, 0.2, (rows, cols))
+    rb, rl = slab(rows, rank, world)
+    gp = eng.ugrid_params(rows, cols, *uprm, row_begin=rb, rows_local=rl)
+    for mode in (FP_STRICT, FP_CONTRACT):
+        for integ in (0, 1, 2):
+            ref = solo.ugrid_rk4(ug, 1e-3, steps, s0.reshape(-1, 6).copy(), fp_mode=mode, integrator=integ).reshape(rows, cols, 6)
+            mine = eng.ugrid_rk4(gp, 1e-3, steps, s0[rb:rb + rl].reshape(-1, 6).copy(), fp_mode=mode, integrator=integ)
+            assert np.array_equal(mine.reshape(rl, cols, 6), ref[rb:rb + rl]), (rank, rows, cols, mode, integ)
+    init = eng.ugrid_initial_state(gp).reshape(rl, cols, 6)
+    assert np.array_equal(init, solo.ugrid_initial_state(ug).reshape(rows, cols, 6)[rb:rb + rl])
+    solo.close()
 
 dist.barrier()
 eng.close()

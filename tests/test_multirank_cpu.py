@@ -118,3 +118,81 @@ def test_slab_halo_schedule_matches_single_domain_oracle(port, tmp_path):
     ref = port.grid2d_rk4(rows, cols, 0, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], steps,
                           W.grid2d_state(rows, cols, p["spacing"]))
     assert np.array_equal(got.ravel(), ref)
+
+
+# ---------------------------------------------------------------- unified 6-state grid: the same slab schedule (ugrid.cu)
+UPRM = [1.0, 0.05, 0.5, 50.0, 0.5, 0.5, 0.0, -1.0, 0.0, 3.14159265358979323846, 3.14159265358979323846 / 2, -3.14159265358979323846 / 2]
+
+
+def _ugrid_state(port, rows, cols):
+    s0 = port.ugrid(rows, cols, UPRM, mode="init")
+    rng = np.random.default_rng(rows * 31 + cols)
+    st = s0 + rng.normal(0, 0.03, s0.shape)
+    st[:, 4] = rng.normal(0, 0.3, rows * cols)
+    return st
+
+
+def _ugrid_worker(rank, world, port_no, rows, cols, steps, integrator, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle.oracle_py import Checker
+    port = Checker("port")
+    full = _ugrid_state(port, rows, cols).reshape(rows, cols, 6)
+    rb, rl = slab(rows, rank, world)
+    has_up, has_dn = rank > 0, rank < world - 1
+    y = full[rb:rb + rl].copy()
+
+    def exchange(buf):
+        """boundary rows to the neighbours, theirs into (top, bottom) ghosts"""
+        reqs, recv = [], {}
+        for peer, send_row, slot in ((rank - 1, buf[0], 0), (rank + 1, buf[-1], 1)):
+            if 0 <= peer < world:
+                t = torch.from_numpy(np.ascontiguousarray(send_row))
+                recv[slot] = torch.empty(cols, 6, dtype=torch.float64)
+                reqs += [dist.isend(t, peer), dist.irecv(recv[slot], peer)]
+        for r in reqs:
+            r.wait()
+        return recv.get(0), recv.get(1)
+
+    def f(buf):
+        """derivative of the slab rows: the oracle on the slab extended by its ghost rows (a ghost row only changes the
+        ghost's own derivative, which is dropped -- exactly what the kernel's ghost loads do)"""
+        top, bot = exchange(buf)
+        parts = ([top.numpy()[None]] if has_up else []) + [buf] + ([bot.numpy()[None]] if has_dn else [])
+        ext = np.concatenate(parts, axis=0)
+        d = port.ugrid(ext.shape[0], cols, UPRM, ext.reshape(-1, 6)).reshape(ext.shape)
+        return d[1 if has_up else 0: ext.shape[0] - (1 if has_dn else 0)]
+
+    dt = 1e-3
+    V, X = [2, 3, 5], [0, 1, 4]
+    for _ in range(steps):
+        if integrator == "rk4":                    # stage buffers A, B exchanged after the kernel that produced them
+            k1 = f(y) * dt; S = k1; A = y + 0.5 * k1
+            k2 = f(A) * dt; S = S + 2.0 * k2; B = y + 0.5 * k2
+            k3 = f(B) * dt; S = S + 2.0 * k3; A = y + k3
+            k4 = f(A) * dt; y = y + (S + k4) / 6.0
+        elif integrator == "symplectic_euler":
+            d = f(y); y = y.copy()
+            y[..., V] += dt * d[..., V]; y[..., X] += dt * y[..., V]
+        else:
+            d = f(y); y = y.copy(); half_dt_sq = 0.5 * dt * dt
+            y[..., X] += dt * y[..., V] + half_dt_sq * d[..., V]
+            dn = f(y)
+            y[..., V] += (0.5 * dt) * (d[..., V] + dn[..., V])
+    np.save(os.path.join(out, f"uslab_{integrator}_{rank}.npy"), y)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "symplectic_euler", "velocity_verlet"])
+def test_unified_grid_slab_schedule_matches_single_domain_oracle(port, tmp_path, integrator):
+    rows, cols, steps, world = 7, 9, 4, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        free_port = s.getsockname()[1]
+    mp.spawn(_ugrid_worker, args=(world, free_port, rows, cols, steps, integrator, str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / f"uslab_{integrator}_{r}.npy") for r in range(world)], axis=0)
+    ref = port.ugrid(rows, cols, UPRM, _ugrid_state(port, rows, cols), 1e-3, steps, integrator)
+    assert np.array_equal(got.reshape(-1, 6), ref)

@@ -1,5 +1,5 @@
 """Time one config's kernel, device-resident, back-to-back launches between CUDA events:
-   python tools/time_cfg.py rocket|ho|lin|grid|grid_strict [n] [steps]"""
+   python tools/time_cfg.py rocket|ho|lin|grid|grid_strict|ugrid [n] [steps]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -47,4 +47,13 @@ elif cfg in ("grid", "grid_strict"):
         ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False, per_stage=per_stage), 2) / 10
         print("%s %d^2 %s: %.3f ms/step  %.3e mass-steps/s  %.1f GB/s at 544 B/mass-step" %
               (cfg, n, "per-stage" if per_stage else "fused", ms, n * n / ms * 1e3, 544.0 * n * n / ms / 1e6))
+elif cfg == "ugrid":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    ug = eng.ugrid_params(n, n, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5)
+    for mode, name in ((FP_STRICT, "strict"), (FP_CONTRACT, "contract")):
+        for integ, iname in ((0, "rk4"), (1, "symplectic euler"), (2, "velocity verlet")):
+            state = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
+            ms = timed(lambda: eng.ugrid_rk4(ug, 1e-3, 6, state, fp_mode=mode, sync=False, integrator=integ), 2) / 6
+            print("ugrid %d^2 %s %s: %.3f ms/step  %.3e mass-steps/s" % (n, name, iname, ms, n * n / ms * 1e3))
+            state.free()
 eng.close()
