@@ -145,12 +145,21 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
         T = Real<S>(l.T_base);
         // P_base * exp(-(g0*M) * (h - h_base) / (R*T_base))                    :62
         const Real<S> arg = Recip<S>(Real<S>(l.exp_den)).of(Real<S>(-(kAtmG0 * kAtmM)) * dh);
-        P = Real<S>(l.P_base) * Real<S>(exp(arg.v));
+        if constexpr (S) P = Real<S>(l.P_base) * Real<S>(exp(arg.v));
+        else P = Real<S>(l.P_base * sbtrig::exp_lean(arg.v));                   // |arg| <= 1.5 within a layer (host check)
     } else {
         const Real<S> Tl = Real<S>(l.T_base) + Real<S>(l.lapse) * dh;           // :50, :63
         T = Tl;
-        const Real<S> ratio = Recip<S>(Tl).of(Real<S>(l.T_base));
-        P = Real<S>(l.P_base) * r_pow<S>(ratio, l.pow_exp);                     // :64
+        if constexpr (S) {
+            const Real<S> ratio = Real<S>(l.T_base) / Tl;
+            P = Real<S>(l.P_base) * r_pow<S>(ratio, l.pow_exp);                 // :64
+        } else {
+            // (T_b / T)^e = exp(e log(T_b / T)) with the lean log-of-a-ratio and exp of trig.cuh (40 FP64 instructions
+            // instead of ~95 through libdevice log + exp).  Their argument ranges hold for every layer of the built-in
+            // table (checked on the host in upload_atmosphere), so there is no fallback path to keep registers alive.
+            const double x = l.pow_exp * sbtrig::log_ratio_lean(l.T_base, Tl.v);
+            P = Real<S>(l.P_base * sbtrig::exp_lean(x));
+        }
     }
 }
 
@@ -480,7 +489,16 @@ int upload_atmosphere(sopot_b200_ctx* ctx) {
     AtmLayer h[7];
     for (int i = 0; i < 7; ++i) {
         h[i] = AtmLayer{L[i][0], L[i][1], L[i][2], L[i][3], L[i][4], 0.0, kAtmR * L[i][2]};
-        if (std::fabs(L[i][3]) >= 1e-10) h[i].pow_exp = kAtmG0 * kAtmM / (kAtmR * L[i][3]);
+        if (std::fabs(L[i][3]) < 1e-10 && std::fabs(kAtmG0 * kAtmM * (L[i][0] - L[i][4]) / h[i].exp_den) > sbtrig::kExpLeanMax)
+            return sb_fail(ctx, SOPOT_B200_EINVAL, "isothermal atmosphere layer outside the range of the lean exp");
+        if (std::fabs(L[i][3]) >= 1e-10) {
+            h[i].pow_exp = kAtmG0 * kAtmM / (kAtmR * L[i][3]);
+            // ranges of the lean log / exp used by the contract-mode power law, at the far end of the layer
+            const double T_top = L[i][2] + L[i][3] * (L[i][0] - L[i][4]);
+            const double z = (L[i][2] - T_top) / (L[i][2] + T_top);
+            if (!(T_top > 0.0) || std::fabs(z) > sbtrig::kLogRatioMaxZ || std::fabs(h[i].pow_exp * std::log(L[i][2] / T_top)) > sbtrig::kExpLeanMax)
+                return sb_fail(ctx, SOPOT_B200_EINVAL, "atmosphere layer outside the range of the lean power law");
+        }
     }
     SB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_atm, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
     return SOPOT_B200_OK;

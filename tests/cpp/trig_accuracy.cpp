@@ -56,6 +56,21 @@ int main(int argc, char** argv) {
         worst_t = std::fmax(worst_t, (double)std::fabs((long double)ts - (sl * cdl + cl * sdl)) / 0x1p-52);
         worst_t = std::fmax(worst_t, (double)std::fabs((long double)tc - (cl * cdl - sl * sdl)) / 0x1p-52);
     }
+    // lean log(num/den) and exp (rocket atmosphere): relative error in ulp over the guarded ranges
+    double worst_l = 0, worst_e = 0;
+    for (long i = 0; i < n; ++i) {
+        const double den = 150.0 + 200.0 * (0.5 + 0.5 * U(rng));
+        const double ratio = 0.70 + 0.73 * (0.5 + 0.5 * U(rng));
+        const double num = den * ratio;
+        if (std::fabs(sbtrig::log_ratio_z(num, den)) > sbtrig::kLogRatioMaxZ) { std::printf("log_ratio range %.17g\n", ratio); return 1; }
+        const long double wl = logl((long double)num / (long double)den);
+        if (std::fabs((double)wl) > 1e-3) worst_l = std::fmax(worst_l, ulp_err(sbtrig::log_ratio_lean(num, den), wl));
+        else if (std::fabs(sbtrig::log_ratio_lean(num, den) - (double)wl) > 1e-18) { std::puts("log_ratio near 1"); return 1; }
+        const double x = (i & 1 ? 40.0 : 690.0) * U(rng);
+        worst_e = std::fmax(worst_e, ulp_err(sbtrig::exp_lean(x), expl((long double)x)));
+    }
+    std::printf("log_ratio_lean max ulp %.3f; exp_lean max ulp %.3f\n", worst_l, worst_e);
+    if (worst_l > 3.0 || worst_e > 2.0) return 3;     // the quotient z carries ~2 ulp (sum, reciprocal, product roundings)
     if (sbtrig::small_angle(0.03126) || !sbtrig::small_angle(-0.03125)) { std::puts("small_angle threshold wrong"); return 1; }
     if (sbtrig::tiny_angle(0x1.0001p-13) || !sbtrig::tiny_angle(-0x1p-13)) { std::puts("tiny_angle threshold wrong"); return 1; }
     std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f, _k %.3f, tiny %.3f\n",
