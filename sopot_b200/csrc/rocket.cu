@@ -63,6 +63,7 @@ struct RocketTablesDev {
     int total;                     // doubles in the packed buffer
     Table2D cd, cl, cs, cmq;       // rows == 0: reference default (host-side copy of the descriptors)
     int desc_off;                  // the same 4 descriptors as 12 doubles (rows, cols, off) inside the packed buffer
+    int inv_off;                   // reciprocal interval widths 1 / (x[i+1] - x[i]) of the four time axes (er + mr + xr + yr)
     int er, mr, xr, yr;
     double burn_time;
     int use_interp;
@@ -83,7 +84,7 @@ struct Lerp {   // io/interpolation.hpp:49-71 on a shared time grid
 // `hint` carries the interval of the previous lookup on this table: simulation time only moves forward, so the
 // interval is almost always unchanged or the next one and the binary search is skipped (same index either way).
 template <bool S>
-__device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv, int& hint) {
+__device__ __forceinline__ Lerp<S> lerp_locate(const double* x, const double* inv, int n, double xv, int& hint) {
     Lerp<S> L;
     L.t = Real<S>(0.0);
     if (xv <= x[0]) { L.i = -1; return L; }
@@ -101,7 +102,8 @@ __device__ __forceinline__ Lerp<S> lerp_locate(const double* x, int n, double xv
     }
     const Real<S> x0(x[i]), x1(x[i + 1]);
     L.i = i;
-    L.t = Recip<S>(x1 - x0).of(Real<S>(xv) - x0);
+    if constexpr (S) L.t = (Real<S>(xv) - x0) / (x1 - x0);
+    else L.t = Real<S>((xv - x0.v) * inv[i]);
     return L;
 }
 
@@ -182,14 +184,15 @@ struct RocketDevParams {
 template <bool AT>
 struct RocketSysT {
     static constexpr int DIM = 14;
-    static constexpr int BLOCK = SB_ROCKET_BLOCK, IPT = 1, MIN_BLOCKS = SB_ROCKET_MINB;
-    static constexpr bool FAST_STEP = false;
+    static constexpr int BLOCK = SB_ROCKET_BLOCK, IPT = 1, MIN_BLOCKS = SB_ROCKET_MINB > 1 ? SB_ROCKET_MINB : (AT ? 1 : 3);   // default model: 3 x 128 threads per SM (<= 168 registers)
+    static constexpr bool FAST_STEP = true;
     using DevParams = RocketDevParams;
     template <bool S> struct Inst {
         Real<S> g, area, len;
         const double* tb;          // shared-memory copy of the packed tables
         int er, mr, xr, yr, use_interp;
         int desc;                  // offset of the aero table descriptors in the shared-memory tables (AT only)
+        int inv;                   // offset of the reciprocal interval widths
         double burn;
         double apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd;
         mutable int h_eng, h_mass, h_ix, h_iyz;   // lerp_locate interval hints
@@ -208,7 +211,7 @@ struct RocketSysT {
         in.tb = s_tab;
         in.er = P.tab.er; in.mr = P.tab.mr; in.xr = P.tab.xr; in.yr = P.tab.yr;
         in.use_interp = P.tab.use_interp; in.burn = P.tab.burn_time;
-        in.desc = P.tab.desc_off;
+        in.desc = P.tab.desc_off; in.inv = P.tab.inv_off;
         const double d = P.diam.at(i);
         in.g = Real<S>(P.g.at(i));
         in.area = Real<S>(kAeroPi) * Real<S>(d) * Real<S>(d) / Real<S>(4.0);   // axisymmetric_aero.hpp:56
@@ -227,17 +230,74 @@ struct RocketSysT {
         y[7] = sy * sp; y[8] = (-cy) * sp; y[9] = sy * cp; y[10] = cy * cp;
     }
 
+    // everything the derivative reads from the TIME-indexed tables: mass / inertia (rocket_body.hpp:121-179) and the engine
+    // columns (interpolated_engine.hpp:103-152).  A pure function of the simulation time, so RK4 stages 2 and 3 (same time)
+    // share one evaluation in the contract-mode step below.
+    template <bool S> struct TimeTab { Real<S> mass, Ix, Iyz, exit_area, exit_pressure, engine_force; bool burning; };
     template <bool S>
-    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&s)[14], Real<S> (&d)[14]) {
+    static __device__ __forceinline__ TimeTab<S> time_tables(const Inst<S>& in, const double time) {
         using R = Real<S>;
-        const R time = s[0], alt = s[3];
-        const R q1 = s[7], q2 = s[8], q3 = s[9], q4 = s[10];
-        const R wx = s[11], wy = s[12], wz = s[13];
         const double* tb = in.tb;
         const double* eng_t = tb;
         const double* mass_t = tb + 5 * in.er;
         const double* ix_t = mass_t + 2 * in.mr;
         const double* iyz_t = ix_t + 2 * in.xr;
+        const double* inv_e = tb + in.inv;
+        const double* inv_m = inv_e + in.er;
+        const double* inv_x = inv_m + in.mr;
+        const double* inv_y = inv_x + in.xr;
+        TimeTab<S> tt{R(100.0), R(10.0), R(100.0), R(0.0), R(0.0), R(0.0), false};
+        if (in.use_interp) {
+            if (in.mr) tt.mass = lerp_locate<S>(mass_t, inv_m, in.mr, time, in.h_mass).eval(mass_t + in.mr, in.mr);
+            if (in.xr) tt.Ix = lerp_locate<S>(ix_t, inv_x, in.xr, time, in.h_ix).eval(ix_t + in.xr, in.xr);
+            if (in.yr) tt.Iyz = lerp_locate<S>(iyz_t, inv_y, in.yr, time, in.h_iyz).eval(iyz_t + in.yr, in.yr);
+        }
+        tt.burning = in.er > 0 && time <= in.burn;
+        if (tt.burning) {
+            const Lerp<S> L = lerp_locate<S>(eng_t, inv_e, in.er, time, in.h_eng);
+            const R d_exit = L.eval(eng_t + in.er, in.er);
+            const R p_comb = L.eval(eng_t + 2 * in.er, in.er);
+            const R press_ratio = L.eval(eng_t + 3 * in.er, in.er);
+            tt.exit_area = r_div_const(R(kEnginePi) * d_exit * d_exit, 4.0);
+            tt.exit_pressure = p_comb * press_ratio;
+            tt.engine_force = L.eval(eng_t + 4 * in.er, in.er);
+        }
+        return tt;
+    }
+
+    template <bool S>
+    static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&s)[14], Real<S> (&d)[14]) {
+        return rhs_tt<S>(in, time_tables<S>(in, s[0].v), s, d);
+    }
+
+    // Contract-mode RK4 step (rk4_step_fast of ensemble.cuh with the table lookups hoisted): the time component advances by
+    // exactly dt/2, dt/2, dt, so stages 2 and 3 read the tables at the same instant.
+    static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[14], const StepConsts& c, const size_t) {
+        Real<false> f[14], F[14], tmp[14];
+        int st = rhs_tt<false>(in, time_tables<false>(in, y[0].v), y, f);
+#pragma unroll
+        for (int d = 0; d < 14; ++d) { F[d] = f[d]; tmp[d].v = fma(c.hdt, f[d].v, y[d].v); }
+        const TimeTab<false> mid = time_tables<false>(in, tmp[0].v);
+        st |= rhs_tt<false>(in, mid, tmp, f);
+#pragma unroll
+        for (int d = 0; d < 14; ++d) { F[d].v = fma(2.0, f[d].v, F[d].v); tmp[d].v = fma(c.hdt, f[d].v, y[d].v); }
+        st |= rhs_tt<false>(in, mid, tmp, f);
+#pragma unroll
+        for (int d = 0; d < 14; ++d) { F[d].v = fma(2.0, f[d].v, F[d].v); tmp[d].v = fma(c.dt, f[d].v, y[d].v); }
+        st |= rhs_tt<false>(in, time_tables<false>(in, tmp[0].v), tmp, f);
+#pragma unroll
+        for (int d = 0; d < 14; ++d) y[d].v = fma(c.dt6, F[d].v + f[d].v, y[d].v);
+        return st;
+    }
+
+    template <bool S>
+    static __device__ __forceinline__ int rhs_tt(const Inst<S>& in, const TimeTab<S>& tt, const Real<S> (&s)[14], Real<S> (&d)[14]) {
+        using R = Real<S>;
+        const R alt = s[3];
+        const R q1 = s[7], q2 = s[8], q3 = s[9], q4 = s[10];
+        const R wx = s[11], wy = s[12], wz = s[13];
+        const double* tb = in.tb;
+        (void)tb;
 
         // ---- rotation matrix, quaternion.hpp:94-112 (once) ----
         const R q1_2 = q1 * q1, q2_2 = q2 * q2, q3_2 = q3 * q3, q4_2 = q4 * q4;
@@ -256,29 +316,14 @@ struct RocketSysT {
         else if (v2.v >= 1.0) sbtrig::sqrt_rsqrt_fast(v2.v, airspeed.v, inv_airspeed.v);   // else: aero off, root unused
         const bool aero_on = S ? !(airspeed.v < 1.0) : (v2.v >= 1.0 && !(airspeed.v < 1.0));
 
-        // ---- mass and inertia, rocket_body.hpp:121-179 ----
-        R mass(100.0), Ix(10.0), Iyz(100.0);
-        if (in.use_interp) {
-            if (in.mr) mass = lerp_locate<S>(mass_t, in.mr, time.v, in.h_mass).eval(mass_t + in.mr, in.mr);
-            if (in.xr) Ix = lerp_locate<S>(ix_t, in.xr, time.v, in.h_ix).eval(ix_t + in.xr, in.xr);
-            if (in.yr) Iyz = lerp_locate<S>(iyz_t, in.yr, time.v, in.h_iyz).eval(iyz_t + in.yr, in.yr);
-        }
+        const R mass = tt.mass, Ix = tt.Ix, Iyz = tt.Iyz;
 
         // ---- thrust, interpolated_engine.hpp:103-152 ----
-        const bool burning = in.er > 0 && time.v <= in.burn;
+        const bool burning = tt.burning;
         R P(0.0), T(0.0);
         if (burning || aero_on) atmosphere<S>(alt, P, T);
         R thrust(0.0);
-        if (burning) {
-            const Lerp<S> L = lerp_locate<S>(eng_t, in.er, time.v, in.h_eng);
-            const R d_exit = L.eval(eng_t + in.er, in.er);
-            const R p_comb = L.eval(eng_t + 2 * in.er, in.er);
-            const R press_ratio = L.eval(eng_t + 3 * in.er, in.er);
-            const R exit_area = r_div_const(R(kEnginePi) * d_exit * d_exit, 4.0);
-            const R exit_pressure = p_comb * press_ratio;
-            const R engine_force = L.eval(eng_t + 4 * in.er, in.er);
-            thrust = engine_force + exit_area * (exit_pressure - P);
-        }
+        if (burning) thrust = tt.engine_force + tt.exit_area * (tt.exit_pressure - P);
 
         // ---- aerodynamic force (ENU) and damping moment (body) ----
         R Fax(0.0), Fay(0.0), Faz(0.0), Mx(0.0), My(0.0), Mz(0.0);
@@ -477,6 +522,15 @@ void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, Ro
     }
     tab.desc_off = (int)out.size();
     for (const Table2D* t : {&tab.cd, &tab.cl, &tab.cs, &tab.cmq}) { out.push_back(t->rows); out.push_back(t->cols); out.push_back(t->off); }
+    // contract mode: the interpolation weight is (x - x_i) * 1/(x_{i+1} - x_i) with the reciprocal read from here instead of
+    // a MUFU seed + 3 dependent FMAs per lookup (n entries per axis, the last one unused)
+    tab.inv_off = (int)out.size();
+    {
+        const size_t offs[4] = {0, 5 * er, 5 * er + 2 * mr, 5 * er + 2 * mr + 2 * xr}, ns[4] = {er, mr, xr, yr};
+        for (int a = 0; a < 4; ++a)
+            for (size_t r = 0; r < ns[a]; ++r)
+                out.push_back(r + 1 < ns[a] ? 1.0 / (out[offs[a] + r + 1] - out[offs[a] + r]) : 0.0);
+    }
     tab.total = (int)out.size();
 }
 
