@@ -133,15 +133,10 @@ __device__ __forceinline__ Real<S> bilinear(const double* tb, const Table2D& t, 
     return v0 + tr * (v1 - v0);
 }
 
+// one layer of the standard atmosphere (standard_atmosphere.hpp:50-64): gradient layers by the power law, isothermal
+// ones by the exponential
 template <bool S>
-__device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S>& T) {
-    const double h = alt.v;
-    if (h <= 0) { P = Real<S>(kAtmP0); T = Real<S>(kAtmT0); return; }          // :45,:57
-    if (h >= 100000.0) { P = Real<S>(1e-4); T = Real<S>(186.95); return; }      // :46,:58
-    int li = 0;
-#pragma unroll
-    for (int k = 6; k >= 0; --k) if (h <= c_atm[k].h_top) li = k;              // first layer with h <= h_top
-    const AtmLayer l = c_atm[li];
+__device__ __forceinline__ void atmosphere_layer(const AtmLayer& l, const Real<S> alt, Real<S>& P, Real<S>& T) {
     const Real<S> dh = alt - Real<S>(l.h_base);
     if (fabs(l.lapse) < 1e-10) {
         T = Real<S>(l.T_base);
@@ -163,6 +158,21 @@ __device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S
             P = Real<S>(l.P_base * sbtrig::exp_lean(x));
         }
     }
+}
+
+template <bool S>
+__device__ __forceinline__ void atmosphere(const Real<S> alt, Real<S>& P, Real<S>& T) {
+    const double h = alt.v;
+    if (h <= 0) { P = Real<S>(kAtmP0); T = Real<S>(kAtmT0); return; }          // :45,:57
+    // the lowest layer first (sounding-rocket altitudes): its constants are read with static constant-bank offsets, and the
+    // search over the other layers (six FP64 compares and a register-indexed constant load) is skipped
+    if (h <= c_atm[0].h_top) { atmosphere_layer<S>(c_atm[0], alt, P, T); return; }
+    if (h >= 100000.0) { P = Real<S>(1e-4); T = Real<S>(186.95); return; }      // :46,:58
+    int li = 6;
+#pragma unroll
+    for (int k = 5; k >= 1; --k) if (h <= c_atm[k].h_top) li = k;              // first layer with h <= h_top
+    const AtmLayer l = c_atm[li];
+    atmosphere_layer<S>(l, alt, P, T);
 }
 
 }  // namespace

@@ -90,6 +90,7 @@ def main():
     control_golden(R)
     cartn_linearize_golden(R)
     rocket_aero_golden(R)
+    rocket_atmosphere_golden(R)
     control_n_golden(R)
     ugrid_golden(R)
     for f in sorted(os.listdir(OUT)):
@@ -175,6 +176,24 @@ def rocket_aero_golden(R):
     out["rhs_state"] = st
     out["rhs"] = R.rocket_rhs(84.0, 30.0, 0.16, 9.80665, w["engine"], w["mass_tab"], st, aero=aero)
     np.savez(os.path.join(OUT, "rocket_aero.npz"), **out)
+
+
+def rocket_atmosphere_golden(R):
+    """One derivative evaluation per atmosphere layer and at every layer boundary (standard_atmosphere.hpp:43-71): the
+    trajectory fixtures never leave the lowest layer."""
+    g = np.load(os.path.join(OUT, "rocket.npz"))
+    alts = np.array([-50.0, 0.0, 1e-3, 5000.0, 10999.999, 11000.0, 11000.001, 15000.0, 20000.0, 20000.5, 26000.0, 32000.0, 32001.0,
+                     40000.0, 47000.0, 47000.25, 49000.0, 51000.0, 51010.0, 60000.0, 71000.0, 71000.5, 85000.0, 99999.0, 100000.0,
+                     120000.0])
+    rng = np.random.default_rng(11)
+    st = np.repeat(g["rhs_state"][:, :1], alts.size, axis=1)
+    st[3] = alts
+    st[0] = np.where(np.arange(alts.size) % 2 == 0, 1.2, 6.0)          # burning / coasting
+    st[4:7] = rng.normal(0, 150.0, (3, alts.size))
+    q = rng.normal(0, 1, (4, alts.size)); st[7:11] = q / np.linalg.norm(q, axis=0)
+    st[11:14] = rng.normal(0, 0.3, (3, alts.size))
+    np.savez(os.path.join(OUT, "rocket_atmosphere.npz"), state=st,
+             rhs=R.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], st))
 
 
 def control_n_golden(R):

@@ -187,6 +187,19 @@ def test_rocket_rhs_golden(engine, fp):
 
 
 @pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_rocket_rhs_all_atmosphere_layers(engine, fp):
+    """Every layer of the standard atmosphere, its boundaries and the two clamps (tests/golden/rocket_atmosphere.npz, from
+    the reference): exercises the isothermal exponential, both lapse signs of the power law (contract mode: the lean
+    log / exp of trig.cuh) and the layer search above the lowest layer."""
+    g, ga = golden("rocket"), golden("rocket_atmosphere")
+    out = engine.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], ga["state"], fp_mode=fp)
+    ref = ga["rhs"]
+    for lo, hi in ((0, 1), (1, 4), (4, 7), (7, 11), (11, 14)):
+        scale = np.maximum(np.abs(ref[lo:hi]).max(axis=0), 1e-6)
+        assert (np.abs(out[lo:hi] - ref[lo:hi]).max(axis=0) / scale).max() <= 1e-11, (lo, hi)
+
+
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
 def test_rocket_golden_trajectories(engine, fp):
     g = golden("rocket")
     st, stats, traj, status = engine.rocket_rk4(g["elev"], g["az"], g["diam"], g["g0"], g["engine"], g["mass_tab"], None,

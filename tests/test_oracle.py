@@ -216,6 +216,14 @@ def test_lqr_port_equals_reference_on_fresh_inputs(port, ref):
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
 
 
+def test_golden_rocket_all_atmosphere_layers(port):
+    """One derivative per layer of the standard atmosphere and at each layer boundary (the trajectory fixtures stay below
+    11 km): isothermal layers, both signs of the lapse rate, the h <= 0 and h >= 100 km clamps -- port == reference."""
+    g, ga = golden("rocket"), golden("rocket_atmosphere")
+    assert ga["state"][3].min() < 0 and ga["state"][3].max() > 1e5
+    assert np.array_equal(port.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], ga["state"]), ga["rhs"])
+
+
 def test_golden_rocket_aero_tables(port):
     """Table-driven aerodynamics (bilinear Cd/Cl/Cs/cmq tables, io/interpolation.hpp:137-181 through
     rocket/axisymmetric_aero.hpp:133-167,276-281): C restatement == the reference's components, bit for bit."""
