@@ -106,8 +106,8 @@ struct DpendSys {
     static constexpr int BLOCK = SB_DPEND_BLOCK, IPT = SB_DPEND_IPT, MIN_BLOCKS = SB_DPEND_MINB;
     static constexpr bool FAST_STEP = true;
     struct DevParams { ParamRef m1, m2, L1, L2, g, th1, th2, w1, w2; };
-    // kol .. gL2l: row-scaled coefficients of the fast step; s1 .. cd: sin/cos carried from step to step (fast_step)
-    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, kol, lam, gL1, gL2l; double s1, c1, sd, cd; };
+    // kol, lam, gL1: row-scaled coefficients of the fast step; s1 .. cd: the scaled sin/cos pairs carried from step to step
+    template <bool S> struct Inst { Real<S> a11, m2L2, m12g, negL1, L1, L2, g, kol, lam, gL1; double s1, c1, sd, cd; };
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
@@ -122,7 +122,7 @@ struct DpendSys {
         if constexpr (!S) {
             in.lam = L1 / L2;                                   // lam = L1/L2, kap = m2 L2 / ((m1+m2) L1)
             in.kol = (in.m2L2 / in.a11) / in.lam;               // kap / lam
-            in.gL1 = g / L1; in.gL2l = (g / L2) / in.lam;
+            in.gL1 = g / L1;
             refresh_trig(in, y[0].v, y[1].v);
         }
     }
@@ -165,16 +165,18 @@ struct DpendSys {
     // 1/a11, row 2 by 1/a22):  with kap = m2 L2 / ((m1+m2) L1), lam = L1 / L2, sd/cd = sin/cos(th1 - th2), P = w2^2, Q = w1^2
     //   B1 = kap P sd - (g/L1) s1,   B2 = -lam Q sd - (g/L2) s2,
     //   a1 = (B1 - kap cd B2) / D,   a2 = (B2 - lam cd B1) / D,    D = 1 - kap lam cd^2  in (0, 1].
-    // The step works on s1 = sin th1, c1 = cos th1 and the SCALED pair S = lam sd, C = lam cd (a rotation is linear,
-    // so the scaled pair rotates like the unit one): lam cd and lam sd are then free, kap cd = (kap/lam) C,
-    // kap sd = (kap/lam) S, and lam sin th2 = s1 C - c1 S replaces a third carried pair.
-    // 18 FP64 instructions + 1 MUFU; 5 of them read three distinct vector registers.
+    // The step works on two SCALED pairs (a rotation is linear, so a scaled pair rotates like the unit one):
+    //   (s1, c1) = (g/L1) (sin th1, cos th1)  and  (S, C) = lam (sd, cd).
+    // Then (g/L1) s1 and lam cd, lam sd are free, kap cd = (kap/lam) C, kap sd = (kap/lam) S, and
+    //   s1 C - c1 S = (g/L1) lam sin th2 = (g/L2) sin th2            [(g/L1) (L1/L2) = g/L2 exactly]
+    // is the second gravity term itself: no third pair, no multiplications by g/L.
+    // 16 FP64 instructions + 1 MUFU; 5 of them read three distinct vector registers.
     static __device__ __forceinline__ void accel(const Inst<false>& in, double s1, double c1, double S, double C,
                                                  double w1, double w2, double& a1, double& a2) {
-        const double s2l = fma(s1, C, -(c1 * S));                   // lam sin(th2)
+        const double g2 = fma(s1, C, -(c1 * S));                    // (g/L2) sin(th2)
         const double kc = in.kol.v * C;                             // kap cd
-        const double B1 = fma(in.kol.v * S, w2 * w2, -(in.gL1.v * s1));
-        const double B2 = -fma(S, w1 * w1, in.gL2l.v * s2l);
+        const double B1 = fma(in.kol.v * S, w2 * w2, -s1);
+        const double B2 = -fma(S, w1 * w1, g2);
         const double D = fma(-kc, C, 1.0);
         const double inv = sbtrig::rcp_fast(D);
         a1 = fma(-kc, B2, B1) * inv;
@@ -183,15 +185,16 @@ struct DpendSys {
     // full evaluation of the carried values from the angles (start of the run, every 8th step, after a large increment)
     static __device__ __forceinline__ void trig_of(const Inst<false>& in, double th1, double delta, double& s1, double& c1,
                                                    double& S, double& C) {
-        sbtrig::sincos<true>(th1, s1, c1);                          // cold call sites: constants loaded on use
-        double sd, cd;
+        double st, ct, sd, cd;
+        sbtrig::sincos<true>(th1, st, ct);                          // cold call sites: constants loaded on use
         sbtrig::sincos<true>(delta, sd, cd);
+        s1 = in.gL1.v * st; c1 = in.gL1.v * ct;
         S = in.lam.v * sd; C = in.lam.v * cd;
     }
     static __device__ __forceinline__ void refresh_trig(Inst<false>& in, double th1, double th2) {
         trig_of(in, th1, th1 - th2, in.s1, in.c1, in.sd, in.cd);     // delta rounded as in the reference (:145)
     }
-    // sin/cos of (th1 + h1) and lam sin/cos of (delta + hd) from the base values: rotation by the small increments,
+    // (g/L1) sin/cos of (th1 + h1) and lam sin/cos of (delta + hd) from the base values: rotation by the small increments,
     // full routine when an increment is large.  (Computing the rotation unconditionally and overriding it in a rarely
     // taken branch measured 3 % slower: ptxas adds WARPSYNC / BREAK / register moves around the override.)
     static __device__ __forceinline__ void stage_trig(const Inst<false>& in, const StepConsts& k, const double th1, const double th2,
@@ -213,7 +216,7 @@ struct DpendSys {
     //   next step: th_new - th            -> rotate the base pair; full sincos every 8th step bounds the accumulated
     //                                        rounding of the carried pair to a few 1e-16
     // Every shortcut has an integer-compare guard on its increment and falls back to the full routine.
-    // 196 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
+    // ~180 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
     static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
         const double th1 = y[0].v, th2 = y[1].v, w1 = y[2].v, w2 = y[3].v;
         const double s1 = in.s1, c1 = in.c1, S = in.sd, C = in.cd;
