@@ -136,6 +136,30 @@ def test_dpend_full_horizon_sample_vs_oracle(engine, port):
     assert np.array_equal(d.download(), st)
 
 
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_dpend_degenerate_parameters_and_large_increments(engine, port, fp):
+    """The contract-mode step carries sin/cos pairs scaled by g/L1 and L1/L2 and rotates them by small increments:
+    g = 0 (first pair identically zero), m2 = 0 (kap = 0: a simple pendulum), very unequal arms, rates so large that
+    the increments leave the small-angle range (|dt w| > 2^-5: full-sincos fallback at every stage) and a coarse step
+    that defeats the tiny-increment shortcut -- all against the oracle."""
+    n = 64
+    rng = np.random.default_rng(5)
+    base = dict(m1=rng.uniform(0.5, 2, n), m2=rng.uniform(0.5, 2, n), L1=rng.uniform(0.5, 2, n), L2=rng.uniform(0.5, 2, n),
+                g=np.full(n, 9.81), th1=rng.uniform(-3, 3, n), th2=rng.uniform(-3, 3, n), w1=rng.uniform(-2, 2, n), w2=rng.uniform(-2, 2, n))
+    cases = {"g0": dict(g=np.zeros(n)), "m2_0": dict(m2=np.zeros(n)), "arms": dict(L1=np.full(n, 0.05), L2=np.full(n, 3.0)),
+             "fast": dict(w1=rng.uniform(-80, 80, n), w2=rng.uniform(-80, 80, n))}
+    for name, over in cases.items():
+        w = {**base, **over}
+        args = _dp_args(w)
+        # coarse steps: increments of 0.04 .. 0.4 rad (RK4 itself stays stable; at dt = 0.02 the 80 rad/s case blows up to
+        # 1e80 in the reference as well)
+        for dt, steps in ((1e-3, 40), (5e-3, 6) if name == "fast" else (2e-2, 3)):
+            got, _, status = engine.dpend_rk4(*args, n, 0.0, dt, steps, fp_mode=fp)
+            ref, _, _ = port.dpend_rk4(*args, 0.0, dt * steps, dt, nthreads=2)
+            assert np.all(status == ST_OK), name
+            assert rel_err(got, ref).max() <= 100 * PER_STEP, (name, dt, rel_err(got, ref).max())
+
+
 # ------------------------------------------------------------------------------------------------ config 3
 @pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
 def test_cartpole_linearize_golden(engine, fp):
