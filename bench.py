@@ -42,13 +42,13 @@ DT = 1e-3
 FLOP_PER_INSTANCE_STEP = 204.0
 # From the ncu capture of this very command (profiles/r1_final_dpend_bench.txt, one launch = 4 Mi x 10 000) and the per-opcode
 # operand analysis of its source page (tools/ncu_fp64_operands.py, profiles/r1_final_dpend_fp64_operands.txt):
-#   187.6 FP64-pipe instructions per instance-step (105.7 DFMA, 71.9 DMUL, 10 DADD) at 2 issue cycles each, of which 41.8
-#   DFMAs read three distinct vector registers and take 3 (profiles/r1_fp64_operand_rule.txt): 417 FP64 issue cycles per
+#   179.6 FP64-pipe instructions per instance-step (105.6 DFMA, 64.0 DMUL, 10 DADD) at 2 issue cycles each, of which 41.8
+#   DFMAs read three distinct vector registers and take 3 (profiles/r1_fp64_operand_rule.txt): 401 FP64 issue cycles per
 #   warp-step.
-#   DRAM traffic per launch 319.2 MB read + 113.4 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
-FP64_INSTR_PER_STEP = 187.6
+#   DRAM traffic per launch 317.7 MB read + 112.1 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
+FP64_INSTR_PER_STEP = 179.6
 FP64_ISSUE_CYCLES_PER_STEP = 2.0 * FP64_INSTR_PER_STEP + 41.8
-NCU_DRAM_BYTES_PER_LAUNCH_4MI = 319181568 + 113387520
+NCU_DRAM_BYTES_PER_LAUNCH_4MI = 317678848 + 112097536
 METRIC = "RK4 instance-steps/s (FP64)"
 UNIT = "instance-steps/s"
 
@@ -175,6 +175,16 @@ def other_configs(eng, hbm_peak, fp64_peak):
                                   fp_mode=FP_CONTRACT, want_status=False, state_out=st, sync=False), 3)
     out["ho_1Mi_x1000"] = {"ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3),
                            "fp64_frac": 44.0 * n * 1000 / (ms * 1e-3) / 1e12 / fp64_peak}
+    # config 2 in the bit-exact arithmetic mode (reference association, IEEE division, libdevice sin/cos; the headline is the
+    # contract mode): 1 Mi instances x 1000 steps
+    w = W.dpend_ensemble(n)
+    dd = [eng.to_device(w[k]) for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+    st4 = eng.empty((4, n))
+    ms = timed(lambda: eng.dpend_rk4(*dd, n, 0.0, 1e-3, 1000, mem=MEM_DEVICE, fp_mode=FP_STRICT, want_status=False,
+                                     state_out=st4, sync=False), 2)
+    out["dpend_strict_1Mi_x1000"] = {"ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3)}
+    for a in (st4, *dd):
+        a.free()
     # config 3: batched linearization, HBM bound, 200 B / point.  4 Mi points per launch (0.84 GB of traffic, far
     # larger than the 126 MB L2, so every output byte really goes to HBM inside the timed region); the BASELINE
     # size of 1 Mi points (210 MB, of which part stays L2-resident) is reported beside it.
