@@ -217,9 +217,11 @@ def other_configs(eng, hbm_peak, fp64_peak):
     out["lqr4_sweep_64Ki"] = {"ms": ms, "gains_per_s": P / (ms * 1e-3), "mean_riccati_iterations": mean_it,
                               "failed": int(np.count_nonzero(st.download()))}
     s0 = [eng.to_device(v) for v in (rng.uniform(-0.5, 0.5, P), rng.uniform(-0.1, 0.1, P), np.zeros(P), np.zeros(P))]
+    cl_state = eng.empty((4, P))
     ms = timed(lambda: eng.cartpole_feedback_rk4(plant["mc"], plant["m"], plant["L"], plant["g"], *s0, K, P, 0.0, 0.002, 2000,
                                                  u_min=-50.0, u_max=50.0, saturate=True, mem=MEM_DEVICE, want_status=False,
-                                                 want_stats=False, sync=False), 2)
+                                                 want_stats=False, sync=False, state_out=cl_state), 2)
+    cl_state.free()
     out["cartpole_closed_loop_64Ki_x2000"] = {"ms": ms, "instance_steps_per_s": P * 2000 / (ms * 1e-3)}
     for a in (dx, du, A, B, K, iters, st, *s0, *plant.values()):
         a.free()

@@ -443,7 +443,7 @@ class Engine:
 
     def cartpole_feedback_rk4(self, mc, m, L, g, x, th, xd, w, K, n, t0, dt, n_steps, x_ref=None, u_min=0.0, u_max=0.0,
                               saturate=False, mem=MEM_HOST, fp_mode=FP_CONTRACT, store_every=0, want_status=True,
-                              want_stats=True, sync=True):
+                              want_stats=True, sync=True, state_out=None):
         """Closed-loop cart-pole ensemble: u = clamp(-K (x - x_ref)) held over each RK4 step."""
         ptrs, mask, keep = self._prep(dict(mc=mc, m=m, L=L, g=g, x=x, th=th, xd=xd, w=w), n, mem)
         params = CartpoleParams(force=None, **ptrs)
@@ -452,7 +452,7 @@ class Engine:
             x_ref = None if x_ref is None else np.ascontiguousarray(x_ref, dtype=np.float64)
         fb = Feedback(_ptr(K), _ptr(x_ref), u_min, u_max, int(bool(saturate)))
         opts = RK4Opts(mem, fp_mode, store_every, mask, 0)
-        state, traj, status = self._outs(4, n, n_steps, store_every, mem, want_status, None, None)
+        state, traj, status = self._outs(4, n, n_steps, store_every, mem, want_status, state_out, None)
         stats = None
         if want_stats:
             stats = np.empty((2, n)) if mem == MEM_HOST else self.empty((2, n))

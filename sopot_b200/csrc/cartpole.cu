@@ -5,6 +5,7 @@
 //                     (core/linearization.hpp:75-114) with Dual<double,5>.
 #include "dual.cuh"
 #include "ensemble.cuh"
+#include "trig.cuh"
 
 // Generic N-link plant.  Arrays are indexed with compile-time constants only (full unrolling; row
 // swaps of the partial-pivot search are predicated element swaps), so everything stays in registers.
@@ -101,19 +102,86 @@ struct CartPlant {
     }
 };
 
+// ---- FP_CONTRACT step of the one-link plant ------------------------------------------------------------------
+// For N = 1 the 2x2 system of :172-203, [[M, mLc], [mLc, mL^2]] [xdd, thdd] = [F + mL s w^2, m g L s] with M = mc + m,
+// has the closed form   xdd = (F + mL s w^2 - m g s c) / D,   thdd = (M g s - c (F + mL s w^2)) / (L D),   D = M - m c^2
+// (15 FP64 instructions + 1 MUFU instead of the pivoted elimination with three IEEE divisions), and, as in the double
+// pendulum (ho_dpend.cu), every sin/cos argument of a step is the base angle plus a small increment: the pair
+// (sin th, cos th) is carried and rotated -- stage 2 and 4 from the base pair (rotate_small), stage 3 relative to stage 2
+// and the next base relative to stage 4 (rotate_tiny), full sincos every 16th step and whenever an increment leaves its
+// guarded range.  D >= mc, so the reference's singular-pivot throw cannot trigger for mc > 0; instances with
+// mc <= 1e-12 take the generic step, which reports it.
+struct CartFast {
+    double mL, mg, Mg, m, M, invL;      // parameter-only products
+    double s, c;                        // carried sin / cos of the pole angle
+    int generic;                        // mc too small for the closed form's no-singularity argument
+    __device__ __forceinline__ void init(double mc, double m_, double L, double g, double th) {
+        M = mc + m_; m = m_; mL = m_ * L; mg = m_ * g; Mg = M * g; invL = 1.0 / L;
+        generic = !(mc > 1e-12);
+        sbtrig::sincos<true>(th, s, c);
+    }
+    __device__ __forceinline__ void accel(double sn, double cs, double w, double F, double& xdd, double& thdd) const {
+        const double b0 = fma(mL * sn, w * w, F);
+        const double D = fma(-(m * cs), cs, M);
+        const double inv = sbtrig::rcp_fast(D);
+        xdd = fma(-(mg * sn), cs, b0) * inv;
+        thdd = fma(Mg, sn, -(cs * b0)) * (inv * invL);
+    }
+    __device__ __forceinline__ void rotate(double s0, double c0, double h, const StepConsts& k, double base_angle, double& so, double& co) const {
+        if (sbtrig::small_angle(h)) sbtrig::rotate_small_k(s0, c0, h, k.rot3, k.rot5, k.cot4, so, co);
+        else sbtrig::sincos<true>(base_angle + h, so, co);
+    }
+    // y = [x, th, xd, w]; F held over the step
+    __device__ __forceinline__ void step(Real<false> (&y)[4], const double F, const StepConsts& k, const size_t step_no) {
+        const double x = y[0].v, th = y[1].v, xd = y[2].v, w = y[3].v;
+        double ax, aw;
+        accel(s, c, w, F, ax, aw);
+        double F0 = xd, F1 = w, F2 = ax, F3 = aw;
+        double ux = fma(k.hdt, ax, xd), uw = fma(k.hdt, aw, w);
+        const double d = k.hdt2 * aw;                                  // stage 3 - stage 2 angle
+        double ss, cs;
+        rotate(s, c, k.hdt * w, k, th, ss, cs);
+        accel(ss, cs, uw, F, ax, aw);
+        F0 = fma(2.0, ux, F0); F1 = fma(2.0, uw, F1); F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3);
+        if (sbtrig::tiny_angle(d)) sbtrig::rotate_tiny_k(ss, cs, d, k.rot3, ss, cs);
+        else rotate(s, c, k.hdt * uw, k, th, ss, cs);
+        ux = fma(k.hdt, ax, xd); uw = fma(k.hdt, aw, w);
+        accel(ss, cs, uw, F, ax, aw);
+        F0 = fma(2.0, ux, F0); F1 = fma(2.0, uw, F1); F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3);
+        const double h4 = k.dt * uw;
+        rotate(s, c, h4, k, th, ss, cs);
+        ux = fma(k.dt, ax, xd); uw = fma(k.dt, aw, w);
+        accel(ss, cs, uw, F, ax, aw);
+        const double nth = fma(k.dt6, F1 + uw, th);
+        y[0].v = fma(k.dt6, F0 + ux, x); y[1].v = nth;
+        y[2].v = fma(k.dt6, F2 + ax, xd); y[3].v = fma(k.dt6, F3 + aw, w);
+        const double gth = nth - th, e = gth - h4;
+        const bool refresh = ((step_no + 1) & 15) == 0;
+        if (!refresh && sbtrig::tiny_angle(e)) sbtrig::rotate_tiny_k(ss, cs, e, k.rot3, s, c);
+        else if (!refresh && sbtrig::small_angle(gth)) sbtrig::rotate_small_k(s, c, gth, k.rot3, k.rot5, k.cot4, s, c);
+        else sbtrig::sincos<true>(nth, s, c);
+    }
+};
+
 // ---- K1: cart-pole (N = 1) integration with a constant force ----------------------------------------
 struct CartpoleSys {
     static constexpr int DIM = 4;
     static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
-    static constexpr bool FAST_STEP = false;
+    static constexpr bool FAST_STEP = true;
     struct DevParams { ParamRef mc, m, L, g, x, th, xd, w, force; };
-    template <bool S> struct Inst { CartPlant<1, Real<S>> plant; Real<S> F; };
+    template <bool S> struct Inst { CartPlant<1, Real<S>> plant; Real<S> F; CartFast fast; };
+    static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
+        if (in.fast.generic) return rk4_step_fast<CartpoleSys>(in, y, k);
+        in.fast.step(y, in.F.v, k, step);
+        return 0;
+    }
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
         in.plant.mc = P.mc.at(i); in.plant.m[0] = P.m.at(i); in.plant.L[0] = P.L.at(i); in.plant.g = P.g.at(i);
         in.F = Real<S>(P.force.at(i));
         y[0] = Real<S>(P.x.at(i)); y[1] = Real<S>(P.th.at(i)); y[2] = Real<S>(P.xd.at(i)); y[3] = Real<S>(P.w.at(i));
+        if constexpr (!S) in.fast.init(in.plant.mc, in.plant.m[0], in.plant.L[0], in.plant.g, y[1].v);
     }
     template <bool S>
     static __device__ __forceinline__ int rhs(const Inst<S>& in, const Real<S> (&y)[4], Real<S> (&dy)[4]) {
@@ -174,7 +242,7 @@ SB_EXPORT int sopot_b200_cartpole_rhs(sopot_b200_ctx* ctx, const sopot_b200_cart
 struct CartpoleFbSys {
     static constexpr int DIM = 4;
     static constexpr int BLOCK = 128, IPT = 1, MIN_BLOCKS = 1;
-    static constexpr bool FAST_STEP = false;
+    static constexpr bool FAST_STEP = true;
     static constexpr bool HAS_BEGIN_STEP = true;
     struct DevParams {
         ParamRef mc, m, L, g, x, th, xd, w;
@@ -190,7 +258,13 @@ struct CartpoleFbSys {
         Real<S> F, K[4], ref[4];
         double u_min, u_max, max_theta, max_u;
         int saturate;
+        CartFast fast;
     };
+    static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
+        if (in.fast.generic) return rk4_step_fast<CartpoleFbSys>(in, y, k);
+        in.fast.step(y, in.F.v, k, step);
+        return 0;
+    }
     template <bool S> static __device__ __forceinline__ void block_setup(const DevParams&) {}
     template <bool S>
     static __device__ __forceinline__ void load(const DevParams& P, size_t i, Inst<S>& in, Real<S> (&y)[4]) {
@@ -203,6 +277,7 @@ struct CartpoleFbSys {
         }
         in.u_min = P.u_min; in.u_max = P.u_max; in.saturate = P.saturate;
         in.F = Real<S>(0.0); in.max_theta = 0.0; in.max_u = 0.0;
+        if constexpr (!S) in.fast.init(in.plant.mc, in.plant.m[0], in.plant.L[0], in.plant.g, y[1].v);
     }
     template <bool S>
     static __device__ __forceinline__ void begin_step(Inst<S>& in, const Real<S> (&y)[4]) {

@@ -47,6 +47,22 @@ elif cfg in ("grid", "grid_strict"):
         ms = timed(lambda: eng.grid2d_rk4(gp, p["dt"], 10, state, fp_mode=mode, sync=False, per_stage=per_stage), 2) / 10
         print("%s %d^2 %s: %.3f ms/step  %.3e mass-steps/s  %.1f GB/s at 544 B/mass-step" %
               (cfg, n, "per-stage" if per_stage else "fused", ms, n * n / ms * 1e3, 544.0 * n * n / ms / 1e6))
+elif cfg == "closed":
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 16
+    rng = np.random.default_rng(3)
+    plant = {k: eng.to_device(v) for k, v in dict(mc=rng.uniform(0.8, 1.5, P), m=rng.uniform(0.05, 0.2, P),
+                                                   L=rng.uniform(0.4, 0.8, P), g=np.full(P, 9.81)).items()}
+    dx, du = eng.to_device(np.zeros((4, P))), eng.to_device(np.zeros(P))
+    A, B, _ = eng.cartpole_linearize(plant["mc"], plant["m"], plant["L"], plant["g"], dx, du, P, mem=MEM_DEVICE, want_status=False)
+    K = eng.empty((4, P))
+    eng.lqr4_gain(A, B, P, np.diag([10.0, 100.0, 1.0, 10.0]), 0.01, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, K=K)
+    s0 = [eng.to_device(v) for v in (rng.uniform(-0.5, 0.5, P), rng.uniform(-0.1, 0.1, P), np.zeros(P), np.zeros(P))]
+    for mode, name in ((FP_CONTRACT, "contract"), (FP_STRICT, "strict")):
+        st = eng.empty((4, P))
+        ms = timed(lambda: eng.cartpole_feedback_rk4(plant["mc"], plant["m"], plant["L"], plant["g"], *s0, K, P, 0.0, 0.002, 2000,
+                                                     u_min=-50.0, u_max=50.0, saturate=True, mem=MEM_DEVICE, want_status=False,
+                                                     want_stats=False, fp_mode=mode, sync=False, state_out=st), 2)
+        print("closed loop %d x 2000 %s: %.3f ms  %.3e inst-steps/s  checksum %.12e" % (P, name, ms, P * 2000 / ms * 1e3, float(st.download().sum())))
 elif cfg == "ugrid":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
     ug = eng.ugrid_params(n, n, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5)
