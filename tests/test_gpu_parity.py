@@ -198,6 +198,39 @@ def test_cartpole_rk4_golden(engine):
     assert np.all(status == ST_OK)
 
 
+def test_cartpole_contract_step_vs_oracle(engine, port):
+    """The contract-mode cart-pole step (closed-form 2x2 solve, carried sin/cos pair) against the oracle's pivoted
+    elimination: swinging poles far from upright, rates and steps large enough to leave the small- and tiny-increment
+    ranges (full-sincos fallbacks), more steps than the 16-step refresh period, and a massless cart (mc = 0: the generic
+    step with the singular-pivot check runs instead of the closed form)."""
+    n = 96
+    rng = np.random.default_rng(8)
+    mc, m, L = rng.uniform(0.5, 2.0, n), rng.uniform(0.05, 0.5, n), rng.uniform(0.3, 1.2, n)
+    g = np.full(n, 9.81)
+    mc[:8] = 0.0
+    s0 = np.stack([rng.uniform(-1, 1, n), rng.uniform(-3.1, 3.1, n), rng.uniform(-1, 1, n), rng.uniform(-3, 3, n)])
+    s0[1, :8] = rng.uniform(0.3, 1.2, 8)                       # massless carts: keep cos(theta) away from +-1 (D = m sin^2)
+    force = rng.uniform(-5, 5, n)
+    for dt, steps, w_scale in ((2e-3, 100, 1.0), (1e-2, 40, 1.0), (1e-3, 30, 25.0)):
+        st0 = s0.copy(); st0[3] *= w_scale
+        got, _, status = engine.cartpole_rk4(mc, m, L, g, st0[0], st0[1], st0[2], st0[3], force, n, 0.0, dt, steps, fp_mode=FP_CONTRACT)
+        ref = port.cartpole_rk4(mc, m, L, g, st0, force, 0.0, dt * steps, dt, nthreads=2)
+        # a massless cart whose pole swings through cos(theta) = +-1 hits the reference's singular-pivot throw: reported as
+        # a status, not compared
+        ok = status == ST_OK
+        assert ok[8:].all() and ok.sum() >= n - 8
+        assert rel_err(got[:, ok], ref[:, ok]).max() <= FINAL, (dt, steps, rel_err(got[:, ok], ref[:, ok]).max())
+    # closed loop, contract mode, saturating controller on large initial angles
+    K = np.tile(np.array([-3.0, 40.0, -4.0, 8.0])[:, None], (1, n))
+    st0 = s0.copy(); st0[1] = rng.uniform(-0.6, 0.6, n); st0[3] = 0.0
+    fin, stats, _, status = engine.cartpole_feedback_rk4(mc, m, L, g, st0[0], st0[1], st0[2], st0[3], K, n, 0.0, 0.002, 400,
+                                                         u_min=-20.0, u_max=20.0, saturate=True, fp_mode=FP_CONTRACT)
+    rfin, rstats = port.cartpole_feedback_rk4(mc, m, L, g, st0, K, None, -20.0, 20.0, 1, 0.0, 0.002, 400, nthreads=2)
+    ok = np.isfinite(rfin).all(axis=0) & (np.abs(rfin).max(axis=0) < 1e3)
+    assert ok.sum() > n // 2
+    assert rel_err(fin[:, ok], rfin[:, ok]).max() <= 1e-7 and rel_err(stats[:, ok], rstats[:, ok]).max() <= 1e-7
+
+
 # ------------------------------------------------------------------------------------------------ config 4
 @pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
 def test_rocket_rhs_golden(engine, fp):
