@@ -10,6 +10,7 @@
 // A warp iterates until its slowest lane has converged; finished lanes idle.
 #include "common.cuh"
 #include "dual.cuh"
+#include "trig.cuh"
 
 namespace {
 
@@ -26,6 +27,16 @@ __device__ __forceinline__ Real<S> frob(const Mat4<S>& M) {          // :140-148
 #pragma unroll
         for (int j = 0; j < N; ++j) sum = sum + M.a[i][j] * M.a[i][j];
     return r_sqrt(sum);
+}
+
+template <bool S>
+__device__ __forceinline__ Real<S> frob2(const Mat4<S>& M) {         // squared Frobenius norm, same summation order
+    Real<S> sum(0.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) sum = sum + M.a[i][j] * M.a[i][j];
+    return sum;
 }
 
 // one LQR<4,1>::solve; returns status, writes K[4] and (optionally) P
@@ -105,8 +116,14 @@ __device__ __forceinline__ int lqr4_solve(const Mat4<S>& A, const Real<S> (&B)[N
         }
         if (fabs(sden.v) < 1e-12) { status = SOPOT_B200_ST_SINGULAR; break; }               // the reference throws (:196-198)
         T Kd[N];
+        if constexpr (S) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) Kd[j] = g[j] / sden;
+            for (int j = 0; j < N; ++j) Kd[j] = g[j] / sden;
+        } else {
+            const T inv(sbtrig::rcp_fast(sden.v));                                          // |sden| >= 1e-12 checked above
+#pragma unroll
+            for (int j = 0; j < N; ++j) Kd[j] = g[j] * inv;
+        }
         Mat4<S> Pn;
 #pragma unroll
         for (int i = 0; i < N; ++i)
@@ -130,12 +147,21 @@ __device__ __forceinline__ int lqr4_solve(const Mat4<S>& A, const Real<S> (&B)[N
         for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int j = 0; j < N; ++j) diff.a[i][j] = Pn.a[i][j] - P.a[i][j];
-        const double change = frob(diff).v, p_norm = frob(Pn).v;
-        const double rel = (p_norm > 1e-10) ? (Real<S>(change) / Real<S>(p_norm)).v : change;
         P = Pn;
         iters = it + 1;
-        if (rel < tol || change < tol) status = 0;                                          // converged (:369)
-        else if (p_norm > 1e15 || change != change) status = -2;                            // diverged (:382)
+        if constexpr (S) {
+            const double change = frob(diff).v, p_norm = frob(Pn).v;
+            const double rel = (p_norm > 1e-10) ? (Real<S>(change) / Real<S>(p_norm)).v : change;
+            if (rel < tol || change < tol) status = 0;                                      // converged (:369)
+            else if (p_norm > 1e15 || change != change) status = -2;                        // diverged (:382)
+        } else {
+            // the same tests on the squared norms: two square roots and a division per iteration are the longest links
+            // of the dependent chain.  change / p_norm < tol  <=>  change^2 < tol^2 p_norm^2 (all quantities >= 0)
+            const double c2 = frob2(diff).v, p2 = frob2(Pn).v, tol2 = tol * tol;
+            const double rel2_lhs = c2, rel2_rhs = (p2 > 1e-20) ? tol2 * p2 : tol2;
+            if (rel2_lhs < rel2_rhs || c2 < tol2) status = 0;
+            else if (p2 > 1e30 || c2 != c2) status = -2;
+        }
     }
     if (status == SOPOT_B200_ST_SINGULAR) return status;
     if (status != 0) {                                                                      // :388-397
@@ -354,7 +380,8 @@ SB_EXPORT int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const d
     qr.R = R;
     if (P) {
         const unsigned grid = sb_grid_for(P, 128);
-        if (opts->fp_mode == SOPOT_B200_FP_STRICT)
+        // the contract kernel compares squared norms with tol^2: below 1e-150 that underflows, use the exact kernel
+        if (opts->fp_mode == SOPOT_B200_FP_STRICT || !(tol >= 1e-150))
             lqr4_kernel<true><<<grid, 128, 0, ctx->stream>>>((const double*)d_A, (const double*)d_B, P, qr, riccati_dt, (int)max_iter,
                                                              tol, (double*)d_K, (double*)d_P, (int32_t*)d_it, (int32_t*)d_st);
         else

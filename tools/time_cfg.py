@@ -63,6 +63,20 @@ elif cfg == "closed":
                                                      u_min=-50.0, u_max=50.0, saturate=True, mem=MEM_DEVICE, want_status=False,
                                                      want_stats=False, fp_mode=mode, sync=False, state_out=st), 2)
         print("closed loop %d x 2000 %s: %.3f ms  %.3e inst-steps/s  checksum %.12e" % (P, name, ms, P * 2000 / ms * 1e3, float(st.download().sum())))
+elif cfg == "lqr":
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 16
+    rng = np.random.default_rng(3)
+    plant = {k: eng.to_device(v) for k, v in dict(mc=rng.uniform(0.8, 1.5, P), m=rng.uniform(0.05, 0.2, P),
+                                                   L=rng.uniform(0.4, 0.8, P), g=np.full(P, 9.81)).items()}
+    dx, du = eng.to_device(np.zeros((4, P))), eng.to_device(np.zeros(P))
+    A, B, _ = eng.cartpole_linearize(plant["mc"], plant["m"], plant["L"], plant["g"], dx, du, P, mem=MEM_DEVICE, want_status=False)
+    K = eng.empty((4, P))
+    Q = np.diag([10.0, 100.0, 1.0, 10.0])
+    for mode, name in ((FP_CONTRACT, "contract"), (FP_STRICT, "strict")):
+        ms = timed(lambda: eng.lqr4_gain(A, B, P, Q, 0.01, mem=MEM_DEVICE, fp_mode=mode, K=K, want_iters=False, sync=False), 2)
+        _, _, iters, st = eng.lqr4_gain(A, B, P, Q, 0.01, mem=MEM_DEVICE, fp_mode=mode, K=K)
+        print("lqr4 %d %s: %.3f ms  %.3e gains/s  mean iterations %.2f  failed %d  checksum %.12e" %
+              (P, name, ms, P / ms * 1e3, float(iters.download().mean()), int(np.count_nonzero(st.download())), float(K.download().sum())))
 elif cfg == "ugrid":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
     ug = eng.ugrid_params(n, n, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5)
