@@ -88,12 +88,17 @@ __device__ __forceinline__ int rk4_step_any(typename Sys::template Inst<S>& in, 
 template <class Sys, class = void> struct sb_has_begin_step : std::false_type {};
 template <class Sys> struct sb_has_begin_step<Sys, std::void_t<decltype(Sys::HAS_BEGIN_STEP)>> : std::true_type {};
 
+// optional: Sys::MIN_BLOCKS_CONTRACT overrides Sys::MIN_BLOCKS for the FP_CONTRACT instantiation of the RK4 kernel (a system
+// whose contract-mode step needs fewer registers than its strict one)
+template <class Sys, class = void> struct sb_min_blocks_contract { static constexpr int value = Sys::MIN_BLOCKS; };
+template <class Sys> struct sb_min_blocks_contract<Sys, std::void_t<decltype(Sys::MIN_BLOCKS_CONTRACT)>> { static constexpr int value = Sys::MIN_BLOCKS_CONTRACT; };
+
 // IPT = instances per thread (Sys::IPT): IPT independent instances are advanced in lock-step by one
 // thread, which gives the scheduler IPT independent dependency chains per warp (FP64 latency hiding)
 // while per-system constants held in registers are shared.  Instance j of a thread is
 // (blockIdx.x*IPT + j)*blockDim.x + threadIdx.x, so every load and store stays fully coalesced.
 template <class Sys, bool S>
-__global__ void __launch_bounds__(Sys::BLOCK, Sys::MIN_BLOCKS)
+__global__ void __launch_bounds__(Sys::BLOCK, S ? Sys::MIN_BLOCKS : sb_min_blocks_contract<Sys>::value)
 rk4_ensemble_kernel(const typename Sys::DevParams P, const size_t n, const double t0, const StepConsts sc,
                     const size_t n_steps, const size_t store_every, double* __restrict__ state_out,
                     double* __restrict__ traj_out, int32_t* __restrict__ status) {
