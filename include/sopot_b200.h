@@ -53,7 +53,7 @@ enum { SOPOT_B200_MEM_DEVICE = 0, SOPOT_B200_MEM_HOST = 1 };
 enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
 /* grid2d: run the four RK stages as four kernels with one 1-row halo exchange each (the literal per-stage
  * schedule) instead of the default fused step kernel with one 4-row halo exchange per step */
-enum { SOPOT_B200_FLAG_GRID_PER_STAGE = 1 };
+enum { SOPOT_B200_FLAG_GRID_PER_STAGE = 1, SOPOT_B200_FLAG_UGRID_STAGE_PAIRS = 2 };
 enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2,
        SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */,
        SOPOT_B200_ST_NOT_CONVERGED = 8 /* LQR::solve returned false (Riccati iteration diverged) */ };
@@ -281,6 +281,10 @@ typedef struct {
 int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, uint32_t mem, double* state);
 int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, const sopot_b200_rk4_opts* opts,
                          const double* state, double* out);
+/* RK4: one kernel per stage (816 B per mass and step, 0.9 of the HBM roofline in contract mode).  With
+ * SOPOT_B200_FLAG_UGRID_STAGE_PAIRS in opts->flags (single rank) two stages run per kernel on a shared-memory tile with a
+ * 2-cell halo (336 B per mass and step); bit-identical in strict mode, measured slower on B200 (barrier / latency bound),
+ * kept as an option. */
 int sopot_b200_ugrid_rk4(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, double dt, size_t n_steps,
                          const sopot_b200_rk4_opts* opts, double* state /* in/out */);
 /* the three integrators of the reference's Grid2DSimulator (wasm/wasm_grid2d.cpp:286-413): RK4 as above; symplectic Euler

@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
+FLAG_UGRID_STAGE_PAIRS = 2
 ABI_VERSION = 3
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
@@ -555,10 +556,11 @@ class Engine:
         self.sync()
         return out
 
-    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, integrator=0):
-        """integrator: 0 RK4, 1 symplectic Euler, 2 velocity Verlet (the reference Grid2DSimulator's three)."""
+    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, integrator=0, stage_pairs=False):
+        """integrator: 0 RK4, 1 symplectic Euler, 2 velocity Verlet (the reference Grid2DSimulator's three).
+        stage_pairs: RK4 with two stages per kernel instead of the default one kernel per stage (single rank, opt-in)."""
         mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
-        opts = RK4Opts(mem, fp_mode, 0, 0, 0)
+        opts = RK4Opts(mem, fp_mode, 0, 0, FLAG_UGRID_STAGE_PAIRS if stage_pairs else 0)
         self._ck(self.lib.sopot_b200_ugrid_integrate(self.ctx, byref(g), integrator, dt, n_steps, byref(opts), _ptr(state)))
         if sync:
             self.sync()

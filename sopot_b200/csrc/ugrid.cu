@@ -102,30 +102,37 @@ __device__ __forceinline__ Body body_at(const UGridDev& g, const UIn& in, const 
     return load_body_t<S>(in.slab, (size_t)lrow * g.cols + col);
 }
 
-template <bool S>
-__device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in, const size_t row /*local*/, const size_t col,
-                                                Real<S> (&d)[6], Body& self) {
+// PointMass2D derivative of the mass at GLOBAL (grow, col) from its own body P and a neighbour accessor nb(drow, dcol):
+// springs in the reference's visiting order -- left (as mass 1), right (as mass 0), upper (as mass 1), lower (as mass 0)
+template <bool S, class Nb>
+__device__ __forceinline__ void derivative_from(const UGridDev& g, const Body& P, const size_t grow, const size_t col, Nb nb,
+                                                Real<S> (&d)[6]) {
     using R = Real<S>;
-    const size_t grow = g.row_begin + row;
-    const long lr = (long)row;
-    const Body P = body_at<S>(g, in, lr, col);
-    self = P;
     R Fx(0.0), Fy(0.0), Tq(0.0), fx, fy, tq;
     if constexpr (S) {
-        if (col > 0) { spring_ft<S>(g, body_at<S>(g, in, lr, col - 1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (col + 1 < g.cols) { spring_ft<S>(g, P, body_at<S>(g, in, lr, col + 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow > 0) { spring_ft<S>(g, body_at<S>(g, in, lr - 1, col), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow + 1 < g.rows) { spring_ft<S>(g, P, body_at<S>(g, in, lr + 1, col), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (col > 0) { spring_ft<S>(g, nb(0, -1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (col + 1 < g.cols) { spring_ft<S>(g, P, nb(0, 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow > 0) { spring_ft<S>(g, nb(-1, 0), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow + 1 < g.rows) { spring_ft<S>(g, P, nb(1, 0), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
     } else {
-        if (col > 0) { spring_ft_fast(g, body_at<S>(g, in, lr, col - 1), P, g.cha0, g.sha0, g.cha1, g.sha1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (col + 1 < g.cols) { spring_ft_fast(g, P, body_at<S>(g, in, lr, col + 1), g.cha0, g.sha0, g.cha1, g.sha1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow > 0) { spring_ft_fast(g, body_at<S>(g, in, lr - 1, col), P, g.cva0, g.sva0, g.cva1, g.sva1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow + 1 < g.rows) { spring_ft_fast(g, P, body_at<S>(g, in, lr + 1, col), g.cva0, g.sva0, g.cva1, g.sva1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (col > 0) { spring_ft_fast(g, nb(0, -1), P, g.cha0, g.sha0, g.cha1, g.sha1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (col + 1 < g.cols) { spring_ft_fast(g, P, nb(0, 1), g.cha0, g.sha0, g.cha1, g.sha1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow > 0) { spring_ft_fast(g, nb(-1, 0), P, g.cva0, g.sva0, g.cva1, g.sva1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (grow + 1 < g.rows) { spring_ft_fast(g, P, nb(1, 0), g.cva0, g.sva0, g.cva1, g.sva1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
     }
     d[0] = R(P.vx); d[1] = R(P.vy);
     d[4] = R(P.om);
     if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); d[5] = Tq / R(g.inertia); }
     else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); d[5] = Tq * R(g.inv_inertia); }
+}
+
+template <bool S>
+__device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in, const size_t row /*local*/, const size_t col,
+                                                Real<S> (&d)[6], Body& self) {
+    const long lr = (long)row;
+    self = body_at<S>(g, in, lr, col);
+    derivative_from<S>(g, self, g.row_begin + row, col,
+                       [&](int dr, int dc) { return body_at<S>(g, in, lr + dr, (size_t)((long)col + dc)); }, d);
 }
 
 // STAGE 0: out <- f(in);  1..4: the RK4 stages with S-accumulator (see ensemble.cuh / grid2d.cu)
@@ -200,6 +207,135 @@ ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict
         store6(acc + off, a);
         store6(out + off, o);
     }
+}
+
+// ---- two RK4 stages per kernel (single rank) ----------------------------------------------------------------------------
+// The per-stage schedule moves 816 B per mass and step through HBM (every stage re-reads y and the accumulator).  Here a
+// CTA loads a 32 x 8 tile with a 2-cell halo into shared memory (SoA: x, y, vx, vy, theta, omega and, in contract mode,
+// sin/cos theta computed once per body), evaluates the first stage of the pair on the tile grown by one cell, keeps the
+// intermediate state in a second shared tile, and evaluates the second stage on the interior:
+//   FIRST  (stages 1+2): in = y            -> acc = k1 + 2 k2,  out = y + k2/2                       144 B per mass
+//   !FIRST (stages 3+4): in = y + k2/2, y, acc -> out = y + ((acc + 2 k3) + k4)/6  (a fresh buffer)   192 B per mass
+// 336 B per mass and step; the ring of the grown tile is evaluated redundantly (1.33x on one of the two stages).  Every
+// operation and its order equal the per-stage kernels', so the strict results are bit-identical to that schedule.
+// MEASURED (4096^2, B200): 2.43 ms per step in contract mode against 2.30 ms for the per-stage schedule, 6.8 against 3.9 ms in
+// strict mode -- the per-stage kernels already run at 0.9 of the HBM roofline, while this kernel stalls on its two barriers,
+// the exposed tile load (long_scoreboard) and the three warps that evaluate the ring; FP64 pipe 45 %, 24 warps per SM
+// (profiles/r1_ugrid_stage_pairs.txt).  Hence opt-in (SOPOT_B200_FLAG_UGRID_STAGE_PAIRS); a winning version needs every
+// spring evaluated once and the ring spread over all warps, as grid_rk4_fused does for the 4-state grid.
+#ifndef SB_UGRID_PAIR_MINB
+#define SB_UGRID_PAIR_MINB 1
+#endif
+constexpr int kPairTX = 32, kPairTY = 8, kPairW = kPairTX + 4, kPairH = kPairTY + 4, kPairCells = kPairW * kPairH;
+
+struct PairTile {
+    double* p;                                                    // [8][kPairCells]
+    __device__ __forceinline__ Body get(int c) const {
+        return Body{p[c], p[kPairCells + c], p[2 * kPairCells + c], p[3 * kPairCells + c], p[4 * kPairCells + c], p[5 * kPairCells + c],
+                    p[6 * kPairCells + c], p[7 * kPairCells + c]};
+    }
+    __device__ __forceinline__ void put(int c, const Body& b) const {
+        p[c] = b.x; p[kPairCells + c] = b.y; p[2 * kPairCells + c] = b.vx; p[3 * kPairCells + c] = b.vy; p[4 * kPairCells + c] = b.th;
+        p[5 * kPairCells + c] = b.om; p[6 * kPairCells + c] = b.s; p[7 * kPairCells + c] = b.c;
+    }
+};
+
+template <bool S, bool FIRST>
+__global__ void __launch_bounds__(kPairTX * kPairTY, SB_UGRID_PAIR_MINB)
+ugrid_pair(const UGridDev g, const double* __restrict__ in, const double* __restrict__ ybase, const double dt_,
+           double* __restrict__ acc, double* __restrict__ out) {
+    using R = Real<S>;
+    extern __shared__ double s_pair[];
+    const PairTile T1{s_pair}, T2{s_pair + 8 * kPairCells};
+    const int tid = threadIdx.x;
+    const long row0 = (long)blockIdx.y * kPairTY - 2, col0 = (long)blockIdx.x * kPairTX - 2;
+    const auto in_grid = [&](long r, long c) { return r >= 0 && c >= 0 && (size_t)r < g.rows && (size_t)c < g.cols; };
+    for (int c = tid; c < kPairCells; c += kPairTX * kPairTY) {
+        const long r = row0 + c / kPairW, cc = col0 + c % kPairW;
+        if (in_grid(r, cc)) T1.put(c, load_body_t<S>(in, (size_t)r * g.cols + (size_t)cc));
+    }
+    __syncthreads();
+    const R dt(dt_);
+    // first stage of the pair on one cell of the grown tile: k = dt f(T1), intermediate state -> T2
+    const auto stage_a = [&](const int c, R (&k)[6], Body& base) {
+        const long r = row0 + c / kPairW, cc = col0 + c % kPairW;
+        const Body self = T1.get(c);
+        R d[6];
+        derivative_from<S>(g, self, (size_t)r, (size_t)cc, [&](int dr, int dc) { return T1.get(c + dr * kPairW + dc); }, d);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) k[j] = d[j] * dt;
+        if constexpr (FIRST) base = self;                                  // stage 2 reads y + k1/2
+        else base = load_body(ybase, (size_t)r * g.cols + (size_t)cc);     // stage 4 reads y + k3
+        const R h(FIRST ? 0.5 : 1.0);
+        Body nb = base;
+        if constexpr (FIRST) {
+            nb.x = (R(base.x) + h * k[0]).v; nb.y = (R(base.y) + h * k[1]).v; nb.vx = (R(base.vx) + h * k[2]).v;
+            nb.vy = (R(base.vy) + h * k[3]).v; nb.th = (R(base.th) + h * k[4]).v; nb.om = (R(base.om) + h * k[5]).v;
+        } else {
+            nb.x = (R(base.x) + k[0]).v; nb.y = (R(base.y) + k[1]).v; nb.vx = (R(base.vx) + k[2]).v;
+            nb.vy = (R(base.vy) + k[3]).v; nb.th = (R(base.th) + k[4]).v; nb.om = (R(base.om) + k[5]).v;
+        }
+        if constexpr (!S) sbtrig::sincos(nb.th, nb.s, nb.c);
+        T2.put(c, nb);
+    };
+    // the thread's own interior cell (its k stays in registers), then the ring of the grown tile spread over the threads
+    const int own = (2 + tid / kPairTX) * kPairW + 2 + tid % kPairTX;
+    const long orow = row0 + own / kPairW, ocol = col0 + own % kPairW;
+    const bool own_valid = in_grid(orow, ocol);
+    R ka[6];
+    Body base;
+    if (own_valid) stage_a(own, ka, base);
+    constexpr int kRing = (kPairTX + 2) * (kPairTY + 2) - kPairTX * kPairTY;   // 84 cells
+    if (tid < kRing) {
+        // ring enumeration: top row, bottom row (kPairTX + 2 each), then the left and right columns
+        int rr, rc;
+        if (tid < kPairTX + 2) { rr = 1; rc = 1 + tid; }
+        else if (tid < 2 * (kPairTX + 2)) { rr = kPairTY + 2; rc = 1 + tid - (kPairTX + 2); }
+        else { const int t = tid - 2 * (kPairTX + 2); rr = 2 + t / 2; rc = (t & 1) ? kPairTX + 2 : 1; }
+        const int c = rr * kPairW + rc;
+        if (in_grid(row0 + rr, col0 + rc)) { R kr[6]; Body b; stage_a(c, kr, b); }
+    }
+    __syncthreads();
+    if (!own_valid) return;
+    // second stage of the pair on the interior
+    R d[6];
+    derivative_from<S>(g, T2.get(own), (size_t)orow, (size_t)ocol, [&](int dr, int dc) { return T2.get(own + dr * kPairW + dc); }, d);
+    R kb[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) kb[j] = d[j] * dt;
+    const size_t off = ((size_t)orow * g.cols + (size_t)ocol) * 6;
+    const R yb[6] = {R(base.x), R(base.y), R(base.vx), R(base.vy), R(base.th), R(base.om)};
+    double o[6];
+    if constexpr (FIRST) {
+        double a[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { a[j] = (ka[j] + 2.0 * kb[j]).v; o[j] = (yb[j] + 0.5 * kb[j]).v; }
+        store6(acc + off, a);
+        store6(out + off, o);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const R s3 = R(acc[off + j]) + 2.0 * ka[j];
+            o[j] = (yb[j] + r_div_const(s3 + kb[j], 6.0)).v;
+        }
+        store6(out + off, o);
+    }
+}
+
+template <bool FIRST>
+int launch_upair(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const double* in, const double* ybase, double dt, double* acc,
+                 double* out) {
+    const dim3 grid((unsigned)((g.cols + kPairTX - 1) / kPairTX), (unsigned)((g.rows + kPairTY - 1) / kPairTY));
+    constexpr size_t smem = 2 * 8 * kPairCells * sizeof(double);
+    if (strict) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(ugrid_pair<true, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ugrid_pair<true, FIRST><<<grid, kPairTX * kPairTY, smem, ctx->stream>>>(g, in, ybase, dt, acc, out);
+    } else {
+        SB_CUDA(ctx, cudaFuncSetAttribute(ugrid_pair<false, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ugrid_pair<false, FIRST><<<grid, kPairTX * kPairTY, smem, ctx->stream>>>(g, in, ybase, dt, acc, out);
+    }
+    ctx->launches++;
+    return SOPOT_B200_OK;
 }
 
 __global__ void ugrid_init_kernel(const size_t rows, const size_t cols, const size_t row_begin, const double spacing,
@@ -328,7 +464,18 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
     double* gh = B + n;                           // ghost rows: above / below for each of the three stencil inputs
     const UIn in_y{y, gh, gh + row_elems}, in_A{A, gh + 2 * row_elems, gh + 3 * row_elems}, in_B{B, gh + 4 * row_elems, gh + 5 * row_elems};
     if ((rc = ugrid_halo(ctx, g, in_y))) return rc;
-    if (integrator == SOPOT_B200_INTEGRATOR_RK4) {
+    if (integrator == SOPOT_B200_INTEGRATOR_RK4 && ctx->nranks == 1 && (opts->flags & SOPOT_B200_FLAG_UGRID_STAGE_PAIRS)) {
+        // opt-in: two stages per kernel (336 instead of 816 B per mass and step); the new state goes to a fresh buffer because the
+        // second kernel still reads the old one for the ring cells of neighbouring tiles
+        double* cur = y;
+        double* nxt = A;
+        for (size_t step = 0; step < n_steps; ++step) {
+            if ((rc = launch_upair<true>(ctx, strict, g, cur, nullptr, dt, acc, B))) return rc;
+            if ((rc = launch_upair<false>(ctx, strict, g, B, cur, dt, acc, nxt))) return rc;
+            double* t = cur; cur = nxt; nxt = t;
+        }
+        if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (integrator == SOPOT_B200_INTEGRATOR_RK4) {
         for (size_t step = 0; step < n_steps; ++step) {
             launch_ustage<1>(ctx, strict, g, in_y, dt, y, acc, A);
             if ((rc = ugrid_halo(ctx, g, in_A))) return rc;

@@ -567,6 +567,30 @@ def test_unified_grid_integrators(engine, port):
         engine.ugrid_rk4(gp, 1e-3, 1, st.copy(), integrator=9)
 
 
+@pytest.mark.parametrize("rows,cols", [(2, 2), (9, 31), (8, 32), (17, 65), (70, 100), (129, 64)])
+def test_unified_grid_stage_pairs_equal_per_stage_schedule(engine, port, rows, cols):
+    """RK4 with two stages per kernel (shared-memory tile + 2-cell halo, opt-in) against the default per-stage
+    schedule: bit-identical in strict mode, within tolerance in contract mode (FMA contraction may differ), and both
+    against the oracle; tile-edge sizes (one short of / exactly / one past a 32 x 8 tile), odd and even step counts."""
+    prm = _ugrid_prm()["repel" if rows % 2 else "wasm"]
+    gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
+    s0 = engine.ugrid_initial_state(gp)
+    rng = np.random.default_rng(rows * 7 + cols)
+    st = s0 + rng.normal(0, 0.02, s0.shape); st[:, 4] = rng.normal(0, 0.3, rows * cols); st[:, 5] = rng.normal(0, 0.3, rows * cols)
+    for steps in (1, 4):
+        ref = port.ugrid(rows, cols, prm, st, 1e-3, steps, "rk4")
+        a = engine.ugrid_rk4(gp, 1e-3, steps, st.copy(), fp_mode=FP_STRICT, stage_pairs=True)
+        b = engine.ugrid_rk4(gp, 1e-3, steps, st.copy(), fp_mode=FP_STRICT)
+        assert np.array_equal(a, b)
+        assert rel_err(a.ravel(), ref.ravel()).max() <= FINAL
+        c = engine.ugrid_rk4(gp, 1e-3, steps, st.copy(), fp_mode=FP_CONTRACT, stage_pairs=True)
+        d = engine.ugrid_rk4(gp, 1e-3, steps, st.copy(), fp_mode=FP_CONTRACT)
+        assert rel_err(c.ravel(), ref.ravel()).max() <= FINAL and rel_err(d.ravel(), ref.ravel()).max() <= FINAL
+        dev = engine.to_device(st)
+        engine.ugrid_rk4(gp, 1e-3, steps, dev, fp_mode=FP_STRICT, stage_pairs=True)
+        assert np.array_equal(dev.download(), a)
+
+
 def test_unified_grid_medium_vs_oracle(engine, port):
     """Sizes the templated reference is not instantiated for: against the runtime-sized oracle; device-pointer path; a rest
     grid whose rest length equals the attachment distance stays at rest exactly."""

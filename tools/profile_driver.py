@@ -49,6 +49,12 @@ elif cfg == "rocket_full":                       # the whole 30 s flight (88 % o
     for _ in range(reps):
         eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, 3000, mem=MEM_DEVICE, want_status=False,
                        state_out=st, stats_out=stats)
+elif cfg in ("ugrid", "ugrid_pairs"):
+    n = 4096
+    ug = eng.ugrid_params(n, n, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5)
+    state = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
+    for _ in range(reps):
+        eng.ugrid_rk4(ug, 1e-3, 2, state, fp_mode=FP_CONTRACT, stage_pairs=cfg == "ugrid_pairs")
 elif cfg == "lqr":
     P = 1 << 14
     rng = np.random.default_rng(3)

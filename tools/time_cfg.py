@@ -85,5 +85,8 @@ elif cfg == "ugrid":
             state = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
             ms = timed(lambda: eng.ugrid_rk4(ug, 1e-3, 6, state, fp_mode=mode, sync=False, integrator=integ), 2) / 6
             print("ugrid %d^2 %s %s: %.3f ms/step  %.3e mass-steps/s" % (n, name, iname, ms, n * n / ms * 1e3))
+            if integ == 0:
+                ms = timed(lambda: eng.ugrid_rk4(ug, 1e-3, 6, state, fp_mode=mode, sync=False, stage_pairs=True), 2) / 6
+                print("ugrid %d^2 %s rk4 stage pairs: %.3f ms/step  %.3e mass-steps/s" % (n, name, ms, n * n / ms * 1e3))
             state.free()
 eng.close()
