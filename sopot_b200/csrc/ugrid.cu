@@ -224,7 +224,7 @@ ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict
 // (profiles/r1_ugrid_stage_pairs.txt).  Hence opt-in (SOPOT_B200_FLAG_UGRID_STAGE_PAIRS); a winning version needs every
 // spring evaluated once and the ring spread over all warps, as grid_rk4_fused does for the 4-state grid.
 #ifndef SB_UGRID_PAIR_MINB
-#define SB_UGRID_PAIR_MINB 1
+#define SB_UGRID_PAIR_MINB 3
 #endif
 constexpr int kPairTX = 32, kPairTY = 8, kPairW = kPairTX + 4, kPairH = kPairTY + 4, kPairCells = kPairW * kPairH;
 
