@@ -23,6 +23,7 @@
 // ghost rows (above / below the slab) that are filled from the neighbouring ranks with
 // ncclSend/ncclRecv in one group after the producing stage kernel.
 #include "common.cuh"
+#include <cstdlib>
 #include "nccl_api.h"
 #include "trig.cuh"
 
@@ -346,14 +347,18 @@ __device__ __forceinline__ void fused_step_body(const GridDev& g, const long lon
 
 template <bool S, int TOPO, int TX, int TY>
 __global__ void __launch_bounds__(TX * TY, 2)
-grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __restrict__ y_out) {
+grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __restrict__ y_out, const unsigned ty_first,
+               const unsigned ty_stride) {
     using T = FusedTile<TX, TY, TOPO>;
     extern __shared__ double fused_smem[];
     double* A = fused_smem;
     double* B = A + 4 * T::CELLS;
     double* F = B + 4 * T::CELLS;
     // GLOBAL grid coordinates of cell (0, 0) of the shared-memory tile
-    const long long r0 = (long long)g.row_begin + (long long)blockIdx.y * TY - T::H;
+    // tile row of this CTA: ty_first + blockIdx.y * ty_stride (a launch covers all tile rows, only the interior ones, or --
+    // with stride = last tile row -- the two boundary ones: see grid_rk4_fused_run)
+    const unsigned tile_row = ty_first + blockIdx.y * ty_stride;
+    const long long r0 = (long long)g.row_begin + (long long)tile_row * TY - T::H;
     const long long c0 = (long long)blockIdx.x * TX - T::H;
     for (int idx = threadIdx.x; idx < T::CELLS; idx += T::THREADS) {
         const int r = idx / T::W, c = idx % T::W;
@@ -437,20 +442,21 @@ void launch_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, int
 
 // exchange the first / last slab row of `buf` into the neighbours' ghost rows (and receive ours)
 int halo_exchange(sopot_b200_ctx* ctx, const GridDev& g, const double* buf, double* ghost_top, double* ghost_bot,
-                  const size_t nrows = 1) {
+                  const size_t nrows = 1, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
     if (ctx->nranks == 1) return SOPOT_B200_OK;
     const size_t row_elems = g.cols * 4 * nrows;      // nrows boundary rows are contiguous in the row-major slab
     const bool up = g.row_begin > 0, down = g.row_begin + g.rows_local < g.rows;
     const NcclApi* n = ctx->nccl;
     SB_NCCL(ctx, n->GroupStart());
     if (up) {
-        SB_NCCL(ctx, n->Send(buf, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
-        SB_NCCL(ctx, n->Recv(ghost_top, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+        SB_NCCL(ctx, n->Send(buf, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, st));
+        SB_NCCL(ctx, n->Recv(ghost_top, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, st));
     }
     if (down) {
         SB_NCCL(ctx, n->Send(buf + (g.rows_local - nrows) * g.cols * 4, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1,
-                             ctx->nccl_comm, ctx->stream));
-        SB_NCCL(ctx, n->Recv(ghost_bot, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+                             ctx->nccl_comm, st));
+        SB_NCCL(ctx, n->Recv(ghost_bot, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, st));
     }
     SB_NCCL(ctx, n->GroupEnd());
     return SOPOT_B200_OK;
@@ -459,19 +465,39 @@ int halo_exchange(sopot_b200_ctx* ctx, const GridDev& g, const double* buf, doub
 // fused schedule: per step one 4-row halo exchange (multi-rank) and one kernel, y ping-pongs with a scratch slab
 constexpr int kFusedTX = 32, kFusedTY = 16;
 
+// tile rows [ty_first, ty_first + n_ty * ty_stride) by steps of ty_stride, on `st`
 template <bool S, int TOPO>
-int launch_fused(sopot_b200_ctx* ctx, const GridDev& g, const StepIn& in, double dt, double* y_out) {
+int launch_fused(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const StepIn& in, double dt, double* y_out, unsigned ty_first,
+                 unsigned n_ty, unsigned ty_stride) {
     using T = FusedTile<kFusedTX, kFusedTY, TOPO>;
     auto kern = grid_rk4_fused<S, TOPO, kFusedTX, kFusedTY>;
     // (a function attribute belongs to the current device: set it on every launch rather than caching a flag that a
     // second context on another GPU of the same process would inherit)
     SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-    const dim3 grid((unsigned)((g.cols + kFusedTX - 1) / kFusedTX), (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY));
-    kern<<<grid, T::THREADS, T::SMEM, ctx->stream>>>(g, in, dt, y_out);
+    const dim3 grid((unsigned)((g.cols + kFusedTX - 1) / kFusedTX), n_ty);
+    kern<<<grid, T::THREADS, T::SMEM, st>>>(g, in, dt, y_out, ty_first, ty_stride);
     SB_CHECK_LAUNCH(ctx);
     return SOPOT_B200_OK;
 }
 
+int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
+                     double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride) {
+#define SB_FUSED_CASE(SS, TT) return launch_fused<SS, TT>(ctx, st, g, in, dt, y_out, ty_first, n_ty, ty_stride)
+    if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
+    else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
+#undef SB_FUSED_CASE
+}
+
+// One rank: one launch per step over all tiles.  Several ranks with slabs of more than 48 rows: the tiles that touch the
+// slab boundary run on a second stream behind the halo exchange, the interior tiles on the main stream beside them --
+//   copy stream:   wait I(s-1) -> ncclSend/Recv of the 4 boundary rows of the current state -> B(s) -> event
+//   main stream:   wait B(s-1) -> I(s) -> event
+// B = the first tile row and the last TWO (the last one may hold fewer than 4 rows, so the one before it can still reach
+// the ghost rows and produce rows a neighbour needs), I = the tile rows between them.  B(s) and I(s) read the same state
+// and write disjoint rows; the exchange only moves rows that B(s-1) wrote (same stream), and the ghost rows are read by
+// B only.  The exchange and the boundary tiles hide behind the interior tiles; thinner slabs exchange first and launch
+// once, as before.  (A first version with all kernels on one stream, B before I, was SLOWER than no overlap at all --
+// 2.48 vs 2.37 ms per step on 2 GPUs: three partial waves instead of one launch cost more than the 30 us exchange.)
 int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool strict, double dt, size_t n_steps, double* y) {
     const size_t slab = g.rows_local * g.cols * 4, ghost = 4 * g.cols * 4;
     if (ctx->nranks > 1 && g.rows_local < 4)
@@ -484,15 +510,32 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
     double* g_bot = g_top + ghost;
     double* cur = y;
     double* nxt = alt;
-    for (size_t step = 0; step < n_steps; ++step) {
-        if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4))) return rc;
-        const StepIn in{cur, g_top, g_bot};
-#define SB_FUSED_CASE(SS, TT) rc = launch_fused<SS, TT>(ctx, g, in, dt, nxt)
-        if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
-        else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
-#undef SB_FUSED_CASE
-        if (rc) return rc;
-        double* t = cur; cur = nxt; nxt = t;
+    const unsigned nty = (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY);
+    // all ranks must take the same branch (slabs differ by at most one row): decide on the smallest slab
+    const bool overlap = ctx->nranks > 1 && (g.rows / (size_t)ctx->nranks) > 3 * (size_t)kFusedTY && !(std::getenv("SOPOT_B200_NO_HALO_OVERLAP"));
+    if (!overlap) {
+        for (size_t step = 0; step < n_steps; ++step) {
+            if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4))) return rc;
+            if ((rc = launch_fused_any(ctx, ctx->stream, strict, topo, g, StepIn{cur, g_top, g_bot}, dt, nxt, 0, nty, 1))) return rc;
+            double* t = cur; cur = nxt; nxt = t;
+        }
+    } else {
+        cudaStream_t main_s = ctx->stream, copy_s = ctx->copy_stream;
+        cudaEvent_t ev_i = ctx->ev_a, ev_b = ctx->ev_b;           // "interior tiles done" (main), "boundary tiles done" (copy)
+        SB_CUDA(ctx, cudaEventRecord(ev_i, main_s));              // whatever produced `cur` counts as I(-1)
+        for (size_t step = 0; step < n_steps; ++step) {
+            const StepIn in{cur, g_top, g_bot};
+            if (step > 0) SB_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_b, 0));     // I(s) reads and overwrites rows B(s-1) used
+            SB_CUDA(ctx, cudaStreamWaitEvent(copy_s, ev_i, 0));                   // B(s) reads rows I(s-1) wrote
+            if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4, copy_s))) return rc;
+            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, 0, 1, 1))) return rc;                // B(s): top
+            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, nty - 2, 2, 1))) return rc;          //       bottom
+            SB_CUDA(ctx, cudaEventRecord(ev_b, copy_s));
+            if ((rc = launch_fused_any(ctx, main_s, strict, topo, g, in, dt, nxt, 1, nty - 3, 1))) return rc;          // I(s)
+            SB_CUDA(ctx, cudaEventRecord(ev_i, main_s));
+            double* t = cur; cur = nxt; nxt = t;
+        }
+        SB_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_b, 0));       // the caller's stream sees the whole new state
     }
     if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, slab * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return SOPOT_B200_OK;

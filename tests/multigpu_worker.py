@@ -35,7 +35,10 @@ for r in range(6):
 
 # (2) grid2d slabs vs single domain (computed redundantly on every rank with a private single-rank engine)
 p = W.GRID2D_PARAMS
-for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2, 3), (4 * world + 1, 70, 0, 5), (1024, 1024, 0, 4)):
+# (slabs of more than 48 rows take the schedule that overlaps the halo exchange with the interior tiles; 49-row slabs end in a
+#  one-row tile, the case where the last TWO tile rows touch the ghost rows)
+for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2, 3), (4 * world + 1, 70, 0, 5), (1024, 1024, 0, 4),
+                                (49 * world + 1, 200, 0, 7), (64 * world + 5, 96, 1, 3), (51 * world, 40, 2, 2)):
     s0 = W.grid2d_state(rows, cols, p["spacing"]).reshape(rows, cols, 4)
     solo = Engine(local)
     ref = solo.grid2d_rk4(solo.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], steps,
