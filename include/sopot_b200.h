@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SOPOT_B200_ABI_VERSION 3
+#define SOPOT_B200_ABI_VERSION 4
 
 enum {
     SOPOT_B200_OK = 0,
@@ -277,6 +277,13 @@ typedef struct {
     double stiffness, rest_length, damping, min_distance, repulsion_stiffness;
     double h_attach0, h_attach1, v_attach0, v_attach1;
     size_t row_begin, rows_local;   /* this rank's slab of rows; rows_local == 0: the whole grid (single rank) */
+    /* topology 1 = makeTriangleGridTopology (constexpr_topology.hpp:436-505, the simulator's "triangle" grid type,
+     * wasm/wasm_grid2d.cpp:466-525): after the horizontal and the vertical springs every cell adds its main diagonal
+     * (r,c)->(r+1,c+1) and its anti-diagonal (r,c+1)->(r+1,c), with their own rest length and attachment angles
+     * (the wrapper uses sqrt(2) * spacing and pi/4, -3pi/4, 3pi/4, -pi/4).  0 = makeGridTopology. */
+    int topology;
+    double diag_rest_length;
+    double d_attach0, d_attach1, a_attach0, a_attach1;
 } sopot_b200_ugrid_params;
 int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, uint32_t mem, double* state);
 int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* g, const sopot_b200_rk4_opts* opts,

@@ -194,8 +194,10 @@ class Checker:
 
     # ---------------- section 8f-2: unified 6-state grid ----------------
     def ugrid(self, rows, cols, prm, state=None, dt=0.0, n_steps=0, mode="rhs"):
-        """prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1."""
-        prm = _f64(prm).reshape(12)
+        """prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1
+        [, topology (0 quad / 1 triangle), diagonal rest length, main-diagonal attach 0/1, anti-diagonal attach 0/1]."""
+        prm = _f64(prm).reshape(-1)
+        prm = np.concatenate([prm, np.zeros(18 - prm.size)])
         n = rows * cols * 6
         out = np.empty(n)
         st = None if state is None else _f64(state).reshape(n)

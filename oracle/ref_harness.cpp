@@ -88,12 +88,16 @@ constexpr auto t4x5 = sopot::unified::makeGridTopology<4, 5>();
 constexpr auto t2x7 = sopot::unified::makeGridTopology<2, 7>();
 constexpr auto t6x6 = sopot::unified::makeGridTopology<6, 6>();
 constexpr auto t10x10 = sopot::unified::makeGridTopology<10, 10>();
+constexpr auto x3x3 = sopot::unified::makeTriangleGridTopology<3, 3>();
+constexpr auto x4x5 = sopot::unified::makeTriangleGridTopology<4, 5>();
+constexpr auto x2x7 = sopot::unified::makeTriangleGridTopology<2, 7>();
+constexpr auto x6x6 = sopot::unified::makeTriangleGridTopology<6, 6>();
 }  // namespace ugrid_topo
 
 // populate exactly as Grid2DSimulator::createQuadSystem does (wasm/wasm_grid2d.cpp:417-462): masses row-major with radius,
 // horizontal springs row-major, then vertical springs; attachment angles per orientation
 template <auto& Topology>
-static int ugrid_run(size_t rows, size_t cols, const double* prm /*12*/, double dt, size_t n_steps, const double* state_in, double* out,
+static int ugrid_run(size_t rows, size_t cols, const double* prm /*18*/, double dt, size_t n_steps, const double* state_in, double* out,
                      int mode /*0 rhs, 1 rk4, 2 initial state*/) {
     using namespace sopot::unified;
     ValidatedSystem<double, Topology, PointMass2D<double>, Spring2D<double>> sys;
@@ -106,6 +110,12 @@ static int ugrid_run(size_t rows, size_t cols, const double* prm /*12*/, double 
         for (size_t cc = 0; cc + 1 < cols; ++cc) sb.add(Spring2D<double>(k, L0, c, mind, krep, prm[8], prm[9]));
     for (size_t r = 0; r + 1 < rows; ++r)
         for (size_t cc = 0; cc < cols; ++cc) sb.add(Spring2D<double>(k, L0, c, mind, krep, prm[10], prm[11]));
+    if (prm[12] == 1.0)      // createTriangleSystem, wasm/wasm_grid2d.cpp:508-524: per cell the main diagonal, then the anti-diagonal
+        for (size_t r = 0; r + 1 < rows; ++r)
+            for (size_t cc = 0; cc + 1 < cols; ++cc) {
+                sb.add(Spring2D<double>(k, prm[13], c, mind, krep, prm[14], prm[15]));
+                sb.add(Spring2D<double>(k, prm[13], c, mind, krep, prm[16], prm[17]));
+            }
     const size_t n = sys.getStateDimension();
     if (n != rows * cols * 6) return 3;
     if (mode == 2) { auto s0 = sys.getInitialState(); std::copy(s0.begin(), s0.end(), out); return 0; }
@@ -471,9 +481,14 @@ int ref_cartn_feedback_rk4(int n_links, size_t n, const double* mc, const double
     return 0;
 }
 
-// prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0, h_attach1, v_attach0, v_attach1
+// prm[18]: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0, h_attach1, v_attach0,
+// v_attach1, topology (0 quad / 1 triangle), diagonal rest length, main-diagonal attach 0/1, anti-diagonal attach 0/1
 int ref_ugrid(size_t rows, size_t cols, const double* prm, double dt, size_t n_steps, const double* state_in, double* out, int mode) {
 #define UG_CASE(R, C, T) if (rows == R && cols == C) return ugrid_run<ugrid_topo::T>(rows, cols, prm, dt, n_steps, state_in, out, mode);
+    if (prm[12] == 1.0) {
+        UG_CASE(3, 3, x3x3) UG_CASE(4, 5, x4x5) UG_CASE(2, 7, x2x7) UG_CASE(6, 6, x6x6)
+        return -1;
+    }
     UG_CASE(3, 3, t3x3) UG_CASE(4, 5, t4x5) UG_CASE(2, 7, t2x7) UG_CASE(6, 6, t6x6) UG_CASE(10, 10, t10x10)
 #undef UG_CASE
     return -1;

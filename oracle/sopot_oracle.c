@@ -717,11 +717,14 @@ ORC_API int orc_cartn_feedback_rk4(int n_links, size_t n, const double* mc, cons
  * Section 8f-2 -- unified 6-state grid: PointMass2D + Spring2D with attachment points and torque
  * (physics/unified/components.hpp:52-138, :206-291) driven as ValidatedSystem::computeDerivatives does
  * (validated_system.hpp:204-301) on makeGridTopology (constexpr_topology.hpp:368-414), runtime sized.
- * prm: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1.
+ * prm[18]: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0/1, v_attach0/1,
+ *          topology (0 quad, 1 triangle = makeTriangleGridTopology, constexpr_topology.hpp:436-505: after the horizontal and the
+ *          vertical springs, per cell in row-major order the main diagonal (r,c)->(r+1,c+1) then the anti-diagonal
+ *          (r,c+1)->(r+1,c)), diagonal rest length, main-diagonal attachment angles 0/1, anti-diagonal attachment angles 0/1.
  * ------------------------------------------------------------------------------------------ */
-typedef struct { size_t rows, cols; double mass, radius, k, L0, c, mind, krep, ha0, ha1, va0, va1; } orc_ugrid_t;
+typedef struct { size_t rows, cols; double mass, radius, k, L0, c, mind, krep, ha0, ha1, va0, va1; int topo; double Ld, da0, da1, aa0, aa1; } orc_ugrid_t;
 static void orc_uspring(const orc_ugrid_t* g, const double* m0, const double* m1, double a0, double a1, double* F /*[rows*cols][3]*/,
-                        size_t i0, size_t i1) {
+                        size_t i0, size_t i1, double L0) {
     const double r0 = g->radius, r1 = g->radius;
     const double wa0 = m0[4] + a0, wa1 = m1[4] + a1;
     const double o0x = r0 * cos(wa0), o0y = r0 * sin(wa0), o1x = r1 * cos(wa1), o1y = r1 * sin(wa1);
@@ -729,7 +732,7 @@ static void orc_uspring(const orc_ugrid_t* g, const double* m0, const double* m1
     const double v0x = m0[2] - m0[5] * o0y, v0y = m0[3] + m0[5] * o0x, v1x = m1[2] - m1[5] * o1y, v1y = m1[3] + m1[5] * o1x;
     const double dx = a1x - a0x, dy = a1y - a0y;
     const double len = sqrt(dx * dx + dy * dy), len_safe = len < 1e-10 ? 1e-10 : len;
-    const double ux = dx / len_safe, uy = dy / len_safe, ext = len - g->L0;
+    const double ux = dx / len_safe, uy = dy / len_safe, ext = len - L0;
     const double dvx = v1x - v0x, dvy = v1y - v0y, rel = dvx * ux + dvy * uy;
     double Fm = g->k * ext + g->c * rel;
     if (g->mind > 0.0 && len < g->mind) { const double rep = -g->krep * (g->mind / len_safe - 1.0); Fm += rep; }
@@ -744,9 +747,16 @@ static void orc_ugrid_rhs_fn(const void* ctx, double t, const double* s, double*
     const size_t n = g->rows * g->cols;
     double* F = (double*)calloc(3 * n, sizeof(double));
     for (size_t r = 0; r < g->rows; ++r)                                               /* horizontal springs, row-major */
-        for (size_t c = 0; c + 1 < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + 1), g->ha0, g->ha1, F, i, i + 1); }
+        for (size_t c = 0; c + 1 < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + 1), g->ha0, g->ha1, F, i, i + 1, g->L0); }
     for (size_t r = 0; r + 1 < g->rows; ++r)                                           /* then vertical springs */
-        for (size_t c = 0; c < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + g->cols), g->va0, g->va1, F, i, i + g->cols); }
+        for (size_t c = 0; c < g->cols; ++c) { const size_t i = r * g->cols + c; orc_uspring(g, s + 6 * i, s + 6 * (i + g->cols), g->va0, g->va1, F, i, i + g->cols, g->L0); }
+    if (g->topo == 1)                                                                  /* then the X of every cell */
+        for (size_t r = 0; r + 1 < g->rows; ++r)
+            for (size_t c = 0; c + 1 < g->cols; ++c) {
+                const size_t tl = r * g->cols + c, tr = tl + 1, bl = tl + g->cols, br = bl + 1;
+                orc_uspring(g, s + 6 * tl, s + 6 * br, g->da0, g->da1, F, tl, br, g->Ld);
+                orc_uspring(g, s + 6 * tr, s + 6 * bl, g->aa0, g->aa1, F, tr, bl, g->Ld);
+            }
     const double I = 0.5 * g->mass * g->radius * g->radius;                            /* components.hpp:98 */
     for (size_t i = 0; i < n; ++i) {
         d[6 * i] = s[6 * i + 2]; d[6 * i + 1] = s[6 * i + 3];
@@ -756,7 +766,8 @@ static void orc_ugrid_rhs_fn(const void* ctx, double t, const double* s, double*
     free(F);
 }
 ORC_API int orc_ugrid(size_t rows, size_t cols, const double* prm, double dt, size_t n_steps, const double* state_in, double* out, int mode) {
-    orc_ugrid_t g = {rows, cols, prm[0], prm[1], prm[3], prm[4], prm[5], prm[6], prm[7] > 0.0 ? prm[7] : 10.0 * prm[3], prm[8], prm[9], prm[10], prm[11]};
+    orc_ugrid_t g = {rows, cols, prm[0], prm[1], prm[3], prm[4], prm[5], prm[6], prm[7] > 0.0 ? prm[7] : 10.0 * prm[3], prm[8], prm[9], prm[10], prm[11],
+                     (int)prm[12], prm[13], prm[14], prm[15], prm[16], prm[17]};
     const size_t n = rows * cols * 6;
     if (mode == 2) {
         for (size_t r = 0; r < rows; ++r) for (size_t c = 0; c < cols; ++c) {

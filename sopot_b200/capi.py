@@ -22,7 +22,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
 FLAG_UGRID_STAGE_PAIRS = 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
@@ -85,7 +85,8 @@ class Dispersion(ctypes.Structure):
 class UGridParams(ctypes.Structure):
     _fields_ = [("rows", c_size_t), ("cols", c_size_t)] + [(k, c_double) for k in (
         "mass", "radius", "spacing", "stiffness", "rest_length", "damping", "min_distance", "repulsion_stiffness",
-        "h_attach0", "h_attach1", "v_attach0", "v_attach1")] + [("row_begin", c_size_t), ("rows_local", c_size_t)]
+        "h_attach0", "h_attach1", "v_attach0", "v_attach1")] + [("row_begin", c_size_t), ("rows_local", c_size_t), ("topology", c_int)] + [
+        (k, c_double) for k in ("diag_rest_length", "d_attach0", "d_attach1", "a_attach0", "a_attach1")]
 
 
 class Grid2DParams(ctypes.Structure):
@@ -537,9 +538,15 @@ class Engine:
     @staticmethod
     def ugrid_params(rows, cols, mass, radius, spacing, k, L0, c, min_distance=0.0, krep=-1.0,
                      attach=(0.0, 3.14159265358979323846, 3.14159265358979323846 / 2.0, -3.14159265358979323846 / 2.0),
-                     row_begin=0, rows_local=0):
-        """rows_local = 0: the whole grid on this rank; else this rank's slab of rows (multi-GPU, like grid2d)."""
-        return UGridParams(rows, cols, mass, radius, spacing, k, L0, c, min_distance, krep, *attach, row_begin, rows_local)
+                     row_begin=0, rows_local=0, triangle=False, diag_rest_length=None,
+                     diag_attach=(3.14159265358979323846 / 4.0, -3.0 * 3.14159265358979323846 / 4.0,
+                                  3.0 * 3.14159265358979323846 / 4.0, -3.14159265358979323846 / 4.0)):
+        """rows_local = 0: the whole grid on this rank; else this rank's slab of rows (multi-GPU, like grid2d).
+        triangle: add the two diagonal springs of every cell (the simulator's "triangle" grid type); their rest length
+        defaults to sqrt(2) * spacing as in the reference wrapper."""
+        Ld = float(np.sqrt(2.0) * spacing) if diag_rest_length is None else diag_rest_length
+        return UGridParams(rows, cols, mass, radius, spacing, k, L0, c, min_distance, krep, *attach, row_begin, rows_local,
+                           1 if triangle else 0, Ld, *diag_attach)
 
     def ugrid_initial_state(self, g, mem=MEM_HOST):
         nm = (g.rows_local or g.rows) * g.cols

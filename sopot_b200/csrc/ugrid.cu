@@ -25,6 +25,10 @@ struct UGridDev {
     double mass, radius, k, L0, c, min_distance, krep, inertia, inv_mass, inv_inertia;
     double ha0, ha1, va0, va1;      // attachment angles: horizontal spring on its left / right mass, vertical on upper / lower
     double cha0, sha0, cha1, sha1, cva0, sva0, cva1, sva1;      // their cos / sin (contract mode: addition theorem)
+    // triangle topology (makeTriangleGridTopology): the two diagonals of every cell
+    int topo;
+    double Ld, da0, da1, aa0, aa1;                              // diagonal rest length; main- / anti-diagonal attachment angles
+    double cda0, sda0, cda1, sda1, caa0, saa0, caa1, saa1;
 };
 
 struct Body { double x, y, vx, vy, th, om; double s, c; };      // s, c = sin / cos(th), filled in contract mode only
@@ -51,7 +55,8 @@ __device__ __forceinline__ void store6(double* p, const double (&v)[6]) {
 // contract mode: the same with sin/cos(theta + attachment angle) from the bodies' own sin/cos and the constant
 // cos/sin of the attachment angle, the spring length and its reciprocal from one rsqrt seed (no IEEE division)
 __device__ __forceinline__ void spring_ft_fast(const UGridDev& g, const Body& m0, const Body& m1, const double ca0, const double sa0,
-                                               const double ca1, const double sa1, const int end, double& fx, double& fy, double& tq) {
+                                               const double ca1, const double sa1, const int end, double& fx, double& fy, double& tq,
+                                               const double L0) {
     const double r = g.radius;
     const double c0 = fma(m0.c, ca0, -(m0.s * sa0)), s0 = fma(m0.s, ca0, m0.c * sa0);
     const double c1 = fma(m1.c, ca1, -(m1.s * sa1)), s1 = fma(m1.s, ca1, m1.c * sa1);
@@ -63,7 +68,7 @@ __device__ __forceinline__ void spring_ft_fast(const UGridDev& g, const Body& m0
     if (len2 >= 1e-20) { sbtrig::sqrt_rsqrt_fast(len2, len, inv); }            // components.hpp:246-247: len_safe = max(len, 1e-10)
     else { len = sqrt(len2); inv = 1e10; }
     const double ux = dx * inv, uy = dy * inv;
-    double F = fma(g.k, len - g.L0, g.c * fma(dvx, ux, dvy * uy));
+    double F = fma(g.k, len - L0, g.c * fma(dvx, ux, dvy * uy));
     if (g.min_distance > 0.0 && len < g.min_distance) F = fma(-g.krep, fma(g.min_distance, inv, -1.0), F);
     if (end == 0) { fx = F * ux; fy = F * uy; tq = fma(o0x, fy, -(o0y * fx)); }
     else { fx = -F * ux; fy = -F * uy; tq = fma(o1x, fy, -(o1y * fx)); }
@@ -71,7 +76,7 @@ __device__ __forceinline__ void spring_ft_fast(const UGridDev& g, const Body& m0
 
 template <bool S>
 __device__ __forceinline__ void spring_ft(const UGridDev& g, const Body& m0, const Body& m1, const double a0, const double a1,
-                                          const int end, Real<S>& fx, Real<S>& fy, Real<S>& tq) {
+                                          const int end, Real<S>& fx, Real<S>& fy, Real<S>& tq, const double L0) {
     using R = Real<S>;
     const R r(g.radius);
     R s0, c0, s1, c1;
@@ -84,7 +89,7 @@ __device__ __forceinline__ void spring_ft(const UGridDev& g, const Body& m0, con
     const R len = r_sqrt(dx * dx + dy * dy);
     const R len_safe = len.v < 1e-10 ? R(1e-10) : len;
     const R ux = dx / len_safe, uy = dy / len_safe;
-    const R ext = len - R(g.L0);
+    const R ext = len - R(L0);
     const R dvx = v1x - v0x, dvy = v1y - v0y;
     const R rel = dvx * ux + dvy * uy;
     R F = R(g.k) * ext + R(g.c) * rel;
@@ -109,16 +114,31 @@ __device__ __forceinline__ void derivative_from(const UGridDev& g, const Body& P
                                                 Real<S> (&d)[6]) {
     using R = Real<S>;
     R Fx(0.0), Fy(0.0), Tq(0.0), fx, fy, tq;
+    const bool left = col > 0, right = col + 1 < g.cols, up = grow > 0, down = grow + 1 < g.rows;
     if constexpr (S) {
-        if (col > 0) { spring_ft<S>(g, nb(0, -1), P, g.ha0, g.ha1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (col + 1 < g.cols) { spring_ft<S>(g, P, nb(0, 1), g.ha0, g.ha1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow > 0) { spring_ft<S>(g, nb(-1, 0), P, g.va0, g.va1, 1, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow + 1 < g.rows) { spring_ft<S>(g, P, nb(1, 0), g.va0, g.va1, 0, fx, fy, tq); Fx += fx; Fy += fy; Tq += tq; }
+        if (left) { spring_ft<S>(g, nb(0, -1), P, g.ha0, g.ha1, 1, fx, fy, tq, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (right) { spring_ft<S>(g, P, nb(0, 1), g.ha0, g.ha1, 0, fx, fy, tq, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (up) { spring_ft<S>(g, nb(-1, 0), P, g.va0, g.va1, 1, fx, fy, tq, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (down) { spring_ft<S>(g, P, nb(1, 0), g.va0, g.va1, 0, fx, fy, tq, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (g.topo == 1) {
+            // diagonals in spring-node order (cells row-major, main before anti): cell (r-1,c-1) main, this mass is its lower
+            // right end; cell (r-1,c) anti, lower left end; cell (r,c-1) anti, upper right end; cell (r,c) main, upper left end
+            if (up && left) { spring_ft<S>(g, nb(-1, -1), P, g.da0, g.da1, 1, fx, fy, tq, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (up && right) { spring_ft<S>(g, nb(-1, 1), P, g.aa0, g.aa1, 1, fx, fy, tq, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (down && left) { spring_ft<S>(g, P, nb(1, -1), g.aa0, g.aa1, 0, fx, fy, tq, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (down && right) { spring_ft<S>(g, P, nb(1, 1), g.da0, g.da1, 0, fx, fy, tq, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+        }
     } else {
-        if (col > 0) { spring_ft_fast(g, nb(0, -1), P, g.cha0, g.sha0, g.cha1, g.sha1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (col + 1 < g.cols) { spring_ft_fast(g, P, nb(0, 1), g.cha0, g.sha0, g.cha1, g.sha1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow > 0) { spring_ft_fast(g, nb(-1, 0), P, g.cva0, g.sva0, g.cva1, g.sva1, 1, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
-        if (grow + 1 < g.rows) { spring_ft_fast(g, P, nb(1, 0), g.cva0, g.sva0, g.cva1, g.sva1, 0, fx.v, fy.v, tq.v); Fx += fx; Fy += fy; Tq += tq; }
+        if (left) { spring_ft_fast(g, nb(0, -1), P, g.cha0, g.sha0, g.cha1, g.sha1, 1, fx.v, fy.v, tq.v, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (right) { spring_ft_fast(g, P, nb(0, 1), g.cha0, g.sha0, g.cha1, g.sha1, 0, fx.v, fy.v, tq.v, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (up) { spring_ft_fast(g, nb(-1, 0), P, g.cva0, g.sva0, g.cva1, g.sva1, 1, fx.v, fy.v, tq.v, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (down) { spring_ft_fast(g, P, nb(1, 0), g.cva0, g.sva0, g.cva1, g.sva1, 0, fx.v, fy.v, tq.v, g.L0); Fx += fx; Fy += fy; Tq += tq; }
+        if (g.topo == 1) {
+            if (up && left) { spring_ft_fast(g, nb(-1, -1), P, g.cda0, g.sda0, g.cda1, g.sda1, 1, fx.v, fy.v, tq.v, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (up && right) { spring_ft_fast(g, nb(-1, 1), P, g.caa0, g.saa0, g.caa1, g.saa1, 1, fx.v, fy.v, tq.v, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (down && left) { spring_ft_fast(g, P, nb(1, -1), g.caa0, g.saa0, g.caa1, g.saa1, 0, fx.v, fy.v, tq.v, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+            if (down && right) { spring_ft_fast(g, P, nb(1, 1), g.cda0, g.sda0, g.cda1, g.sda1, 0, fx.v, fy.v, tq.v, g.Ld); Fx += fx; Fy += fy; Tq += tq; }
+        }
     }
     d[0] = R(P.vx); d[1] = R(P.vy);
     d[4] = R(P.om);
@@ -364,6 +384,11 @@ int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev&
     g.inv_mass = 1.0 / g.mass; g.inv_inertia = 1.0 / g.inertia;
     g.cha0 = std::cos(g.ha0); g.sha0 = std::sin(g.ha0); g.cha1 = std::cos(g.ha1); g.sha1 = std::sin(g.ha1);
     g.cva0 = std::cos(g.va0); g.sva0 = std::sin(g.va0); g.cva1 = std::cos(g.va1); g.sva1 = std::sin(g.va1);
+    if (p->topology != 0 && p->topology != 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "ugrid topology must be 0 (quad) or 1 (triangle)");
+    g.topo = p->topology; g.Ld = p->diag_rest_length;
+    g.da0 = p->d_attach0; g.da1 = p->d_attach1; g.aa0 = p->a_attach0; g.aa1 = p->a_attach1;
+    g.cda0 = std::cos(g.da0); g.sda0 = std::sin(g.da0); g.cda1 = std::cos(g.da1); g.sda1 = std::sin(g.da1);
+    g.caa0 = std::cos(g.aa0); g.saa0 = std::sin(g.aa0); g.caa1 = std::cos(g.aa1); g.saa1 = std::sin(g.aa1);
     return SOPOT_B200_OK;
 }
 

@@ -4,6 +4,7 @@
 // with the TypedODESystem-like surface of ValidatedSystem (physics/unified/validated_system.hpp: getStateDimension,
 // getInitialState, computeDerivatives).  Runtime sized; the derivative and the RK4 stages run in csrc/ugrid.cu.
 #pragma once
+#include <cmath>
 #include <stdexcept>
 #include <vector>
 #include "../../core/solver.hpp"
@@ -15,6 +16,13 @@ struct GridConfig {
     double stiffness = 50.0, rest_length = 0.5, damping = 0.5, min_distance = 0.0, repulsion_stiffness = -1.0;
     // attachment angles: horizontal springs on their left / right mass, vertical springs on their upper / lower mass
     double h_attach0 = 0.0, h_attach1 = 3.14159265358979323846, v_attach0 = 3.14159265358979323846 / 2.0, v_attach1 = -3.14159265358979323846 / 2.0;
+    // the simulator's "triangle" grid type (createTriangleSystem, wasm/wasm_grid2d.cpp:466-525, on makeTriangleGridTopology):
+    // both diagonals of every cell; rest length < 0 means sqrt(2) * spacing; attachment angles of the main diagonal on its
+    // upper-left / lower-right mass and of the anti-diagonal on its upper-right / lower-left mass
+    bool triangle = false;
+    double diag_rest_length = -1.0;
+    double d_attach0 = 3.14159265358979323846 / 4.0, d_attach1 = -3.0 * 3.14159265358979323846 / 4.0;
+    double a_attach0 = 3.0 * 3.14159265358979323846 / 4.0, a_attach1 = -3.14159265358979323846 / 4.0;
 };
 
 // the three schemes of the reference's Grid2DSimulator (wasm/wasm_grid2d.cpp:38-42, :286-413)
@@ -25,12 +33,15 @@ class UnifiedGridSystem {
 public:
     UnifiedGridSystem(size_t rows, size_t cols, const GridConfig& c = {})
         : m_p{rows, cols, c.mass, c.radius, c.spacing, c.stiffness, c.rest_length, c.damping, c.min_distance, c.repulsion_stiffness,
-              c.h_attach0, c.h_attach1, c.v_attach0, c.v_attach1} {
+              c.h_attach0, c.h_attach1, c.v_attach0, c.v_attach1, 0, 0, c.triangle ? 1 : 0,
+              c.diag_rest_length < 0.0 ? std::sqrt(2.0) * c.spacing : c.diag_rest_length, c.d_attach0, c.d_attach1, c.a_attach0, c.a_attach1} {
         if (rows * cols < 2) throw std::invalid_argument("the grid needs at least two masses");
         if (!(c.mass > 0.0) || !(c.radius > 0.0)) throw std::invalid_argument("mass and radius must be positive");
     }
     size_t getStateDimension() const noexcept { return 6 * m_p.rows * m_p.cols; }
-    size_t getNodeCount() const noexcept { return m_p.rows * m_p.cols + m_p.rows * (m_p.cols - 1) + (m_p.rows - 1) * m_p.cols; }
+    size_t getNodeCount() const noexcept {      // masses + springs (constexpr_topology.hpp:370-373, :437-442)
+        return m_p.rows * m_p.cols + m_p.rows * (m_p.cols - 1) + (m_p.rows - 1) * m_p.cols + (m_p.topology ? 2 * (m_p.rows - 1) * (m_p.cols - 1) : 0);
+    }
     std::vector<double> getInitialState() const {
         std::vector<double> s(getStateDimension());
         b200::Engine& eng = b200::Engine::shared();

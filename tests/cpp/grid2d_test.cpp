@@ -100,6 +100,19 @@ int main() {
             ug.integrate(yv, 1e-3, 100, unified::Integrator::VelocityVerlet, fp);
             for (int j = 0; j < 6; ++j) { ASSERT_NEAR(ye[4 * 6 + j], se4[j], 1e-9 * 26.0); ASSERT_NEAR(yv[4 * 6 + j], vv4[j], 1e-9 * 26.0); }
         }
+        // the simulator's "triangle" grid type: both diagonals of every cell (makeTriangleGridTopology, createTriangleSystem)
+        {
+            unified::GridConfig tc; tc.triangle = true;
+            unified::UnifiedGridSystem tri(3, 3, tc);
+            ASSERT_TRUE(tri.getNodeCount() == 9 + 6 + 6 + 8);
+            auto dt4 = tri.computeDerivatives(0.0, s);
+            const double e4[6] = {0.0, 0.0, -16.043417617551782, 0.034385918659547876, 0.0, 324.8571509671915};
+            for (int j = 0; j < 6; ++j) ASSERT_NEAR(dt4[4 * 6 + j], e4[j], 1e-12 * 325.0);
+            auto yt = s;
+            tri.integrate(yt, 1e-3, 100, b200::FpMode::Strict);
+            const double r4[6] = {0.5354162697126642, 0.49921997063637474, -1.0503719607409456, -0.018609478585536958, 2.1729978058446977, 23.806551307485407};
+            for (int j = 0; j < 6; ++j) ASSERT_NEAR(yt[4 * 6 + j], r4[j], 1e-9 * 24.0);
+        }
         unified::UnifiedGridSystem large(512, 384);
         auto y = large.getInitialState();
         y[(256 * 384 + 192) * 6] += 0.1;

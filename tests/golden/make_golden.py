@@ -220,6 +220,9 @@ UGRID_PARAMS = {   # mass, radius, spacing, stiffness, rest_length, damping, min
 }
 
 
+UGRID_TRIANGLE = UGRID_PARAMS["wasm"] + [1.0, float(np.sqrt(2.0) * 0.5), UGRID_PI / 4, -3 * UGRID_PI / 4, 3 * UGRID_PI / 4, -UGRID_PI / 4]
+
+
 def ugrid_golden(R):
     """Unified 6-state grid: ValidatedSystem<double, makeGridTopology<R,C>, PointMass2D, Spring2D> (the wasm Grid2DSimulator's
     system): initial state, one derivative evaluation of a perturbed state, 50 RK4Solver steps."""
@@ -241,3 +244,13 @@ def ugrid_golden(R):
         for mode in ("symplectic_euler", "velocity_verlet"):
             integ[f"u{rows}x{cols}_{mode}"] = R.ugrid(rows, cols, UGRID_PARAMS["wasm"], out[f"u{rows}x{cols}_wasm_state"], 1e-3, 80, mode)
     np.savez(os.path.join(OUT, "ugrid_integrators.npz"), **integ)
+    # the "triangle" grid type (makeTriangleGridTopology + createTriangleSystem): diagonal springs of rest length sqrt(2) spacing
+    tri = {}
+    for rows, cols in ((3, 3), (4, 5), (2, 7), (6, 6)):
+        prm = UGRID_TRIANGLE
+        key = f"x{rows}x{cols}"
+        st = out[f"u{rows}x{cols}_wasm_state"]
+        tri[key + "_rhs"] = R.ugrid(rows, cols, prm, st)
+        tri[key + "_rk4"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
+        tri[key + "_verlet"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "velocity_verlet")
+    np.savez(os.path.join(OUT, "ugrid_triangle.npz"), **tri)

@@ -69,14 +69,14 @@ assert np.array_equal(part, whole[:, b:e])
 # (4) unified 6-state grid: slabs + 1-row halo per stencil input vs single domain, RK4 / symplectic Euler / velocity Verlet
 PI = 3.14159265358979323846
 uprm = (1.0, 0.05, 0.5, 50.0, 0.5, 0.5, 0.0, -1.0)
-for rows, cols, steps in ((world, 40, 3), (4 * world + 1, 70, 5), (257, 129, 4)):
+for rows, cols, steps, tri in ((world, 40, 3, False), (4 * world + 1, 70, 5, True), (257, 129, 4, False), (3 * world + 2, 33, 3, True)):
     solo = Engine(local)
-    ug = solo.ugrid_params(rows, cols, *uprm)
+    ug = solo.ugrid_params(rows, cols, *uprm, triangle=tri)
     s0 = solo.ugrid_initial_state(ug).reshape(rows, cols, 6)
     rng = np.random.default_rng(rows)
     s0 = s0 + rng.normal(0, 0.02, s0.shape); s0[..., 4] = rng.normal(0, 0.2, (rows, cols))
     rb, rl = slab(rows, rank, world)
-    gp = eng.ugrid_params(rows, cols, *uprm, row_begin=rb, rows_local=rl)
+    gp = eng.ugrid_params(rows, cols, *uprm, row_begin=rb, rows_local=rl, triangle=tri)
     for mode in (FP_STRICT, FP_CONTRACT):
         for integ in (0, 1, 2):
             ref = solo.ugrid_rk4(ug, 1e-3, steps, s0.reshape(-1, 6).copy(), fp_mode=mode, integrator=integ).reshape(rows, cols, 6)

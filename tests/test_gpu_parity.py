@@ -591,6 +591,46 @@ def test_unified_grid_stage_pairs_equal_per_stage_schedule(engine, port, rows, c
         assert np.array_equal(dev.download(), a)
 
 
+def test_unified_grid_triangle_topology(engine, port):
+    """The "triangle" grid type: golden vectors of the reference (derivative, RK4, velocity Verlet), a size the reference is
+    not instantiated for against the oracle, the opt-in stage-pair schedule (bit-identical in strict mode) and a rest state
+    whose diagonal rest length equals the diagonal attachment distance."""
+    from sopot_b200.capi import INTEGRATOR_VELOCITY_VERLET
+    g, gt = golden("ugrid"), golden("ugrid_triangle")
+    prm = _ugrid_prm()["wasm"]
+    tri = list(prm) + [1.0, float(np.sqrt(2.0) * 0.5), np.pi / 4, -3 * np.pi / 4, 3 * np.pi / 4, -np.pi / 4]
+    for rows, cols in ((3, 3), (4, 5), (2, 7), (6, 6)):
+        gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]), triangle=True)
+        st = g[f"u{rows}x{cols}_wasm_state"]
+        key = f"x{rows}x{cols}"
+        for mode in (FP_STRICT, FP_CONTRACT):
+            d = engine.ugrid_rhs(gp, st.copy(), fp_mode=mode)
+            assert np.abs(d - gt[key + "_rhs"]).max() <= 1e-12 * np.abs(gt[key + "_rhs"]).max()
+            out = engine.ugrid_rk4(gp, 1e-3, 50, st.copy(), fp_mode=mode)
+            assert rel_err(out.ravel(), gt[key + "_rk4"].ravel()).max() <= FINAL
+            out = engine.ugrid_rk4(gp, 1e-3, 50, st.copy(), fp_mode=mode, integrator=INTEGRATOR_VELOCITY_VERLET)
+            assert rel_err(out.ravel(), gt[key + "_verlet"].ravel()).max() <= FINAL
+    rows, cols = 41, 67
+    gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]), triangle=True)
+    s0 = engine.ugrid_initial_state(gp)
+    rng = np.random.default_rng(9)
+    st = s0 + rng.normal(0, 0.02, s0.shape); st[:, 4] = rng.normal(0, 0.2, rows * cols)
+    ref = port.ugrid(rows, cols, tri, st, 1e-3, 8, "rk4")
+    a = engine.ugrid_rk4(gp, 1e-3, 8, st.copy(), fp_mode=FP_STRICT)
+    b = engine.ugrid_rk4(gp, 1e-3, 8, st.copy(), fp_mode=FP_STRICT, stage_pairs=True)
+    c = engine.ugrid_rk4(gp, 1e-3, 8, st.copy(), fp_mode=FP_CONTRACT)
+    assert np.array_equal(a, b) and rel_err(a.ravel(), ref.ravel()).max() <= FINAL and rel_err(c.ravel(), ref.ravel()).max() <= FINAL
+    # at rest: orthogonal rest length = spacing - 2 r, diagonal rest length = sqrt(2) spacing - 2 r
+    gp = engine.ugrid_params(48, 48, prm[0], 0.05, 0.5, prm[3], 0.4, prm[5], 0.0, -1.0, tuple(prm[8:12]), triangle=True,
+                             diag_rest_length=float(np.sqrt(2.0) * 0.5 - 0.1))
+    s0 = engine.ugrid_initial_state(gp)
+    out = engine.ugrid_rk4(gp, 1e-3, 5, s0.copy(), fp_mode=FP_STRICT)
+    assert np.abs(out - s0).max() < 1e-12
+    with pytest.raises(Exception):
+        bad = engine.ugrid_params(4, 4, *prm[:8], tuple(prm[8:12])); bad.topology = 7
+        engine.ugrid_rk4(bad, 1e-3, 1, engine.ugrid_initial_state(engine.ugrid_params(4, 4, *prm[:8], tuple(prm[8:12]))))
+
+
 def test_unified_grid_medium_vs_oracle(engine, port):
     """Sizes the templated reference is not instantiated for: against the runtime-sized oracle; device-pointer path; a rest
     grid whose rest length equals the attachment distance stays at rest exactly."""

@@ -279,6 +279,26 @@ def test_golden_unified_grid(port):
     assert np.abs(d[:, 2:4].sum(axis=0)).max() < 1e-10
 
 
+def test_golden_unified_grid_triangle_topology(port):
+    """The simulator's "triangle" grid type (makeTriangleGridTopology, constexpr_topology.hpp:436-505, populated as
+    createTriangleSystem does): diagonal springs with their own rest length and attachment angles, accumulated per mass in
+    spring-node order -- port == reference bit for bit (derivative, RK4, velocity Verlet)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    g, gt = golden("ugrid"), golden("ugrid_triangle")
+    for rows, cols in ((3, 3), (4, 5), (2, 7), (6, 6)):
+        st = g[f"u{rows}x{cols}_wasm_state"]
+        key = f"x{rows}x{cols}"
+        assert np.array_equal(port.ugrid(rows, cols, mg.UGRID_TRIANGLE, st), gt[key + "_rhs"])
+        assert np.array_equal(port.ugrid(rows, cols, mg.UGRID_TRIANGLE, st, 1e-3, 50, "rk4"), gt[key + "_rk4"])
+        assert np.array_equal(port.ugrid(rows, cols, mg.UGRID_TRIANGLE, st, 1e-3, 50, "velocity_verlet"), gt[key + "_verlet"])
+        assert not np.array_equal(gt[key + "_rhs"], g[f"u{rows}x{cols}_wasm_rhs"])      # the diagonals do act
+    # forces still sum to zero (Newton's third law over all eight spring directions)
+    d = port.ugrid(4, 5, mg.UGRID_TRIANGLE, g["u4x5_wasm_state"])
+    assert np.abs(d[:, 2:4].sum(axis=0)).max() < 1e-9
+
+
 def test_golden_unified_grid_integrators(port):
     """Grid2DSimulator's symplectic Euler and velocity Verlet (wasm/wasm_grid2d.cpp:329-413) around the reference's
     computeDerivatives: the port repeats them bit for bit; both stay within O(dt) / O(dt^2) of the RK4 trajectory."""
