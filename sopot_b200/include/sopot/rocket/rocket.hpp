@@ -17,29 +17,13 @@
 #include <vector>
 #include "../core/solver.hpp"
 #include "../core/typed_component.hpp"
+#include "../io/csv_parser.hpp"
 
 namespace sopot::rocket {
 
 namespace detail {
 inline std::vector<std::vector<double>> parse_csv(const std::string& filename, char delimiter = ',') {
-    std::ifstream file(filename);
-    if (!file.is_open()) throw std::runtime_error("Cannot open file: " + filename);
-    std::vector<std::vector<double>> rows;
-    std::string line;
-    while (std::getline(file, line)) {
-        if (line.empty() || line[0] == '#') continue;
-        std::vector<double> row;
-        std::stringstream ss(line);
-        std::string cell;
-        while (std::getline(ss, cell, delimiter)) {
-            const size_t a = cell.find_first_not_of(" \t\r\n"), b = cell.find_last_not_of(" \t\r\n");
-            if (a == std::string::npos) continue;
-            cell = cell.substr(a, b - a + 1);
-            try { row.push_back(std::stod(cell)); } catch (...) { /* header cell */ }
-        }
-        if (!row.empty()) rows.push_back(std::move(row));
-    }
-    return rows;
+    return io::CsvParser::parseFile(filename, delimiter).data;
 }
 inline std::vector<double> flatten(const std::vector<std::vector<double>>& rows, size_t cols, const char* what) {
     std::vector<double> out;

@@ -110,6 +110,16 @@ int main() {
         const auto tab = engine_table();
         for (size_t r = 0; r < tab.size() / 8; ++r) { for (int c = 0; c < 8; ++c) e << (c ? "," : "") << tab[r * 8 + c]; e << "\n"; }
     }
+    {   // io::CsvParser (io/csv_parser.hpp): comments, header cells, blank lines, both table shapes
+        const std::string text = "# engine\ntime, thrust, note\n0.0, 10.5, a\n\n 1.0 ,\t20.5\n2.0,30.5,7\n";
+        const auto t = io::CsvParser::parseString(text);
+        ASSERT_TRUE(t.rows() == 3 && t.cols() == 2 && t(1, 1) == 20.5 && t.row(2).size() == 3);
+        ASSERT_TRUE((t.column(0) == std::vector<double>{0.0, 1.0, 2.0}) && (t.column(2) == std::vector<double>{7.0}));
+        const auto t2 = io::CsvParser::parseString("x, 0.5, 1.0, 2.0\n0, 1, 2, 3\n10, 4, 5, 6\n", ',', true);
+        ASSERT_TRUE(t2.rows() == 3 && (t2.row(0) == std::vector<double>{0.5, 1.0, 2.0}) && (t2.row(2) == std::vector<double>{4.0, 5.0, 6.0}));
+        ASSERT_THROWS(io::CsvParser::parseFile("/nonexistent/table.csv"), std::runtime_error);
+        ASSERT_THROWS(t(5, 0), std::out_of_range);
+    }
     Rocket<double> from_csv;
     from_csv.loadEngineData("/tmp/sopot_b200_");
     ASSERT_TRUE(from_csv.tables().engine == engine_table());
