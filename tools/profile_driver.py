@@ -55,6 +55,17 @@ elif cfg in ("ugrid", "ugrid_pairs"):
     state = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
     for _ in range(reps):
         eng.ugrid_rk4(ug, 1e-3, 2, state, fp_mode=FP_CONTRACT, stage_pairs=cfg == "ugrid_pairs")
+elif cfg == "closed":
+    P = 1 << 20
+    rng = np.random.default_rng(3)
+    plant = {k: eng.to_device(v) for k, v in dict(mc=rng.uniform(0.8, 1.5, P), m=rng.uniform(0.05, 0.2, P),
+                                                   L=rng.uniform(0.4, 0.8, P), g=np.full(P, 9.81)).items()}
+    K = eng.to_device(np.tile(np.array([-3.0, 40.0, -4.0, 8.0])[:, None], (1, P)))
+    s0 = [eng.to_device(v) for v in (rng.uniform(-0.5, 0.5, P), rng.uniform(-0.1, 0.1, P), np.zeros(P), np.zeros(P))]
+    st = eng.empty((4, P))
+    for _ in range(reps):
+        eng.cartpole_feedback_rk4(plant["mc"], plant["m"], plant["L"], plant["g"], *s0, K, P, 0.0, 0.002, 500, u_min=-50.0, u_max=50.0,
+                                  saturate=True, mem=MEM_DEVICE, want_status=False, want_stats=False, state_out=st)
 elif cfg == "lqr":
     P = 1 << 14
     rng = np.random.default_rng(3)
