@@ -41,6 +41,22 @@ for mode, mname in ((FP_CONTRACT, "contract"), (FP_STRICT, "strict")):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[f"{mname}_{'per_stage' if per_stage else 'fused'}_ms_per_step"] = float(t.item())
+# the unified 6-state grid (Grid2DSimulator's system) on half the edge length: per-stage kernels, 1-row halo per stencil input
+nu = n // 2
+ug = eng.ugrid_params(nu, nu, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5, row_begin=slab(nu, rank, world)[0], rows_local=slab(nu, rank, world)[1])
+ustate = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
+for integ, iname in ((0, "rk4"), (2, "velocity_verlet")):
+    eng.ugrid_rk4(ug, 1e-3, 3, ustate, fp_mode=FP_CONTRACT, integrator=integ)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.event_record(0)
+    eng.ugrid_rk4(ug, 1e-3, steps, ustate, fp_mode=FP_CONTRACT, integrator=integ, sync=False)
+    eng.event_record(1)
+    t = torch.tensor([eng.elapsed_ms(0, 1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out[f"unified_{nu}_contract_{iname}_ms_per_step"] = float(t.item())
 if rank == 0:
     out["mass_steps_per_s_contract_fused"] = n * n / (out["contract_fused_ms_per_step"] * 1e-3)
     print(json.dumps(out), flush=True)
