@@ -10,9 +10,12 @@
 // spring (as mass 0).  The kernels below are the gather form of that: one thread per mass evaluates its incident springs
 // in exactly this order.  State is AoS [rows][cols][6] (48 B per mass), the reference's node order.
 // One RK4 step = four stage kernels with the running accumulator of ensemble.cuh (1.5x the traffic of the 4-state grid).
-// Multi-GPU: contiguous slabs of rows per rank (params row_begin / rows_local), one ghost row above and below each
-// stencil input, refreshed from the neighbouring ranks with ncclSend/ncclRecv after the kernel that produced the buffer.
+// Multi-GPU: contiguous slabs of rows per rank (params row_begin / rows_local).  Default: one exchange of H boundary rows per
+// step into H ghost rows at both ends of every buffer, the stages evaluated on shrinking row ranges (see
+// sopot_b200_ugrid_integrate); for slabs thinner than H rows: one ghost row above and below each stencil input, refreshed
+// from the neighbouring ranks with ncclSend/ncclRecv after the kernel that produced the buffer.
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "nccl_api.h"
 #include "trig.cuh"
@@ -21,7 +24,8 @@ namespace {
 
 struct UGridDev {
     size_t rows, cols;              // the GLOBAL grid
-    size_t row_begin, rows_local;   // rows [row_begin, row_begin + rows_local) live on this rank
+    long row_begin;                 // global row of local row 0 (negative for a buffer that starts with ghost rows above row 0)
+    size_t rows_local;              // rows [row_begin, row_begin + rows_local) are addressable on this rank
     double mass, radius, k, L0, c, min_distance, krep, inertia, inv_mass, inv_inertia;
     double ha0, ha1, va0, va1;      // attachment angles: horizontal spring on its left / right mass, vertical on upper / lower
     double cha0, sha0, cha1, sha1, cva0, sva0, cva1, sva1;      // their cos / sin (contract mode: addition theorem)
@@ -151,7 +155,7 @@ __device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in
                                                 Real<S> (&d)[6], Body& self) {
     const long lr = (long)row;
     self = body_at<S>(g, in, lr, col);
-    derivative_from<S>(g, self, g.row_begin + row, col,
+    derivative_from<S>(g, self, (size_t)(g.row_begin + (long)row), col,
                        [&](int dr, int dc) { return body_at<S>(g, in, lr + dr, (size_t)((long)col + dc)); }, d);
 }
 
@@ -159,10 +163,10 @@ __device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in
 template <bool S, int STAGE>
 __global__ void __launch_bounds__(256)
 ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
-            double* __restrict__ out) {
+            double* __restrict__ out, const size_t r_lo, const size_t r_hi) {
     using R = Real<S>;
-    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
-    if (col >= g.cols || row >= g.rows_local) return;
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = r_lo + (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (col >= g.cols || row >= r_hi) return;
     R d[6];
     Body self;
     body_derivative<S>(g, in, row, col, d, self);
@@ -372,9 +376,9 @@ int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev&
     if (p->rows < 1 || p->cols < 1 || p->rows * p->cols < 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "the grid needs at least two masses");
     if (!(p->mass > 0.0) || !(p->radius > 0.0))
         return sb_fail(ctx, SOPOT_B200_EINVAL, "mass and radius must be positive (I = m r^2 / 2 divides the torque)");
-    g.row_begin = p->rows_local ? p->row_begin : 0;
+    g.row_begin = p->rows_local ? (long)p->row_begin : 0;
     g.rows_local = p->rows_local ? p->rows_local : p->rows;
-    if (g.row_begin + g.rows_local > p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [row_begin, row_begin + rows_local) exceeds the grid");
+    if ((size_t)g.row_begin + g.rows_local > p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [row_begin, row_begin + rows_local) exceeds the grid");
     if (ctx->nranks == 1 && g.rows_local != p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "a single-rank ctx must own the whole grid");
     g.rows = p->rows; g.cols = p->cols; g.mass = p->mass; g.radius = p->radius; g.k = p->stiffness; g.L0 = p->rest_length;
     g.c = p->damping; g.min_distance = p->min_distance;
@@ -392,11 +396,15 @@ int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev&
     return SOPOT_B200_OK;
 }
 
+// rows [r_lo, r_hi) of the local buffer (default: all of them)
 template <int STAGE>
-void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const UIn& in, double dt, double* y, double* acc, double* out) {
-    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows_local + 3) / 4));
-    if (strict) ugrid_stage<true, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
-    else ugrid_stage<false, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out);
+void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const UIn& in, double dt, double* y, double* acc, double* out,
+                   size_t r_lo = 0, size_t r_hi = (size_t)-1) {
+    if (r_hi == (size_t)-1) r_hi = g.rows_local;
+    if (r_hi <= r_lo) return;
+    const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((r_hi - r_lo + 3) / 4));
+    if (strict) ugrid_stage<true, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi);
+    else ugrid_stage<false, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi);
     ctx->launches++;
 }
 
@@ -410,7 +418,7 @@ int ugrid_halo(sopot_b200_ctx* ctx, const UGridDev& g, const UIn& in) {
         SB_NCCL(ctx, n->Send(in.slab, row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
         SB_NCCL(ctx, n->Recv(const_cast<double*>(in.top), row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
     }
-    if (g.row_begin + g.rows_local < g.rows) {
+    if ((size_t)g.row_begin + g.rows_local < g.rows) {
         SB_NCCL(ctx, n->Send(in.slab + (g.rows_local - 1) * row_elems, row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
         SB_NCCL(ctx, n->Recv(const_cast<double*>(in.bot), row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
     }
@@ -431,7 +439,7 @@ SB_EXPORT int sopot_b200_ugrid_initial_state(sopot_b200_ctx* ctx, const sopot_b2
     void* d;
     if ((rc = sg.out(state, bytes, &d))) return rc;
     const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((g.rows_local + 3) / 4));
-    ugrid_init_kernel<<<grid, block, 0, ctx->stream>>>(g.rows_local, g.cols, g.row_begin, p->spacing, (double*)d);
+    ugrid_init_kernel<<<grid, block, 0, ctx->stream>>>(g.rows_local, g.cols, (size_t)g.row_begin, p->spacing, (double*)d);
     SB_CHECK_LAUNCH(ctx);
     return sg.finish();
 }
@@ -480,6 +488,65 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
         sg.outs.push_back({state, y, n * 8});
     } else {
         y = state;
+    }
+    // Several ranks, slabs at least as tall as the step has stages: ONE exchange per step.  Every buffer carries H ghost rows
+    // above and below the slab (H = derivative evaluations per step: 4 RK4, 2 Verlet, 1 Euler); the H boundary rows of the
+    // state travel once, and stage s is evaluated on the buffer shrunk by s rows at both ends, so the rows next to the slab
+    // boundary are computed redundantly by both neighbours (12 extra row-evaluations per RK4 step) instead of being
+    // exchanged after every stage.  Same operations per mass, so the result equals the single-domain run bit for bit.
+    const size_t H = integrator == SOPOT_B200_INTEGRATOR_RK4 ? 4 : (integrator == SOPOT_B200_INTEGRATOR_VELOCITY_VERLET ? 2 : 1);
+    if (ctx->nranks > 1 && g.rows / (size_t)ctx->nranks >= H && !std::getenv("SOPOT_B200_UGRID_HALO_PER_STAGE")) {
+        UGridDev ge = g;
+        ge.row_begin = g.row_begin - (long)H;
+        ge.rows_local = g.rows_local + 2 * H;
+        const size_t ne = ge.rows_local * g.cols * 6;
+        void* scr2;
+        if ((rc = sb_scratch(ctx, 4 * ne * 8 + 1024, &scr2))) return rc;
+        double* Y = static_cast<double*>(scr2);
+        double* ACC = Y + ne;
+        double* EA = ACC + ne;
+        double* EB = EA + ne;
+        SB_CUDA(ctx, cudaMemcpyAsync(Y + H * row_elems, y, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        const bool up = g.row_begin > 0, down = (size_t)g.row_begin + g.rows_local < g.rows;
+        const NcclApi* nc = ctx->nccl;
+        const auto exchange = [&](double* buf) -> int {                 // H boundary rows of the slab <-> the neighbours' ghost rows
+            SB_NCCL(ctx, nc->GroupStart());
+            if (up) {
+                SB_NCCL(ctx, nc->Send(buf + H * row_elems, H * row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+                SB_NCCL(ctx, nc->Recv(buf, H * row_elems, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+            }
+            if (down) {
+                SB_NCCL(ctx, nc->Send(buf + g.rows_local * row_elems, H * row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+                SB_NCCL(ctx, nc->Recv(buf + (H + g.rows_local) * row_elems, H * row_elems, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+            }
+            SB_NCCL(ctx, nc->GroupEnd());
+            return SOPOT_B200_OK;
+        };
+        // rows of the extended buffer on which evaluation number s (1-based) of a step has valid inputs, inside the global grid
+        const auto lo = [&](size_t s) { const long l = (long)s, gmin = -ge.row_begin; return (size_t)(l > gmin ? l : gmin); };
+        const auto hi = [&](size_t s) { const long h = (long)(ge.rows_local - s), gmax = (long)g.rows - ge.row_begin; return (size_t)(h < gmax ? h : gmax); };
+        const auto ext = [](const double* b) { return UIn{b, nullptr, nullptr}; };
+        double* cur = Y;
+        double* nxt = EA;
+        for (size_t step = 0; step < n_steps; ++step) {
+            if ((rc = exchange(cur))) return rc;
+            if (integrator == SOPOT_B200_INTEGRATOR_RK4) {
+                launch_ustage<1>(ctx, strict, ge, ext(Y), dt, Y, ACC, EA, lo(1), hi(1));
+                launch_ustage<2>(ctx, strict, ge, ext(EA), dt, Y, ACC, EB, lo(2), hi(2));
+                launch_ustage<3>(ctx, strict, ge, ext(EB), dt, Y, ACC, EA, lo(3), hi(3));
+                launch_ustage<4>(ctx, strict, ge, ext(EA), dt, Y, ACC, nullptr, lo(4), hi(4));
+            } else if (integrator == SOPOT_B200_INTEGRATOR_SYMPLECTIC_EULER) {
+                launch_ustage<5>(ctx, strict, ge, ext(cur), dt, nullptr, nullptr, nxt, lo(1), hi(1));
+                double* t = cur; cur = nxt; nxt = t;
+            } else {
+                launch_ustage<6>(ctx, strict, ge, ext(cur), dt, nullptr, ACC, EB, lo(1), hi(1));
+                launch_ustage<7>(ctx, strict, ge, ext(EB), dt, nullptr, ACC, nxt, lo(2), hi(2));
+                double* t = cur; cur = nxt; nxt = t;
+            }
+        }
+        SB_CUDA(ctx, cudaMemcpyAsync(y, cur + H * row_elems, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        SB_CUDA(ctx, cudaGetLastError());
+        return sg.finish();
     }
     void* scr;
     if ((rc = sb_scratch(ctx, (3 * n + 6 * row_elems) * 8 + 1024, &scr))) return rc;
