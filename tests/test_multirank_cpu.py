@@ -186,6 +186,80 @@ def _ugrid_worker(rank, world, port_no, rows, cols, steps, integrator, out):
     dist.destroy_process_group()
 
 
+def _ugrid_deep_worker(rank, world, port_no, rows, cols, steps, integrator, out):
+    """The default multi-rank schedule of ugrid.cu: H ghost rows at both ends of every buffer, ONE exchange of the H boundary
+    rows per step, evaluation s of the step on the buffer shrunk by s rows (clamped to the global grid)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle.oracle_py import Checker
+    port = Checker("port")
+    full = _ugrid_state(port, rows, cols).reshape(rows, cols, 6)
+    rb, rl = slab(rows, rank, world)
+    H = {"rk4": 4, "velocity_verlet": 2, "symplectic_euler": 1}[integrator]
+    ext_rows, g0 = rl + 2 * H, rb - H                      # global row of extended row 0 (negative on rank 0)
+    Y = np.zeros((ext_rows, cols, 6)); Y[H:H + rl] = full[rb:rb + rl]
+
+    def exchange(buf):
+        reqs, recv = [], {}
+        for peer, send, slot in ((rank - 1, buf[H:2 * H], 0), (rank + 1, buf[rl:rl + H], 1)):
+            if 0 <= peer < world:
+                recv[slot] = torch.empty(H, cols, 6, dtype=torch.float64)
+                reqs += [dist.isend(torch.from_numpy(np.ascontiguousarray(send)), peer), dist.irecv(recv[slot], peer)]
+        for r in reqs:
+            r.wait()
+        if 0 in recv:
+            buf[:H] = recv[0].numpy()
+        if 1 in recv:
+            buf[H + rl:] = recv[1].numpy()
+
+    def rng(s):                                             # rows on which evaluation s has valid inputs, inside the grid
+        return max(s, -g0), min(ext_rows - s, rows - g0)
+
+    def f(buf, lo, hi):                                     # derivative of rows [lo, hi): the oracle on them plus one context row
+        a = lo - 1 if g0 + lo > 0 else lo
+        b = hi + 1 if g0 + hi < rows else hi
+        d = port.ugrid(b - a, cols, UPRM, buf[a:b].reshape(-1, 6)).reshape(b - a, cols, 6)
+        return d[lo - a: lo - a + hi - lo]
+
+    dt = 1e-3
+    V, X = [2, 3, 5], [0, 1, 4]
+    for _ in range(steps):
+        exchange(Y)
+        if integrator == "rk4":
+            S, A, B = np.zeros_like(Y), np.zeros_like(Y), np.zeros_like(Y)
+            lo, hi = rng(1); k = f(Y, lo, hi) * dt; S[lo:hi] = k; A[lo:hi] = Y[lo:hi] + 0.5 * k
+            lo, hi = rng(2); k = f(A, lo, hi) * dt; S[lo:hi] = S[lo:hi] + 2.0 * k; B[lo:hi] = Y[lo:hi] + 0.5 * k
+            lo, hi = rng(3); k = f(B, lo, hi) * dt; S[lo:hi] = S[lo:hi] + 2.0 * k; A[lo:hi] = Y[lo:hi] + k
+            lo, hi = rng(4); k = f(A, lo, hi) * dt; Y[lo:hi] = Y[lo:hi] + (S[lo:hi] + k) / 6.0
+        elif integrator == "symplectic_euler":
+            lo, hi = rng(1); d = f(Y, lo, hi); N = Y.copy()
+            N[lo:hi][..., V] += dt * d[..., V]; N[lo:hi][..., X] += dt * N[lo:hi][..., V]
+            Y = N
+        else:
+            lo, hi = rng(1); d = f(Y, lo, hi); Bp = Y.copy(); An = np.zeros_like(Y); An[lo:hi] = d
+            Bp[lo:hi][..., X] += dt * Y[lo:hi][..., V] + (0.5 * dt * dt) * d[..., V]
+            lo, hi = rng(2); dn = f(Bp, lo, hi); N = Bp.copy()
+            N[lo:hi][..., V] += (0.5 * dt) * (An[lo:hi][..., V] + dn[..., V])
+            Y = N
+    np.save(os.path.join(out, f"udeep_{integrator}_{rank}.npy"), Y[H:H + rl])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "symplectic_euler", "velocity_verlet"])
+def test_unified_grid_one_exchange_per_step_matches_single_domain_oracle(port, tmp_path, integrator):
+    rows, cols, steps, world = 9, 8, 3, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        free_port = s.getsockname()[1]
+    mp.spawn(_ugrid_deep_worker, args=(world, free_port, rows, cols, steps, integrator, str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / f"udeep_{integrator}_{r}.npy") for r in range(world)], axis=0)
+    ref = port.ugrid(rows, cols, UPRM, _ugrid_state(port, rows, cols), 1e-3, steps, integrator)
+    assert np.array_equal(got.reshape(-1, 6), ref)
+
+
 @pytest.mark.parametrize("integrator", ["rk4", "symplectic_euler", "velocity_verlet"])
 def test_unified_grid_slab_schedule_matches_single_domain_oracle(port, tmp_path, integrator):
     rows, cols, steps, world = 7, 9, 4, 2
