@@ -195,13 +195,6 @@ SB_HD void rotate_tiny_k(double s, double c, double d, double T3, double& s_out,
     c_out = fma(c, cd, -(s * sd));
 }
 
-// sin(x) only (both polynomials, one select: cheaper on the RF than selecting 6 coefficient pairs)
-SB_HD double sin1(double x) {
-    double s, c;
-    sincos(x, s, c);
-    return s;
-}
-
 // 1/x to <= 1 ulp for normal, finite x: MUFU.RCP64H seed (relative error 2^-20, measured:
 // tools/microbench/rcp_accuracy.cu) + one cubically convergent step, y (1 + e + e^2) with e = 1 - x y  ->  2^-60.
 // No special-case branch (the IEEE division sequence carries a data-dependent slow path; callers guarantee |x|
