@@ -131,9 +131,6 @@ def control_golden(R):
     np.savez(os.path.join(OUT, "control.npz"), **out)
 
 
-if __name__ == "__main__":
-    main()
-
 
 def cartn_linearize_golden(R):
     """N-link linearization (makeLinearizer<2(N+1),1> around CartNPendulum<N,Dual<double,2N+3>>), N = 1, 2, 6."""
@@ -254,3 +251,7 @@ def ugrid_golden(R):
         tri[key + "_rk4"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
         tri[key + "_verlet"] = R.ugrid(rows, cols, prm, st, 1e-3, 50, "velocity_verlet")
     np.savez(os.path.join(OUT, "ugrid_triangle.npz"), **tri)
+
+
+if __name__ == "__main__":
+    main()
