@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from oracle.oracle_py import Checker  # noqa: E402
 from sopot_b200 import workloads as W  # noqa: E402
 
-OUT = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("SOPOT_GOLDEN_OUT") or os.path.dirname(os.path.abspath(__file__))     # fixtures are written here
 
 
 def main():

@@ -311,3 +311,23 @@ def test_golden_unified_grid_integrators(port):
         rk = port.ugrid(rows, cols, prm, st, 1e-3, 50, "rk4")
         err = [np.abs(port.ugrid(rows, cols, prm, st, 1e-3, 50, m) - rk).max() for m in ("symplectic_euler", "velocity_verlet")]
         assert err[0] < 0.05 and err[1] < 0.05
+
+
+def test_golden_generator_reproduces_the_committed_fixtures(ref, tmp_path):
+    """tests/golden/make_golden.py, run as a script against the reference harness, regenerates every committed fixture bit for
+    bit (needs /root/reference-built oracle/_ref: skipped where the `ref` fixture is unavailable)."""
+    import subprocess
+    import sys
+    gold = os.path.join(ROOT, "tests", "golden")
+    env = dict(os.environ, SOPOT_GOLDEN_OUT=str(tmp_path))
+    # the atmosphere fixture is derived from rocket.npz of the same output directory: generated in order by main()
+    r = subprocess.run([sys.executable, os.path.join(gold, "make_golden.py")], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    names = sorted(f for f in os.listdir(gold) if f.endswith(".npz"))
+    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
+    for f in names:
+        a, b = np.load(os.path.join(gold, f)), np.load(tmp_path / f)
+        assert sorted(a.keys()) == sorted(b.keys()), f
+        for k in a.keys():
+            assert np.array_equal(a[k], b[k], equal_nan=True), (f, k)
+
