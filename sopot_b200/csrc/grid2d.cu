@@ -108,7 +108,8 @@ __device__ __forceinline__ void mass_derivative_from(const GridDev& g, const Mas
         if (has_d && has_r) { spring_force<S>(P, nb(1, 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
     }
     d[0] = R(P.vx); d[1] = R(P.vy);
-    d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass);
+    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); }
+    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); }          // contract: as the fused step does
 }
 
 template <bool S, int TOPO>
