@@ -145,7 +145,15 @@ template <bool S> __device__ __forceinline__ void r_sincos(Real<S> a, Real<S>& s
 }
 // x / d where the reference divides: IEEE division when Strict, reciprocal multiply otherwise
 template <bool S> __device__ __forceinline__ Real<S> r_div_const(Real<S> a, double d) {
-    if constexpr (S) return Real<S>(SB_DIV(a.v, d)); else return Real<S>(a.v * (1.0 / d));
+#ifdef __CUDA_ARCH__
+    if constexpr (S) return Real<S>(sb_div_by(a.v, d, 1.0 / d)); else return Real<S>(a.v * (1.0 / d));   // d is a literal: 1/d folds
+#else
+    if constexpr (S) return Real<S>(a.v / d); else return Real<S>(a.v * (1.0 / d));
+#endif
+}
+// a / d for a divisor that is constant over the launch, inv = RN(1 / d) from the host
+template <bool S> __device__ __forceinline__ Real<S> r_div_by(Real<S> a, double d, double inv) {
+    if constexpr (S) return Real<S>(sb_div_by(a.v, d, inv)); else return Real<S>(a.v * inv);
 }
 
 inline unsigned sb_grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }

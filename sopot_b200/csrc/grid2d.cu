@@ -108,8 +108,7 @@ __device__ __forceinline__ void mass_derivative_from(const GridDev& g, const Mas
         if (has_d && has_r) { spring_force<S>(P, nb(1, 1), g.k, g.c, g.L_diag, fx, fy); Fx += fx; Fy += fy; }
     }
     d[0] = R(P.vx); d[1] = R(P.vy);
-    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); }
-    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); }          // contract: as the fused step does
+    d[2] = r_div_by<S>(Fx, g.mass, g.inv_mass); d[3] = r_div_by<S>(Fy, g.mass, g.inv_mass);      // strict: correctly rounded
 }
 
 template <bool S, int TOPO>
@@ -278,8 +277,7 @@ __device__ __forceinline__ void fused_update(const GridDev& g, const double dt_,
     }
     R d[4];
     d[0] = R(in_pl[2 * T::CELLS + o]); d[1] = R(in_pl[3 * T::CELLS + o]);           // {vx, vy, Fx/m, Fy/m}
-    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); }
-    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); }
+    d[2] = r_div_by<S>(Fx, g.mass, g.inv_mass); d[3] = r_div_by<S>(Fy, g.mass, g.inv_mass);
     const R dt(dt_);
     R k[4];
 #pragma unroll

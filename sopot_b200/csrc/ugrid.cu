@@ -146,8 +146,8 @@ __device__ __forceinline__ void derivative_from(const UGridDev& g, const Body& P
     }
     d[0] = R(P.vx); d[1] = R(P.vy);
     d[4] = R(P.om);
-    if constexpr (S) { d[2] = Fx / R(g.mass); d[3] = Fy / R(g.mass); d[5] = Tq / R(g.inertia); }
-    else { d[2] = Fx * R(g.inv_mass); d[3] = Fy * R(g.inv_mass); d[5] = Tq * R(g.inv_inertia); }
+    d[2] = r_div_by<S>(Fx, g.mass, g.inv_mass); d[3] = r_div_by<S>(Fy, g.mass, g.inv_mass);
+    d[5] = r_div_by<S>(Tq, g.inertia, g.inv_inertia);
 }
 
 template <bool S>

@@ -1,5 +1,5 @@
 // exact_math_check.cu -- are the branch-light IEEE division / sqrt sequences of csrc/ieee.cuh correctly rounded?
-// Compares sb_div_rn / sb_sqrt_rn with the compiler's IEEE `a / b` and `sqrt(a)` (nvcc -prec-div=true -prec-sqrt=true)
+// Compares sb_div_rn / sb_div_by / sb_sqrt_rn with the compiler's IEEE `a / b` and `sqrt(a)` (nvcc -prec-div=true -prec-sqrt=true)
 // bit for bit over random mantissas and exponents, exact zeros, near-1 quotients and perfect squares.
 // Exit code 0 = identical on every sample.  Run on the GPU by tests/test_gpu_parity.py.
 #include <cstdio>
@@ -26,6 +26,11 @@ __global__ void check(unsigned long long* bad, unsigned long long* first, int it
         if (cls == 3) a = b * (1.0 + 1e-15 * (double)(int)(ra & 15));  // quotient next to 1
         const double q0 = a / b, q1 = sb_div_rn(a, b);
         if (__double_as_longlong(q0) != __double_as_longlong(q1) && !(q0 != q0 && q1 != q1)) { if (!nbad) { first[0] = __double_as_longlong(a); first[1] = __double_as_longlong(b); } ++nbad; }
+        // division by a launch-constant divisor with its correctly rounded reciprocal precomputed (sb_div_by)
+        const double q2 = sb_div_by(a, b, 1.0 / b);
+        if (__double_as_longlong(q0) != __double_as_longlong(q2) && !(q0 != q0 && q2 != q2)) { if (!nbad) { first[0] = __double_as_longlong(a); first[1] = __double_as_longlong(b) ^ 1ull << 63; } ++nbad; }
+        const double q6 = sb_div_by(a, 6.0, 1.0 / 6.0);
+        if (__double_as_longlong(a / 6.0) != __double_as_longlong(q6) && !(q6 != q6 && a != a)) { if (!nbad) { first[0] = __double_as_longlong(a); first[1] = 6; } ++nbad; }
         const double x = cls == 3 ? fabs(a) * fabs(a) : fabs(a);
         const double r0 = sqrt(x), r1 = sb_sqrt_rn(x);
         if (__double_as_longlong(r0) != __double_as_longlong(r1) && !(r0 != r0 && r1 != r1)) { if (!nbad) { first[0] = __double_as_longlong(x); first[1] = 0; } ++nbad; }
