@@ -131,6 +131,12 @@ int sopot_b200_dpend_rk4(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, 
 /* one derivative evaluation per instance (computeDerivatives), state/out [4][n] */
 int sopot_b200_dpend_rhs(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n,
                          const sopot_b200_rk4_opts* opts, const double* state, double* out);
+/* Batched 4x4 state Jacobians d f_i / d x_j of the double pendulum by forward-mode AD: computeJacobian
+ * (core/typed_component.hpp:486-512) on DoublePendulum<Dual<double,4>> (tests/double_pendulum_test.cpp:383-412).
+ * Reads m1, m2, L1, L2, g of `p` (arrays of n, or broadcast scalars) and state[4][n]; writes J[16][n], row-major 4x4 per
+ * point, SoA over the points. */
+int sopot_b200_dpend_jacobian(sopot_b200_ctx* ctx, const sopot_b200_dpend_params* p, size_t n,
+                              const sopot_b200_rk4_opts* opts, const double* state, double* J);
 
 /* control::CartNPendulum<1,double>(mc, {m}, {L}, g, {x,th,xd,w}) with a constant control force
  * (setControlForce), physics/control/cart_n_pendulum.hpp:83-221 */

@@ -116,6 +116,13 @@ class Checker:
                 P, _p(x), _p(u), _p(mc), _p(m), _p(L), _p(g), _p(A), _p(B), nthreads)
         return A, B
 
+    def dpend_jacobian(self, m1, m2, L1, L2, g, state):
+        state = _f64(state); n = state.shape[1]
+        m1, m2, L1, L2, g = (_f64(a, n).reshape(-1) for a in (m1, m2, L1, L2, g))
+        J = np.empty((16, n))
+        self._fn("dpend_jacobian", [_sz] + [_dp] * 7)(n, _p(m1), _p(m2), _p(L1), _p(L2), _p(g), _p(state), _p(J))
+        return J
+
     def cartpole_rk4(self, mc, m, L, g, s0, force, t0, t1, dt, nthreads=1):
         s0 = _f64(s0); n = s0.shape[1]
         mc, m, L, g, force = (_f64(a, n) for a in (mc, m, L, g, force))

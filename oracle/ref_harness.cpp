@@ -481,6 +481,20 @@ int ref_cartn_feedback_rk4(int n_links, size_t n, const double* mc, const double
     return 0;
 }
 
+// computeJacobian of the reference (core/typed_component.hpp:486-512) on DoublePendulum<Dual<double,4>>, as
+// tests/double_pendulum_test.cpp:383-412 calls it; J[16][n] row-major 4x4 per point, SoA over the points
+void ref_dpend_jacobian(size_t n, const double* m1, const double* m2, const double* L1, const double* L2, const double* g,
+                        const double* state, double* J) {
+    using D4 = sopot::Dual<double, 4>;
+    for (size_t p = 0; p < n; ++p) {
+        auto sys = sopot::makeTypedODESystem<D4>(sopot::pendulum::DoublePendulum<D4>(m1[p], m2[p], L1[p], L2[p], g[p], 0.0, 0.0, 0.0, 0.0));
+        const std::array<double, 4> x{state[p], state[n + p], state[2 * n + p], state[3 * n + p]};
+        const auto jac = sopot::computeJacobian(sys, 0.0, x);
+        for (size_t i = 0; i < 4; ++i)
+            for (size_t j = 0; j < 4; ++j) J[(i * 4 + j) * n + p] = jac[i][j];
+    }
+}
+
 // prm[18]: mass, radius, spacing, stiffness, rest_length, damping, min_distance, repulsion_stiffness, h_attach0, h_attach1, v_attach0,
 // v_attach1, topology (0 quad / 1 triangle), diagonal rest length, main-diagonal attach 0/1, anti-diagonal attach 0/1
 int ref_ugrid(size_t rows, size_t cols, const double* prm, double dt, size_t n_steps, const double* state_in, double* out, int mode) {

@@ -262,6 +262,35 @@ static dual_t d_cos(dual_t x) {                     /* :192-201 */
     for (int i = 0; i < DN; ++i) r.d[i] = ns * x.d[i];
     r.v = cos(x.v); return r; }
 
+/* computeJacobian (core/typed_component.hpp:486-512) on DoublePendulum<Dual<double,4>> (physics/pendulum/
+ * double_pendulum.hpp:126-179; the reference's test: tests/double_pendulum_test.cpp:383-412): state variable i carries
+ * seed i, J[i][j] = derivative j of f_i.  dual_t holds DN = 5 partials; partials never mix, so the first four are exactly
+ * those of Dual<double,4>.  J is [16][n], row-major 4x4 per point, SoA over the points. */
+ORC_API void orc_dpend_jacobian(size_t n, const double* m1_, const double* m2_, const double* L1_, const double* L2_,
+                                const double* g_, const double* state /*[4][n]*/, double* J /*[16][n]*/) {
+    for (size_t p = 0; p < n; ++p) {
+        dual_t y[4];
+        for (int i = 0; i < 4; ++i) y[i] = d_var(state[(size_t)i * n + p], i);
+        const dual_t theta1 = y[0], theta2 = y[1], omega1 = y[2], omega2 = y[3];
+        const dual_t delta = d_sub(theta1, theta2);
+        const dual_t sin_delta = d_sin(delta), cos_delta = d_cos(delta);
+        const dual_t sin_theta1 = d_sin(theta1), sin_theta2 = d_sin(theta2);
+        const dual_t m1 = d_const(m1_[p]), m2 = d_const(m2_[p]), L1 = d_const(L1_[p]), L2 = d_const(L2_[p]), g = d_const(g_[p]);
+        const dual_t a11 = d_mul(d_add(m1, m2), L1);
+        const dual_t a12 = d_mul(d_mul(m2, L2), cos_delta);
+        const dual_t a21 = d_mul(L1, cos_delta);
+        const dual_t a22 = L2;
+        const dual_t b1 = d_sub(d_mul(d_mul(d_mul(d_mul(m2, L2), omega2), omega2), sin_delta), d_mul(d_mul(d_add(m1, m2), g), sin_theta1));
+        const dual_t negL1 = d_sub(d_const(0.0), L1);                  /* unary minus of the reference: -L1 (value -L1) */
+        const dual_t b2 = d_sub(d_mul(d_mul(d_mul(negL1, omega1), omega1), sin_delta), d_mul(g, sin_theta2));
+        const dual_t det = d_sub(d_mul(a11, a22), d_mul(a12, a21));
+        const dual_t f[4] = {omega1, omega2, d_div(d_sub(d_mul(b1, a22), d_mul(b2, a12)), det),
+                             d_div(d_sub(d_mul(a11, b2), d_mul(a21, b1)), det)};
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) J[(size_t)(i * 4 + j) * n + p] = f[i].d[j];
+    }
+}
+
 /* CartNPendulum<1, Dual5>::derivatives. status: 0 ok, 1 singular mass matrix (:331-333 throws) */
 static int orc_cartpole_dual_rhs(double mc, double m, double L, double g_, const dual_t local[4],
                                  dual_t F, dual_t deriv[4]) {

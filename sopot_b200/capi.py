@@ -139,6 +139,7 @@ SYMBOLS = {
     "sopot_b200_dpend_rk4": (c_int, [_ctx, POINTER(DpendParams), c_size_t, c_double, c_double, c_size_t,
                                      POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
     "sopot_b200_dpend_rhs": (c_int, [_ctx, POINTER(DpendParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
+    "sopot_b200_dpend_jacobian": (c_int, [_ctx, POINTER(DpendParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_cartpole_rk4": (c_int, [_ctx, POINTER(CartpoleParams), c_size_t, c_double, c_double, c_size_t,
                                         POINTER(RK4Opts), c_void_p, c_void_p, c_void_p]),
     "sopot_b200_cartpole_linearize": (c_int, [_ctx, POINTER(CartpolePlant), c_void_p, c_void_p, c_size_t,
@@ -372,6 +373,22 @@ class Engine:
         self._ck(self.lib.sopot_b200_dpend_rhs(self.ctx, byref(p), n, byref(opts), _ptr(state), _ptr(out)))
         self.sync()
         return out
+
+    def dpend_jacobian(self, m1, m2, L1, L2, g, state, fp_mode=FP_STRICT, mem=MEM_HOST, J=None, sync=True):
+        """d f_i / d x_j of the double pendulum at every column of state[4][n] -> J[16][n] (row-major 4x4 per point)."""
+        if mem == MEM_HOST:
+            state = np.ascontiguousarray(state, dtype=np.float64)
+        n = state.shape[1]
+        ptrs, mask, keep = self._prep(dict(m1=m1, m2=m2, L1=L1, L2=L2, g=g), n, mem)
+        p = DpendParams(**ptrs)
+        opts = RK4Opts(mem, fp_mode, 0, mask, 0)
+        if J is None:
+            J = np.empty((16, n)) if mem == MEM_HOST else self.empty((16, n))
+        self._ck(self.lib.sopot_b200_dpend_jacobian(self.ctx, byref(p), n, byref(opts), _ptr(state), _ptr(J)))
+        self._keep = keep
+        if sync:
+            self.sync()
+        return J
 
     def cartpole_rk4(self, mc, m, L, g, x, th, xd, w, force, n, t0, dt, n_steps, mem=MEM_HOST,
                      fp_mode=FP_CONTRACT, store_every=0, want_status=True, sync=True):

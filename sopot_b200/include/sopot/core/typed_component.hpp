@@ -293,6 +293,22 @@ SOPOT_HD auto makeTypedODESystem(Components&&... c) {
     return TypedODESystem<T, std::decay_t<Components>...>(std::forward<Components>(c)...);
 }
 
+// computeJacobian (reference :486-512): d f_i / d x_j of a system instantiated on Dual<double, N>.  Seeds the N state
+// variables and evaluates the system's derivatives once -- for a shipped pack that evaluation is the batched forward-mode
+// kernel behind its SystemBinding (rhs_dual), for a user pack the generic device kernel; nothing differentiates on the host.
+template <size_t N, TypedComponentConcept... Components>
+std::array<std::array<double, N>, N> computeJacobian(const TypedODESystem<Dual<double, N>, Components...>& system, double t,
+                                                     const std::array<double, N>& state_values) {
+    static_assert(N == (Components::state_size + ...), "State size mismatch");
+    std::vector<Dual<double, N>> state(N);
+    for (size_t i = 0; i < N; ++i) state[i] = Dual<double, N>::variable(state_values[i], i);
+    const auto derivs = system.computeDerivatives(Dual<double, N>::constant(t), state);
+    std::array<std::array<double, N>, N> jacobian{};
+    for (size_t i = 0; i < N; ++i)
+        for (size_t j = 0; j < N; ++j) jacobian[i][j] = derivs[i].derivative(j);
+    return jacobian;
+}
+
 template <typename S> struct is_typed_ode_system : std::false_type {};
 template <typename T, typename... C> struct is_typed_ode_system<TypedODESystem<T, C...>> : std::true_type {};
 

@@ -159,4 +159,36 @@ struct SystemBinding<pendulum::DoublePendulum<double>> {
         return one(t, y0).integrate(eng, n_steps, t0, dt, o);
     }
 };
+// DoublePendulum<Dual<double,K>>: the derivative in dual arithmetic = value from the derivative kernel, partials by the
+// chain rule through the 4x4 state Jacobian of sopot_b200_dpend_jacobian (forward-mode AD on the device) and the caller's
+// seeds -- what computeJacobian (core/typed_component.hpp) and the linearizers evaluate.
+template <size_t K>
+struct SystemBinding<pendulum::DoublePendulum<Dual<double, K>>> {
+    static constexpr bool available = true;
+    using D = Dual<double, K>;
+    using Tuple = std::tuple<pendulum::DoublePendulum<D>>;
+    static std::vector<D> rhs_dual(Engine& eng, const Tuple& t, const std::vector<D>& s) {
+        const auto& c = std::get<0>(t);
+        const double m1 = c.getMass1(), m2 = c.getMass2(), L1 = c.getLength1(), L2 = c.getLength2(), g = c.getGravity();
+        const double x0[4] = {s[0].value(), s[1].value(), s[2].value(), s[3].value()};
+        EnsembleOptions o; o.fp_mode = FpMode::Strict;
+        const auto opts = make_opts(o, 0);
+        const sopot_b200_dpend_params p{&m1, &m2, &L1, &L2, &g, nullptr, nullptr, nullptr, nullptr};
+        double J[16], f[4];
+        eng.check(sopot_b200_dpend_jacobian(eng.ctx(), &p, 1, &opts, x0, J));
+        eng.check(sopot_b200_dpend_rhs(eng.ctx(), &p, 1, &opts, x0, f));
+        eng.sync();
+        std::vector<D> out(4);
+        for (size_t i = 0; i < 4; ++i) {
+            std::array<double, K> d{};
+            for (size_t k = 0; k < K; ++k) {
+                double acc = 0.0;
+                for (size_t j = 0; j < 4; ++j) acc += J[i * 4 + j] * s[j].derivative(k);
+                d[k] = acc;
+            }
+            out[i] = D(f[i], d);
+        }
+        return out;
+    }
+};
 }  // namespace sopot::b200

@@ -64,6 +64,23 @@ int main() {
     for (size_t i = 0; i < 4 * n; ++i) { scale = std::max(scale, std::abs(b.state[i])); err = std::max(err, std::abs(a.state[i] - b.state[i])); }
     ASSERT_TRUE(err <= 1e-9 * scale);
     for (auto st : a.status) ASSERT_TRUE(st == 0);
+    // Test 8 of the reference (tests/double_pendulum_test.cpp:383-412): autodiff Jacobian of DoublePendulum<Dual<double,4>>
+    {
+        using Dual4 = Dual<double, 4>;
+        auto dsys = makeTypedODESystem<Dual4>(DoublePendulum<Dual4>(1.0, 1.0, 1.0, 1.0, 9.81, 0.5, 0.3, 0.1, -0.1));
+        auto dstate = dsys.getInitialState();
+        std::array<double, 4> values;
+        for (size_t i = 0; i < 4; ++i) values[i] = value_of(dstate[i]);
+        const auto jac = computeJacobian(dsys, 0.0, values);
+        ASSERT_NEAR(jac[0][2], 1.0, 1e-10);
+        ASSERT_NEAR(jac[1][3], 1.0, 1e-10);
+        ASSERT_NEAR(jac[0][0], 0.0, 1e-10);
+        ASSERT_NEAR(jac[0][1], 0.0, 1e-10);
+        // the reference's own numbers for this point (oracle/_ref, tests/golden/dpend_jacobian.npz column 0)
+        const double row2[4] = {-14.735500613870823, 7.007393204894467, 0.03746318109240295, -0.03822513892364516};
+        const double row3[4] = {13.177970444475825, -14.975761621293028, -0.07645027784729032, 0.03746318109240295};
+        for (int j = 0; j < 4; ++j) { ASSERT_NEAR(jac[2][j], row2[j], 1e-12 * 15.0); ASSERT_NEAR(jac[3][j], row3[j], 1e-12 * 15.0); }
+    }
     std::puts("double_pendulum_test: OK");
     return 0;
 }

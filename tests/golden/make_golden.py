@@ -91,6 +91,7 @@ def main():
     cartn_linearize_golden(R)
     rocket_aero_golden(R)
     rocket_atmosphere_golden(R)
+    dpend_jacobian_golden(R)
     control_n_golden(R)
     ugrid_golden(R)
     for f in sorted(os.listdir(OUT)):
@@ -191,6 +192,18 @@ def rocket_atmosphere_golden(R):
     st[11:14] = rng.normal(0, 0.3, (3, alts.size))
     np.savez(os.path.join(OUT, "rocket_atmosphere.npz"), state=st,
              rhs=R.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], st))
+
+
+def dpend_jacobian_golden(R):
+    """computeJacobian (core/typed_component.hpp:486-512) on DoublePendulum<Dual<double,4>>; point 0 is the reference test's
+    (tests/double_pendulum_test.cpp:387-389)."""
+    rng = np.random.default_rng(17)
+    n = 48
+    m1, m2, L1, L2 = (rng.uniform(0.5, 2, n) for _ in range(4)); g = np.full(n, 9.81)
+    st = np.stack([rng.uniform(-3, 3, n), rng.uniform(-3, 3, n), rng.uniform(-5, 5, n), rng.uniform(-5, 5, n)])
+    m1[0], m2[0], L1[0], L2[0] = 1, 1, 1, 1; st[:, 0] = [0.5, 0.3, 0.1, -0.1]       # the reference test's point
+    np.savez(os.path.join(OUT, "dpend_jacobian.npz"), m1=m1, m2=m2, L1=L1, L2=L2, g=g, state=st,
+             J=R.dpend_jacobian(m1, m2, L1, L2, g, st))
 
 
 def control_n_golden(R):

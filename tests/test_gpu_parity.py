@@ -137,6 +137,24 @@ def test_dpend_full_horizon_sample_vs_oracle(engine, port):
 
 
 @pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
+def test_dpend_jacobian_golden_and_batch(engine, port, fp):
+    """Batched forward-mode Jacobians of the double pendulum (sopot_b200_dpend_jacobian) against the reference's computeJacobian
+    (golden vectors) and, for a ragged batch through device pointers, against the oracle; broadcast parameters."""
+    g = golden("dpend_jacobian")
+    J = engine.dpend_jacobian(g["m1"], g["m2"], g["L1"], g["L2"], g["g"], g["state"], fp_mode=fp)
+    scale = np.abs(g["J"]).reshape(4, 4, -1).max(axis=(0, 1))
+    assert (np.abs(J - g["J"]) / scale).max() <= PER_STEP
+    n = 10007
+    rng = np.random.default_rng(23)
+    st = np.stack([rng.uniform(-3, 3, n), rng.uniform(-3, 3, n), rng.uniform(-5, 5, n), rng.uniform(-5, 5, n)])
+    m1, L2 = rng.uniform(0.5, 2, n), rng.uniform(0.5, 2, n)
+    ref = port.dpend_jacobian(m1, np.full(n, 0.7), np.full(n, 1.3), L2, np.full(n, 9.81), st)
+    dJ = engine.dpend_jacobian(engine.to_device(m1), 0.7, 1.3, engine.to_device(L2), 9.81, engine.to_device(st), fp_mode=fp, mem=MEM_DEVICE)
+    scale = np.abs(ref).reshape(4, 4, -1).max(axis=(0, 1))
+    assert (np.abs(dJ.download() - ref) / scale).max() <= PER_STEP
+
+
+@pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
 def test_dpend_degenerate_parameters_and_large_increments(engine, port, fp):
     """The contract-mode step carries sin/cos pairs scaled by g/L1 and L1/L2 and rotates them by small increments:
     g = 0 (first pair identically zero), m2 = 0 (kap = 0: a simple pendulum), very unequal arms, rates so large that

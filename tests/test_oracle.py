@@ -216,6 +216,24 @@ def test_lqr_port_equals_reference_on_fresh_inputs(port, ref):
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
 
 
+def test_golden_dpend_jacobian(port):
+    """Forward-mode Jacobian of the double pendulum (computeJacobian on DoublePendulum<Dual<double,4>>): the C dual numbers of
+    the port == the reference's, bit for bit; the structure the reference's own test asserts
+    (tests/double_pendulum_test.cpp:405-409) and a central-difference cross-check of the angular rows."""
+    g = golden("dpend_jacobian")
+    J = port.dpend_jacobian(g["m1"], g["m2"], g["L1"], g["L2"], g["g"], g["state"])
+    assert np.array_equal(J, g["J"])
+    J0 = J[:, 0].reshape(4, 4)
+    assert abs(J0[0, 2] - 1.0) < 1e-10 and abs(J0[1, 3] - 1.0) < 1e-10 and abs(J0[0, 0]) < 1e-10 and abs(J0[0, 1]) < 1e-10
+    h = 1e-6
+    for j in range(4):
+        sp, sm = g["state"].copy(), g["state"].copy()
+        sp[j] += h; sm[j] -= h
+        fd = (port.dpend_rhs(g["m1"], g["m2"], g["L1"], g["L2"], g["g"], sp) - port.dpend_rhs(g["m1"], g["m2"], g["L1"], g["L2"], g["g"], sm)) / (2 * h)
+        col = J.reshape(4, 4, -1)[:, j, :]
+        assert np.abs(fd - col).max() <= 1e-5 * max(1.0, np.abs(col).max())
+
+
 def test_golden_rocket_all_atmosphere_layers(port):
     """One derivative per layer of the standard atmosphere and at each layer boundary (the trajectory fixtures stay below
     11 km): isothermal layers, both signs of the lapse rate, the h <= 0 and h >= 100 km clamps -- port == reference."""
