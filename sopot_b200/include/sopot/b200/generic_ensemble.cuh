@@ -124,6 +124,31 @@ rhs_kernel(const Factory make, const size_t n, const double t, const double* __r
     for (size_t d = 0; d < D; ++d) out[d * n + i] = dy[d];
 }
 
+// one derivative evaluation of a pack instantiated on Dual<double,K>: state and result travel as [D][K+1][n] doubles
+// (value, then the K partials); the arithmetic is the components' own code in the reference's Dual formulas (core/dual.hpp)
+template <typename Factory>
+__global__ void __launch_bounds__(128)
+rhs_dual_kernel(const Factory make, const size_t n, const double t, const double* __restrict__ state, double* __restrict__ out) {
+    using System = system_of_t<Factory>;
+    using T = typename System::scalar_type;
+    constexpr size_t D = System::getStateDimension(), K = T::num_derivatives;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    System sys = make(i);
+    sys.initializeOffsets();
+    T y[D], dy[D];
+#pragma unroll
+    for (size_t d = 0; d < D; ++d)
+        y[d] = T::make(state[(d * (K + 1)) * n + i], [&](size_t k) { return state[(d * (K + 1) + 1 + k) * n + i]; });
+    sys.computeDerivativesInto(T::constant(t), y, dy);
+#pragma unroll
+    for (size_t d = 0; d < D; ++d) {
+        out[(d * (K + 1)) * n + i] = dy[d].value();
+#pragma unroll
+        for (size_t k = 0; k < K; ++k) out[(d * (K + 1) + 1 + k) * n + i] = dy[d].derivative(k);
+    }
+}
+
 // RAII device buffer on the engine's device
 template <typename U>
 struct DeviceBuffer {
@@ -187,6 +212,34 @@ std::vector<double> rhs_one(const System& sys, const std::vector<double>& state)
     eng.check(sopot_b200_note_launches(eng.ctx(), 1));
     cuda_check(cudaMemcpyAsync(out.data(), d_out.p, D * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H derivative");
     cuda_check(cudaStreamSynchronize(st), "generic rhs kernel");
+    return out;
+}
+
+template <typename System>
+std::vector<typename System::scalar_type> rhs_one_dual(const System& sys, const std::vector<typename System::scalar_type>& state) {
+    using T = typename System::scalar_type;
+    static_assert(System::device_differentiable, "every stateful component needs SOPOT_HD derivatives() and must be trivially copyable");
+    constexpr size_t D = System::getStateDimension(), K = T::num_derivatives, W = D * (K + 1);
+    Engine& eng = Engine::shared();
+    cudaStream_t st = stream_of(eng);
+    std::vector<double> flat(W), res(W);
+    for (size_t d = 0; d < D; ++d) {
+        flat[d * (K + 1)] = state[d].value();
+        for (size_t k = 0; k < K; ++k) flat[d * (K + 1) + 1 + k] = state[d].derivative(k);
+    }
+    DeviceBuffer<double> d_in(W), d_out(W);
+    cuda_check(cudaMemcpyAsync(d_in.p, flat.data(), W * sizeof(double), cudaMemcpyHostToDevice, st), "H2D dual state");
+    rhs_dual_kernel<CopyFactory<System>><<<1, 128, 0, st>>>(CopyFactory<System>{sys}, 1, 0.0, d_in.p, d_out.p);
+    cuda_check(cudaGetLastError(), "generic dual rhs kernel launch");
+    eng.check(sopot_b200_note_launches(eng.ctx(), 1));
+    cuda_check(cudaMemcpyAsync(res.data(), d_out.p, W * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H dual derivative");
+    cuda_check(cudaStreamSynchronize(st), "generic dual rhs kernel");
+    std::vector<T> out(D);
+    for (size_t d = 0; d < D; ++d) {
+        std::array<double, K> part{};
+        for (size_t k = 0; k < K; ++k) part[k] = res[d * (K + 1) + 1 + k];
+        out[d] = T(res[d * (K + 1)], part);
+    }
     return out;
 }
 

@@ -141,6 +141,8 @@ template <typename... Components> struct SystemBinding { static constexpr bool a
 namespace b200::generic {
 // defined in b200/generic_ensemble.cuh (nvcc only): N = 1 launches of the kernel instantiated for `System`
 template <typename System> std::vector<double> rhs_one(const System& sys, const std::vector<double>& state);
+// the same for a pack instantiated on Dual<double,K>: one derivative evaluation in dual arithmetic on the device
+template <typename System> std::vector<typename System::scalar_type> rhs_one_dual(const System& sys, const std::vector<typename System::scalar_type>& state);
 template <typename System>
 EnsembleResult solve_one(Engine& eng, const System& sys, const std::vector<double>& y0, size_t n_steps, double t0, double dt,
                          const EnsembleOptions& o);
@@ -168,6 +170,9 @@ public:
     // every stateful component carries the reference's derivatives(): the pack can be compiled into a kernel
     static constexpr bool device_integrable = std::is_same_v<T, double> && (stateless_or_has_derivatives<Components>() && ...) &&
                                               (std::is_trivially_copyable_v<Components> && ...);
+    // ... or, instantiated on Dual<double,K>, into the forward-mode derivative kernel (computeJacobian, linearizers)
+    static constexpr bool device_differentiable = is_dual_v<T> && (stateless_or_has_derivatives<Components>() && ...) &&
+                                                  (std::is_trivially_copyable_v<Components> && ...);
 
     SOPOT_HD explicit TypedODESystem(Components... c) : m_components(std::move(c)...) { initializeOffsets(); }
     // reference :306-325.  Public here: a kernel calls it on its local copy of a system that arrived through kernel
@@ -218,7 +223,7 @@ public:
     //   shipped pack, T = Dual<double,K>  -> batched linearization kernel + chain rule over the caller's seeds
     //   user pack (nvcc)                  -> the kernel instantiated for this pack by b200/generic_ensemble.cuh
     std::vector<T> computeDerivatives(T /*t*/, const std::vector<T>& state) const {
-        static_assert(Binding::available || (device_integrable && SOPOT_B200_DEVICE_COMPILER),
+        static_assert(Binding::available || ((device_integrable || device_differentiable) && SOPOT_B200_DEVICE_COMPILER),
                       "this component pack has no B200 kernel: it is not one of the shipped systems, and either its "
                       "stateful components lack SOPOT_HD derivatives() / are not trivially copyable or the program is not "
                       "compiled with nvcc (sopot-b200 has no host fallback)");
@@ -238,6 +243,8 @@ public:
             } else {
                 return Binding::rhs_dual(b200::Engine::shared(), m_components, state);
             }
+        } else if constexpr (is_dual_v<T>) {
+            return b200::generic::rhs_one_dual(*this, state);
         } else {
             std::vector<double> out = b200::generic::rhs_one(*this, state);
             if (auto* tr = b200::detail::active_trace()) {

@@ -275,6 +275,33 @@ int main() {
                                   -0.02227360805387352, -0.02304653899042201};
         for (size_t j = 0; j < NS; ++j) CHECK(std::abs(r5.at(29, j, 0) - ref15[j]) <= 1e-5);    // gains agree to 1e-6 relative
     }
+    // 6. the same user-defined pack instantiated on Dual<double,4>: computeDerivatives in dual arithmetic and computeJacobian
+    //    (core/typed_component.hpp:486-512; the reference's autodiff tests, tests/autodiff_test.cpp:387-427) run the components'
+    //    own code in the forward-mode kernel.  d/dt [x1, v1, x2, v2] = [v1, F/m1, v2, -F/m2], F = -k (x1 - x2 - L0) - c (v1 - v2)
+    {
+        using D4 = Dual<double, 4>;
+        const double m1 = 1.2, m2 = 0.7, k = 4.0, L0 = 1.0, c = 0.3;
+        auto dsys = makeTypedODESystem<D4>(coupled::PointMass<coupled::mass1::TagSet, D4>(m1, 0.2, -0.1),
+                                           coupled::PointMass<coupled::mass2::TagSet, D4>(m2, 1.9, 0.4),
+                                           coupled::Spring<coupled::mass1::TagSet, coupled::mass2::TagSet, D4>(k, L0, c), coupled::EnergyMonitor<D4>());
+        const std::array<double, 4> x{0.2, -0.1, 1.9, 0.4};
+        const auto J = computeJacobian(dsys, 0.0, x);
+        const double expect[4][4] = {{0, 1, 0, 0}, {-k / m1, -c / m1, k / m1, c / m1}, {0, 0, 0, 1}, {k / m2, c / m2, -k / m2, -c / m2}};
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) CHECK(std::abs(J[i][j] - expect[i][j]) <= 1e-14);
+        // seeds of the caller's choice travel through as well: directional derivative along (1, 0, 1, 0) (a rigid shift) is 0
+        std::vector<D4> st(4);
+        for (size_t i = 0; i < 4; ++i) st[i] = D4(x[i], {i % 2 == 0 ? 1.0 : 0.0, 0.0, 0.0, 0.0});
+        const auto d = dsys.computeDerivatives(D4::constant(0.0), st);
+        const double F = -k * (x[0] - x[2] - L0) - c * (x[1] - x[3]);
+        CHECK(std::abs(d[1].value() - F / m1) <= 1e-14 && std::abs(d[3].value() + F / m2) <= 1e-14);
+        for (size_t i = 0; i < 4; ++i) CHECK(std::abs(d[i].derivative(0)) <= 1e-14);
+        // state functions of a Dual system stay host-side pure functions: dE/dv1 = m1 v1
+        std::vector<D4> sv(4);
+        for (size_t i = 0; i < 4; ++i) sv[i] = D4::variable(x[i], i);
+        const D4 E = dsys.computeStateFunction<coupled::system::TotalEnergy>(sv);
+        CHECK(std::abs(E.derivative(1) - m1 * x[1]) <= 1e-14 && std::abs(E.derivative(0) - k * (x[0] - x[2] - L0)) <= 1e-14);
+    }
     std::puts("user_components: OK");
     return 0;
 }
