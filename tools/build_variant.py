@@ -24,9 +24,9 @@ for line in (r.stdout + r.stderr).splitlines():
     if "registers" in line or "spill" in line:
         last = line.strip()
 open(obj + ".ptxas.log", "w").write(r.stdout + r.stderr)
-objs = [os.path.join(B.OBJ, f) for f in os.listdir(B.OBJ) if f.endswith(".o") and "_" + tag not in f
-        and f != unit[:-3] + ".o" and not any(f.endswith(f"_{t}.o") for t in os.listdir(vdir) if False)]
-objs = [o for o in objs if os.path.basename(o) in [os.path.basename(s)[:-3] + ".o" for s in os.listdir(B.CSRC) if s.endswith(".cu")]]
+# link the variant object with the stock objects of every OTHER translation unit (objects of earlier variants are skipped)
+stock = {os.path.basename(src)[:-3] + ".o" for src in os.listdir(B.CSRC) if src.endswith(".cu")} - {unit[:-3] + ".o"}
+objs = [os.path.join(B.OBJ, f) for f in sorted(stock)]
 out = os.path.join(vdir, f"libsopot_b200_{tag}.so")
 subprocess.run([B._nvcc(), "-shared", "-o", out, obj] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                   "-Xcompiler", "-fPIC", "-ldl", "-lpthread"], check=True)
