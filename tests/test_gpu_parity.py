@@ -136,6 +136,23 @@ def test_dpend_full_horizon_sample_vs_oracle(engine, port):
     assert np.array_equal(d.download(), st)
 
 
+def test_dpend_contract_error_per_step_across_a_refresh_period(engine, port):
+    """The contract-mode step carries rotated sin/cos pairs for 16 steps between full evaluations: the error against the
+    oracle after k = 1 .. 35 steps (two refresh periods and a bit) stays within k * 1e-12, i.e. the per-step promise holds at
+    every phase of the period, not only right after a refresh."""
+    n = 2048
+    w = W.dpend_ensemble(n, seed=33)
+    args = _dp_args(w)
+    worst = 0.0
+    for k in (1, 2, 3, 7, 15, 16, 17, 31, 32, 35):
+        got, _, status = engine.dpend_rk4(*args, n, 0.0, 1e-3, k, fp_mode=FP_CONTRACT)
+        ref, _, _ = port.dpend_rk4(*args, 0.0, k * 1e-3, 1e-3, nthreads=4)
+        err = rel_err(got, ref).max()
+        worst = max(worst, err / k)
+        assert np.all(status == ST_OK) and err <= k * PER_STEP, (k, err)
+    assert worst <= PER_STEP
+
+
 @pytest.mark.parametrize("fp", [FP_STRICT, FP_CONTRACT])
 def test_dpend_jacobian_golden_and_batch(engine, port, fp):
     """Batched forward-mode Jacobians of the double pendulum (sopot_b200_dpend_jacobian) against the reference's computeJacobian
