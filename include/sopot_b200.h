@@ -251,6 +251,11 @@ int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* values, size_
  * default the whole RK4 step is one kernel (all four stages on a shared-memory tile with a 4-cell halo) and
  * FOUR boundary rows are exchanged once per step -- same values bit for bit, a quarter of the messages and
  * 64 instead of 544 bytes of HBM traffic per mass and step.
+ * Slab contract (nranks > 1): rank r must own exactly the r-th block of the even contiguous partition of the
+ * rows (base = rows / nranks rows each, the first rows % nranks ranks one more; sopot_b200/distributed.py::slab).
+ * Every rank derives its exchange schedule from rows / nranks alone, so any other decomposition -- or fewer rows
+ * than ranks -- is rejected with SOPOT_B200_EINVAL before the first exchange instead of hanging in it.  The same
+ * holds for the unified grid below.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     size_t rows, cols;            /* GLOBAL grid size                         */

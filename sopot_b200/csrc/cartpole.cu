@@ -212,14 +212,19 @@ SB_EXPORT int sopot_b200_cartpole_rhs(sopot_b200_ctx* ctx, const sopot_b200_cart
                                       const sopot_b200_rk4_opts* opts, const double* state, double* out) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     Staging sg(ctx, opts->mem);
     int rc;
     if (sg.host && (rc = sb_arena_begin(ctx, 9 * sb_align(n * 8) + 2 * sb_align(4 * n * 8) + 4096))) return rc;
     sopot_b200_cartpole_params q = *p;
-    if (!q.x) q.x = state; if (!q.th) q.th = state; if (!q.xd) q.xd = state; if (!q.w) q.w = state;
+    uint32_t bc = opts->broadcast;                     // aliased slots are arrays, never host scalars (see sopot_b200_ho_rhs)
+    if (!q.x) { q.x = state; bc &= ~(1u << 4); }
+    if (!q.th) { q.th = state; bc &= ~(1u << 5); }
+    if (!q.xd) { q.xd = state; bc &= ~(1u << 6); }
+    if (!q.w) { q.w = state; bc &= ~(1u << 7); }
     const double* user[9] = {q.mc, q.m, q.L, q.g, q.x, q.th, q.xd, q.w, q.force};
     ParamRef r[9];
-    if ((rc = sb_stage_params(sg, user, 9, n, opts->broadcast, r))) return rc;
+    if ((rc = sb_stage_params(sg, user, 9, n, bc, r))) return rc;
     CartpoleSys::DevParams P{r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]};
     const void* d_state; void* d_out;
     if ((rc = sg.in(state, 4 * n * 8, &d_state))) return rc;
@@ -362,6 +367,7 @@ SB_EXPORT int sopot_b200_cartpole_linearize(sopot_b200_ctx* ctx, const sopot_b20
                                             int32_t* status) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!plant || !x0 || !u0 || !opts || !A || !B) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
     Staging sg(ctx, opts->mem);
     int rc;

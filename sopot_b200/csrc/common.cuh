@@ -156,4 +156,26 @@ template <bool S> __device__ __forceinline__ Real<S> r_div_by(Real<S> a, double 
     if constexpr (S) return Real<S>(sb_div_by(a.v, d, inv)); else return Real<S>(a.v * inv);
 }
 
+// The slab contract of the multi-rank grid entry points: rank r of R owns the contiguous block of rows that
+// sopot_b200/distributed.py::partition assigns (sizes differ by at most one row).  Every rank derives its schedule
+// (fused / overlapped / per-stage, one exchange per step or per stage) from rows / nranks alone, so the branches -- and
+// with them the ncclSend/ncclRecv pairs -- agree across ranks only for exactly this decomposition: anything else is
+// rejected up front instead of hanging in the first exchange.
+inline void sb_partition(size_t n, int rank, int nranks, size_t* begin, size_t* count) {
+    const size_t base = n / (size_t)nranks, rem = n % (size_t)nranks, r = (size_t)rank;
+    *begin = r * base + (r < rem ? r : rem);
+    *count = base + (r < rem ? 1 : 0);
+}
+inline int sb_check_slab(sopot_b200_ctx* ctx, size_t rows, size_t row_begin, size_t rows_local) {
+    if (ctx->nranks <= 1) return SOPOT_B200_OK;
+    size_t b, c;
+    sb_partition(rows, ctx->rank, ctx->nranks, &b, &c);
+    if (rows < (size_t)ctx->nranks)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "%zu rows cannot be split over %d ranks", rows, ctx->nranks);
+    if (row_begin != b || rows_local != c)
+        return sb_fail(ctx, SOPOT_B200_EINVAL, "rank %d of %d must own rows [%zu, %zu) of %zu (the even contiguous partition), got [%zu, %zu)",
+                       ctx->rank, ctx->nranks, b, b + c, rows, row_begin, row_begin + rows_local);
+    return SOPOT_B200_OK;
+}
+
 inline unsigned sb_grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }

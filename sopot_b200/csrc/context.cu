@@ -6,7 +6,7 @@
 #include <dlfcn.h>
 #include <mutex>
 
-static std::string g_init_error;
+static thread_local std::string g_init_error;   // per host thread: sopot_b200_init may run concurrently, one ctx per thread
 
 int sb_fail(sopot_b200_ctx* ctx, int code, const char* fmt, ...) {
     char buf[1024];
@@ -106,9 +106,14 @@ SB_EXPORT int sopot_b200_init(sopot_b200_ctx** out, int device, const void* nccl
         g_init_error = "cudaStreamCreate failed";
         return bail(SOPOT_B200_ECUDA);
     }
-    for (auto& ev : ctx->events) cudaEventCreate(&ev);
-    cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming);
+    bool ev_ok = true;
+    for (auto& ev : ctx->events) ev_ok &= cudaEventCreate(&ev) == cudaSuccess;
+    ev_ok &= cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) == cudaSuccess;
+    ev_ok &= cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) {
+        g_init_error = "cudaEventCreate failed";
+        return bail(SOPOT_B200_ECUDA);
+    }
 
     if (nranks > 1) {
         if (!nccl_unique_id) {

@@ -401,6 +401,7 @@ int check_grid(sopot_b200_ctx* ctx, const sopot_b200_grid2d_params* p, GridDev& 
     if (p->rows_local == 0 || p->row_begin + p->rows_local > p->rows)
         return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [%zu, %zu) outside grid of %zu rows", p->row_begin,
                        p->row_begin + p->rows_local, p->rows);
+    if (int rc = sb_check_slab(ctx, p->rows, p->row_begin, p->rows_local)) return rc;
     g.rows = p->rows; g.cols = p->cols; g.row_begin = p->row_begin; g.rows_local = p->rows_local;
     g.mass = p->mass; g.k = p->stiffness; g.c = p->damping; g.inv_mass = 1.0 / p->mass;
     // rest lengths, connectivity_matrix_2d.hpp:190-192: spacing * sqrt(dx*dx + dy*dy)
@@ -511,7 +512,9 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
     double* nxt = alt;
     const unsigned nty = (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY);
     // all ranks must take the same branch (slabs differ by at most one row): decide on the smallest slab
-    const bool overlap = ctx->nranks > 1 && (g.rows / (size_t)ctx->nranks) > 3 * (size_t)kFusedTY && !(std::getenv("SOPOT_B200_NO_HALO_OVERLAP"));
+    // (check_grid admits only the even partition, so rows / nranks > 48 means rows_local >= 49 and nty >= 4 on every rank)
+    const bool overlap = ctx->nranks > 1 && (g.rows / (size_t)ctx->nranks) > 3 * (size_t)kFusedTY && nty >= 4 &&
+                         !(std::getenv("SOPOT_B200_NO_HALO_OVERLAP"));
     if (!overlap) {
         for (size_t step = 0; step < n_steps; ++step) {
             if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4))) return rc;
@@ -565,6 +568,7 @@ SB_EXPORT int sopot_b200_grid2d_rhs(sopot_b200_ctx* ctx, const sopot_b200_grid2d
     int rc = check_grid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (g.rows_local != g.rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "grid2d_rhs works on a whole grid only");
     const size_t bytes = g.rows_local * g.cols * 32;
     Staging sg(ctx, opts->mem);
@@ -585,6 +589,7 @@ SB_EXPORT int sopot_b200_grid2d_rk4(sopot_b200_ctx* ctx, const sopot_b200_grid2d
     int rc = check_grid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
     if (ctx->nranks == 1 && g.rows_local != g.rows)
         return sb_fail(ctx, SOPOT_B200_EINVAL, "a single-rank ctx must own the whole grid");

@@ -71,14 +71,19 @@ SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
                                 const sopot_b200_rk4_opts* opts, const double* state, double* out) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     Staging sg(ctx, opts->mem);
     int rc;
     if (sg.host && (rc = sb_arena_begin(ctx, 5 * sb_align(n * 8) + 2 * sb_align(2 * n * 8) + 4096))) return rc;
     sopot_b200_ho_params q = *p;
-    if (!q.x0) q.x0 = state; if (!q.v0) q.v0 = state;      // ICs are overwritten by `state`
+    // the initial-condition slots are not read by a derivative evaluation: a missing one aliases `state` as an ARRAY (its
+    // broadcast bit is cleared -- a broadcast slot is dereferenced on the host, and `state` may be a device pointer)
+    uint32_t bc = opts->broadcast;
+    if (!q.x0) { q.x0 = state; bc &= ~(1u << 3); }
+    if (!q.v0) { q.v0 = state; bc &= ~(1u << 4); }
     const double* user[5] = {q.m, q.k, q.c, q.x0, q.v0};
     ParamRef r[5];
-    if ((rc = sb_stage_params(sg, user, 5, n, opts->broadcast, r))) return rc;
+    if ((rc = sb_stage_params(sg, user, 5, n, bc, r))) return rc;
     HoSys::DevParams P{r[0], r[1], r[2], r[3], r[4]};
     return launch_rhs<HoSys>(ctx, P, sg, n, opts->fp_mode == SOPOT_B200_FP_STRICT, state, out);
 }
@@ -183,7 +188,7 @@ struct DpendSys {
         a1 = fma(-kc, B2, B1) * inv;
         a2 = fma(-C, B1, B2) * inv;
     }
-    // full evaluation of the carried values from the angles (start of the run, every 8th step, after a large increment)
+    // full evaluation of the carried values from the angles (start of the run, every SB_DPEND_REFRESH-th step, after a large increment)
     static __device__ __forceinline__ void trig_of(const Inst<false>& in, double th1, double delta, double& s1, double& c1,
                                                    double& S, double& C) {
         double st, ct, sd, cd;
@@ -214,7 +219,7 @@ struct DpendSys {
     //   stage 2: th + (dt/2) w            -> rotate the base pair (sbtrig::rotate_small, |h| <= 2^-5)
     //   stage 3: stage 2 + (dt/2)^2 a_1   -> rotate the stage-2 pair by a tiny increment (rotate_tiny, |d| <= 2^-13)
     //   stage 4: th + dt u_3              -> rotate the base pair
-    //   next step: th_new - th            -> rotate the base pair; full sincos every 8th step bounds the accumulated
+    //   next step: th_new - th            -> rotate the base pair; full sincos every SB_DPEND_REFRESH-th (16th) step bounds the accumulated
     //                                        rounding of the carried pair to a few 1e-16
     // Every shortcut has an integer-compare guard on its increment and falls back to the full routine.
     // ~180 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
@@ -298,14 +303,19 @@ SB_EXPORT int sopot_b200_dpend_rhs(sopot_b200_ctx* ctx, const sopot_b200_dpend_p
                                    const sopot_b200_rk4_opts* opts, const double* state, double* out) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     Staging sg(ctx, opts->mem);
     int rc;
     // the ICs are overwritten by `state`; reuse th1 as a valid pointer when the caller passes none
     sopot_b200_dpend_params q = *p;
-    if (!q.th1) q.th1 = state; if (!q.th2) q.th2 = state; if (!q.w1) q.w1 = state; if (!q.w2) q.w2 = state;
+    uint32_t bc = opts->broadcast;                     // aliased slots are arrays, never host scalars (see sopot_b200_ho_rhs)
+    if (!q.th1) { q.th1 = state; bc &= ~(1u << 5); }
+    if (!q.th2) { q.th2 = state; bc &= ~(1u << 6); }
+    if (!q.w1) { q.w1 = state; bc &= ~(1u << 7); }
+    if (!q.w2) { q.w2 = state; bc &= ~(1u << 8); }
     if (sg.host && (rc = sb_arena_begin(ctx, 9 * sb_align(n * 8) + 2 * sb_align(4 * n * 8) + 4096))) return rc;
     DpendSys::DevParams P;
-    if ((rc = dpend_stage(ctx, sg, &q, n, opts->broadcast, P))) return rc;
+    if ((rc = dpend_stage(ctx, sg, &q, n, bc, P))) return rc;
     const void* d_state; void* d_out;
     if ((rc = sg.in(state, 4 * n * 8, &d_state))) return rc;
     if ((rc = sg.out(out, 4 * n * 8, &d_out))) return rc;
@@ -368,13 +378,18 @@ SB_EXPORT int sopot_b200_dpend_jacobian(sopot_b200_ctx* ctx, const sopot_b200_dp
                                         const sopot_b200_rk4_opts* opts, const double* state, double* J) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!p || !opts || !state || !J) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     Staging sg(ctx, opts->mem);
     int rc;
     sopot_b200_dpend_params q = *p;                     // the initial-condition arrays are not read
-    if (!q.th1) q.th1 = state; if (!q.th2) q.th2 = state; if (!q.w1) q.w1 = state; if (!q.w2) q.w2 = state;
+    uint32_t bc = opts->broadcast;                     // aliased slots are arrays, never host scalars (see sopot_b200_ho_rhs)
+    if (!q.th1) { q.th1 = state; bc &= ~(1u << 5); }
+    if (!q.th2) { q.th2 = state; bc &= ~(1u << 6); }
+    if (!q.w1) { q.w1 = state; bc &= ~(1u << 7); }
+    if (!q.w2) { q.w2 = state; bc &= ~(1u << 8); }
     if (sg.host && (rc = sb_arena_begin(ctx, 9 * sb_align(n * 8) + sb_align(4 * n * 8) + sb_align(16 * n * 8) + 4096))) return rc;
     DpendSys::DevParams P;
-    if ((rc = dpend_stage(ctx, sg, &q, n, opts->broadcast, P))) return rc;
+    if ((rc = dpend_stage(ctx, sg, &q, n, bc, P))) return rc;
     const void* d_state; void* d_J;
     if ((rc = sg.in(state, 4 * n * 8, &d_state))) return rc;
     if ((rc = sg.out(J, 16 * n * 8, &d_J))) return rc;

@@ -313,21 +313,21 @@ lqr_block_kernel(const double* __restrict__ Ain, const double* __restrict__ Bin,
         __syncthreads();
         if (s_state != -1) { ++it; break; }
     }
+    // Every thread reads the loop's verdict BEFORE thread 0 may rewrite it, and the barriers below are executed by all
+    // threads whatever the verdict (a barrier inside `if (st != 0)` would be divergent when a late warp sees the rewritten
+    // value): read -> barrier -> thread 0 decides the fallback -> barrier -> read.
     int st = s_state;
-    if (st != SOPOT_B200_ST_SINGULAR) {
-        if (st != 0) {                                                         // not converged cleanly (:388-397)
-            if (tid == 0) {
-                T sum(0.0);
-                for (int a = 0; a < NS; ++a)
-                    for (int b = 0; b < NS; ++b) sum = sum + T(Pm[a][b]) * T(Pm[a][b]);
-                const double fn = r_sqrt(sum).v;
-                s_state = (!(fn < 1e10) || fn != fn) ? SOPOT_B200_ST_NOT_CONVERGED : 0;
-            }
-            __syncthreads();
-            st = s_state;
-        }
-        if (st == 0 && fabs(R_) < 1e-12) st = SOPOT_B200_ST_SINGULAR;
+    __syncthreads();
+    if (tid == 0 && st != SOPOT_B200_ST_SINGULAR && st != 0) {                 // not converged cleanly (:388-397)
+        T sum(0.0);
+        for (int a = 0; a < NS; ++a)
+            for (int b = 0; b < NS; ++b) sum = sum + T(Pm[a][b]) * T(Pm[a][b]);
+        const double fn = r_sqrt(sum).v;
+        s_state = (!(fn < 1e10) || fn != fn) ? SOPOT_B200_ST_NOT_CONVERGED : 0;
     }
+    __syncthreads();
+    st = s_state;
+    if (st == 0 && fabs(R_) < 1e-12) st = SOPOT_B200_ST_SINGULAR;
     const double bad = __longlong_as_double(0x7ff8000000000000LL);
     if (i == 0) {
         double kv = bad;
@@ -362,6 +362,7 @@ SB_EXPORT int sopot_b200_lqr4_gain(sopot_b200_ctx* ctx, const double* A, const d
                                    int32_t* status) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!A || !B || !Q16 || !opts || !K) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
     if (!(riccati_dt > 0.0) || max_iter > 0x7fffffff) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad riccati_dt / max_iter");
     Staging sg(ctx, opts->mem);
@@ -400,6 +401,7 @@ SB_EXPORT int sopot_b200_lqr_gain(sopot_b200_ctx* ctx, int state_dim, const doub
     if (state_dim != 6 && state_dim != 14)
         return sb_fail(ctx, SOPOT_B200_EINVAL, "LQR kernels exist for state dimensions 4, 6 and 14 (1, 2 and 6 links)");
     if (!A || !B || !Q || !opts || !K) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
     if (!(riccati_dt > 0.0) || max_iter > 0x7fffffff || P > 0x7fffffff) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad riccati_dt / max_iter / P");
     const size_t ns = (size_t)state_dim, nn = ns * ns;

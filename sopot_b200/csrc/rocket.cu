@@ -710,6 +710,7 @@ SB_EXPORT int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket
                                     const sopot_b200_rk4_opts* opts, const double* state, double* out) {
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     Staging sg(ctx, opts->mem);
     int rc;
     if (sg.host && (rc = sb_arena_begin(ctx, 4 * sb_align(n * 8) + 2 * sb_align(14 * n * 8) + 4096))) return rc;

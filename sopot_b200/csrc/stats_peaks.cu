@@ -68,6 +68,41 @@ dispersion_final_kernel(const Partial* __restrict__ partials, const int nblk, do
     }
 }
 
+// Second pass: centred second moment  M2 = sum (x - mean)^2  per row, with the GLOBAL mean = sum / count taken from the
+// all-reduced first-pass sums (identical bits on every rank).  sumsq / count - mean^2 on raw moments loses
+// (mean / stddev)^2 * eps of relative accuracy (an apogee near 1e5 m with a 1 m spread keeps ~6 digits and can go
+// negative); the centred sum keeps full precision and costs one more read of the rows (tens of microseconds).
+// grid (nblk, rows), block 256: m2_partials[row][blk]
+__global__ void __launch_bounds__(256)
+dispersion_m2_partial_kernel(const double* __restrict__ v, const size_t n, const double* __restrict__ sums,
+                             double* __restrict__ m2_partials) {
+    const double* row = v + (size_t)blockIdx.y * n;
+    const double cnt = sums[4 * blockIdx.y], mean = cnt > 0 ? sums[4 * blockIdx.y + 1] / cnt : 0.0;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = __ldg(row + i);
+        if (isfinite(x)) { const double d = x - mean; acc = fma(d, d, acc); }
+    }
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        m2_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+// grid (rows), one warp: fixed summation order, so the result does not depend on scheduling
+__global__ void dispersion_m2_final_kernel(const double* __restrict__ m2_partials, const int nblk, double* __restrict__ m2) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += 32) acc += m2_partials[(size_t)blockIdx.x * nblk + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) m2[blockIdx.x] = acc;
+}
+
 // ---- roofline probes ----------------------------------------------------------------------------------
 // 8 independent DFMA chains per thread: pure FP64-pipe issue rate, FMA = 2 flop.  The multiplicand is a per-thread
 // vector register: x = fma(x, y, U) issues every 2.02 cycles per sub-partition, the best of the operand placements
@@ -105,32 +140,40 @@ SB_EXPORT int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* val
     const int nblk = (int)std::min<size_t>(std::max<size_t>((n_local + 255) / 256, 1), (size_t)ctx->sm_count * 4);
     void* scr;
     const size_t part_bytes = sb_align(sizeof(Partial) * rows * nblk);
-    if ((rc = sb_scratch(ctx, part_bytes + sb_align(rows * 6 * 8) + 256, &scr))) return rc;
+    if ((rc = sb_scratch(ctx, part_bytes + sb_align(rows * 7 * 8) + 256, &scr))) return rc;
     Partial* partials = static_cast<Partial*>(scr);
     double* d_sum = reinterpret_cast<double*>(static_cast<char*>(scr) + part_bytes);
     double* d_min = d_sum + 4 * rows;
     double* d_max = d_min + rows;
+    double* d_m2 = d_max + rows;
     dispersion_partial_kernel<<<dim3(nblk, (unsigned)rows), 256, 0, ctx->stream>>>((const double*)d_v, n_local, partials);
     SB_CHECK_LAUNCH(ctx);
     dispersion_final_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(partials, nblk, d_sum, d_min, d_max);
     SB_CHECK_LAUNCH(ctx);
     if (ctx->nranks > 1) {
-        // the path's only exchange: <= 6*rows doubles, latency bound
+        // the path's only exchange: <= 7*rows doubles in four small all-reduces, latency bound
         const NcclApi* n = ctx->nccl;
         SB_NCCL(ctx, n->AllReduce(d_sum, d_sum, 4 * rows, SB_NCCL_FLOAT64, SB_NCCL_SUM, ctx->nccl_comm, ctx->stream));
         SB_NCCL(ctx, n->AllReduce(d_min, d_min, rows, SB_NCCL_FLOAT64, SB_NCCL_MIN, ctx->nccl_comm, ctx->stream));
         SB_NCCL(ctx, n->AllReduce(d_max, d_max, rows, SB_NCCL_FLOAT64, SB_NCCL_MAX, ctx->nccl_comm, ctx->stream));
     }
-    std::vector<double> h(6 * rows);
-    SB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_sum, 6 * rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // centred second moment about the global mean (the partials buffer is free again: reuse it as doubles)
+    double* m2_partials = reinterpret_cast<double*>(partials);
+    dispersion_m2_partial_kernel<<<dim3(nblk, (unsigned)rows), 256, 0, ctx->stream>>>((const double*)d_v, n_local, d_sum, m2_partials);
+    SB_CHECK_LAUNCH(ctx);
+    dispersion_m2_final_kernel<<<(unsigned)rows, 32, 0, ctx->stream>>>(m2_partials, nblk, d_m2);
+    SB_CHECK_LAUNCH(ctx);
+    if (ctx->nranks > 1)
+        SB_NCCL(ctx, ctx->nccl->AllReduce(d_m2, d_m2, rows, SB_NCCL_FLOAT64, SB_NCCL_SUM, ctx->nccl_comm, ctx->stream));
+    std::vector<double> h(7 * rows);
+    SB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_sum, 7 * rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t r = 0; r < rows; ++r) {
         sopot_b200_dispersion& o = out[r];
         o.count = h[4 * r]; o.sum = h[4 * r + 1]; o.sumsq = h[4 * r + 2]; o.nonfinite = h[4 * r + 3];
         o.min = h[4 * rows + r]; o.max = h[5 * rows + r];
         o.mean = o.count > 0 ? o.sum / o.count : NAN;
-        const double var = o.count > 0 ? o.sumsq / o.count - o.mean * o.mean : NAN;
-        o.stddev = var > 0 ? std::sqrt(var) : (o.count > 0 ? 0.0 : NAN);   // population standard deviation
+        o.stddev = o.count > 0 ? std::sqrt(h[6 * rows + r] / o.count) : NAN;   // population standard deviation, from M2
     }
     return SOPOT_B200_OK;
 }

@@ -380,6 +380,7 @@ int check_ugrid(sopot_b200_ctx* ctx, const sopot_b200_ugrid_params* p, UGridDev&
     g.rows_local = p->rows_local ? p->rows_local : p->rows;
     if ((size_t)g.row_begin + g.rows_local > p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "slab [row_begin, row_begin + rows_local) exceeds the grid");
     if (ctx->nranks == 1 && g.rows_local != p->rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "a single-rank ctx must own the whole grid");
+    if (int rc = sb_check_slab(ctx, p->rows, (size_t)g.row_begin, g.rows_local)) return rc;
     g.rows = p->rows; g.cols = p->cols; g.mass = p->mass; g.radius = p->radius; g.k = p->stiffness; g.L0 = p->rest_length;
     g.c = p->damping; g.min_distance = p->min_distance;
     g.krep = p->repulsion_stiffness > 0.0 ? p->repulsion_stiffness : 10.0 * p->stiffness;       // components.hpp:186
@@ -450,6 +451,7 @@ SB_EXPORT int sopot_b200_ugrid_rhs(sopot_b200_ctx* ctx, const sopot_b200_ugrid_p
     int rc = check_ugrid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (g.rows_local != g.rows) return sb_fail(ctx, SOPOT_B200_EINVAL, "ugrid_rhs evaluates a whole grid (no slab)");
     const size_t bytes = g.rows * g.cols * 48;
     Staging sg(ctx, opts->mem);
@@ -474,6 +476,7 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
     int rc = check_ugrid(ctx, p, g);
     if (rc) return rc;
     if (!opts || !state) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
     if (integrator < 0 || integrator > 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "integrator must be RK4, SYMPLECTIC_EULER or VELOCITY_VERLET");
     if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
     const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
