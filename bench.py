@@ -40,15 +40,12 @@ N_PER_GPU = 1 << 22
 N_STEPS = 10000
 DT = 1e-3
 FLOP_PER_INSTANCE_STEP = 204.0
-# From the ncu capture of this very command (profiles/r1_final_dpend_bench.txt, one launch = 4 Mi x 10 000) and the per-opcode
-# operand analysis of its source page (tools/ncu_fp64_operands.py, profiles/r1_final_dpend_fp64_operands.txt):
-#   179.6 FP64-pipe instructions per instance-step (105.6 DFMA, 64.0 DMUL, 10 DADD) at 2 issue cycles each, of which 41.8
-#   DFMAs read three distinct vector registers and take 3 (profiles/r1_fp64_operand_rule.txt): 401 FP64 issue cycles per
-#   warp-step.
-#   DRAM traffic per launch 317.7 MB read + 112.1 MB written (algorithmic: 9 parameter arrays in, 4 state arrays out).
-FP64_INSTR_PER_STEP = 179.6
-FP64_ISSUE_CYCLES_PER_STEP = 2.0 * FP64_INSTR_PER_STEP + 41.8
-NCU_DRAM_BYTES_PER_LAUNCH_4MI = 317678848 + 112097536
+# ncu counters of the headline kernel (DRAM bytes per launch, FP64 instructions per instance-step, three-register DFMAs)
+# are NOT literals here: tools/ncu_counters.py writes them to profiles/dpend_bench_counters.json together with the SHA-256
+# of the kernel's SASS, and load_counters() below hands them out only while the loaded library still holds that code.
+COUNTERS_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "dpend_bench_counters.json")
+ROCKET_OPCOUNT_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "rocket_opcount.json")
+ROCKET_FLOP_AS_WRITTEN = 1870.0         # the reference's RHS as written (re-evaluated sub-trees)
 METRIC = "RK4 instance-steps/s (FP64)"
 UNIT = "instance-steps/s"
 
@@ -149,6 +146,199 @@ def run_reference(args):
     return 0
 
 
+def load_counters(n_instances):
+    """(counters dict or None, reason).  The profile must belong to the code that is running: same SASS hash of
+    rk4_ensemble_kernel<DpendSys,false> in the loaded library, and (for the DRAM traffic) the same batch size."""
+    if not os.path.exists(COUNTERS_FILE):
+        return None, "profiles/dpend_bench_counters.json not present"
+    try:
+        c = json.load(open(COUNTERS_FILE))
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from kernel_hash import kernel_hash
+        from sopot_b200.capi import LIB_PATH
+        live = kernel_hash(LIB_PATH, c["kernel_mangled"])["sass_sha256"]
+    except Exception as e:
+        return None, "cannot hash the loaded kernel: " + repr(e)
+    if live != c["sass_sha256"]:
+        return None, "counters are stale: captured on SASS %s..., the loaded library has %s..." % (c["sass_sha256"][:12], live[:12])
+    c["traffic_valid"] = int(c["units_per_launch"]) == int(n_instances) * N_STEPS
+    return c, "profiles/dpend_bench_counters.json (SASS hash matches the loaded library)"
+
+
+def parity_check(eng, w, keys):
+    """The timed configuration tied to the oracle: the first 256 instances of THIS bench's inputs, 1000 steps (t = 1 s, the
+    hard gate of SURVEY.md section 8c for the chaotic config), contract mode on the GPU against the CPU checker.  Part of
+    the checker leg (after the timed region); a miss fails the run."""
+    from oracle.oracle_py import Checker, build, have_reference
+    from sopot_b200.capi import FP_CONTRACT
+    build()
+    kind = "reference" if have_reference() else "port"
+    chk = Checker(kind)
+    m = 256
+    args = [np.ascontiguousarray(w[k][:m]) for k in keys]
+    got, _, status = eng.dpend_rk4(*args, m, 0.0, DT, 1000, fp_mode=FP_CONTRACT)
+    ref, _, _ = chk.dpend_rk4(*args, 0.0, 1.0, DT, nthreads=min(8, chk.hardware_threads()))
+    err = float((np.abs(got - ref).max(axis=0) / np.maximum(np.abs(ref).max(axis=0), 1e-300)).max())
+    return {"instances": m, "steps": 1000, "checker": kind, "max_rel_err": err, "tolerance": 1e-9,
+            "ok": bool(err <= 1e-9 and not np.any(status))}
+
+
+def multi_gpu_configs(eng, rank, world, local, hbm_peak):
+    """The communicating paths at N > 1 (every rank calls this; rank 0 gets the rows):
+      * grid2d 8192^2 (BASELINE config 5) STRONG scaling: row slabs, halo exchange over NCCL inside the library; fused step
+        (one 4-row exchange per step) and per-stage schedule (four 1-row exchanges), both arithmetic modes.  Beside the
+        multi-rank time: the same slab on a single-rank context (same tiles, no exchange) = what the kernels alone cost,
+        and the whole grid on rank 0 alone = this run's own N = 1, so efficiency needs no other run.
+      * the unified 6-state grid 4096^2 the same way (RK4, contract).
+      * rocket Monte Carlo (config 4), 1 Mi trajectories split over the ranks + the dispersion all-reduce.
+      * a 512 x 512 strict run on the slabs against the single-rank bits (SHA-256 of the assembled state on rank 0).
+    Device times are CUDA events on the library's stream, max over ranks."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from sopot_b200 import workloads as W
+    from sopot_b200.capi import FP_CONTRACT, FP_STRICT, MEM_DEVICE, Engine
+    from sopot_b200.distributed import partition, slab
+    out = {}
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ranks(x):
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def timed(e, fn, steps):
+        fn(3)                                              # warm-up: NCCL channels, function attributes, scratch
+        e.sync(); dist.barrier(); torch.cuda.synchronize()
+        e.event_record(2)
+        fn(steps)
+        e.event_record(3)
+        return e.elapsed_ms(2, 3) / steps
+
+    p = W.GRID2D_PARAMS
+    n, steps = 8192, 10
+    rb, rl = slab(n, rank, world)
+    solo = Engine(local)                                   # single-rank context on the same GPU
+    gp = eng.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"], row_begin=rb, rows_local=rl)
+    gp_slab = solo.grid2d_params(rl, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    gp_full = solo.grid2d_params(n, n, 0, p["mass"], p["spacing"], p["k"], p["c"])
+    state = eng.grid2d_initial_state(gp, mem=MEM_DEVICE)
+    rows = {}
+    for mode, mname in ((FP_CONTRACT, "contract"), (FP_STRICT, "strict")):
+        for per_stage in (False, True):
+            ms = timed(eng, lambda k: eng.grid2d_rk4(gp, p["dt"], k, state, fp_mode=mode, sync=False, per_stage=per_stage), steps)
+            per_rank = all_ranks(ms)
+            ms_slab = timed(solo, lambda k: solo.grid2d_rk4(gp_slab, p["dt"], k, state, fp_mode=mode, sync=False, per_stage=per_stage), steps)
+            per_rank_slab = all_ranks(ms_slab)
+            rows[f"{mname}_{'per_stage' if per_stage else 'fused'}"] = {
+                "ms_per_step": max(per_rank), "ms_per_step_per_rank": per_rank,
+                "slab_kernels_only_ms_per_rank": per_rank_slab,
+                "exchange_and_sync_ms": max(per_rank) - max(per_rank_slab),
+                "mass_steps_per_s": n * n / (max(per_rank) * 1e-3)}
+    state.free()
+    dist.barrier()
+    if rank == 0:                                          # this run's own N = 1: the whole grid on one GPU
+        full = solo.grid2d_initial_state(gp_full, mem=MEM_DEVICE)
+        for mode, mname in ((FP_CONTRACT, "contract"), (FP_STRICT, "strict")):
+            for per_stage in (False, True):
+                key = f"{mname}_{'per_stage' if per_stage else 'fused'}"
+                solo.grid2d_rk4(gp_full, p["dt"], 2, full, fp_mode=mode, per_stage=per_stage)
+                solo.event_record(2)
+                solo.grid2d_rk4(gp_full, p["dt"], steps, full, fp_mode=mode, sync=False, per_stage=per_stage)
+                solo.event_record(3)
+                n1 = solo.elapsed_ms(2, 3) / steps
+                r = rows[key]
+                r["n1_ms_per_step_same_run"] = n1
+                r["speedup_vs_n1"] = n1 / r["ms_per_step"]
+                r["strong_scaling_efficiency"] = n1 / r["ms_per_step"] / world
+                # the limiter, named: kernels on a 1/N slab against the exchange (+ stream ordering) on top of them
+                kern = max(r["slab_kernels_only_ms_per_rank"])
+                r["limiter"] = ("slab kernels (%.3f ms = %.2fx the ideal n1/N %.3f ms: tile-row quantisation and tail of a small grid)"
+                                % (kern, kern / (n1 / world), n1 / world)) if kern - n1 / world >= r["exchange_and_sync_ms"] else \
+                               ("ncclSend/Recv group + stream ordering (%.3f ms on top of %.3f ms of kernels)" % (r["exchange_and_sync_ms"], kern))
+        full.free()
+    dist.barrier()
+    out["grid2d_8192x8192_strong_scaling"] = dict(rows, n_gpus=world, steps_timed=steps,
+                                                  halo_bytes_per_step_fused=2 * 4 * n * 32, halo_bytes_per_step_per_stage=2 * 4 * n * 32)
+
+    # unified 6-state grid, 4096^2, RK4 contract: one exchange of 4 boundary rows per step
+    nu = 4096
+    ub, ul = slab(nu, rank, world)
+    ug = eng.ugrid_params(nu, nu, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5, row_begin=ub, rows_local=ul)
+    ustate = eng.ugrid_initial_state(ug, mem=MEM_DEVICE)
+    ms = max_over_ranks(timed(eng, lambda k: eng.ugrid_rk4(ug, 1e-3, k, ustate, fp_mode=FP_CONTRACT, sync=False), 5))
+    ustate.free()
+    row = {"ms_per_step": ms, "mass_steps_per_s": nu * nu / (ms * 1e-3), "n_gpus": world}
+    if rank == 0:
+        ugf = solo.ugrid_params(nu, nu, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5)
+        uf = solo.ugrid_initial_state(ugf, mem=MEM_DEVICE)
+        solo.ugrid_rk4(ugf, 1e-3, 2, uf, fp_mode=FP_CONTRACT)
+        solo.event_record(2)
+        solo.ugrid_rk4(ugf, 1e-3, 5, uf, fp_mode=FP_CONTRACT, sync=False)
+        solo.event_record(3)
+        n1 = solo.elapsed_ms(2, 3) / 5
+        uf.free()
+        row.update(n1_ms_per_step_same_run=n1, speedup_vs_n1=n1 / ms, strong_scaling_efficiency=n1 / ms / world)
+    dist.barrier()
+    out["unified_grid_4096x4096_contract_rk4_strong_scaling"] = row
+
+    # rocket Monte Carlo: 1 Mi trajectories over the ranks, then the path's one collective (dispersion all-reduce)
+    n_total = 1 << 20
+    b, e = partition(n_total, rank, world)
+    w = W.rocket_ensemble(n_total)
+    d = {k: eng.to_device(w[k][b:e]) for k in ("elev", "az", "diam", "g0")}
+    st, stats = eng.empty((14, e - b)), eng.empty((8, e - b))
+
+    def fly(_k):
+        eng.rocket_rk4(d["elev"], d["az"], d["diam"], d["g0"], w["engine"], w["mass_tab"], None, None, e - b, 0.01, 3000,
+                       mem=MEM_DEVICE, want_status=False, state_out=st, stats_out=stats, sync=False)
+    fly(1); eng.sync(); dist.barrier(); torch.cuda.synchronize()
+    eng.event_record(2); fly(1); eng.event_record(3)
+    ms_fly = max_over_ranks(eng.elapsed_ms(2, 3))
+    eng.dispersion_stats(stats)                            # warm-up of the reduction + NCCL channels
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    disp = eng.dispersion_stats(stats)                     # device reduction + 4 small ncclAllReduce + D2H (synchronous call)
+    ms_disp = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    out["rocket_1Mi_x3000_sharded_with_dispersion_allreduce"] = {
+        "n_gpus": world, "trajectories_total": n_total, "ms_integrate": ms_fly, "ms_dispersion_allreduce_call": ms_disp,
+        "instance_steps_per_s": n_total * 3000 / ((ms_fly + ms_disp) * 1e-3),
+        "count_all_ranks": disp[0]["count"], "count_ok": bool(disp[0]["count"] == n_total),
+        "apogee_mean_m": disp[0]["mean"], "apogee_std_m": disp[0]["stddev"],
+        "max_speed_mean": disp[2]["mean"], "downrange_east_std_m": disp[6]["stddev"]}
+    for a in (st, stats, *d.values()):
+        a.free()
+
+    # bit-exactness of the slab decomposition, in this very run: 512 x 512 strict, 8 steps, both schedules
+    R = C = 512
+    s0 = W.grid2d_state(R, C, p["spacing"]).reshape(R, C, 4)
+    ref = solo.grid2d_rk4(solo.grid2d_params(R, C, 0, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], 8,
+                          s0.reshape(-1, 4).copy(), fp_mode=FP_STRICT).reshape(R, C, 4)
+    rb2, rl2 = slab(R, rank, world)
+    gps = eng.grid2d_params(R, C, 0, p["mass"], p["spacing"], p["k"], p["c"], row_begin=rb2, rows_local=rl2)
+    check = {"grid": [R, C], "steps": 8, "fp_mode": "strict"}
+    for per_stage in (False, True):
+        mine = eng.grid2d_rk4(gps, p["dt"], 8, s0[rb2:rb2 + rl2].reshape(-1, 4).copy(), fp_mode=FP_STRICT, per_stage=per_stage)
+        parts = [None] * world
+        dist.all_gather_object(parts, mine.tobytes())
+        if rank == 0:
+            name = "per_stage" if per_stage else "fused"
+            check[name + "_sha256"] = hashlib.sha256(b"".join(parts)).hexdigest()
+            check[name + "_equals_single_rank"] = check[name + "_sha256"] == hashlib.sha256(ref.tobytes()).hexdigest()
+    if rank == 0:
+        check["single_rank_sha256"] = hashlib.sha256(ref.tobytes()).hexdigest()
+        check["ok"] = bool(check["fused_equals_single_rank"] and check["per_stage_equals_single_rank"])
+    out["grid2d_512x512_multirank_bitexact"] = check
+    solo.close()
+    dist.barrier()
+    return out
+
+
 def other_configs(eng, hbm_peak, fp64_peak):
     """One timed pass (after one warm-up) of the other four BASELINE configs at full size, N = 1."""
     from sopot_b200 import workloads as W
@@ -175,6 +365,19 @@ def other_configs(eng, hbm_peak, fp64_peak):
                                   fp_mode=FP_CONTRACT, want_status=False, state_out=st, sync=False), 3)
     out["ho_1Mi_x1000"] = {"ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3),
                            "fp64_frac": 44.0 * n * 1000 / (ms * 1e-3) / 1e12 / fp64_peak}
+    # config 1, FULL-TRAJECTORY mode (HBM-write bound, 16 B per instance-step): every step (16.8 GB
+    # written per launch) and every 10th step; the fraction is written bytes / time against the HBM copy peak
+    for every in (1, 10):
+        traj = eng.empty((1000 // every, 2, n))
+        ms = timed(lambda: eng.ho_rk4(d["m"], d["k"], d["c"], d["x0"], d["v0"], n, 0.0, 0.01, 1000, mem=MEM_DEVICE,
+                                      fp_mode=FP_CONTRACT, store_every=every, want_status=False, state_out=st, traj_out=traj,
+                                      sync=False), 2)
+        wbytes = 16.0 * n * (1000 // every)
+        out[f"ho_1Mi_x1000_trajectory_every_{every}"] = {
+            "ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3), "bytes_written": wbytes,
+            "write_GBs": wbytes / (ms * 1e-3) / 1e9, "hbm_frac": wbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+            "fp64_frac": 44.0 * n * 1000 / (ms * 1e-3) / 1e12 / fp64_peak}
+        traj.free()
     # config 2 in the bit-exact arithmetic mode (reference association, IEEE division, libdevice sin/cos; the headline is the
     # contract mode): 1 Mi instances x 1000 steps
     w = W.dpend_ensemble(n)
@@ -183,6 +386,16 @@ def other_configs(eng, hbm_peak, fp64_peak):
     ms = timed(lambda: eng.dpend_rk4(*dd, n, 0.0, 1e-3, 1000, mem=MEM_DEVICE, fp_mode=FP_STRICT, want_status=False,
                                      state_out=st4, sync=False), 2)
     out["dpend_strict_1Mi_x1000"] = {"ms": ms, "instance_steps_per_s": n * 1000 / (ms * 1e-3)}
+    # config 2 with a stored trajectory (32 B per stored instance-step, every 100th step as SURVEY.md section 8d recommends):
+    # 1 Mi instances x 10 000 steps -> 100 snapshots = 3.4 GB written beside the FP64-bound integration
+    traj = eng.empty((100, 4, n))
+    ms = timed(lambda: eng.dpend_rk4(*dd, n, 0.0, 1e-3, 10000, mem=MEM_DEVICE, fp_mode=FP_CONTRACT, store_every=100,
+                                     want_status=False, state_out=st4, traj_out=traj, sync=False), 1)
+    out["dpend_1Mi_x10000_trajectory_every_100"] = {
+        "ms": ms, "instance_steps_per_s": n * 10000 / (ms * 1e-3), "bytes_written": 32.0 * n * 100,
+        "write_GBs": 32.0 * n * 100 / (ms * 1e-3) / 1e9, "hbm_frac": 32.0 * n * 100 / (ms * 1e-3) / 1e9 / hbm_peak,
+        "fp64_frac": FLOP_PER_INSTANCE_STEP * n * 10000 / (ms * 1e-3) / 1e12 / fp64_peak}
+    traj.free()
     for a in (st4, *dd):
         a.free()
     # config 3: batched linearization, HBM bound, 200 B / point.  4 Mi points per launch (0.84 GB of traffic, far
@@ -234,8 +447,21 @@ def other_configs(eng, hbm_peak, fp64_peak):
                                       0.01, 3000, mem=MEM_DEVICE, want_status=False, state_out=st, stats_out=stats,
                                       sync=False), 1)
     disp = eng.dispersion_stats(stats)
-    out["rocket_1Mi_x3000"] = {"ms": ms, "instance_steps_per_s": n * 3000 / (ms * 1e-3),
-                               "apogee_mean_m": disp[0]["mean"], "apogee_std_m": disp[0]["stddev"]}
+    rate = n * 3000 / (ms * 1e-3)
+    own = json.load(open(ROCKET_OPCOUNT_FILE)) if os.path.exists(ROCKET_OPCOUNT_FILE) else None
+    out["rocket_1Mi_x3000"] = {
+        "ms": ms, "instance_steps_per_s": rate, "apogee_mean_m": disp[0]["mean"], "apogee_std_m": disp[0]["stddev"],
+        # FP64 roofline two ways: the flop count of the engine's OWN de-duplicated derivative
+        # (counting scalar over RocketSysT::rhs, flight-phase weighted, tools/rocket_opcount.py) and, beside it, the
+        # reference's RHS as written, which re-evaluates shared sub-trees and therefore flatters the fraction
+        "roofline": {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s",
+                     "flop_per_unit_own_count": own["flop_per_instance_step"] if own else None,
+                     "achieved_own_count": own["flop_per_instance_step"] * rate / 1e12 if own else None,
+                     "frac_own_count": own["flop_per_instance_step"] * rate / 1e12 / fp64_peak if own else None,
+                     "own_count_source": "profiles/rocket_opcount.json" if own else "profiles/rocket_opcount.json not present",
+                     "flop_per_unit_as_written": ROCKET_FLOP_AS_WRITTEN,
+                     "achieved_as_written": ROCKET_FLOP_AS_WRITTEN * rate / 1e12,
+                     "frac_as_written": ROCKET_FLOP_AS_WRITTEN * rate / 1e12 / fp64_peak}}
     for a in (st, stats, *d.values()):
         a.free()
     # config 5: grid2d 8192^2, 10 RK4 steps.  Default schedule = fused step kernel (64 B of HBM traffic per mass-step:
@@ -277,7 +503,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=N_PER_GPU, help="instances per GPU (default: the BASELINE config)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the other four configs and the CPU baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs, the parity check and the CPU baseline")
+    ap.add_argument("--extras-timeout", type=float, default=420.0, help="seconds after which the extras are abandoned")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -363,6 +590,7 @@ def main():
     value = total_units / (ms_total * 1e-3)
     e2e_value = total_units / (ms_e2e * 1e-3)
 
+    line = None
     if rank == 0:
         fp64_peak = eng.measure_fp64_peak()
         hbm_peak_live = eng.measure_hbm_peak(1 << 30)
@@ -371,6 +599,7 @@ def main():
         if os.path.exists(peaks_path):
             hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
         kernel_ms = ms_total / max(launches, 1) if world == 1 else None
+        counters, counters_src = load_counters(n)
         per_gpu_rate = float(n) * N_STEPS * args.steps / (ms_total * 1e-3)
         achieved = FLOP_PER_INSTANCE_STEP * per_gpu_rate / 1e12
         line = {
@@ -390,37 +619,76 @@ def main():
                          "frac": achieved / fp64_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, same command); only valid
                          # for the BASELINE batch size the capture was taken at
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_4MI if n == N_PER_GPU else None,
-                         "fp64_instr_per_unit": FP64_INSTR_PER_STEP,
+                         "traffic": counters["dram_bytes_per_launch"] if counters and counters["traffic_valid"] else None,
+                         "fp64_instr_per_unit": counters["fp64_instr_per_unit"] if counters else None,
+                         "dfma3_per_unit": counters["dfma3_per_unit"] if counters else None,
+                         "counters_source": counters_src,
                          "kernel": "rk4_ensemble_kernel<DpendSys,false>", "kernel_ms": kernel_ms,
                          "flop_per_unit": FLOP_PER_INSTANCE_STEP,
                          # share of the FP64 pipe's issue cycles the kernel's own instructions need at this rate
                          # (148 SMs x 4 sub-partitions, clock = median SM clock sampled during the timed region)
-                         "fp64_issue_frac": (per_gpu_rate / 32.0 * FP64_ISSUE_CYCLES_PER_STEP /
+                         "fp64_issue_frac": (per_gpu_rate / 32.0 * counters["fp64_issue_cycles_per_warp_unit"] /
                                              (148 * 4 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6))
-                         if clocks and clocks.get("sm_mhz") else None,
+                         if counters and clocks and clocks.get("sm_mhz") else None,
                          "peak_source": "DFMA issue rate measured in this run (sopot_b200_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm_copy_live_gbs": hbm_peak_live},
         }
-        if not args.no_extras and world == 1:
+    # ---- beyond the headline: the other configs (N = 1) or the communicating paths (N > 1), the parity check of the timed
+    # inputs against the oracle and the CPU baseline.  None of it may cost the headline line: a watchdog prints the line as
+    # it stands and leaves if a collective of the extras hangs (one rank failing inside them would block the others).
+    rc = 0
+    done = threading.Event()
+
+    def bail_out():
+        if done.is_set():
+            return
+        if rank == 0:
+            line.setdefault("other_configs", {"error": "extras timed out"})
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    if not args.no_extras:
+        watchdog = threading.Timer(args.extras_timeout, bail_out)
+        watchdog.daemon = True
+        watchdog.start()
+        for a in list(dev.values()) + [d_state]:
+            a.free()
+        if world > 1:
             try:
-                for a in list(dev.values()) + [d_state]:
-                    a.free()
-                line["other_configs"] = other_configs(eng, hbm_peak, fp64_peak)
-            except Exception as e:                      # extras must never cost the headline number
-                line["other_configs"] = {"error": repr(e)}
-            try:
-                r, cores, kind, sample, _ = cpu_reference_rate(12.0)
-                line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+                mg = multi_gpu_configs(eng, rank, world, local, hbm_peak if rank == 0 else None)
             except Exception as e:
-                line["cpu_baseline"] = {"error": repr(e)}
+                mg = {"error": repr(e)}
+            if rank == 0:
+                line["other_configs"] = mg
+        elif rank == 0:
+            try:
+                line["other_configs"] = other_configs(eng, hbm_peak, fp64_peak)
+            except Exception as e:
+                line["other_configs"] = {"error": repr(e)}
+        if rank == 0:
+            try:
+                line["parity_check"] = parity_check(eng, w, keys)
+                if not line["parity_check"]["ok"]:
+                    rc = 1
+            except Exception as e:
+                line["parity_check"] = {"error": repr(e), "ok": False}
+                rc = 1
+            if world == 1:
+                try:
+                    r, cores, kind, sample, _ = cpu_reference_rate(12.0)
+                    line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+                except Exception as e:
+                    line["cpu_baseline"] = {"error": repr(e)}
+        done.set()
+        watchdog.cancel()
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

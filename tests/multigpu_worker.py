@@ -33,6 +33,35 @@ for r in range(6):
     assert d[r]["min"] == row.min() and d[r]["max"] == row.max()
     assert abs(d[r]["mean"] - row.mean()) < 1e-12 * abs(row.mean()) and abs(d[r]["stddev"] - row.std()) < 1e-9
 
+# narrow spread on a large mean: the centred second moment (second pass about the all-reduced mean) keeps the deviation
+big = np.stack([1.0e5 + rng.normal(0.0, 1.0, 300007), 2.0e7 + rng.normal(0.0, 1e-2, 300007)])
+b, e = partition(big.shape[1], rank, world)
+for r, dd in enumerate(eng.dispersion_stats(np.ascontiguousarray(big[:, b:e]))):
+    assert abs(dd["mean"] - big[r].mean()) <= 1e-13 * big[r].mean() and abs(dd["stddev"] - big[r].std()) <= 1e-9 * big[r].std(), (r, dd)
+
+# the slab contract: anything but the even contiguous partition is rejected on every rank BEFORE the first exchange
+from sopot_b200.capi import SopotB200Error  # noqa: E402
+if world > 1:
+    rows = 40 * world + 3
+    rb, rl = slab(rows, rank, world)
+    bad_rl = rl - 1 if rank == 0 else rl                       # rank 0 short by one row, the others shifted up by one
+    bad_rb = rb if rank == 0 else rb - 1
+    if rank == world - 1:
+        bad_rl += 1
+    pg = W.GRID2D_PARAMS
+    try:
+        eng.grid2d_rk4(eng.grid2d_params(rows, 32, 0, pg["mass"], pg["spacing"], pg["k"], pg["c"], row_begin=bad_rb, rows_local=bad_rl),
+                       pg["dt"], 1, np.zeros((bad_rl * 32, 4)))
+        raise AssertionError("uneven slab accepted")
+    except SopotB200Error as ex:
+        assert "even contiguous partition" in str(ex), str(ex)
+    try:
+        eng.ugrid_rk4(eng.ugrid_params(rows, 32, 1.0, 0.05, 0.5, 50.0, 0.5, 0.5, row_begin=bad_rb, rows_local=bad_rl), 1e-3, 1,
+                      np.zeros((bad_rl * 32, 6)))
+        raise AssertionError("uneven slab accepted")
+    except SopotB200Error as ex:
+        assert "even contiguous partition" in str(ex), str(ex)
+
 # (2) grid2d slabs vs single domain (computed redundantly on every rank with a private single-rank engine)
 p = W.GRID2D_PARAMS
 # (slabs of more than 48 rows take the schedule that overlaps the halo exchange with the interior tiles; 49-row slabs end in a

@@ -46,3 +46,25 @@ def test_product_arm_prints_the_contract_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["unit"] == "TFLOP/s" and r["bound"] == "fp64"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+
+
+def test_roofline_counters_are_tied_to_the_built_kernel(tmp_path, monkeypatch):
+    """bench.py reports ncu counters (DRAM traffic, FP64 instructions per step) only while the SASS of the headline kernel in the
+    library it loads is the one the counters were captured on; any other hash yields None plus the reason."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from sopot_b200 import build
+    build.build()
+    c, why = bench.load_counters(bench.N_PER_GPU)
+    committed = json.load(open(bench.COUNTERS_FILE))
+    if c is not None:
+        assert c["sass_sha256"] == committed["sass_sha256"] and c["traffic_valid"] and c["fp64_instr_per_unit"] > 50
+        assert bench.load_counters(1 << 10)[0]["traffic_valid"] is False       # another batch size: no traffic figure
+    else:
+        assert "stale" in why
+    stale = dict(committed, sass_sha256="0" * 64)
+    f = tmp_path / "c.json"
+    f.write_text(json.dumps(stale))
+    monkeypatch.setattr(bench, "COUNTERS_FILE", str(f))
+    c, why = bench.load_counters(bench.N_PER_GPU)
+    assert c is None and "stale" in why

@@ -86,6 +86,23 @@ def test_bad_arguments_report_errors(engine):
         engine.ho_rk4([2.0], [9.0], [0.1], [1.5], [0.0], 1, 0.0, -0.01, 10)
     with pytest.raises(SopotB200Error):
         engine.grid2d_rk4(engine.grid2d_params(1, 5, 0, 1.0, 0.5, 50.0, 0.5), 1e-3, 1, np.zeros((5, 4)))
+    # every entry point validates opts (mem, fp_mode in {0, 1}), not only the ensemble integrators
+    st = np.zeros((4, 3))
+    with pytest.raises(SopotB200Error, match="bad opts"):
+        engine.dpend_rhs(1.0, 1.0, 1.0, 1.0, 9.81, st, fp_mode=7)
+    with pytest.raises(SopotB200Error, match="bad opts"):
+        engine.grid2d_rhs(engine.grid2d_params(4, 4, 0, 1.0, 0.5, 50.0, 0.5), np.zeros((16, 4)), fp_mode=2)
+    # a derivative evaluation without initial-condition arrays, all parameters broadcast, device-resident state: the
+    # missing IC slots alias `state` as arrays (never dereferenced on the host)
+    from sopot_b200.capi import DpendParams, RK4Opts, _ptr
+    import ctypes
+    d_state, d_out = engine.to_device(np.full((4, 3), 0.25)), engine.empty((4, 3))
+    prm = [np.array([v]) for v in (1.0, 1.0, 1.0, 1.0, 9.81)]
+    p = DpendParams(*[a.ctypes.data for a in prm], None, None, None, None)
+    opts = RK4Opts(MEM_DEVICE, FP_STRICT, 0, 0x1FF, 0)
+    engine._ck(engine.lib.sopot_b200_dpend_rhs(engine.ctx, ctypes.byref(p), 3, ctypes.byref(opts), _ptr(d_state), _ptr(d_out)))
+    engine.sync()
+    assert np.array_equal(d_out.download(), engine.dpend_rhs(1.0, 1.0, 1.0, 1.0, 9.81, np.full((4, 3), 0.25), fp_mode=FP_STRICT))
 
 
 # ------------------------------------------------------------------------------------------------ config 2
@@ -339,6 +356,13 @@ def test_rocket_monte_carlo_sample_and_dispersion(engine, port):
         assert d["min"] == row.min() and d["max"] == row.max()
         assert abs(d["mean"] - row.mean()) <= 1e-12 * max(abs(row.mean()), 1.0)
         assert abs(d["stddev"] - row.std()) <= 1e-6 * max(row.std(), 1e-9)
+    # a narrow spread on a large mean (apogee-like: 1e5 m +- 1 m): the centred second moment keeps the standard deviation
+    # to ~1e-10 relative where sumsq/count - mean^2 on raw moments would keep ~6 digits
+    rng = np.random.default_rng(7)
+    v = np.stack([1.0e5 + rng.normal(0.0, 1.0, 200001), 3.0e7 + rng.normal(0.0, 1e-2, 200001), np.full(200001, 12345.678)])
+    for r, dd in enumerate(engine.dispersion_stats(v)):
+        assert abs(dd["mean"] - v[r].mean()) <= 1e-13 * abs(v[r].mean())
+        assert abs(dd["stddev"] - v[r].std()) <= 1e-9 * max(v[r].std(), 1e-6), (r, dd["stddev"], v[r].std())
     # non-finite entries are skipped and counted, ragged sizes reduce correctly
     v = np.arange(7 * 1001, dtype=np.float64).reshape(7, 1001)
     v[3, 17] = np.nan

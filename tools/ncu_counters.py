@@ -1,0 +1,75 @@
+"""Counters of one profiled kernel launch as JSON, tied to the code by the kernel's SASS hash:
+
+    python tools/ncu_counters.py X.ncu-rep <work items per launch> <kernel_hash.json> > profiles/NAME_counters.json
+
+<kernel_hash.json> is the output of tools/kernel_hash.py run on the SAME snapshot that was profiled (the GPU-side command
+writes it next to the report).  bench.py reads the result and reports these counters only when the hash equals the one of
+the library it has loaded.  Fields: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), FP64-pipe
+instructions per work item by opcode, DFMAs with three distinct vector-register sources per work item (3 issue cycles
+instead of 2, profiles/r1_fp64_operand_rule.txt), the resulting FP64 issue cycles per warp-item, and the key utilisation
+figures of the raw page."""
+import collections
+import csv
+import io
+import json
+import re
+import subprocess
+import sys
+
+rep, units, hash_file = sys.argv[1], float(sys.argv[2]), sys.argv[3]
+h = json.load(open(hash_file))
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+m = {k: (x, uu) for k, uu, x in zip(rows[0], rows[1], rows[-1])}
+
+
+def num(key, scale=None):
+    if key not in m:
+        return None
+    v, unit = float(m[key][0].replace(",", "")), m[key][1].lower()
+    if scale == "bytes":
+        v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1)
+    if scale == "ms":
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(unit.replace("second", "s").replace("msecond", "ms"), 1)
+    return v
+
+
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+srows = list(csv.reader(io.StringIO(src)))
+hdr = next(i for i, r in enumerate(srows) if r and r[0] == "Address")
+hh = srows[hdr]
+si, ei = hh.index("Source"), hh.index("Instructions Executed")
+per_op, dfma3, total = collections.Counter(), 0, 0
+for r in srows[hdr + 1:]:
+    if len(r) <= ei or not r[ei]:
+        continue
+    n = int(r[ei])
+    total += n
+    mm = re.match(r"\s*(@!?U?P\d+\s+)?(D(?:FMA|MUL|ADD|SETP|MNMX))\S*\s+(.*)", r[si])
+    if not mm:
+        if re.match(r"\s*(@!?U?P\d+\s+)?MUFU", r[si]):
+            per_op["MUFU"] += n
+        continue
+    per_op[mm.group(2)] += n
+    regs = set()
+    for o in mm.group(3).split(",")[1:]:
+        q = re.match(r"R(\d+)", o.strip().lstrip("-|"))
+        if q:
+            regs.add(q.group(1))
+    if mm.group(2) == "DFMA" and len(regs) == 3:
+        dfma3 += n
+w = units / 32.0                                  # warp-items per launch
+fp64 = sum(v for k, v in per_op.items() if k != "MUFU")
+out = {
+    "kernel": m.get("Kernel Name", ("?",))[0], "report": rep.split("/")[-1], "sass_sha256": h["sass_sha256"],
+    "kernel_mangled": h["kernel"], "units_per_launch": units,
+    "duration_ms_under_ncu": num("gpu__time_duration.sum", "ms"),
+    "dram_bytes_per_launch": (num("dram__bytes_read.sum", "bytes") or 0) + (num("dram__bytes_write.sum", "bytes") or 0),
+    "fp64_instr_per_unit": fp64 / w, "dfma_per_unit": per_op["DFMA"] / w, "dmul_per_unit": per_op["DMUL"] / w,
+    "dadd_per_unit": per_op["DADD"] / w, "mufu_per_unit": per_op["MUFU"] / w, "dfma3_per_unit": dfma3 / w,
+    "fp64_issue_cycles_per_warp_unit": (2.0 * fp64 + dfma3) / w, "thread_instr_per_unit": total / w,
+    "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+    "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+    "registers_per_thread": num("launch__registers_per_thread"),
+}
+print(json.dumps(out, indent=1))
