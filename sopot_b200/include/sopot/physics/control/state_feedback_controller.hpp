@@ -44,29 +44,44 @@ private:
     bool m_saturate = false;
 };
 
+// :124-212: the six-state controller of the cart + double pendulum
+class InvertedDoublePendulumController : public StateFeedbackController<6, 1> {
+public:
+    using Base = StateFeedbackController<6, 1>;
+    explicit InvertedDoublePendulumController(const GainMatrix& K) : Base(K) {}
+    static InvertedDoublePendulumController createWithLQR(double mc, double m1, double m2, double L1, double L2, double g,
+                                                          const std::array<double, 6>& q_diag = {10.0, 100.0, 100.0, 1.0, 10.0, 10.0},
+                                                          double r = 0.01) {
+        auto [A, B] = linearizeCartDoublePendulum(mc, m1, m2, L1, L2, g);
+        LQR<6, 1>::StateWeightMatrix Q{};
+        for (size_t i = 0; i < 6; ++i) Q[i][i] = q_diag[i];
+        LQR<6, 1>::InputWeightMatrix R{};
+        R[0][0] = r;
+        LQR<6, 1> lqr;
+        lqr.solve(A, B, Q, R);              // the reference uses the gain whether or not the iteration met its tolerance (:196-204)
+        return InvertedDoublePendulumController(lqr.getGain());
+    }
+    double computeForce(double x, double theta1, double theta2, double xdot, double omega1, double omega2) const {
+        return compute(StateVector{x, theta1, theta2, xdot, omega1, omega2})[0];
+    }
+};
+
 template <size_t NLinks>
 class CartNPendulumController : public StateFeedbackController<2 * (NLinks + 1), 1> {
-    static_assert(NLinks == 1, "sopot-b200 ships the one-link (cart-pole) kernels only");
 public:
     static constexpr size_t state_dim = 2 * (NLinks + 1);
     using Base = StateFeedbackController<state_dim, 1>;
     using typename Base::GainMatrix;
     explicit CartNPendulumController(const GainMatrix& K) : Base(K) {}
     // :234-260.  The reference linearizes analytically (linearizeCartNPendulum); here the upright Jacobians come from
-    // the Dual<double,5> kernel (equal to the analytic ones to ~4e-15), the Riccati iteration
-    // from the LQR kernel.
+    // the forward-mode kernels (equal to the analytic ones to ~4e-15), the Riccati iteration
+    // from the LQR kernel.  One link works under any host compiler, N > 1 under nvcc (see linearizeCartNPendulum).
     static CartNPendulumController createWithLQR(double mc, const std::array<double, NLinks>& masses,
                                                  const std::array<double, NLinks>& lengths, double g,
                                                  const std::array<double, state_dim>& q_diag, double r, double riccati_dt = 0.002) {
-        auto J = linearizeCartPoleBatch(b200::Engine::shared(), mc, masses[0], lengths[0], g, std::vector<double>(4, 0.0),
-                                        std::vector<double>(1, 0.0), b200::FpMode::Strict);
-        typename LQR<state_dim, 1>::StateMatrix A{}, Q{};
-        typename LQR<state_dim, 1>::InputMatrix B{};
-        for (size_t i = 0; i < state_dim; ++i) {
-            for (size_t j = 0; j < state_dim; ++j) A[i][j] = J.a(i, j, 0);
-            B[i][0] = J.b(i, 0);
-            Q[i][i] = q_diag[i];
-        }
+        auto [A, B] = linearizeCartNPendulum<NLinks>(mc, masses, lengths, g);
+        typename LQR<state_dim, 1>::StateWeightMatrix Q{};
+        for (size_t i = 0; i < state_dim; ++i) Q[i][i] = q_diag[i];
         typename LQR<state_dim, 1>::InputWeightMatrix R{};
         R[0][0] = r;
         LQR<state_dim, 1> lqr;
