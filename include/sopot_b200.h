@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SOPOT_B200_ABI_VERSION 4
+#define SOPOT_B200_ABI_VERSION 5
 
 enum {
     SOPOT_B200_OK = 0,
@@ -231,6 +231,17 @@ int sopot_b200_rocket_rk4(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p
 /* one derivative evaluation per instance, state/out [14][n] (per-trajectory params as above) */
 int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n,
                           const sopot_b200_rk4_opts* opts, const double* state, double* out);
+/* The reference's state functions (rocket/rocket_tags.hpp) that are intermediates of the derivative, evaluated at
+ * state[14][n] in strict arithmetic: replaces Rocket<T>::queryStateFunction<Tag> (rocket/rocket.hpp:222-228) and, through
+ * it, SimulationResult::query<Tag>(t) (rocket/simulation_result.hpp:111-115).  out[SOPOT_B200_ROCKET_PROBE_VALUES][n], rows:
+ *   0 dynamics::Mass | 1-3 dynamics::MomentOfInertia (Ix, Iyz, Iyz) | 4-6 dynamics::TotalForceENU | 7-9 dynamics::TotalTorqueBody
+ *   10 dynamics::GravityAcceleration | 11-13 aero::AeroForceBody | 14-16 aero::AeroForceENU | 17-19 aero::AeroMomentBody
+ *   20 environment::AtmosphericDensity | 21 ::AtmosphericPressure | 22 ::AtmosphericTemperature | 23 ::SpeedOfSound
+ *   24 propulsion::MassFlowRate | 25-27 propulsion::ThrustForceBody
+ * (kinematics::* and propulsion::Time are slices of the state vector and need no kernel.) */
+#define SOPOT_B200_ROCKET_PROBE_VALUES 28
+int sopot_b200_rocket_state_functions(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n,
+                                      const sopot_b200_rk4_opts* opts, const double* state, double* out);
 
 /* Dispersion statistics over per-trajectory rows (e.g. stats_out above): for each of `rows` rows of
  * values[rows][n_local]: count, sum, sum of squares, min, max -- reduced on the device, then summed /

@@ -278,6 +278,19 @@ class Checker:
         assert rc == 0
         return out
 
+    def rocket_state_functions(self, elev, az, diam, g0, engine, mass_tab, state, aero=None, engine_on=True):
+        """reference only: the registry's state functions at state[14][n] -> [28][n] (rows as in include/sopot_b200.h)"""
+        assert self.kind == "reference"
+        state = _f64(state); n = state.shape[1]
+        er, engine = self._tab(engine, 8)
+        mr, mass_tab = self._tab(mass_tab, 2)
+        out = np.empty((28, n))
+        blob = self.aero_blob(aero, engine_on)
+        rc = self._fn("rocket_state_functions", [_sz, _d, _d, _d, _d, _sz, _dp, _sz, _dp, _dp, _dp, _dp])(
+            n, elev, az, diam, g0, er, _p(engine), mr, _p(mass_tab), _p(state), _p(out), _p(blob))
+        assert rc == 0
+        return out
+
     def engine_thrust(self, engine, tq, patm):
         er, engine = self._tab(engine, 8)
         tq, patm = _f64(tq), _f64(patm)

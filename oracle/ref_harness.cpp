@@ -675,6 +675,57 @@ int ref_rocket_rhs_aero(size_t n, double elev_deg, double az_deg, double diamete
     rmdir(dir.c_str());
     return 0;
 }
+// the state functions of rocket/rocket_tags.hpp that the registry of the full rocket provides, at given states [14][n]:
+// out[28][n] in the row order of sopot_b200_rocket_state_functions (include/sopot_b200.h)
+int ref_rocket_state_functions(size_t n, double elev_deg, double az_deg, double diameter, double g0,
+                               size_t engine_rows, const double* engine, size_t mass_rows, const double* mass_tab,
+                               const double* state, double* out, const double* aero_blob) {
+    using namespace sopot::rocket;
+    char tmpl[] = "/tmp/sopot_ref_XXXXXX";
+    char* d = mkdtemp(tmpl);
+    if (!d) return 1;
+    std::string dir(d);
+    std::string f_eng = write_csv(dir, "sim_engine.csv", engine_rows, 8, engine);
+    std::string f_mass = write_csv(dir, "sim_mass.csv", mass_rows, 2, mass_tab);
+    InterpolatedEngine<double> engine0; engine0.loadFromFile(f_eng);
+    RocketBody<double> body0; body0.loadMass(f_mass);
+    RotationKinematics<double> att; att.setInitialFromLauncherAngles(elev_deg, az_deg);
+    AxisymmetricAerodynamics<double> aero0(diameter);
+    std::vector<std::string> aero_files;
+    apply_aero_blob(aero0, aero_blob, dir, aero_files);
+    auto sys = makeTypedODESystem<double>(
+        SimulationTime<double>(), TranslationKinematics<double>(), TranslationDynamics<double>(),
+        std::move(att), RotationDynamics<double>(), StandardAtmosphere<double>(),
+        Gravity<double>(g0), std::move(body0), std::move(engine0),
+        std::move(aero0), ForceAggregator<double>());
+    for (size_t i = 0; i < n; ++i) {
+        std::vector<double> s(14);
+        for (int j = 0; j < 14; ++j) s[j] = state[j * n + i];
+        double r[28];
+        r[0] = sys.computeStateFunction<sopot::rocket::dynamics::Mass>(s);
+        const auto I = sys.computeStateFunction<sopot::rocket::dynamics::MomentOfInertia>(s);
+        const auto F = sys.computeStateFunction<sopot::rocket::dynamics::TotalForceENU>(s);
+        const auto Tq = sys.computeStateFunction<sopot::rocket::dynamics::TotalTorqueBody>(s);
+        const auto Fab = sys.computeStateFunction<sopot::rocket::aero::AeroForceBody>(s);
+        const auto Fae = sys.computeStateFunction<sopot::rocket::aero::AeroForceENU>(s);
+        const auto Mab = sys.computeStateFunction<sopot::rocket::aero::AeroMomentBody>(s);
+        const auto Th = sys.computeStateFunction<sopot::rocket::propulsion::ThrustForceBody>(s);
+        for (int k = 0; k < 3; ++k) {
+            r[1 + k] = I[k]; r[4 + k] = F[k]; r[7 + k] = Tq[k]; r[11 + k] = Fab[k]; r[14 + k] = Fae[k]; r[17 + k] = Mab[k]; r[25 + k] = Th[k];
+        }
+        r[10] = sys.computeStateFunction<sopot::rocket::dynamics::GravityAcceleration>(s);
+        r[20] = sys.computeStateFunction<sopot::rocket::environment::AtmosphericDensity>(s);
+        r[21] = sys.computeStateFunction<sopot::rocket::environment::AtmosphericPressure>(s);
+        r[22] = sys.computeStateFunction<sopot::rocket::environment::AtmosphericTemperature>(s);
+        r[23] = sys.computeStateFunction<sopot::rocket::environment::SpeedOfSound>(s);
+        r[24] = sys.computeStateFunction<sopot::rocket::propulsion::MassFlowRate>(s);
+        for (int k = 0; k < 28; ++k) out[k * n + i] = r[k];
+    }
+    unlink(f_eng.c_str()); unlink(f_mass.c_str());
+    for (auto& f : aero_files) unlink(f.c_str());
+    rmdir(dir.c_str());
+    return 0;
+}
 int ref_rocket_rhs(size_t n, double elev_deg, double az_deg, double diameter, double g0, size_t engine_rows, const double* engine,
                    size_t mass_rows, const double* mass_tab, const double* state, double* out) {
     return ref_rocket_rhs_aero(n, elev_deg, az_deg, diameter, g0, engine_rows, engine, mass_rows, mass_tab, state, out, nullptr);

@@ -22,7 +22,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
 FLAG_UGRID_STAGE_PAIRS = 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
          # SOPOT_B200_ABI_VERSION of include/sopot_b200.h this table was written against
 ST_OK, ST_NONFINITE, ST_SINGULAR = 0, 1, 2
@@ -147,6 +147,7 @@ SYMBOLS = {
     "sopot_b200_rocket_rk4": (c_int, [_ctx, POINTER(RocketParams), c_size_t, c_double, c_size_t,
                                       POINTER(RK4Opts), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sopot_b200_rocket_rhs": (c_int, [_ctx, POINTER(RocketParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
+    "sopot_b200_rocket_state_functions": (c_int, [_ctx, POINTER(RocketParams), c_size_t, POINTER(RK4Opts), c_void_p, c_void_p]),
     "sopot_b200_dispersion_stats": (c_int, [_ctx, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(Dispersion)]),
     "sopot_b200_grid2d_initial_state": (c_int, [_ctx, POINTER(Grid2DParams), c_uint32, c_void_p]),
     "sopot_b200_grid2d_rk4": (c_int, [_ctx, POINTER(Grid2DParams), c_double, c_size_t, POINTER(RK4Opts), c_void_p]),
@@ -536,6 +537,21 @@ class Engine:
         opts = RK4Opts(MEM_HOST, fp_mode, 0, mask, 0)
         out = np.empty((14, n))
         self._ck(self.lib.sopot_b200_rocket_rhs(self.ctx, byref(p), n, byref(opts), _ptr(state), _ptr(out)))
+        self.sync()
+        return out
+
+    ROCKET_PROBE = dict(mass=0, inertia=slice(1, 4), total_force_enu=slice(4, 7), total_torque_body=slice(7, 10), gravity=10,
+                        aero_force_body=slice(11, 14), aero_force_enu=slice(14, 17), aero_moment_body=slice(17, 20), density=20,
+                        pressure=21, temperature=22, speed_of_sound=23, mass_flow_rate=24, thrust_force_body=slice(25, 28))
+
+    def rocket_state_functions(self, elev, az, diam, g0, engine, mass_tab, state, ix_tab=None, iyz_tab=None, aero=None):
+        """The reference's state functions at state[14][n] -> [28][n] (rows: Engine.ROCKET_PROBE)."""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        n = state.shape[1]
+        p, mask, keep = self._rocket_params(elev, az, diam, g0, engine, mass_tab, ix_tab, iyz_tab, n, MEM_HOST, aero)
+        opts = RK4Opts(MEM_HOST, FP_STRICT, 0, mask, 0)
+        out = np.empty((28, n))
+        self._ck(self.lib.sopot_b200_rocket_state_functions(self.ctx, byref(p), n, byref(opts), _ptr(state), _ptr(out)))
         self.sync()
         return out
 

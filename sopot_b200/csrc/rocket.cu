@@ -64,6 +64,7 @@ struct RocketTablesDev {
     Table2D cd, cl, cs, cmq;       // rows == 0: reference default (host-side copy of the descriptors)
     int desc_off;                  // the same 4 descriptors as 12 doubles (rows, cols, off) inside the packed buffer
     int inv_off;                   // reciprocal interval widths 1 / (x[i+1] - x[i]) of the four time axes (er + mr + xr + yr)
+    int mdot_off;                  // mass-flow column of the engine table (er values; read by the state-function probe only)
     int er, mr, xr, yr;
     double burn_time;
     int use_interp;
@@ -209,6 +210,7 @@ struct RocketSysT {
         int er, mr, xr, yr, use_interp;
         int desc;                  // offset of the aero table descriptors in the shared-memory tables (AT only)
         int inv;                   // offset of the reciprocal interval widths
+        int mdot;                  // offset of the mass-flow column
         int soff;                  // offset of the per-thread state arrays behind the tables
         double burn;
         double apogee, apogee_t, vmax, vmax_t, bo_alt, bo_spd;
@@ -231,7 +233,7 @@ struct RocketSysT {
         in.tb = s_tab;
         in.er = P.tab.er; in.mr = P.tab.mr; in.xr = P.tab.xr; in.yr = P.tab.yr;
         in.use_interp = P.tab.use_interp; in.burn = P.tab.burn_time;
-        in.desc = P.tab.desc_off; in.inv = P.tab.inv_off; in.soff = (P.tab.total + 1) & ~1;
+        in.desc = P.tab.desc_off; in.inv = P.tab.inv_off; in.mdot = P.tab.mdot_off; in.soff = (P.tab.total + 1) & ~1;
         const double d = P.diam.at(i);
         in.g = Real<S>(P.g.at(i));
         in.area = Real<S>(kAeroPi) * Real<S>(d) * Real<S>(d) / Real<S>(4.0);   // axisymmetric_aero.hpp:56
@@ -253,8 +255,8 @@ struct RocketSysT {
     // everything the derivative reads from the TIME-indexed tables: mass / inertia (rocket_body.hpp:121-179) and the engine
     // columns (interpolated_engine.hpp:103-152).  A pure function of the simulation time, so RK4 stages 2 and 3 (same time)
     // share one evaluation in the contract-mode step below.
-    template <bool S> struct TimeTab { Real<S> mass, Ix, Iyz, exit_area, exit_pressure, engine_force; bool burning; };
-    template <bool S>
+    template <bool S> struct TimeTab { Real<S> mass, Ix, Iyz, exit_area, exit_pressure, engine_force, mass_flow; bool burning; };
+    template <bool S, bool PROBE = false>
     static __device__ __forceinline__ TimeTab<S> time_tables(const Inst<S>& in, const double time) {
         using R = Real<S>;
         const double* tb = in.tb;
@@ -266,7 +268,7 @@ struct RocketSysT {
         const double* inv_m = inv_e + in.er;
         const double* inv_x = inv_m + in.mr;
         const double* inv_y = inv_x + in.xr;
-        TimeTab<S> tt{R(100.0), R(10.0), R(100.0), R(0.0), R(0.0), R(0.0), false};
+        TimeTab<S> tt{R(100.0), R(10.0), R(100.0), R(0.0), R(0.0), R(0.0), R(0.0), false};
         if (in.use_interp) {
             if (in.mr) tt.mass = lerp_locate<S>(mass_t, inv_m, in.mr, time, in.h_mass).eval(mass_t + in.mr, in.mr);
             if (in.xr) tt.Ix = lerp_locate<S>(ix_t, inv_x, in.xr, time, in.h_ix).eval(ix_t + in.xr, in.xr);
@@ -281,6 +283,7 @@ struct RocketSysT {
             tt.exit_area = r_div_const(R(kEnginePi) * d_exit * d_exit, 4.0);
             tt.exit_pressure = p_comb * press_ratio;
             tt.engine_force = L.eval(eng_t + 4 * in.er, in.er);
+            if constexpr (PROBE) tt.mass_flow = L.eval(tb + in.mdot, in.er);
         }
         return tt;
     }
@@ -334,8 +337,11 @@ struct RocketSysT {
     }
 #endif
 
-    template <bool S>
-    static __device__ __forceinline__ int rhs_tt(const Inst<S>& in, const TimeTab<S>& tt, const Real<S> (&s)[14], Real<S> (&d)[14]) {
+    // PROBE: also write the values of the reference's state functions (rocket_tags.hpp) that are intermediates of the derivative
+    // to probe[kProbeValues] -- what SimulationResult::query<Tag>(t) / Rocket::queryStateFunction<Tag> return.
+    template <bool S, bool PROBE = false>
+    static __device__ __forceinline__ int rhs_tt(const Inst<S>& in, const TimeTab<S>& tt, const Real<S> (&s)[14], Real<S> (&d)[14],
+                                                 double* probe = nullptr) {
         using R = Real<S>;
         const R alt = s[3];
         const R q1 = s[7], q2 = s[8], q3 = s[9], q4 = s[10];
@@ -365,7 +371,7 @@ struct RocketSysT {
         // ---- thrust, interpolated_engine.hpp:103-152 ----
         const bool burning = tt.burning;
         R P(0.0), T(0.0);
-        if (burning || aero_on) atmosphere<S>(alt, P, T);
+        if (PROBE || burning || aero_on) atmosphere<S>(alt, P, T);
         R thrust(0.0);
         if (burning) thrust = tt.engine_force + tt.exit_area * (tt.exit_pressure - P);
 
@@ -412,6 +418,7 @@ struct RocketSysT {
                     cmq = bilinear<S>(tb, t_cmq, aoa_signed_deg.v, mach.v);
                 }
             }
+            if constexpr (PROBE) { probe[11] = fbx.v; probe[12] = fby.v; probe[13] = fbz.v; }
             Fax = R00 * fbx + R01 * fby + R02 * fbz;                              // :251-253
             Fay = R10 * fbx + R11 * fby + R12 * fbz;
             Faz = R20 * fbx + R21 * fby + R22 * fbz;
@@ -427,6 +434,20 @@ struct RocketSysT {
         const R Fy = R10 * thrust + Fay;
         const R Fz = ((-in.g) * mass + R20 * thrust) + Faz;
 
+        if constexpr (PROBE) {
+            probe[0] = mass.v; probe[1] = Ix.v; probe[2] = Iyz.v; probe[3] = Iyz.v;
+            probe[4] = Fx.v; probe[5] = Fy.v; probe[6] = Fz.v;                    // dynamics::TotalForceENU
+            probe[7] = Mx.v; probe[8] = My.v; probe[9] = Mz.v;                    // dynamics::TotalTorqueBody (= the aero moment)
+            probe[10] = in.g.v;                                                   // dynamics::GravityAcceleration
+            if (!aero_on) { probe[11] = 0.0; probe[12] = 0.0; probe[13] = 0.0; }  // aero::AeroForceBody (:186: zero below 1 m/s)
+            probe[14] = Fax.v; probe[15] = Fay.v; probe[16] = Faz.v;              // aero::AeroForceENU
+            probe[17] = Mx.v; probe[18] = My.v; probe[19] = Mz.v;                 // aero::AeroMomentBody
+            probe[20] = (P / (R(kAtmRs) * T)).v;                                  // environment::AtmosphericDensity (:70)
+            probe[21] = P.v; probe[22] = T.v;
+            probe[23] = r_sqrt(R(kAtmGamma * kAtmRs) * T).v;                      // environment::SpeedOfSound (:71)
+            probe[24] = tt.mass_flow.v;                                           // propulsion::MassFlowRate
+            probe[25] = thrust.v; probe[26] = 0.0; probe[27] = 0.0;               // propulsion::ThrustForceBody (along body +X)
+        }
         d[0] = R(1.0);                                                            // simulation_time.hpp:46-54
         d[1] = s[4]; d[2] = s[5]; d[3] = s[6];                                    // translation_kinematics.hpp:46-55
         const Recip<S> by_mass(mass);
@@ -462,6 +483,26 @@ struct RocketSysT {
         return 0;
     }
 };
+
+constexpr int kProbeValues = 28;
+
+// one evaluation of the state functions per instance: out[kProbeValues][n]
+template <class Sys>
+__global__ void __launch_bounds__(Sys::BLOCK)
+rocket_probe_kernel(const typename Sys::DevParams P, const size_t n, const double* __restrict__ state, double* __restrict__ out) {
+    Sys::template block_setup<true>(P);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Sys::template Inst<true> in;
+    Real<true> y[14], dy[14];
+    Sys::template load<true>(P, i, in, y);
+#pragma unroll
+    for (int d = 0; d < 14; ++d) y[d] = Real<true>(state[(size_t)d * n + i]);
+    double probe[kProbeValues];
+    Sys::template rhs_tt<true, true>(in, Sys::template time_tables<true, true>(in, y[0].v), y, dy, probe);
+#pragma unroll
+    for (int k = 0; k < kProbeValues; ++k) out[(size_t)k * n + i] = probe[k];
+}
 
 using RocketSys = RocketSysT<false>;
 using RocketSysTables = RocketSysT<true>;
@@ -504,6 +545,7 @@ double nozzle_pressure_ratio(double k, double area_ratio) {
 void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, RocketTablesDev& tab) {
     const size_t er = p->engine_rows, mr = p->mass_rows, xr = p->ix_rows, yr = p->iyz_rows;
     out.assign(5 * er + 2 * mr + 2 * xr + 2 * yr, 0.0);
+    std::vector<double> mdot_col(er, 0.0);
     if (er) {
         std::vector<double> t(er), col(8 * er);
         for (size_t r = 0; r < er; ++r)
@@ -531,6 +573,7 @@ void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, Ro
                 eff * std::sqrt(2.0 * k / (k - 1.0) * Rspec * temp * (1.0 - std::pow(ratio, (k - 1.0) / k)));
             o_t[r] = tt; o_exit[r] = col[2 * er + r]; o_pc[r] = col[3 * er + r];
             o_pr[r] = ratio; o_f[r] = mdot * exit_velocity;
+            mdot_col[r] = mdot;
         }
     }
     double* o = out.data() + 5 * er;
@@ -575,6 +618,9 @@ void pack_tables(const sopot_b200_rocket_params* p, std::vector<double>& out, Ro
             for (size_t r = 0; r < ns[a]; ++r)
                 out.push_back(r + 1 < ns[a] ? 1.0 / (out[offs[a] + r + 1] - out[offs[a] + r]) : 0.0);
     }
+    // propulsion::MassFlowRate (interpolated_engine.hpp:97-100,176-222): not part of the derivative, read by the probe only
+    tab.mdot_off = (int)out.size();
+    out.insert(out.end(), mdot_col.begin(), mdot_col.end());
     tab.total = (int)out.size();
 }
 
@@ -728,6 +774,39 @@ SB_EXPORT int sopot_b200_rocket_rhs(sopot_b200_ctx* ctx, const sopot_b200_rocket
         else rc = strict ? rocket_launch_rhs<RocketSys, true>(ctx, P, n, smem, (const double*)d_state, (double*)d_out)
                          : rocket_launch_rhs<RocketSys, false>(ctx, P, n, smem, (const double*)d_state, (double*)d_out);
         if (rc) return rc;
+        SB_CHECK_LAUNCH(ctx);
+    }
+    return sg.finish();
+}
+
+
+// State functions of the rocket at given states (strict arithmetic): the values behind Rocket::queryStateFunction<Tag> and
+// SimulationResult::query<Tag>(t) (rocket/rocket.hpp:222-228, rocket/simulation_result.hpp:111-115) for every tag that is an
+// intermediate of the derivative; out[SOPOT_B200_ROCKET_PROBE_VALUES][n], rows documented in include/sopot_b200.h.
+SB_EXPORT int sopot_b200_rocket_state_functions(sopot_b200_ctx* ctx, const sopot_b200_rocket_params* p, size_t n,
+                                                const sopot_b200_rk4_opts* opts, const double* state, double* out) {
+    if (!ctx) return SOPOT_B200_EINVAL;
+    if (!p || !opts || !state || !out) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
+    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
+    static_assert(kProbeValues == SOPOT_B200_ROCKET_PROBE_VALUES, "header and kernel disagree on the record size");
+    Staging sg(ctx, opts->mem);
+    int rc;
+    if (sg.host && (rc = sb_arena_begin(ctx, 4 * sb_align(n * 8) + sb_align(14 * n * 8) + sb_align(kProbeValues * n * 8) + 4096))) return rc;
+    RocketSys::DevParams P;
+    if ((rc = rocket_prepare(ctx, p, n, opts->broadcast, sg, P))) return rc;
+    const void* d_state; void* d_out;
+    if ((rc = sg.in(state, 14 * n * 8, &d_state))) return rc;
+    if ((rc = sg.out(out, (size_t)kProbeValues * n * 8, &d_out))) return rc;
+    const size_t smem = RocketSys::smem_bytes(P);
+    if (n) {
+        const bool tables = P.tab.cd.rows || P.tab.cl.rows || P.tab.cs.rows || P.tab.cmq.rows;
+        if (tables) {
+            if (smem > 48 * 1024) SB_CUDA(ctx, cudaFuncSetAttribute(rocket_probe_kernel<RocketSysTables>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rocket_probe_kernel<RocketSysTables><<<sb_grid_for(n, RocketSysTables::BLOCK), RocketSysTables::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        } else {
+            if (smem > 48 * 1024) SB_CUDA(ctx, cudaFuncSetAttribute(rocket_probe_kernel<RocketSys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rocket_probe_kernel<RocketSys><<<sb_grid_for(n, RocketSys::BLOCK), RocketSys::BLOCK, smem, ctx->stream>>>(P, n, (const double*)d_state, (double*)d_out);
+        }
         SB_CHECK_LAUNCH(ctx);
     }
     return sg.finish();

@@ -8,7 +8,8 @@
 //
 // A host callable cannot be launched on the device and this library has no host integrator.  The callable is
 // therefore traced once (b200/trace.hpp) to find the compiled system it evaluates, the RK4 kernel of that system
-// integrates all steps on the GPU, and the callable is re-checked against the traced system at the final state.
+// integrates all steps on the GPU, and the callable is re-checked against the traced system at three interior stored
+// states and at the final one.
 // A callable that is not a plain evaluation of one compiled system throws std::runtime_error.  Step count,
 // accumulated time stamps and the stored trajectory follow core/solver.hpp:74-132 exactly
 // (while (t < t_end - dt*0.5); t += dt; every step stored, initial state first).
@@ -120,10 +121,21 @@ public:
         b200::EnsembleResult r = rec.solve(eng, initial_state, n_steps, t_start, dt, opt);
         r.throwOnFailure();
         SolutionResult out = unpack(r, state_dim, n_steps, t_start, dt, initial_state);
-        // the callable must still describe the traced system at the end (no parameter was changed under way)
-        if (derivs(out.times.back(), StateView(out.states.back())) != rec.rhs(eng, out.states.back()))
-            throw std::runtime_error("sopot-b200: the derivative callable changed system parameters during the "
-                                     "integration (e.g. a feedback force); use the batched closed-loop entry points");
+        // The callable must describe the traced system along the WHOLE run, not only where it was traced: it is evaluated
+        // again at three interior stored states and at the final one and compared with the traced system's own derivative
+        // there.  A callable that depends on t (a forcing term that vanishes at t_start), on hidden state, or that changes a
+        // parameter on the way (a feedback force) would otherwise be integrated silently as the traced system.
+        const size_t last = out.size() - 1;
+        size_t probes[4] = {last / 4, last / 2, (3 * last) / 4, last};
+        size_t prev = 0;                                      // index 0 is the traced call itself
+        for (size_t i : probes) {
+            if (i == prev) continue;
+            prev = i;
+            if (derivs(out.times[i], StateView(out.states[i])) != rec.rhs(eng, out.states[i]))
+                throw std::runtime_error("sopot-b200: the derivative callable is not the traced system along the run (it "
+                                         "depends on t or hidden state, or changed system parameters during the integration, "
+                                         "e.g. a feedback force); use the batched closed-loop entry points");
+        }
         out.total_time = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - wall0).count();
         return out;
     }

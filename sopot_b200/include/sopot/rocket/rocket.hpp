@@ -18,6 +18,7 @@
 #include "../core/solver.hpp"
 #include "../core/typed_component.hpp"
 #include "../io/csv_parser.hpp"
+#include "rocket_tags.hpp"
 
 namespace sopot::rocket {
 
@@ -227,13 +228,38 @@ public:
         }
         return out;
     }
-    // convenience accessors (:229-262): plain slices of the state vector
-    T getTime(const std::vector<T>& s) const { return s[0]; }
-    std::array<T, 3> getPosition(const std::vector<T>& s) const { return {s[1], s[2], s[3]}; }
-    std::array<T, 3> getVelocity(const std::vector<T>& s) const { return {s[4], s[5], s[6]}; }
-    std::array<T, 4> getQuaternion(const std::vector<T>& s) const { return {s[7], s[8], s[9], s[10]}; }
-    T getAltitude(const std::vector<T>& s) const { return s[3]; }
-    T getSpeed(const std::vector<T>& s) const { return std::sqrt(s[4] * s[4] + s[5] * s[5] + s[6] * s[6]); }
+    // Any state function of the rocket at `state` (:222-228).  Kinematic tags and the time are slices of the state vector;
+    // every other tag is an intermediate of the derivative and comes from one strict-mode launch of the state-function
+    // kernel (sopot_b200_rocket_state_functions), so a query sees exactly the value the integrator used.
+    template <RocketTag Tag>
+    auto queryStateFunction(const std::vector<T>& state) const {
+        need();
+        if (state.size() != 14) throw std::invalid_argument("state has the wrong dimension");
+        if constexpr (Tag::source == TagSource::Slice) return rocketTagValue<Tag>(state.data());
+        else return rocketTagValue<Tag>(stateFunctions(state).data());
+    }
+    // the whole record at once (28 values, rows as in include/sopot_b200.h): one launch for several queries
+    std::array<double, SOPOT_B200_ROCKET_PROBE_VALUES> stateFunctions(const std::vector<T>& state) const {
+        need();
+        b200::Engine& eng = b200::Engine::shared();
+        const auto e = ensemble();
+        uint32_t bc;
+        sopot_b200_aero_tables aero_view;
+        const auto p = e.params(bc, aero_view);
+        const auto opts = b200::make_opts(strictOpts(), bc);
+        std::array<double, SOPOT_B200_ROCKET_PROBE_VALUES> out{};
+        eng.check(sopot_b200_rocket_state_functions(eng.ctx(), &p, 1, &opts, state.data(), out.data()));
+        eng.sync();
+        return out;
+    }
+    // convenience accessors (:229-262)
+    T getTime(const std::vector<T>& s) const { return queryStateFunction<propulsion::Time>(s); }
+    Vector3<T> getPosition(const std::vector<T>& s) const { return queryStateFunction<kinematics::PositionENU>(s); }
+    Vector3<T> getVelocity(const std::vector<T>& s) const { return queryStateFunction<kinematics::VelocityENU>(s); }
+    Quaternion<T> getQuaternion(const std::vector<T>& s) const { return queryStateFunction<kinematics::AttitudeQuaternion>(s); }
+    T getAltitude(const std::vector<T>& s) const { return queryStateFunction<kinematics::Altitude>(s); }
+    T getMass(const std::vector<T>& s) const { return queryStateFunction<dynamics::Mass>(s); }
+    T getSpeed(const std::vector<T>& s) const { return getVelocity(s).norm(); }
 
     RocketEnsemble ensemble() const { return {1, m_elevation_deg, m_azimuth_deg, m_diameter, m_gravity, m_tables}; }
 

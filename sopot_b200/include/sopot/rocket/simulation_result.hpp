@@ -1,6 +1,6 @@
 // rocket::SimulationResult<RocketType> and rocket::simulate(rocket, t_end, dt) -- interface of
 // rocket/simulation_result.hpp:20-245 and rocket/rocket.hpp:308-318: time-indexed access to a stored trajectory
-// (findIndex / interpolateState / position(t), altitude(t), ...), flight statistics and profiles.  Host-side
+// (findIndex / interpolateState / query<Tag>(t) / position(t), altitude(t), mass(t), ...), flight statistics and profiles.  Host-side
 // post-processing of what the device integrated; the statistics scan is the reference's (:151-189) and equals, bit for
 // bit, what the ensemble kernel accumulates on the fly (RocketEnsembleResult::stat), which is how Monte-Carlo runs get
 // their apogee / burnout numbers without storing trajectories.
@@ -45,11 +45,15 @@ public:
         for (size_t j = 0; j < r.size(); ++j) r[j] = s0[j] + alpha * (s1[j] - s0[j]);
         return r;
     }
-    std::array<T, 3> position(double t) const { return m_rocket->getPosition(interpolateState(t)); }
-    std::array<T, 3> velocity(double t) const { return m_rocket->getVelocity(interpolateState(t)); }
-    T altitude(double t) const { return m_rocket->getAltitude(interpolateState(t)); }
-    T speed(double t) const { return m_rocket->getSpeed(interpolateState(t)); }
-    std::array<T, 4> attitude(double t) const { return m_rocket->getQuaternion(interpolateState(t)); }
+    // any state function at time t (:111-115): interpolate the stored trajectory, then ask the rocket
+    template <StateTagConcept Tag>
+    auto query(double t) const { return m_rocket->template queryStateFunction<Tag>(interpolateState(t)); }
+    Vector3<T> position(double t) const { return query<kinematics::PositionENU>(t); }
+    Vector3<T> velocity(double t) const { return query<kinematics::VelocityENU>(t); }
+    T altitude(double t) const { return query<kinematics::Altitude>(t); }
+    T speed(double t) const { return velocity(t).norm(); }
+    T mass(double t) const { return query<dynamics::Mass>(t); }
+    Quaternion<T> attitude(double t) const { return query<kinematics::AttitudeQuaternion>(t); }
 
     void computeStatistics(double burn_time = 0) const {                       // :151-189
         if (m_stats_computed) return;

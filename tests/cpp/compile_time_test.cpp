@@ -88,6 +88,21 @@ int main() {
         return r;
     };
     ASSERT_THROWS(solver.solve(post_processed, 2, 0.0, 1.0, 0.01, single_system.getInitialState()), std::runtime_error);
+    // ... also when the difference only shows up mid-run: a forcing term that is zero where the callable is traced (t = 0)
+    // and zero again at the end (a hat on [0.2, 0.8]), and a callable with hidden state that starts to deviate after 30 calls
+    auto time_dependent = [&single_system](double t, StateView s) {
+        auto r = single_system.computeDerivatives(t, std::vector<double>(s.begin(), s.end()));
+        if (t > 0.2 && t < 0.8) r[1] += 0.5;
+        return r;
+    };
+    ASSERT_THROWS(solver.solve(time_dependent, 2, 0.0, 1.0, 0.01, single_system.getInitialState()), std::runtime_error);
+    int calls = 0;
+    auto hidden_state = [&single_system, &calls](double t, StateView s) {
+        auto r = single_system.computeDerivatives(t, std::vector<double>(s.begin(), s.end()));
+        if (++calls == 3) r[0] *= 2.0;                // the traced call is #1, the first interior re-check #2
+        return r;
+    };
+    ASSERT_THROWS(solver.solve(hidden_state, 2, 0.0, 1.0, 0.01, single_system.getInitialState()), std::runtime_error);
 
     // 9. ensemble: 1000 jittered oscillators in one launch == 1000 single solves, bit for bit (strict mode)
     const size_t n = 1000;

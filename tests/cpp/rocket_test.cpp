@@ -100,6 +100,31 @@ int main() {
         ASSERT_NEAR(sim.altitude(12.3456), a0 + alpha * (a1 - a0), 1e-9);
         ASSERT_TRUE(sim.altitude(-1.0) == 0.0 && sim.altitude(99.0) == sim.stateAt(3000)[3]);
         ASSERT_TRUE(sim.altitudeProfile().size() == 3001 && sim.speed(3.0) > 100.0);
+        // query<Tag>(t) (rocket/simulation_result.hpp:111-115) for any tag of rocket_tags.hpp: slices of the interpolated state ...
+        const auto st = sim.interpolateState(2.0);
+        const auto pos = sim.query<rocket::kinematics::PositionENU>(2.0);
+        ASSERT_TRUE(pos.x == st[1] && pos.y == st[2] && pos.z == st[3] && sim.position(2.0)[2] == st[3]);
+        ASSERT_TRUE(sim.query<rocket::propulsion::Time>(2.0) == st[0] && sim.attitude(2.0).q4 == st[10]);
+        ASSERT_NEAR(sim.velocity(2.0).norm(), sim.speed(2.0), 0.0);
+        // ... and intermediates of the derivative from the state-function kernel: mass table (20 -> 14.75 kg over 3.5 s), thrust on
+        // the plateau, the standard atmosphere at that altitude, Newton's second law against computeDerivatives
+        ASSERT_NEAR(sim.mass(2.0), 20.0 + (14.75 - 20.0) * 2.0 / 3.5, 1e-12 * 20.0);
+        ASSERT_NEAR(sim.query<rocket::dynamics::Mass>(10.0), 14.75, 0.0);
+        const auto thrust = sim.query<rocket::propulsion::ThrustForceBody>(2.0);
+        ASSERT_TRUE(thrust.x > 1400.0 && thrust.x < 1600.0 && thrust.y == 0.0 && thrust.z == 0.0);
+        ASSERT_TRUE(sim.query<rocket::propulsion::ThrustForceBody>(10.0).x == 0.0 && sim.query<rocket::propulsion::MassFlowRate>(10.0) == 0.0);
+        ASSERT_TRUE(sim.query<rocket::propulsion::MassFlowRate>(2.0) > 0.5);
+        const double T_alt = sim.query<rocket::environment::AtmosphericTemperature>(2.0);
+        ASSERT_NEAR(T_alt, 288.15 - 0.0065 * st[3], 1e-12 * 288.15);
+        ASSERT_NEAR(sim.query<rocket::environment::AtmosphericDensity>(2.0),
+                    sim.query<rocket::environment::AtmosphericPressure>(2.0) / ((8.3144598 / 0.0289644) * T_alt), 1e-15 * 1.3);
+        ASSERT_NEAR(sim.query<rocket::dynamics::GravityAcceleration>(2.0), 9.80665, 0.0);
+        const auto F = sim.query<rocket::dynamics::TotalForceENU>(2.0);
+        const auto dv = rocket.computeDerivatives(0.0, st);
+        for (int k = 0; k < 3; ++k) ASSERT_NEAR(F[k] / sim.mass(2.0), dv[4 + k], 1e-13 * std::abs(dv[6]));
+        const auto Fa = sim.query<rocket::aero::AeroForceENU>(2.0);
+        ASSERT_TRUE(Fa.norm() > 1.0 && sim.query<rocket::aero::AeroMomentBody>(2.0).norm() == sim.query<rocket::dynamics::TotalTorqueBody>(2.0).norm());
+        ASSERT_NEAR(rocket.getMass(st), sim.mass(2.0), 0.0);
     }
 
     // CSV path of the reference (rocket/rocket.hpp:124-133): numeric rows, header cells skipped

@@ -91,6 +91,7 @@ def main():
     cartn_linearize_golden(R)
     rocket_aero_golden(R)
     rocket_atmosphere_golden(R)
+    rocket_state_functions_golden(R)
     dpend_jacobian_golden(R)
     control_n_golden(R)
     ugrid_golden(R)
@@ -192,6 +193,19 @@ def rocket_atmosphere_golden(R):
     st[11:14] = rng.normal(0, 0.3, (3, alts.size))
     np.savez(os.path.join(OUT, "rocket_atmosphere.npz"), state=st,
              rhs=R.rocket_rhs(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], st))
+
+
+def rocket_state_functions_golden(R):
+    """Every state function the reference's registry provides for the full rocket (rocket_tags.hpp), at the states of the
+    atmosphere fixture (all layers, burning and coasting) and, with coefficient tables, at the states of the aero fixture."""
+    g = np.load(os.path.join(OUT, "rocket.npz"))
+    st = np.load(os.path.join(OUT, "rocket_atmosphere.npz"))["state"]
+    out = dict(state=st, values=R.rocket_state_functions(85.0, 0.0, 0.16, 9.80665, g["engine"], g["mass_tab"], st))
+    a = np.load(os.path.join(OUT, "rocket_aero.npz"))
+    out["aero_state"] = a["rhs_state"]
+    out["aero_values"] = R.rocket_state_functions(84.0, 30.0, 0.16, 9.80665, a["engine"], a["mass_tab"], a["rhs_state"],
+                                                  aero=rocket_aero_tables())
+    np.savez(os.path.join(OUT, "rocket_state_functions.npz"), **out)
 
 
 def dpend_jacobian_golden(R):

@@ -336,6 +336,30 @@ def test_rocket_inertia_tables_and_single_step(engine, port):
     assert rel_err(st0, ref0).max() <= FINAL
 
 
+def test_rocket_state_functions_golden(engine):
+    """Every state function the reference's registry answers for the full rocket (rocket_tags.hpp; what queryStateFunction<Tag>
+    and SimulationResult::query<Tag>(t) return), from the device record, against the reference at states in every atmosphere
+    layer (burning and coasting) and with coefficient tables loaded."""
+    g, r = golden("rocket_state_functions"), golden("rocket")
+    got = engine.rocket_state_functions(85.0, 0.0, 0.16, 9.80665, r["engine"], r["mass_tab"], g["state"])
+    # vectors: relative to the vector's norm (components that cancel to ~0 carry the rounding of the large terms)
+    for name, rows in engine.ROCKET_PROBE.items():
+        ref, mine = g["values"][rows], got[rows]
+        den = np.maximum(np.linalg.norm(np.atleast_2d(ref), axis=0), 1e-6)
+        assert (np.abs(mine - ref) / den).max() <= PER_STEP, (name, (np.abs(mine - ref) / den).max())
+    a = golden("rocket_aero")
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    got = engine.rocket_state_functions(84.0, 30.0, 0.16, 9.80665, a["engine"], a["mass_tab"], g["aero_state"], aero=mg.rocket_aero_tables())
+    for name, rows in engine.ROCKET_PROBE.items():
+        ref, mine = g["aero_values"][rows], got[rows]
+        den = np.maximum(np.linalg.norm(np.atleast_2d(ref), axis=0), 1e-6)
+        assert (np.abs(mine - ref) / den).max() <= PER_STEP, ("tables", name, (np.abs(mine - ref) / den).max())
+
+
 def test_rocket_monte_carlo_sample_and_dispersion(engine, port):
     n = 1 << 14
     w = W.rocket_ensemble(n)
