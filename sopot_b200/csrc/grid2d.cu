@@ -201,14 +201,17 @@ grid_stage_gather(const GridDev g, const StencilIn in, const size_t r_lo, const 
 template <int TX, int TY, int TOPO>
 struct FusedTile {
     static constexpr int H = 4;
-    static constexpr int W = TX + 2 * H, HT = TY + 2 * H, CELLS = W * HT;
+    // WS = row stride of the planes in shared memory.  W = 40 doubles is 8 mod 16 bank pairs: the halo-ring cells of the two
+    // side columns (one cell per row, consecutive lanes) hit 2-4 bank pairs -- 0.75 conflicts per shared access in round 1's
+    // ncu capture.  An odd stride spreads any column over all banks.
+    static constexpr int W = TX + 2 * H, HT = TY + 2 * H, WS = W + 1, CELLS = WS * HT;
     static constexpr int THREADS = TX * TY;
     static constexpr int FPLANES = TOPO == 0 ? 4 : 8;
     static constexpr size_t SMEM = (size_t)(8 + FPLANES) * CELLS * sizeof(double);
     // halo cells with margin >= m (margin = distance to the tile edge), m = 0..3; margin 4 = interior
     static constexpr int ring(int m) { return 2 * (W - 2 * m) + 2 * (HT - 2 * m - 2); }
     static constexpr int upto(int m) { int n = 0; for (int k = H - 1; k >= m; --k) n += ring(k); return n; }
-    static_assert(upto(0) == CELLS - TX * TY && upto(0) <= THREADS, "one halo cell per thread");
+    static_assert(upto(0) == W * HT - TX * TY && upto(0) <= THREADS, "one halo cell per thread");
 };
 
 // y of the local slab plus FOUR ghost rows on either side (ghost_top row j = global row row_begin - 4 + j,
@@ -229,7 +232,7 @@ template <bool S, int TOPO, int TX, int TY, bool FULL>
 __device__ __forceinline__ void fused_springs(const GridDev& g, const double* __restrict__ in_pl, double* __restrict__ F,
                                               const int r, const int c, const long long gr, const long long gc) {
     using T = FusedTile<TX, TY, TOPO>;
-    const int o = r * T::W + c;
+    const int o = r * T::WS + c;
     const bool here = FULL || (gr >= 0 && gc >= 0 && gr < (long long)g.rows && gc < (long long)g.cols);
     const bool right = c + 1 < T::W && here && (FULL || gc + 1 < (long long)g.cols);
     const bool down = r + 1 < T::HT && here && (FULL || gr + 1 < (long long)g.rows);
@@ -237,12 +240,12 @@ __device__ __forceinline__ void fused_springs(const GridDev& g, const double* __
     if (right || down) P = tile_cell<T::CELLS>(in_pl, o);
     Real<S> fx, fy;
     if (right) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + 1), g.k, g.c, g.L_orth, fx, fy); F[o] = fx.v; F[T::CELLS + o] = fy.v; }
-    if (down) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W), g.k, g.c, g.L_orth, fx, fy); F[2 * T::CELLS + o] = fx.v; F[3 * T::CELLS + o] = fy.v; }
+    if (down) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::WS), g.k, g.c, g.L_orth, fx, fy); F[2 * T::CELLS + o] = fx.v; F[3 * T::CELLS + o] = fy.v; }
     if constexpr (TOPO != 0) {
         const bool dr = down && c + 1 < T::W && (FULL || gc + 1 < (long long)g.cols);
         const bool dl = down && c >= 1 && (FULL || gc >= 1);
-        if (dr) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W + 1), g.k, g.c, g.L_diag, fx, fy); F[4 * T::CELLS + o] = fx.v; F[5 * T::CELLS + o] = fy.v; }
-        if (dl) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::W - 1), g.k, g.c, g.L_diag, fx, fy); F[6 * T::CELLS + o] = fx.v; F[7 * T::CELLS + o] = fy.v; }
+        if (dr) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::WS + 1), g.k, g.c, g.L_diag, fx, fy); F[4 * T::CELLS + o] = fx.v; F[5 * T::CELLS + o] = fy.v; }
+        if (dl) { spring_force<S>(P, tile_cell<T::CELLS>(in_pl, o + T::WS - 1), g.k, g.c, g.L_diag, fx, fy); F[6 * T::CELLS + o] = fx.v; F[7 * T::CELLS + o] = fy.v; }
     }
 }
 
@@ -255,23 +258,23 @@ __device__ __forceinline__ void fused_update(const GridDev& g, const double dt_,
     using R = Real<S>;
     using T = FusedTile<TX, TY, TOPO>;
     if (!FULL && (gr < 0 || gc < 0 || gr >= (long long)g.rows || gc >= (long long)g.cols)) return;
-    const int o = r * T::W + c;
+    const int o = r * T::WS + c;
     const bool has_l = FULL || gc > 0, has_r = FULL || gc + 1 < (long long)g.cols;
     const bool has_u = FULL || gr > 0, has_d = FULL || gr + 1 < (long long)g.rows;
     R Fx(0.0), Fy(0.0);
     // horizontals then verticals: left(-), right(+), up(-), down(+)
     if (has_l) { Fx -= R(F[o - 1]); Fy -= R(F[T::CELLS + o - 1]); }
     if (has_r) { Fx += R(F[o]); Fy += R(F[T::CELLS + o]); }
-    if (has_u) { Fx -= R(F[2 * T::CELLS + o - T::W]); Fy -= R(F[3 * T::CELLS + o - T::W]); }
+    if (has_u) { Fx -= R(F[2 * T::CELLS + o - T::WS]); Fy -= R(F[3 * T::CELLS + o - T::WS]); }
     if (has_d) { Fx += R(F[2 * T::CELLS + o]); Fy += R(F[3 * T::CELLS + o]); }
     if constexpr (TOPO == 1) {        // main diagonals, then anti-diagonals
-        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::W - 1]); Fy -= R(F[5 * T::CELLS + o - T::W - 1]); }
+        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::WS - 1]); Fy -= R(F[5 * T::CELLS + o - T::WS - 1]); }
         if (has_d && has_r) { Fx += R(F[4 * T::CELLS + o]); Fy += R(F[5 * T::CELLS + o]); }
-        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::W + 1]); Fy -= R(F[7 * T::CELLS + o - T::W + 1]); }
+        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::WS + 1]); Fy -= R(F[7 * T::CELLS + o - T::WS + 1]); }
         if (has_d && has_l) { Fx += R(F[6 * T::CELLS + o]); Fy += R(F[7 * T::CELLS + o]); }
     } else if constexpr (TOPO == 2) { // per cell: main then anti
-        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::W - 1]); Fy -= R(F[5 * T::CELLS + o - T::W - 1]); }
-        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::W + 1]); Fy -= R(F[7 * T::CELLS + o - T::W + 1]); }
+        if (has_u && has_l) { Fx -= R(F[4 * T::CELLS + o - T::WS - 1]); Fy -= R(F[5 * T::CELLS + o - T::WS - 1]); }
+        if (has_u && has_r) { Fx -= R(F[6 * T::CELLS + o - T::WS + 1]); Fy -= R(F[7 * T::CELLS + o - T::WS + 1]); }
         if (has_d && has_l) { Fx += R(F[6 * T::CELLS + o]); Fy += R(F[7 * T::CELLS + o]); }
         if (has_d && has_r) { Fx += R(F[4 * T::CELLS + o]); Fy += R(F[5 * T::CELLS + o]); }
     }
@@ -320,7 +323,7 @@ __device__ __forceinline__ void fused_step_body(const GridDev& g, const long lon
         else if (q < 2 * w) { rr = T::HT - 1 - mr; cr = mr + q - w; }
         else { q -= 2 * w; rr = mr + 1 + (q >> 1); cr = (q & 1) ? T::W - 1 - mr : mr; }
     }
-    const int oi = ri * T::W + ci, orr = rr * T::W + cr;
+    const int oi = ri * T::WS + ci, orr = rr * T::WS + cr;
     R yi[4], yr[4], Sacc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { yi[j] = R(A[j * T::CELLS + oi]); yr[j] = R(mr >= 0 ? A[j * T::CELLS + orr] : 0.0); }
@@ -359,7 +362,7 @@ grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __rest
     const unsigned tile_row = ty_first + blockIdx.y * ty_stride;
     const long long r0 = (long long)g.row_begin + (long long)tile_row * TY - T::H;
     const long long c0 = (long long)blockIdx.x * TX - T::H;
-    for (int idx = threadIdx.x; idx < T::CELLS; idx += T::THREADS) {
+    for (int idx = threadIdx.x; idx < T::W * T::HT; idx += T::THREADS) {
         const int r = idx / T::W, c = idx % T::W;
         const long long gr = r0 + r, gc = c0 + c;
         double2 a = make_double2(0.0, 0.0), b = a;
@@ -372,13 +375,254 @@ grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __rest
             a = __ldg(reinterpret_cast<const double2*>(rowp + 4 * gc));
             b = __ldg(reinterpret_cast<const double2*>(rowp + 4 * gc) + 1);
         }
-        A[idx] = a.x; A[T::CELLS + idx] = a.y; A[2 * T::CELLS + idx] = b.x; A[3 * T::CELLS + idx] = b.y;
+        const int o = r * T::WS + c;
+        A[o] = a.x; A[T::CELLS + o] = a.y; A[2 * T::CELLS + o] = b.x; A[3 * T::CELLS + o] = b.y;
     }
     __syncthreads();
     // tiles that lie entirely inside the global grid (all but the boundary tiles) skip every existence test
     const bool full = r0 >= 0 && c0 >= 0 && r0 + T::HT <= (long long)g.rows && c0 + T::W <= (long long)g.cols;
     if (full) fused_step_body<S, TOPO, TX, TY, true>(g, r0, c0, dt, A, B, F, y_out);
     else fused_step_body<S, TOPO, TX, TY, false>(g, r0, c0, dt, A, B, F, y_out);
+}
+
+// ---- fused RK4 step, marching form (quad topology): one warp per strip of columns, rows streamed through the warp --------
+// The tile kernel above spends most of its cycles on barriers, shared-memory latency and index arithmetic (ncu, round 1:
+// FP64 pipe 34 % busy, 0.75 bank conflicts per shared access, ~700 integer / control instructions per mass-step).  Here a warp
+// owns a strip of 32 consecutive columns and marches down the rows with the four RK stages in a software pipeline.  Tick r:
+//     load y[r+1] (prefetch);  stage 1 on row r-1;  stage 2 on row r-3;  stage 3 on row r-5;  stage 4 on row r-7 -> store.
+// Stage s on row q needs its input (y, A1, A2 or A3) on rows q and q+1 only: every spring is evaluated ONCE, by its first
+// endpoint -- the right spring by the lane itself (neighbour state by warp shuffle, the force handed to the right lane by a
+// second shuffle), the down spring from rows q and q+1, and its force is CARRIED in registers to the next tick, where it is the
+// up spring of row q+1.  The reference's "+= on edge.first, -= on edge.second" in edge-list order left(-), right(+), up(-),
+// down(+) (force_aggregator_2d.hpp:69-81) is kept, so FP_STRICT results equal the tile kernel's, the per-stage schedule's and
+// the reference's bit for bit.  The lags 1, 3, 5, 7 make the four stages of one tick INDEPENDENT of each other (stage s reads
+// what stage s-1 produced in the two previous ticks), which is where the instruction-level parallelism comes from: four
+// spring / update chains interleave in one basic block, no barrier, no block-level communication at all.
+// What a stage produces is handed on in registers (it is the `next` row one tick later and the `current` row two ticks later);
+// the two things that live longer -- y of the last 8 rows (the base of every stage update) and the stage accumulator S of the
+// rows between stage 1 and stage 4 -- sit in a warp-private shared-memory ring [8 rows][4][32 lanes]: every lane touches only
+// its own column, so there is no synchronisation and no bank conflict (64-bit accesses, consecutive lanes).
+// Redundancy instead of exchange: lanes 0-3 and 28-31 of a warp recompute the 4-column halo of the neighbouring strips (stage s
+// is valid on lanes s .. 31-s, 24 of 32 lanes own an output column), and a chunk of rows runs its pipeline 10 ticks longer.
+constexpr int kMarchRing = 8;                    // rows of y / S kept in shared memory per warp
+constexpr int kMarchWarps = 4;
+constexpr size_t kMarchSmem = (size_t)kMarchWarps * 2 * kMarchRing * 4 * 32 * sizeof(double);     // 64 KiB per CTA
+
+template <bool S>
+struct MarchAcc { Real<S> v[4]; };
+
+__device__ __forceinline__ void ring_store(double* ring, const long long row, const Mass4& m) {
+    double* p = ring + (size_t)(row & (kMarchRing - 1)) * 128;
+    p[0] = m.x; p[32] = m.y; p[64] = m.vx; p[96] = m.vy;
+}
+__device__ __forceinline__ Mass4 ring_load(const double* ring, const long long row) {
+    const double* p = ring + (size_t)(row & (kMarchRing - 1)) * 128;
+    return Mass4{p[0], p[32], p[64], p[96]};
+}
+
+// contract-mode spring in two halves, so that the two springs a lane evaluates per stage share ONE test for coincident
+// masses: geometry (difference vector, length, reciprocal length by the fast route) and force
+struct SpringGeom { double dx, dy, l2, length, inv; };
+__device__ __forceinline__ SpringGeom march_geom(const Mass4& pi, const Mass4& pj) {
+    SpringGeom s;
+    s.dx = pj.x - pi.x; s.dy = pj.y - pi.y;
+    s.l2 = fma(s.dx, s.dx, s.dy * s.dy);
+    sbtrig::sqrt_rsqrt_fast(s.l2, s.length, s.inv);
+    return s;
+}
+__device__ __forceinline__ void march_geom_generic(SpringGeom& s) {       // indexed_spring_2d.hpp:118-128, any l2 >= 0
+    s.length = sqrt(s.l2);
+    s.inv = 1.0 / (s.length < 1e-10 ? 1e-10 : s.length);
+}
+__device__ __forceinline__ void march_spring(const SpringGeom& s, const Mass4& pi, const Mass4& pj, const double k, const double c,
+                                             const double L0, Real<false>& fx, Real<false>& fy) {
+    const double ux = s.dx * s.inv, uy = s.dy * s.inv;
+    const double rel = (pj.vx - pi.vx) * ux + (pj.vy - pi.vy) * uy;
+    const double F = k * (s.length - L0) + c * rel;                                         // :140
+    fx.v = F * ux; fy.v = F * uy;
+}
+
+template <bool S, bool EDGE>
+__device__ __forceinline__ void march_forces(const GridDev& g, const Mass4& cur, const Mass4& nxt, const bool here, const bool has_l,
+                                             const bool has_r, const bool has_u, const bool has_d, Real<S>& ufx, Real<S>& ufy,
+                                             Real<S>& Fx, Real<S>& Fy) {
+    using R = Real<S>;
+    constexpr unsigned FULLMASK = 0xffffffffu;
+    // right spring (this lane -> lane + 1): neighbour state by shuffle, evaluated once, handed on to the right neighbour
+    Mass4 rt{__shfl_down_sync(FULLMASK, cur.x, 1), __shfl_down_sync(FULLMASK, cur.y, 1),
+             __shfl_down_sync(FULLMASK, cur.vx, 1), __shfl_down_sync(FULLMASK, cur.vy, 1)};
+    // lane 31 has no right neighbour in the warp (the shuffle hands it its own state): give its discarded pseudo-spring a
+    // unit length, so that neither arithmetic mode sees a zero-length spring there (generic / IEEE slow paths)
+    if ((threadIdx.x & 31) == 31) rt.x = cur.x + 1.0;
+    R rfx, rfy, dfx, dfy;
+    if constexpr (S) {
+        spring_force<true>(cur, rt, g.k, g.c, g.L_orth, rfx, rfy);
+        spring_force<true>(cur, nxt, g.k, g.c, g.L_orth, dfx, dfy);
+    } else {
+        // both springs by the fast route; a warp in which any lane sees (nearly) coincident masses -- in practice never --
+        // redoes those lanes through the generic route.  The test is conservative and cheap: one integer compare of the high
+        // words (l2 >= 0, so their order is the floating-point order; a length a hair above the threshold merely takes the
+        // generic route, which is valid for every length).
+        SpringGeom sr = march_geom(cur, rt), sd = march_geom(cur, nxt);
+        constexpr int kHi = 0x3bc79ca1;                       // high word of 1e-20 (0x3bc79ca10c924223)
+        const bool deg_r = __double2hiint(sr.l2) <= kHi, deg_d = __double2hiint(sd.l2) <= kHi;
+        if (__any_sync(FULLMASK, deg_r || deg_d)) {
+            if (deg_r) march_geom_generic(sr);
+            if (deg_d) march_geom_generic(sd);
+        }
+        march_spring(sr, cur, rt, g.k, g.c, g.L_orth, rfx, rfy);
+        march_spring(sd, cur, nxt, g.k, g.c, g.L_orth, dfx, dfy);
+    }
+    const R lfx(__shfl_up_sync(FULLMASK, rfx.v, 1)), lfy(__shfl_up_sync(FULLMASK, rfy.v, 1));
+    Fx = R(0.0); Fy = R(0.0);
+    if constexpr (EDGE) {
+        // a spring that does not exist contributes nothing: the reference skips it, and so does a select (never an added 0)
+        if (here && has_l) { Fx -= lfx; Fy -= lfy; }
+        if (here && has_r) { Fx += rfx; Fy += rfy; }
+        if (here && has_u) { Fx -= ufx; Fy -= ufy; }
+        if (here && has_d) { Fx += dfx; Fy += dfy; }
+    } else {
+        Fx -= lfx; Fy -= lfy;
+        Fx += rfx; Fy += rfy;
+        Fx -= ufx; Fy -= ufy;
+        Fx += dfx; Fy += dfy;
+    }
+    ufx = dfx; ufy = dfy;        // the down spring of this row is the up spring of the next one
+}
+
+// stage arithmetic of rk4_step (ensemble.cuh) for one mass: k = dt * {vx, vy, Fx/m, Fy/m}
+template <bool S, int STAGE>
+__device__ __forceinline__ void march_update(const GridDev& g, const Real<S> dt, const Mass4& cur, const Real<S> Fx, const Real<S> Fy,
+                                             const Mass4& y, MarchAcc<S>& acc, Mass4& out) {
+    using R = Real<S>;
+    R d[4] = {R(cur.vx), R(cur.vy), r_div_by<S>(Fx, g.mass, g.inv_mass), r_div_by<S>(Fy, g.mass, g.inv_mass)};
+    R k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = d[j] * dt;
+    const R yv[4] = {R(y.x), R(y.y), R(y.vx), R(y.vy)};
+    R o[4];
+    if constexpr (STAGE == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = yv[j] + r_div_const(acc.v[j] + k[j], 6.0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc.v[j] = (STAGE == 1) ? k[j] : acc.v[j] + 2.0 * k[j];
+            o[j] = (STAGE == 3) ? yv[j] + k[j] : yv[j] + 0.5 * k[j];
+        }
+    }
+    out = Mass4{o[0].v, o[1].v, o[2].v, o[3].v};
+}
+
+template <bool S, bool EDGE>
+__device__ __forceinline__ void march_body(const GridDev& g, const StepIn& in, const double dt_, double* __restrict__ y_out,
+                                           const long long row_lo, const long long row_hi, const long long gc, double* yring,
+                                           double* sring) {
+    using R = Real<S>;
+    const R dt(dt_);
+    const int lane = threadIdx.x & 31;
+    const bool col_ok = gc >= 0 && gc < (long long)g.cols;
+    const bool has_l = gc > 0, has_r = gc + 1 < (long long)g.cols;
+    const bool owner = lane >= 4 && lane < 28 && col_ok;
+    const long long slab_lo = (long long)g.row_begin, slab_hi = (long long)(g.row_begin + g.rows_local);
+    const long long nrows = (long long)g.rows;
+    const long long last_load = row_hi + 3;       // rows beyond it are outside the dependency cone of this chunk
+
+    auto load_row = [&](long long gr) -> Mass4 {
+        if (gr > last_load) gr = last_load;
+        // a cell outside the grid: a placeholder at its own lattice position (never a zero-length pseudo-spring)
+        if (EDGE && !(col_ok && gr >= 0 && gr < nrows)) return Mass4{(double)gc, (double)gr, 0.0, 0.0};
+        const long long rl = gr - slab_lo;
+        const double* rowp = rl < 0 ? in.ghost_top + (size_t)(rl + 4) * g.cols * 4
+                           : gr >= slab_hi ? in.ghost_bot + (size_t)(gr - slab_hi) * g.cols * 4
+                           : in.slab + (size_t)rl * g.cols * 4;
+        return load_mass(rowp, (size_t)gc);
+    };
+    auto exists = [&](const long long q) { return !EDGE || (col_ok && q >= 0 && q < nrows); };
+
+    // inputs of the four stages on the rows they process this tick (cur) and the row below (nxt)
+    // (before the pipeline has filled they hold placeholders on distinct lattice positions, outside every dependency cone)
+    const double px = (double)gc;
+    Mass4 c1{}, n1{}, c2{px, -2.0, 0.0, 0.0}, n2{px, -1.0, 0.0, 0.0}, c3 = c2, n3 = n2, c4 = c2, n4 = n2;
+    R u1x(0.0), u1y(0.0), u2x(0.0), u2y(0.0), u3x(0.0), u3y(0.0), u4x(0.0), u4y(0.0);   // carried up-spring forces per stage
+    // first tick: r = row_lo - 3; stage 1 then processes row_lo - 4, whose down spring is the first force inside the cone
+    long long r = row_lo - 3;
+    n1 = load_row(r - 1);
+    Mass4 pre = load_row(r);
+    ring_store(yring, r - 1, n1);
+    for (; r < row_hi + 7; ++r) {
+        c1 = n1; n1 = pre;                                   // y[r-1], y[r]
+        ring_store(yring, r, n1);
+        pre = load_row(r + 1);
+        Mass4 o1, o2, o3, o4;
+        R Fx, Fy;
+        {   // stage 1 on row r-1
+            const long long q = r - 1;
+            march_forces<S, EDGE>(g, c1, n1, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u1x, u1y, Fx, Fy);
+            MarchAcc<S> acc;
+            march_update<S, 1>(g, dt, c1, Fx, Fy, c1, acc, o1);                       // o1 = A1[r-1]
+            ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
+        }
+        {   // stage 2 on row r-3: A1 rows r-3 (c2), r-2 (n2)
+            const long long q = r - 3;
+            march_forces<S, EDGE>(g, c2, n2, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u2x, u2y, Fx, Fy);
+            const Mass4 sv = ring_load(sring, q);
+            MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
+            march_update<S, 2>(g, dt, c2, Fx, Fy, ring_load(yring, q), acc, o2);      // o2 = A2[r-3]
+            ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
+        }
+        {   // stage 3 on row r-5: A2 rows r-5 (c3), r-4 (n3)
+            const long long q = r - 5;
+            march_forces<S, EDGE>(g, c3, n3, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u3x, u3y, Fx, Fy);
+            const Mass4 sv = ring_load(sring, q);
+            MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
+            march_update<S, 3>(g, dt, c3, Fx, Fy, ring_load(yring, q), acc, o3);      // o3 = A3[r-5]
+            ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
+        }
+        {   // stage 4 on row r-7: A3 rows r-7 (c4), r-6 (n4)
+            const long long q = r - 7;
+            march_forces<S, EDGE>(g, c4, n4, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u4x, u4y, Fx, Fy);
+            const Mass4 sv = ring_load(sring, q);
+            MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
+            march_update<S, 4>(g, dt, c4, Fx, Fy, ring_load(yring, q), acc, o4);      // o4 = y_new[r-7]
+            if (owner && q >= row_lo && q < row_hi)
+                store4(y_out + ((size_t)(q - slab_lo) * g.cols + (size_t)gc) * 4, o4.x, o4.y, o4.vx, o4.vy);
+        }
+        // what stage s produced is the `next` row of stage s+1 in the coming tick and its `current` row in the one after
+        c2 = n2; n2 = o1;
+        c3 = n3; n3 = o2;
+        c4 = n4; n4 = o3;
+    }
+}
+
+#ifndef SB_MARCH_MINB
+#define SB_MARCH_MINB 3
+#endif
+template <bool S>
+__global__ void __launch_bounds__(32 * kMarchWarps, SB_MARCH_MINB)
+grid_rk4_march(const GridDev g, const StepIn in, const double dt, double* __restrict__ y_out, const unsigned row_lo_local,
+               const unsigned row_hi_local, const unsigned rows_per_chunk) {
+    constexpr int OWN = 24;                       // output columns per warp
+    extern __shared__ double march_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* yring = march_smem + (size_t)warp * 2 * kMarchRing * 128 + lane;
+    double* sring = yring + kMarchRing * 128;
+    const long long strip = (long long)blockIdx.x * kMarchWarps + warp;
+    const long long gc = strip * OWN - 4 + lane;
+    if (strip * OWN >= (long long)g.cols) return;            // whole warp: no column to own
+    const long long lo = (long long)g.row_begin + row_lo_local + (long long)blockIdx.y * rows_per_chunk;
+    long long hi = lo + rows_per_chunk;
+    const long long end = (long long)g.row_begin + row_hi_local;
+    if (hi > end) hi = end;
+    if (lo >= hi) return;
+    // rows the pipeline reads before it has written them hold zeros, not whatever the previous CTA left: their (discarded)
+    // results stay finite and ordinary, so the strict-mode operand votes are not failed by garbage
+#pragma unroll
+    for (int k = 0; k < 2 * kMarchRing * 4; ++k) yring[k * 32] = 0.0;
+    // a strip / chunk that reaches outside the global grid takes the predicated body
+    const bool edge = strip * OWN - 4 < 0 || strip * OWN - 4 + 32 > (long long)g.cols || lo - 11 < 0 || hi + 8 > (long long)g.rows;
+    if (edge) march_body<S, true>(g, in, dt, y_out, lo, hi, gc, yring, sring);
+    else march_body<S, false>(g, in, dt, y_out, lo, hi, gc, yring, sring);
 }
 
 __global__ void grid_init_kernel(const size_t rows_local, const size_t cols, const size_t row_begin,
@@ -480,8 +724,36 @@ int launch_fused(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
     return SOPOT_B200_OK;
 }
 
+// quad topology: the marching kernel over local rows [ty_first * 16, (ty_first + n_ty) * 16) (callers count in tile rows of 16)
+template <bool S>
+int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const StepIn& in, double dt, double* y_out, unsigned ty_first,
+                 unsigned n_ty) {
+    const unsigned r_lo = ty_first * kFusedTY;
+    unsigned r_hi = (ty_first + n_ty) * kFusedTY;
+    if (r_hi > g.rows_local) r_hi = (unsigned)g.rows_local;
+    if (r_hi <= r_lo) return SOPOT_B200_OK;
+    // rows per chunk: every chunk runs its pipeline 10 ticks longer than it has rows, a longer chunk leaves fewer warps to
+    // balance over the SMs; 128 rows measured best at 8192^2 (3.19 ms per step; 64: 3.37, 256: 3.22, 512: 3.43)
+    static const unsigned env_rows = std::getenv("SOPOT_B200_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_MARCH_ROWS")) : 0u;
+    const unsigned strips = (unsigned)((g.cols + 23) / 24), ctas_x = (strips + kMarchWarps - 1) / kMarchWarps;
+    const unsigned chunk = env_rows ? env_rows : 128u;
+    const dim3 grid(ctas_x, (r_hi - r_lo + chunk - 1) / chunk);
+    SB_CUDA(ctx, cudaFuncSetAttribute(grid_rk4_march<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarchSmem));
+    grid_rk4_march<S><<<grid, 32 * kMarchWarps, kMarchSmem, st>>>(g, in, dt, y_out, r_lo, r_hi, chunk);
+    SB_CHECK_LAUNCH(ctx);
+    return SOPOT_B200_OK;
+}
+
 int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
                      double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride) {
+    // SOPOT_B200_GRID_TILE_KERNEL=1 keeps the shared-memory tile kernel for the quad topology too (comparison runs, tests)
+    // Strict arithmetic stays on the tile kernel: its IEEE root and quotients carry guard branches per operation, which the
+    // marching kernel (8 springs per lane and tick in one basic block) pays for in registers and control flow -- measured
+    // 8.1 ms per step at 8192^2 against the tile kernel's 7.2 (SOPOT_B200_GRID_MARCH_STRICT=1 selects it anyway).
+    static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
+    static const bool march_strict = std::getenv("SOPOT_B200_GRID_MARCH_STRICT") != nullptr;
+    if (topo == 0 && ty_stride == 1 && !tile_only && (!strict || march_strict))
+        return strict ? launch_march<true>(ctx, st, g, in, dt, y_out, ty_first, n_ty) : launch_march<false>(ctx, st, g, in, dt, y_out, ty_first, n_ty);
 #define SB_FUSED_CASE(SS, TT) return launch_fused<SS, TT>(ctx, st, g, in, dt, y_out, ty_first, n_ty, ty_stride)
     if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
     else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
