@@ -98,12 +98,30 @@ struct Real {
     __host__ __device__ __forceinline__ explicit operator double() const { return v; }
 };
 
-#ifdef __CUDA_ARCH__
+// SB_COUNT_OPS (tools/rocket_opcount.py builds one translation unit with it): every strict-mode operation of thread 0 of
+// block 0 is tallied by kind -- the "counting scalar" of SURVEY.md section 8d applied to the engine's OWN derivative, on the
+// device, in the arithmetic the reference uses (one count per + - * / sqrt and per transcendental call).
+#if defined(SB_COUNT_OPS)
+static __device__ unsigned long long g_sb_ops[8];     // 0 add/sub, 1 mul, 2 div, 3 sqrt, 4 transcendental
+#endif
+#if defined(SB_COUNT_OPS) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void sb_count(int k) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_sb_ops[k], 1ull); }
+#define SB_ADD(a, b) (sb_count(0), __dadd_rn((a), (b)))
+#define SB_MUL(a, b) (sb_count(1), __dmul_rn((a), (b)))
+#define SB_DIV(a, b) (sb_count(2), sb_div_rn((a), (b)))
+#define SB_SQRT(a) (sb_count(3), sb_sqrt_rn((a)))
+#define SB_COUNT_TRANSCENDENTAL() sb_count(4)
+#define SB_COUNT_DIV() sb_count(2)
+#elif defined(__CUDA_ARCH__)
+#define SB_COUNT_TRANSCENDENTAL() ((void)0)
+#define SB_COUNT_DIV() ((void)0)
 #define SB_ADD(a, b) __dadd_rn((a), (b))
 #define SB_MUL(a, b) __dmul_rn((a), (b))
 #define SB_DIV(a, b) sb_div_rn((a), (b))
 #define SB_SQRT(a) sb_sqrt_rn((a))
 #else
+#define SB_COUNT_TRANSCENDENTAL() ((void)0)
+#define SB_COUNT_DIV() ((void)0)
 #define SB_ADD(a, b) ((a) + (b))
 #define SB_MUL(a, b) ((a) * (b))
 #define SB_DIV(a, b) ((a) / (b))
@@ -138,22 +156,23 @@ template <bool S> __host__ __device__ __forceinline__ bool operator<=(Real<S> a,
 template <bool S> __host__ __device__ __forceinline__ bool operator>=(Real<S> a, Real<S> b) { return a.v >= b.v; }
 
 template <bool S> __device__ __forceinline__ Real<S> r_sqrt(Real<S> a) { return Real<S>(SB_SQRT(a.v)); }
-template <bool S> __device__ __forceinline__ Real<S> r_sin(Real<S> a) { return Real<S>(sin(a.v)); }
-template <bool S> __device__ __forceinline__ Real<S> r_cos(Real<S> a) { return Real<S>(cos(a.v)); }
+template <bool S> __device__ __forceinline__ Real<S> r_sin(Real<S> a) { SB_COUNT_TRANSCENDENTAL(); return Real<S>(sin(a.v)); }
+template <bool S> __device__ __forceinline__ Real<S> r_cos(Real<S> a) { SB_COUNT_TRANSCENDENTAL(); return Real<S>(cos(a.v)); }
 template <bool S> __device__ __forceinline__ void r_sincos(Real<S> a, Real<S>& s, Real<S>& c) {
+    SB_COUNT_TRANSCENDENTAL(); SB_COUNT_TRANSCENDENTAL();
     double sv, cv; sincos(a.v, &sv, &cv); s = Real<S>(sv); c = Real<S>(cv);
 }
 // x / d where the reference divides: IEEE division when Strict, reciprocal multiply otherwise
 template <bool S> __device__ __forceinline__ Real<S> r_div_const(Real<S> a, double d) {
 #ifdef __CUDA_ARCH__
-    if constexpr (S) return Real<S>(sb_div_by(a.v, d, 1.0 / d)); else return Real<S>(a.v * (1.0 / d));   // d is a literal: 1/d folds
+    if constexpr (S) { SB_COUNT_DIV(); return Real<S>(sb_div_by(a.v, d, 1.0 / d)); } else return Real<S>(a.v * (1.0 / d));   // d is a literal: 1/d folds
 #else
     if constexpr (S) return Real<S>(a.v / d); else return Real<S>(a.v * (1.0 / d));
 #endif
 }
 // a / d for a divisor that is constant over the launch, inv = RN(1 / d) from the host
 template <bool S> __device__ __forceinline__ Real<S> r_div_by(Real<S> a, double d, double inv) {
-    if constexpr (S) return Real<S>(sb_div_by(a.v, d, inv)); else return Real<S>(a.v * inv);
+    if constexpr (S) { SB_COUNT_DIV(); return Real<S>(sb_div_by(a.v, d, inv)); } else return Real<S>(a.v * inv);
 }
 
 // The slab contract of the multi-rank grid entry points: rank r of R owns the contiguous block of rows that

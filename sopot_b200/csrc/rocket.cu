@@ -50,7 +50,7 @@ struct Recip {
 // |e log(base)| * ulp-level ~ 1e-15, two orders inside the 1e-12 per-step promise, at a quarter of the instructions.
 template <bool S>
 __device__ __forceinline__ Real<S> r_pow(Real<S> base, double e) {
-    if constexpr (S) return Real<S>(pow(base.v, e)); else return Real<S>(exp(e * log(base.v)));
+    if constexpr (S) { SB_COUNT_TRANSCENDENTAL(); return Real<S>(pow(base.v, e)); } else return Real<S>(exp(e * log(base.v)));
 }
 
 // one effective coefficient table inside the packed buffer: row_vals[rows], col_vals[cols], data[rows][cols] from `off`
@@ -143,7 +143,7 @@ __device__ __forceinline__ void atmosphere_layer(const AtmLayer& l, const Real<S
         T = Real<S>(l.T_base);
         // P_base * exp(-(g0*M) * (h - h_base) / (R*T_base))                    :62
         const Real<S> arg = Recip<S>(Real<S>(l.exp_den)).of(Real<S>(-(kAtmG0 * kAtmM)) * dh);
-        if constexpr (S) P = Real<S>(l.P_base) * Real<S>(exp(arg.v));
+        if constexpr (S) { SB_COUNT_TRANSCENDENTAL(); P = Real<S>(l.P_base) * Real<S>(exp(arg.v)); }
         else P = Real<S>(l.P_base * sbtrig::exp_lean(arg.v));                   // |arg| <= 1.5 within a layer (host check)
     } else {
         const Real<S> Tl = Real<S>(l.T_base) + Real<S>(l.lapse) * dh;           // :50, :63
@@ -468,6 +468,9 @@ struct RocketSysT {
     static __device__ __forceinline__ void observe(Inst<S>& in, double t, const Real<S> (&y)[14]) {
         const double alt = y[3].v;
         const Real<S> sp2 = y[4] * y[4] + y[5] * y[5] + y[6] * y[6];
+#if defined(SB_COUNT_OPS) && defined(__CUDA_ARCH__)
+        if (S) sb_count(3);                                   // the statistics' own root (plain sqrt below)
+#endif
         const double spd = sqrt(sp2.v);
         if (alt > in.apogee) { in.apogee = alt; in.apogee_t = t; }
         if (spd > in.vmax) { in.vmax = spd; in.vmax_t = t; }
@@ -811,3 +814,14 @@ SB_EXPORT int sopot_b200_rocket_state_functions(sopot_b200_ctx* ctx, const sopot
     }
     return sg.finish();
 }
+
+#ifdef SB_COUNT_OPS
+// variant builds only (tools/rocket_opcount.py): read (and optionally clear) the operation tallies of thread 0 / block 0
+SB_EXPORT int sopot_b200_debug_opcounts(sopot_b200_ctx* ctx, unsigned long long* out8, int reset) {
+    if (!ctx || !out8) return SOPOT_B200_EINVAL;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyFromSymbol(out8, g_sb_ops, 8 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[8] = {}; SB_CUDA(ctx, cudaMemcpyToSymbol(g_sb_ops, z, sizeof z)); }
+    return SOPOT_B200_OK;
+}
+#endif

@@ -41,6 +41,14 @@ elif cfg == "rocket":
     for _ in range(reps):
         eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, 600, mem=MEM_DEVICE, want_status=False,
                        state_out=st, stats_out=stats)
+elif cfg == "rocket_1mi":                        # the bench ensemble itself: 1 Mi trajectories x 3000 steps
+    n = 1 << 20
+    w = W.rocket_ensemble(n)
+    d = [eng.to_device(w[k]) for k in ("elev", "az", "diam", "g0")]
+    st, stats = eng.empty((14, n)), eng.empty((8, n))
+    for _ in range(reps):
+        eng.rocket_rk4(*d, w["engine"], w["mass_tab"], None, None, n, 0.01, 3000, mem=MEM_DEVICE, want_status=False,
+                       state_out=st, stats_out=stats)
 elif cfg == "rocket_full":                       # the whole 30 s flight (88 % of it is coast), a quarter of the bench ensemble
     n = 1 << 18
     w = W.rocket_ensemble(n)
