@@ -1,3 +1,6 @@
-python tools/time_cfg.py rocket > gpurun_out/r2_rocket_timing.log 2>&1; cat gpurun_out/r2_rocket_timing.log
-SOPOT_B200_LIB=sopot_b200/lib/variants/libsopot_b200_opcount.so python tools/rocket_opcount.py > gpurun_out/rocket_opcount.json 2> gpurun_out/rocket_opcount.err; tail -3 gpurun_out/rocket_opcount.err; head -c 600 gpurun_out/rocket_opcount.json
-python tools/profile_driver.py rocket_1mi 1 && ncu --set full --import-source on --clock-control none -k regex:rk4_ensemble_kernel -c 1 -f -o gpurun_out/prof_rocket_1mi python tools/profile_driver.py rocket_1mi 1 > gpurun_out/ncu_rocket_1mi.log 2>&1; tail -1 gpurun_out/ncu_rocket_1mi.log
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "rocket" > gpurun_out/r2_rocket_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2_rocket_tests.log; tail -3 gpurun_out/r2_rocket_tests.log
+(
+echo "== stock (stage loop, 4 CTAs)"; python tools/time_cfg.py rocket
+for v in rl3 rl5 rnoloop; do echo "== $v"; SOPOT_B200_LIB=sopot_b200/lib/variants/libsopot_b200_$v.so python tools/time_cfg.py rocket; done
+) > gpurun_out/r2_rocket_timing.log 2>&1
+cat gpurun_out/r2_rocket_timing.log
