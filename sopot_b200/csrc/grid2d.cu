@@ -473,22 +473,110 @@ __device__ __forceinline__ void march_forces(const GridDev& g, const Mass4& cur,
         march_spring(sr, cur, rt, g.k, g.c, g.L_orth, rfx, rfy);
         march_spring(sd, cur, nxt, g.k, g.c, g.L_orth, dfx, dfy);
     }
-    const R lfx(__shfl_up_sync(FULLMASK, rfx.v, 1)), lfy(__shfl_up_sync(FULLMASK, rfy.v, 1));
-    Fx = R(0.0); Fy = R(0.0);
-    if constexpr (EDGE) {
-        // a spring that does not exist contributes nothing: the reference skips it, and so does a select (never an added 0)
-        if (here && has_l) { Fx -= lfx; Fy -= lfy; }
-        if (here && has_r) { Fx += rfx; Fy += rfy; }
-        if (here && has_u) { Fx -= ufx; Fy -= ufy; }
-        if (here && has_d) { Fx += dfx; Fy += dfy; }
-    } else {
-        Fx -= lfx; Fy -= lfy;
-        Fx += rfx; Fy += rfy;
-        Fx -= ufx; Fy -= ufy;
-        Fx += dfx; Fy += dfy;
-    }
+    const double lfx = __shfl_up_sync(FULLMASK, rfx.v, 1), lfy = __shfl_up_sync(FULLMASK, rfy.v, 1);
+    // aggregation with explicit, never-contracted additions: the forces are values in their own right (shuffled, carried), and
+    // the predicated (EDGE) and plain bodies must round alike -- a mass may be computed by either, depending on how the rows
+    // are cut into chunks and slabs, and the result must not depend on that in contract mode either.
+    // A spring that does not exist contributes nothing: the reference skips it, and so does a select (never an added 0).
+    double ax = 0.0, ay = 0.0;
+    if (!EDGE || (here && has_l)) { ax = __dadd_rn(ax, -lfx); ay = __dadd_rn(ay, -lfy); }
+    if (!EDGE || (here && has_r)) { ax = __dadd_rn(ax, rfx.v); ay = __dadd_rn(ay, rfy.v); }
+    if (!EDGE || (here && has_u)) { ax = __dadd_rn(ax, -ufx.v); ay = __dadd_rn(ay, -ufy.v); }
+    if (!EDGE || (here && has_d)) { ax = __dadd_rn(ax, dfx.v); ay = __dadd_rn(ay, dfy.v); }
+    Fx = R(ax); Fy = R(ay);
     ufx = dfx; ufy = dfy;        // the down spring of this row is the up spring of the next one
 }
+
+// ---- strict arithmetic in the marching kernel --------------------------------------------------------------------------------
+// spring_force<true> carries three guarded IEEE operations (a root, two quotients), each with a branch to an out-of-line
+// fallback; eight springs per lane and tick made the strict marching kernel slower than the tile kernel (8.1 against 7.0 ms
+// per step at 8192^2).  Here a whole RK stage of one mass is computed with the UNGUARDED inline sequences (ieee.cuh: exactly
+// the guarded functions' fast branches, the reciprocal of the spring length shared by its two quotients), every operand whose
+// range the guards would have tested raises one flag, the warp votes once per stage, and the rare warp with a raised flag
+// recomputes the stage with the guarded functions.  Same bits on both routes: verified against the oracle like every strict
+// path, and a parity test forces the guarded route (tiny and huge operands).
+template <bool GUARDED>
+__device__ __forceinline__ bool strict_spring(const Mass4& pi, const Mass4& pj, const double k, const double c, const double L0,
+                                              double& fx, double& fy) {
+    if constexpr (GUARDED) {
+        Real<true> gx, gy;
+        spring_force<true>(pi, pj, k, c, L0, gx, gy);
+        fx = gx.v; fy = gy.v;
+        return false;
+    } else {
+        const double dx = __dadd_rn(pj.x, -pi.x), dy = __dadd_rn(pj.y, -pi.y);
+        const double l2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        // l2 in [2e-20, 2^500): the root is mid-exponent and at least 1.4e-10, so the len_safe clamp (:125) is inactive and
+        // the divisor of the two quotients is the root itself; their numerators must be zero or mid-exponent
+        constexpr unsigned kLo = 0x3bd79ca1u, kSpan = ((1023u + 500u) << 20) - kLo;       // high word of 2e-20 .. of 2^500
+        const bool bad = ((unsigned)__double2hiint(l2) - kLo) >= kSpan || sb_out_of_range(dx) || sb_out_of_range(dy);
+        const double length = sb_sqrt_seq(l2);
+        const double y = sb_rcp_seq(length);
+        const double ux = sb_div_seq_pos(dx, length, y), uy = sb_div_seq_pos(dy, length, y);
+        const double extension = __dadd_rn(length, -L0);
+        const double dvx = __dadd_rn(pj.vx, -pi.vx), dvy = __dadd_rn(pj.vy, -pi.vy);
+        const double rel = __dadd_rn(__dmul_rn(dvx, ux), __dmul_rn(dvy, uy));
+        const double F = __dadd_rn(__dmul_rn(k, extension), __dmul_rn(c, rel));             // :140
+        fx = __dmul_rn(F, ux); fy = __dmul_rn(F, uy);
+        return bad;
+    }
+}
+
+// one RK stage of one mass in strict arithmetic: forces of its two springs, aggregation in edge-list order, stage update.
+// Results go to (dfx, dfy) = the down spring's force, acc_out, out; returns the lane's out-of-range flag (always false when GUARDED).
+template <bool EDGE, int STAGE, bool GUARDED>
+__device__ __forceinline__ bool strict_stage(const GridDev& g, const double dt, const Mass4& cur, const Mass4& nxt, const Mass4& rt,
+                                             const bool here, const bool has_l, const bool has_r, const bool has_u, const bool has_d,
+                                             const double ufx, const double ufy, const Mass4& y, const MarchAcc<true>& acc,
+                                             double& dfx, double& dfy, MarchAcc<true>& acc_out, Mass4& out) {
+    constexpr unsigned FULLMASK = 0xffffffffu;
+    double rfx, rfy;
+    bool bad = !GUARDED && !sb_mid_exponent(g.mass);                // the divisor of Fx / m, Fy / m (uniform)
+    bad |= strict_spring<GUARDED>(cur, rt, g.k, g.c, g.L_orth, rfx, rfy);
+    bad |= strict_spring<GUARDED>(cur, nxt, g.k, g.c, g.L_orth, dfx, dfy);
+    const double lfx = __shfl_up_sync(FULLMASK, rfx, 1), lfy = __shfl_up_sync(FULLMASK, rfy, 1);
+    double Fx = 0.0, Fy = 0.0;
+    if (!EDGE || (here && has_l)) { Fx = __dadd_rn(Fx, -lfx); Fy = __dadd_rn(Fy, -lfy); }
+    if (!EDGE || (here && has_r)) { Fx = __dadd_rn(Fx, rfx); Fy = __dadd_rn(Fy, rfy); }
+    if (!EDGE || (here && has_u)) { Fx = __dadd_rn(Fx, -ufx); Fy = __dadd_rn(Fy, -ufy); }
+    if (!EDGE || (here && has_d)) { Fx = __dadd_rn(Fx, dfx); Fy = __dadd_rn(Fy, dfy); }
+    double d[4] = {cur.vx, cur.vy, 0.0, 0.0};
+    if constexpr (GUARDED) {
+        d[2] = sb_div_by(Fx, g.mass, g.inv_mass); d[3] = sb_div_by(Fy, g.mass, g.inv_mass);
+    } else {
+        bad |= sb_out_of_range(Fx) || sb_out_of_range(Fy);
+        d[2] = sb_div_seq_pos(Fx, g.mass, g.inv_mass); d[3] = sb_div_seq_pos(Fy, g.mass, g.inv_mass);
+    }
+    double k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = __dmul_rn(d[j], dt);
+    const double yv[4] = {y.x, y.y, y.vx, y.vy};
+    double o[4];
+    if constexpr (STAGE == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double sum = __dadd_rn(acc.v[j].v, k[j]);
+            double q;
+            if constexpr (GUARDED) q = sb_div_by(sum, 6.0, 1.0 / 6.0);
+            else { bad |= sb_out_of_range(sum); q = sb_div_seq_pos(sum, 6.0, 1.0 / 6.0); }
+            o[j] = __dadd_rn(yv[j], q);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc_out.v[j].v = (STAGE == 1) ? k[j] : __dadd_rn(acc.v[j].v, __dmul_rn(2.0, k[j]));
+            o[j] = (STAGE == 3) ? __dadd_rn(yv[j], k[j]) : __dadd_rn(yv[j], __dmul_rn(0.5, k[j]));
+        }
+    }
+    out = Mass4{o[0], o[1], o[2], o[3]};
+    return bad;
+}
+
+// one stage of the marching pipeline for one lane: springs, aggregation, update; (ufx, ufy) carried force in / out, acc in / out
+template <bool S, bool EDGE, int STAGE>
+__device__ __forceinline__ void march_stage(const GridDev& g, const Real<S> dt, const Mass4& cur, const Mass4& nxt, const bool here,
+                                            const bool has_l, const bool has_r, const bool has_u, const bool has_d, Real<S>& ufx,
+                                            Real<S>& ufy, const Mass4& y, MarchAcc<S>& acc, Mass4& out);
 
 // stage arithmetic of rk4_step (ensemble.cuh) for one mass: k = dt * {vx, vy, Fx/m, Fy/m}
 template <bool S, int STAGE>
@@ -512,6 +600,33 @@ __device__ __forceinline__ void march_update(const GridDev& g, const Real<S> dt,
         }
     }
     out = Mass4{o[0].v, o[1].v, o[2].v, o[3].v};
+}
+
+template <bool S, bool EDGE, int STAGE>
+__device__ __forceinline__ void march_stage(const GridDev& g, const Real<S> dt, const Mass4& cur, const Mass4& nxt, const bool here,
+                                            const bool has_l, const bool has_r, const bool has_u, const bool has_d, Real<S>& ufx,
+                                            Real<S>& ufy, const Mass4& y, MarchAcc<S>& acc, Mass4& out) {
+    if constexpr (!S) {
+        Real<S> Fx, Fy;
+        march_forces<S, EDGE>(g, cur, nxt, here, has_l, has_r, has_u, has_d, ufx, ufy, Fx, Fy);
+        march_update<S, STAGE>(g, dt, cur, Fx, Fy, y, acc, out);
+    } else {
+        constexpr unsigned FULLMASK = 0xffffffffu;
+        Mass4 rt{__shfl_down_sync(FULLMASK, cur.x, 1), __shfl_down_sync(FULLMASK, cur.y, 1),
+                 __shfl_down_sync(FULLMASK, cur.vx, 1), __shfl_down_sync(FULLMASK, cur.vy, 1)};
+        if ((threadIdx.x & 31) == 31) rt.x = cur.x + 1.0;            // see march_forces
+        double dfx, dfy;
+        MarchAcc<true> acc_new = acc;
+        const bool bad = strict_stage<EDGE, STAGE, false>(g, dt.v, cur, nxt, rt, here, has_l, has_r, has_u, has_d, ufx.v, ufy.v, y, acc,
+                                                          dfx, dfy, acc_new, out);
+        if (__any_sync(FULLMASK, bad)) {
+            acc_new = acc;
+            strict_stage<EDGE, STAGE, true>(g, dt.v, cur, nxt, rt, here, has_l, has_r, has_u, has_d, ufx.v, ufy.v, y, acc, dfx, dfy,
+                                            acc_new, out);
+        }
+        ufx.v = dfx; ufy.v = dfy;
+        acc = acc_new;
+    }
 }
 
 template <bool S, bool EDGE>
@@ -558,33 +673,45 @@ __device__ __forceinline__ void march_body(const GridDev& g, const StepIn& in, c
         R Fx, Fy;
         {   // stage 1 on row r-1
             const long long q = r - 1;
-            march_forces<S, EDGE>(g, c1, n1, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u1x, u1y, Fx, Fy);
             MarchAcc<S> acc;
-            march_update<S, 1>(g, dt, c1, Fx, Fy, c1, acc, o1);                       // o1 = A1[r-1]
+            if constexpr (S) march_stage<S, EDGE, 1>(g, dt, c1, n1, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u1x, u1y, c1, acc, o1);
+            else {
+                march_forces<S, EDGE>(g, c1, n1, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u1x, u1y, Fx, Fy);
+                march_update<S, 1>(g, dt, c1, Fx, Fy, c1, acc, o1);                   // o1 = A1[r-1]
+            }
             ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
         }
         {   // stage 2 on row r-3: A1 rows r-3 (c2), r-2 (n2)
             const long long q = r - 3;
-            march_forces<S, EDGE>(g, c2, n2, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u2x, u2y, Fx, Fy);
             const Mass4 sv = ring_load(sring, q);
             MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
-            march_update<S, 2>(g, dt, c2, Fx, Fy, ring_load(yring, q), acc, o2);      // o2 = A2[r-3]
+            if constexpr (S) march_stage<S, EDGE, 2>(g, dt, c2, n2, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u2x, u2y, ring_load(yring, q), acc, o2);
+            else {
+                march_forces<S, EDGE>(g, c2, n2, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u2x, u2y, Fx, Fy);
+                march_update<S, 2>(g, dt, c2, Fx, Fy, ring_load(yring, q), acc, o2);
+            }      // o2 = A2[r-3]
             ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
         }
         {   // stage 3 on row r-5: A2 rows r-5 (c3), r-4 (n3)
             const long long q = r - 5;
-            march_forces<S, EDGE>(g, c3, n3, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u3x, u3y, Fx, Fy);
             const Mass4 sv = ring_load(sring, q);
             MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
-            march_update<S, 3>(g, dt, c3, Fx, Fy, ring_load(yring, q), acc, o3);      // o3 = A3[r-5]
+            if constexpr (S) march_stage<S, EDGE, 3>(g, dt, c3, n3, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u3x, u3y, ring_load(yring, q), acc, o3);
+            else {
+                march_forces<S, EDGE>(g, c3, n3, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u3x, u3y, Fx, Fy);
+                march_update<S, 3>(g, dt, c3, Fx, Fy, ring_load(yring, q), acc, o3);
+            }      // o3 = A3[r-5]
             ring_store(sring, q, Mass4{acc.v[0].v, acc.v[1].v, acc.v[2].v, acc.v[3].v});
         }
         {   // stage 4 on row r-7: A3 rows r-7 (c4), r-6 (n4)
             const long long q = r - 7;
-            march_forces<S, EDGE>(g, c4, n4, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u4x, u4y, Fx, Fy);
             const Mass4 sv = ring_load(sring, q);
             MarchAcc<S> acc{{R(sv.x), R(sv.y), R(sv.vx), R(sv.vy)}};
-            march_update<S, 4>(g, dt, c4, Fx, Fy, ring_load(yring, q), acc, o4);      // o4 = y_new[r-7]
+            if constexpr (S) march_stage<S, EDGE, 4>(g, dt, c4, n4, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u4x, u4y, ring_load(yring, q), acc, o4);
+            else {
+                march_forces<S, EDGE>(g, c4, n4, exists(q), has_l, has_r, q > 0, q + 1 < nrows, u4x, u4y, Fx, Fy);
+                march_update<S, 4>(g, dt, c4, Fx, Fy, ring_load(yring, q), acc, o4);
+            }      // o4 = y_new[r-7]
             if (owner && q >= row_lo && q < row_hi)
                 store4(y_out + ((size_t)(q - slab_lo) * g.cols + (size_t)gc) * 4, o4.x, o4.y, o4.vx, o4.vy);
         }
@@ -747,12 +874,10 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
 int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
                      double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride) {
     // SOPOT_B200_GRID_TILE_KERNEL=1 keeps the shared-memory tile kernel for the quad topology too (comparison runs, tests)
-    // Strict arithmetic stays on the tile kernel: its IEEE root and quotients carry guard branches per operation, which the
-    // marching kernel (8 springs per lane and tick in one basic block) pays for in registers and control flow -- measured
-    // 8.1 ms per step at 8192^2 against the tile kernel's 7.2 (SOPOT_B200_GRID_MARCH_STRICT=1 selects it anyway).
+    // (SOPOT_B200_GRID_TILE_STRICT=1: tile kernel for strict arithmetic only)
     static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
-    static const bool march_strict = std::getenv("SOPOT_B200_GRID_MARCH_STRICT") != nullptr;
-    if (topo == 0 && ty_stride == 1 && !tile_only && (!strict || march_strict))
+    static const bool tile_strict = std::getenv("SOPOT_B200_GRID_TILE_STRICT") != nullptr;
+    if (topo == 0 && ty_stride == 1 && !tile_only && !(strict && tile_strict))
         return strict ? launch_march<true>(ctx, st, g, in, dt, y_out, ty_first, n_ty) : launch_march<false>(ctx, st, g, in, dt, y_out, ty_first, n_ty);
 #define SB_FUSED_CASE(SS, TT) return launch_fused<SS, TT>(ctx, st, g, in, dt, y_out, ty_first, n_ty, ty_stride)
     if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }

@@ -505,6 +505,22 @@ def test_grid2d_fused_step_equals_per_stage_schedule(engine, port, rows, cols, t
     assert np.array_equal(engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT).ravel(), ref)
 
 
+@pytest.mark.parametrize("spacing", [1e-160, 1e-12, 1e100])
+def test_grid2d_strict_guarded_route_tiny_and_huge_operands(engine, port, spacing):
+    """The strict marching kernel computes a stage with unguarded inline root / quotient sequences and falls back to the guarded
+    functions when any operand of the warp leaves their range.  Grids on absurd length scales drive every stage down the
+    guarded route (spacing 1e-160: numerators below 2^-500; 1e-12: springs shorter than the 2e-20 threshold on l2, i.e. the
+    len_safe region; 1e100: l2 above 2^500): bit-identical to the per-stage schedule and to the oracle there too."""
+    rows, cols, steps = 70, 100, 3
+    s0 = W.grid2d_state(rows, cols, 0.5) * spacing / 0.5
+    gp = engine.grid2d_params(rows, cols, 0, 1.0, spacing, 50.0, 0.5)
+    fused = engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT)
+    staged = engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT, per_stage=True)
+    assert np.array_equal(fused, staged)
+    ref = port.grid2d_rk4(rows, cols, 0, 1.0, spacing, 50.0, 0.5, 1e-3, steps, s0, nthreads=4)
+    assert np.array_equal(fused.ravel(), ref) and np.all(np.isfinite(ref))
+
+
 def test_inline_ieee_division_and_sqrt_are_correctly_rounded(tmp_path):
     """csrc/ieee.cuh (the branch-light division / sqrt every strict kernel uses) against nvcc's own IEEE operators,
     bit for bit on 6e8 samples on the device: random mantissas and exponents, exact zeros, quotients next to 1,
