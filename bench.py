@@ -258,7 +258,8 @@ def multi_gpu_configs(eng, rank, world, local, hbm_peak):
                 r["strong_scaling_efficiency"] = n1 / r["ms_per_step"] / world
                 # the limiter, named: kernels on a 1/N slab against the exchange (+ stream ordering) on top of them
                 kern = max(r["slab_kernels_only_ms_per_rank"])
-                r["limiter"] = ("slab kernels (%.3f ms = %.2fx the ideal n1/N %.3f ms: tile-row quantisation and tail of a small grid)"
+                r["limiter"] = ("slab kernels (%.3f ms = %.2fx the ideal n1/N %.3f ms: pipeline fill of the row chunks / halo recomputation "
+                                "of the tiles weighs more on a 1/N slab, plus the tail of a smaller launch)"
                                 % (kern, kern / (n1 / world), n1 / world)) if kern - n1 / world >= r["exchange_and_sync_ms"] else \
                                ("ncclSend/Recv group + stream ordering (%.3f ms on top of %.3f ms of kernels)" % (r["exchange_and_sync_ms"], kern))
         full.free()
