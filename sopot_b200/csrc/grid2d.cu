@@ -859,11 +859,26 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
     unsigned r_hi = (ty_first + n_ty) * kFusedTY;
     if (r_hi > g.rows_local) r_hi = (unsigned)g.rows_local;
     if (r_hi <= r_lo) return SOPOT_B200_OK;
-    // rows per chunk: every chunk runs its pipeline 10 ticks longer than it has rows, a longer chunk leaves fewer warps to
-    // balance over the SMs; 128 rows measured best at 8192^2 (3.19 ms per step; 64: 3.37, 256: 3.22, 512: 3.43)
+    // Rows per chunk.  Every chunk runs its pipeline 10 ticks longer than it has rows, and the CTAs of a launch are scheduled in
+    // waves of (SMs x resident CTAs): the chunk length is chosen to minimise  waves x (rows per chunk + 10)  over all ways of
+    // cutting the rows into equal chunks of 64 .. 512 rows.  At 8192 rows on one GPU that is 128 +- a few rows (measured: 64 ->
+    // 3.06 ms, 128 -> 2.90, 256 -> 2.97, 512 -> 3.14 at that stage of development); on a 1/8 slab of 1024 rows it is 205 rows = 430
+    // CTAs = one wave on 148 SMs instead of 688 CTAs = 1.55 waves with 128 (8 GPUs, strict: 1.00 -> 0.85 ms per step).
     static const unsigned env_rows = std::getenv("SOPOT_B200_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_MARCH_ROWS")) : 0u;
     const unsigned strips = (unsigned)((g.cols + 23) / 24), ctas_x = (strips + kMarchWarps - 1) / kMarchWarps;
-    const unsigned chunk = env_rows ? env_rows : 128u;
+    unsigned chunk = env_rows;
+    if (!chunk) {
+        const unsigned rows = r_hi - r_lo, slots = (unsigned)ctx->sm_count * SB_MARCH_MINB;
+        unsigned long long best = ~0ull;
+        for (unsigned nch = 1; nch <= rows; ++nch) {
+            const unsigned c = (rows + nch - 1) / nch;
+            if (c > 512 && nch < rows) continue;
+            if (c < 64 && nch > 1) break;
+            const unsigned long long waves = ((unsigned long long)ctas_x * nch + slots - 1) / slots, cost = waves * (c + 10);
+            if (cost < best) { best = cost; chunk = c; }
+        }
+        if (!chunk) chunk = rows;
+    }
     const dim3 grid(ctas_x, (r_hi - r_lo + chunk - 1) / chunk);
     SB_CUDA(ctx, cudaFuncSetAttribute(grid_rk4_march<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarchSmem));
     grid_rk4_march<S><<<grid, 32 * kMarchWarps, kMarchSmem, st>>>(g, in, dt, y_out, r_lo, r_hi, chunk);

@@ -160,17 +160,11 @@ __device__ __forceinline__ void body_derivative(const UGridDev& g, const UIn& in
 }
 
 // STAGE 0: out <- f(in);  1..4: the RK4 stages with S-accumulator (see ensemble.cuh / grid2d.cu)
+// what a stage does with the derivative d of the body `self` at element offset off: shared by the gather and marching kernels
 template <bool S, int STAGE>
-__global__ void __launch_bounds__(256)
-ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
-            double* __restrict__ out, const size_t r_lo, const size_t r_hi) {
+__device__ __forceinline__ void ustage_apply(const Body& self, const Real<S> (&d)[6], const size_t off, const double dt_,
+                                             double* __restrict__ y, double* __restrict__ acc, double* __restrict__ out) {
     using R = Real<S>;
-    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = r_lo + (size_t)blockIdx.y * blockDim.y + threadIdx.y;
-    if (col >= g.cols || row >= r_hi) return;
-    R d[6];
-    Body self;
-    body_derivative<S>(g, in, row, col, d, self);
-    const size_t off = (row * g.cols + col) * 6;
     double o[6];
     if constexpr (STAGE == 0) {
 #pragma unroll
@@ -230,6 +224,134 @@ ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict
         }
         store6(acc + off, a);
         store6(out + off, o);
+    }
+}
+
+template <bool S, int STAGE>
+__global__ void __launch_bounds__(256)
+ugrid_stage(const UGridDev g, const UIn in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
+            double* __restrict__ out, const size_t r_lo, const size_t r_hi) {
+    using R = Real<S>;
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x, row = r_lo + (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (col >= g.cols || row >= r_hi) return;
+    R d[6];
+    Body self;
+    body_derivative<S>(g, in, row, col, d, self);
+    ustage_apply<S, STAGE>(self, d, (row * g.cols + col) * 6, dt_, y, acc, out);
+}
+
+// ---- one stage, marching form (quad topology): every spring ONCE ---------------------------------------------------------
+// The gather kernel evaluates each spring at both of its ends (4 spring evaluations and, in strict arithmetic, 8 libm sincos
+// per mass and stage): that made the strict RK4 step and the one- / two-evaluation steps of symplectic Euler and velocity
+// Verlet FP64-bound at half of the HBM roofline.  Here a warp owns a strip of 32 columns (30 output columns + one halo lane
+// on each side) and marches down a chunk of rows: per tick the lane evaluates the RIGHT spring of its body (neighbour by warp
+// shuffle; the force and torque on the neighbour's end go back by a second shuffle) and the DOWN spring (the end-1 force and
+// torque are carried in registers to the next tick, where they belong to the row below) -- two spring evaluations and four
+// sincos per mass and stage, accumulated in the reference's visiting order left (as mass 1), right (as mass 0), upper (as
+// mass 1), lower (as mass 0).  Force on end 1 = exact negation of the force on end 0, torque on end 1 from the negated force
+// with the reference's own expression: the bits of the gather form (hence of ValidatedSystem) in strict mode.
+template <bool S>
+__device__ __forceinline__ void spring_both(const UGridDev& g, const Body& m0, const Body& m1, const double a0, const double a1,
+                                            const double ca0, const double sa0, const double ca1, const double sa1, const double L0,
+                                            Real<S>& fx, Real<S>& fy, Real<S>& tq0, Real<S>& tq1) {
+    using R = Real<S>;
+    if constexpr (S) {
+        const R r(g.radius);
+        R s0, c0, s1, c1;
+        r_sincos(R(m0.th) + R(a0), s0, c0); r_sincos(R(m1.th) + R(a1), s1, c1);
+        const R o0x = r * c0, o0y = r * s0, o1x = r * c1, o1y = r * s1;
+        const R a0x = R(m0.x) + o0x, a0y = R(m0.y) + o0y, a1x = R(m1.x) + o1x, a1y = R(m1.y) + o1y;
+        const R v0x = R(m0.vx) - R(m0.om) * o0y, v0y = R(m0.vy) + R(m0.om) * o0x;
+        const R v1x = R(m1.vx) - R(m1.om) * o1y, v1y = R(m1.vy) + R(m1.om) * o1x;
+        const R dx = a1x - a0x, dy = a1y - a0y;
+        const R len = r_sqrt(dx * dx + dy * dy);
+        const R len_safe = len.v < 1e-10 ? R(1e-10) : len;
+        const R ux = dx / len_safe, uy = dy / len_safe;
+        const R ext = len - R(L0);
+        const R dvx = v1x - v0x, dvy = v1y - v0y;
+        const R rel = dvx * ux + dvy * uy;
+        R F = R(g.k) * ext + R(g.c) * rel;
+        if (g.min_distance > 0.0 && len.v < g.min_distance)
+            F = F + (-R(g.krep)) * (R(g.min_distance) / len_safe - R(1.0));
+        fx = F * ux; fy = F * uy; tq0 = o0x * fy - o0y * fx;
+        const R gx = -fx, gy = -fy;                         // (-F) * ux == -(F * ux) exactly
+        tq1 = o1x * gy - o1y * gx;
+    } else {
+        const double r = g.radius;
+        const double c0 = fma(m0.c, ca0, -(m0.s * sa0)), s0 = fma(m0.s, ca0, m0.c * sa0);
+        const double c1 = fma(m1.c, ca1, -(m1.s * sa1)), s1 = fma(m1.s, ca1, m1.c * sa1);
+        const double o0x = r * c0, o0y = r * s0, o1x = r * c1, o1y = r * s1;
+        const double dx = (m1.x + o1x) - (m0.x + o0x), dy = (m1.y + o1y) - (m0.y + o0y);
+        const double dvx = fma(-m1.om, o1y, m1.vx) - fma(-m0.om, o0y, m0.vx), dvy = fma(m1.om, o1x, m1.vy) - fma(m0.om, o0x, m0.vy);
+        const double len2 = fma(dx, dx, dy * dy);
+        double len, inv;
+        if (len2 >= 1e-20) { sbtrig::sqrt_rsqrt_fast(len2, len, inv); }
+        else { len = sqrt(len2); inv = 1e10; }
+        const double ux = dx * inv, uy = dy * inv;
+        double F = fma(g.k, len - L0, g.c * fma(dvx, ux, dvy * uy));
+        if (g.min_distance > 0.0 && len < g.min_distance) F = fma(-g.krep, fma(g.min_distance, inv, -1.0), F);
+        fx.v = F * ux; fy.v = F * uy; tq0.v = fma(o0x, fy.v, -(o0y * fx.v));
+        tq1.v = fma(o1x, -fy.v, o1y * fx.v);
+    }
+}
+
+__device__ __forceinline__ Body shfl_body_down(const Body& b) {
+    constexpr unsigned M = 0xffffffffu;
+    return Body{__shfl_down_sync(M, b.x, 1), __shfl_down_sync(M, b.y, 1), __shfl_down_sync(M, b.vx, 1), __shfl_down_sync(M, b.vy, 1),
+                __shfl_down_sync(M, b.th, 1), __shfl_down_sync(M, b.om, 1), __shfl_down_sync(M, b.s, 1), __shfl_down_sync(M, b.c, 1)};
+}
+
+constexpr int kUMarchOwn = 30, kUMarchWarps = 4;
+template <bool S, int STAGE>
+__global__ void __launch_bounds__(32 * kUMarchWarps)
+ugrid_stage_march(const UGridDev g, const UIn in, const double dt_, double* __restrict__ y, double* __restrict__ acc,
+                  double* __restrict__ out, const size_t r_lo, const size_t r_hi, const unsigned rows_per_chunk) {
+    using R = Real<S>;
+    constexpr unsigned M = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long strip = (long)blockIdx.x * kUMarchWarps + (threadIdx.x >> 5);
+    if (strip * kUMarchOwn >= (long)g.cols) return;
+    const long col = strip * kUMarchOwn - 1 + lane;
+    const bool col_ok = col >= 0 && col < (long)g.cols;
+    const bool owner = lane >= 1 && lane <= kUMarchOwn && col_ok;
+    const bool has_l = col > 0, has_r = col + 1 < (long)g.cols;
+    const long lo = (long)r_lo + (long)blockIdx.y * rows_per_chunk;
+    long hi = lo + rows_per_chunk;
+    if (hi > (long)r_hi) hi = (long)r_hi;
+    if (lo >= hi) return;
+    // body of local row lr (ghost rows at -1 / rows_local); a cell outside the global grid is a placeholder on its own
+    // lattice position (its springs are never used, and never of zero length)
+    const auto load = [&](const long lr) -> Body {
+        const long gr = g.row_begin + lr;
+        if (!col_ok || gr < 0 || gr >= (long)g.rows) return Body{(double)col, (double)gr, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0};
+        return body_at<S>(g, in, lr, (size_t)col);
+    };
+    Body cur = load(lo - 1), nxt = load(lo);
+    R ufx(0.0), ufy(0.0), utq(0.0);                       // force / torque of the spring from the row above on THIS row's body
+    for (long q = lo - 1; q < hi; ++q) {                   // the first tick only produces the up spring of row lo
+        const Body pre = load(q + 2 <= hi ? q + 2 : hi);
+        Body rt = shfl_body_down(cur);
+        if (lane == 31) rt.x = cur.x + 1.0;                // no right neighbour in the warp: a unit-length pseudo-spring, discarded
+        R rfx, rfy, rtq0, rtq1, dfx, dfy, dtq0, dtq1;
+        spring_both<S>(g, cur, rt, g.ha0, g.ha1, g.cha0, g.sha0, g.cha1, g.sha1, g.L0, rfx, rfy, rtq0, rtq1);
+        spring_both<S>(g, cur, nxt, g.va0, g.va1, g.cva0, g.sva0, g.cva1, g.sva1, g.L0, dfx, dfy, dtq0, dtq1);
+        // what the left lane's right spring does to this body (its end 1): the negated force, its own torque
+        const R lfx(-__shfl_up_sync(M, rfx.v, 1)), lfy(-__shfl_up_sync(M, rfy.v, 1)), ltq(__shfl_up_sync(M, rtq1.v, 1));
+        const long gr = g.row_begin + q;
+        if (q >= lo && owner) {
+            R Fx(0.0), Fy(0.0), Tq(0.0);
+            if (has_l) { Fx += lfx; Fy += lfy; Tq += ltq; }
+            if (has_r) { Fx += rfx; Fy += rfy; Tq += rtq0; }
+            if (gr > 0) { Fx += ufx; Fy += ufy; Tq += utq; }
+            if (gr + 1 < (long)g.rows) { Fx += dfx; Fy += dfy; Tq += dtq0; }
+            R d[6];
+            d[0] = R(cur.vx); d[1] = R(cur.vy); d[4] = R(cur.om);
+            d[2] = r_div_by<S>(Fx, g.mass, g.inv_mass); d[3] = r_div_by<S>(Fy, g.mass, g.inv_mass);
+            d[5] = r_div_by<S>(Tq, g.inertia, g.inv_inertia);
+            ustage_apply<S, STAGE>(cur, d, ((size_t)q * g.cols + (size_t)col) * 6, dt_, y, acc, out);
+        }
+        ufx = -dfx; ufy = -dfy; utq = dtq1;                // the down spring acts on the next row's body as its end 1
+        cur = nxt; nxt = pre;
     }
 }
 
@@ -403,6 +525,23 @@ void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const UI
                    size_t r_lo = 0, size_t r_hi = (size_t)-1) {
     if (r_hi == (size_t)-1) r_hi = g.rows_local;
     if (r_hi <= r_lo) return;
+    // Quad topology: the marching kernel (every spring once) wherever the gather kernel is FP64-bound -- strict arithmetic
+    // (4096^2 RK4 step 3.96 -> 2.83 ms, symplectic Euler 0.89 -> 0.57, velocity Verlet 1.86 -> 1.24) and the contract-mode Euler /
+    // Verlet stages (0.49 -> 0.37, 1.06 -> 1.02).  The contract-mode RK4 stages stay on the gather kernel: they are HBM-bound
+    // there (0.88 of peak) and the marching form, with fewer loads in flight per SM, measured 3 % slower (2.44 against 2.38 ms).
+    // SOPOT_B200_UGRID_GATHER=1 keeps the gather kernel everywhere, SOPOT_B200_UGRID_MARCH=1 marches everywhere.
+    static const bool gather_only = std::getenv("SOPOT_B200_UGRID_GATHER") != nullptr;
+    static const bool march_all = std::getenv("SOPOT_B200_UGRID_MARCH") != nullptr;
+    static const unsigned env_rows = std::getenv("SOPOT_B200_UGRID_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_UGRID_MARCH_ROWS")) : 0u;
+    if (g.topo == 0 && STAGE != 0 && !gather_only && (strict || STAGE >= 5 || march_all)) {
+        // 16 rows per chunk (one extra tick each): 16 -> 2.83 ms, 32 -> 2.87, 64 -> 3.08, 128 -> 3.23 (strict RK4 step)
+        const unsigned strips = (unsigned)((g.cols + kUMarchOwn - 1) / kUMarchOwn), chunk = env_rows ? env_rows : 16u;
+        const dim3 mgrid((strips + kUMarchWarps - 1) / kUMarchWarps, (unsigned)((r_hi - r_lo + chunk - 1) / chunk));
+        if (strict) ugrid_stage_march<true, STAGE><<<mgrid, 32 * kUMarchWarps, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi, chunk);
+        else ugrid_stage_march<false, STAGE><<<mgrid, 32 * kUMarchWarps, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi, chunk);
+        ctx->launches++;
+        return;
+    }
     const dim3 block(64, 4), grid((unsigned)((g.cols + 63) / 64), (unsigned)((r_hi - r_lo + 3) / 4));
     if (strict) ugrid_stage<true, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi);
     else ugrid_stage<false, STAGE><<<grid, block, 0, ctx->stream>>>(g, in, dt, y, acc, out, r_lo, r_hi);
