@@ -854,7 +854,7 @@ int launch_fused(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
 // quad topology: the marching kernel over local rows [ty_first * 16, (ty_first + n_ty) * 16) (callers count in tile rows of 16)
 template <bool S>
 int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const StepIn& in, double dt, double* y_out, unsigned ty_first,
-                 unsigned n_ty) {
+                 unsigned n_ty, unsigned fixed_chunk) {
     const unsigned r_lo = ty_first * kFusedTY;
     unsigned r_hi = (ty_first + n_ty) * kFusedTY;
     if (r_hi > g.rows_local) r_hi = (unsigned)g.rows_local;
@@ -866,7 +866,9 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
     // CTAs = one wave on 148 SMs instead of 688 CTAs = 1.55 waves with 128 (8 GPUs, strict: 1.00 -> 0.85 ms per step).
     static const unsigned env_rows = std::getenv("SOPOT_B200_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_MARCH_ROWS")) : 0u;
     const unsigned strips = (unsigned)((g.cols + 23) / 24), ctas_x = (strips + kMarchWarps - 1) / kMarchWarps;
-    unsigned chunk = env_rows;
+    // (fixed_chunk: the interior launch of the overlapped multi-rank schedule keeps 128-row chunks -- a launch tuned to fill
+    //  exactly one wave would leave the boundary CTAs on the other stream no slot to run beside it)
+    unsigned chunk = env_rows ? env_rows : fixed_chunk;
     if (!chunk) {
         const unsigned rows = r_hi - r_lo, slots = (unsigned)ctx->sm_count * SB_MARCH_MINB;
         unsigned long long best = ~0ull;
@@ -887,13 +889,14 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
 }
 
 int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
-                     double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride) {
+                     double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride, unsigned fixed_chunk = 0) {
     // SOPOT_B200_GRID_TILE_KERNEL=1 keeps the shared-memory tile kernel for the quad topology too (comparison runs, tests)
     // (SOPOT_B200_GRID_TILE_STRICT=1: tile kernel for strict arithmetic only)
     static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
     static const bool tile_strict = std::getenv("SOPOT_B200_GRID_TILE_STRICT") != nullptr;
     if (topo == 0 && ty_stride == 1 && !tile_only && !(strict && tile_strict))
-        return strict ? launch_march<true>(ctx, st, g, in, dt, y_out, ty_first, n_ty) : launch_march<false>(ctx, st, g, in, dt, y_out, ty_first, n_ty);
+        return strict ? launch_march<true>(ctx, st, g, in, dt, y_out, ty_first, n_ty, fixed_chunk)
+                      : launch_march<false>(ctx, st, g, in, dt, y_out, ty_first, n_ty, fixed_chunk);
 #define SB_FUSED_CASE(SS, TT) return launch_fused<SS, TT>(ctx, st, g, in, dt, y_out, ty_first, n_ty, ty_stride)
     if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
     else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
@@ -954,7 +957,7 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
             if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, 0, 1, 1))) return rc;                // B(s): top
             if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, nty - 2, 2, 1))) return rc;          //       bottom
             SB_CUDA(ctx, cudaEventRecord(ev_b, copy_s));
-            if ((rc = launch_fused_any(ctx, main_s, strict, topo, g, in, dt, nxt, 1, nty - 3, 1))) return rc;          // I(s)
+            if ((rc = launch_fused_any(ctx, main_s, strict, topo, g, in, dt, nxt, 1, nty - 3, 1, 128))) return rc;     // I(s)
             SB_CUDA(ctx, cudaEventRecord(ev_i, main_s));
             double* t = cur; cur = nxt; nxt = t;
         }
