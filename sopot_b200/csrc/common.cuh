@@ -37,6 +37,17 @@ struct sopot_b200_ctx {
     // NCCL (nranks > 1)
     void* nccl_comm = nullptr;
     const NcclApi* nccl = nullptr;
+    // grid2d halo exchange over NVLink peer memory (grid2d.cu): ghost rows and sequence flags that the NEIGHBOURING ranks'
+    // kernels write directly, mapped into their address spaces with CUDA IPC
+    struct P2P {
+        bool tried = false, ready = false;
+        size_t slot_doubles = 0;                       // capacity of one ghost slot (4 boundary rows)
+        double* ghost = nullptr;                       // [2 parity][2 side: from-up, from-down][slot_doubles]
+        unsigned* flags = nullptr;                     // [0] from the rank above, [32] from the rank below, [64..65] CTA counters, [96] error
+        double* peer_ghost[2] = {nullptr, nullptr};    // the rank above / below: its `ghost`
+        unsigned* peer_flags[2] = {nullptr, nullptr};  // ... and its `flags`
+        unsigned seq = 0;                              // exchanges completed (same on every rank)
+    } p2p;
 };
 
 int sb_fail(sopot_b200_ctx* ctx, int code, const char* fmt, ...);

@@ -141,6 +141,12 @@ SB_EXPORT void sopot_b200_destroy(sopot_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->p2p.peer_ghost[k]) cudaIpcCloseMemHandle(ctx->p2p.peer_ghost[k]);
+        if (ctx->p2p.peer_flags[k]) cudaIpcCloseMemHandle(ctx->p2p.peer_flags[k]);
+    }
+    if (ctx->p2p.ghost) cudaFree(ctx->p2p.ghost);
+    if (ctx->p2p.flags) cudaFree(ctx->p2p.flags);
     if (ctx->nccl_comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->nccl_comm);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);

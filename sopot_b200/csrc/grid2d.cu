@@ -404,6 +404,114 @@ grid_rk4_fused(const GridDev g, const StepIn in, const double dt, double* __rest
 // its own column, so there is no synchronisation and no bank conflict (64-bit accesses, consecutive lanes).
 // Redundancy instead of exchange: lanes 0-3 and 28-31 of a warp recompute the 4-column halo of the neighbouring strips (stage s
 // is valid on lanes s .. 31-s, 24 of 32 lanes own an output column), and a chunk of rows runs its pipeline 10 ticks longer.
+// ---- halo exchange over NVLink peer memory, fused into the step kernel (several ranks) -----------------------------------
+// With NCCL the fused step costs, per RK4 step, a send/recv group (a proxy-driven kernel per peer) in front of the compute
+// kernel.  Here the step kernel itself does the exchange: the warps that produce the first / last four rows of the slab store
+// them a second time, straight into the ghost rows of the rank above / below (its buffer is mapped into this process with
+// CUDA IPC, the stores travel over NVLink), every warp ends with  __threadfence_system + atomic count, and the last one to
+// finish raises a sequence flag in both neighbours' memory (st.release.sys).  The only warps that ever WAIT are those of the
+// first and the last chunk of rows, which read ghost rows: they poll their own flag (ld.acquire.sys) while all other chunks
+// already compute -- the transfer hides behind the interior of the slab.  Ghost rows are double-buffered by the parity of the
+// exchange number; a writer can only get one exchange ahead of the reader it writes to (it needs the reader's rows first),
+// which is exactly what two buffers cover.  No collective call on the step path at all.
+struct MarchP2P {
+    int on = 0;
+    unsigned wait_seq = 0, signal_seq = 0, done_target = 0;
+    const unsigned* flag_up = nullptr;        // raised by the rank above when its rows for exchange wait_seq are in my ghost buffer
+    const unsigned* flag_down = nullptr;
+    unsigned* peer_up_flag = nullptr;         // the rank above: its "from below" flag;  the rank below: its "from above" flag
+    unsigned* peer_down_flag = nullptr;
+    double* peer_up_slot = nullptr;           // the rank above: its from-below ghost slot of the NEXT exchange's parity
+    double* peer_down_slot = nullptr;         // the rank below: its from-above ghost slot
+    unsigned* done = nullptr;                 // warps of this launch series that have finished
+    unsigned* err = nullptr;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// ONE thread of a CTA polls until *flag has reached seq (sequence numbers wrap: compare the difference), relaxed loads with a
+// back-off and one acquire fence at the end -- hundreds of warps hammering a flag with system-scope acquire loads slow down the
+// very stores they wait for; gives up after ~4 s and raises err
+__device__ __noinline__ void p2p_wait(const unsigned* flag, const unsigned seq, unsigned* err) {
+    const long long t0 = clock64();
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - seq) >= 0) break;
+        __nanosleep(500);
+        if (clock64() - t0 > 8000000000ll) { atomicExch(err, 1u); break; }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+// every warp of a chunk that borders a neighbouring rank calls this exactly once when it is done (the other warps write no
+// peer memory and take no part): the last one signals both neighbours
+__device__ __noinline__ void p2p_finish(const MarchP2P& x, const bool has_up, const bool has_down) {
+    const bool first = blockIdx.y == 0, last = blockIdx.y == gridDim.y - 1;
+    if (!((first && has_up) || (last && has_down))) return;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence_system();                                  // this warp's peer stores before its count
+        if (atomicAdd(x.done, 1u) + 1u == x.done_target) {
+            __threadfence_system();
+            if (has_up) st_release_sys(x.peer_up_flag, x.signal_seq);
+            if (has_down) st_release_sys(x.peer_down_flag, x.signal_seq);
+        }
+    }
+}
+
+// The slab's first / last four rows of the NEW state are the neighbours' ghost rows of the next step: the lanes that just stored
+// them read them back (L2) and store them a second time, straight into the neighbour's memory over NVLink.  A separate function
+// behind a call on purpose: the same stores inside the tick loop cost the loop 11 %, and even inlined after the loop they changed
+// its schedule (the row prefetch lost its distance: long_scoreboard 0 -> 1.5 warps per issue cycle, 2.44 -> 2.94 ms).
+__device__ __noinline__ void p2p_push_rows(const MarchP2P& x, const GridDev& g, const double* y_out, const long long lo, const long long hi,
+                                           const long long gc, const bool has_up, const bool has_down) {
+    const int lane = threadIdx.x & 31;
+    const long long slab_lo = (long long)g.row_begin, slab_hi = (long long)(g.row_begin + g.rows_local);
+    if (!(lane >= 4 && lane < 28 && gc >= 0 && gc < (long long)g.cols)) return;
+    for (int r = 0; r < 4; ++r) {
+        const long long qu = slab_lo + r, qd = slab_hi - 4 + r;
+        if (has_up && qu >= lo && qu < hi) {
+            const double2* src = reinterpret_cast<const double2*>(y_out + ((size_t)r * g.cols + (size_t)gc) * 4);
+            const double2 a = __ldcg(src), b = __ldcg(src + 1);
+            store4(x.peer_up_slot + ((size_t)r * g.cols + (size_t)gc) * 4, a.x, a.y, b.x, b.y);
+        }
+        if (has_down && qd >= lo && qd < hi) {
+            const double2* src = reinterpret_cast<const double2*>(y_out + ((size_t)(qd - slab_lo) * g.cols + (size_t)gc) * 4);
+            const double2 a = __ldcg(src), b = __ldcg(src + 1);
+            store4(x.peer_down_slot + ((size_t)r * g.cols + (size_t)gc) * 4, a.x, a.y, b.x, b.y);
+        }
+    }
+}
+
+// first exchange of a call: boundary rows of the caller's state -> the neighbours' ghost slots (after the neighbours have
+// finished reading that slot in their previous call: their flags have reached wait_seq), then the same count-and-signal
+__global__ void __launch_bounds__(256) p2p_publish_kernel(const MarchP2P x, const double* __restrict__ first_rows,
+                                                          const double* __restrict__ last_rows, const size_t n2 /*double2 per slot*/,
+                                                          const int has_up, const int has_down) {
+    if (threadIdx.x == 0) {
+        if (has_up) p2p_wait(x.flag_up, x.wait_seq, x.err);
+        if (has_down) p2p_wait(x.flag_down, x.wait_seq, x.err);
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        if (has_up) reinterpret_cast<double2*>(x.peer_up_slot)[i] = reinterpret_cast<const double2*>(first_rows)[i];
+        if (has_down) reinterpret_cast<double2*>(x.peer_down_slot)[i] = reinterpret_cast<const double2*>(last_rows)[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(x.done, 1u) + 1u == x.done_target) {
+        __threadfence_system();
+        if (has_up) st_release_sys(x.peer_up_flag, x.signal_seq);
+        if (has_down) st_release_sys(x.peer_down_flag, x.signal_seq);
+    }
+}
+
 constexpr int kMarchRing = 8;                    // rows of y / S kept in shared memory per warp
 constexpr int kMarchWarps = 4;
 constexpr size_t kMarchSmem = (size_t)kMarchWarps * 2 * kMarchRing * 4 * 32 * sizeof(double);     // 64 KiB per CTA
@@ -725,10 +833,10 @@ __device__ __forceinline__ void march_body(const GridDev& g, const StepIn& in, c
 #ifndef SB_MARCH_MINB
 #define SB_MARCH_MINB 3
 #endif
-template <bool S>
+template <bool S, bool P2P>
 __global__ void __launch_bounds__(32 * kMarchWarps, SB_MARCH_MINB)
 grid_rk4_march(const GridDev g, const StepIn in, const double dt, double* __restrict__ y_out, const unsigned row_lo_local,
-               const unsigned row_hi_local, const unsigned rows_per_chunk) {
+               const unsigned row_hi_local, const unsigned rows_per_chunk, const MarchP2P x) {
     constexpr int OWN = 24;                       // output columns per warp
     extern __shared__ double march_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -736,12 +844,27 @@ grid_rk4_march(const GridDev g, const StepIn in, const double dt, double* __rest
     double* sring = yring + kMarchRing * 128;
     const long long strip = (long long)blockIdx.x * kMarchWarps + warp;
     const long long gc = strip * OWN - 4 + lane;
-    if (strip * OWN >= (long long)g.cols) return;            // whole warp: no column to own
     const long long lo = (long long)g.row_begin + row_lo_local + (long long)blockIdx.y * rows_per_chunk;
     long long hi = lo + rows_per_chunk;
     const long long end = (long long)g.row_begin + row_hi_local;
     if (hi > end) hi = end;
-    if (lo >= hi) return;
+    const bool has_up = g.row_begin > 0, has_down = g.row_begin + g.rows_local < g.rows;
+    if constexpr (P2P) {
+        // only the CTAs of the chunks that read ghost rows (the first and the last one) wait for the neighbour's rows of this
+        // exchange: one thread polls, the CTA's one and only barrier releases the others
+        const bool first = blockIdx.y == 0 && has_up, last = blockIdx.y == gridDim.y - 1 && has_down;
+        if (first || last) {
+            if (threadIdx.x == 0) {
+                if (first) p2p_wait(x.flag_up, x.wait_seq, x.err);
+                if (last) p2p_wait(x.flag_down, x.wait_seq, x.err);
+            }
+            __syncthreads();
+        }
+    }
+    if (strip * OWN >= (long long)g.cols || lo >= hi) {      // whole warp: no column / no row to own
+        if constexpr (P2P) p2p_finish(x, has_up, has_down);
+        return;
+    }
     // rows the pipeline reads before it has written them hold zeros, not whatever the previous CTA left: their (discarded)
     // results stay finite and ordinary, so the strict-mode operand votes are not failed by garbage
 #pragma unroll
@@ -750,6 +873,10 @@ grid_rk4_march(const GridDev g, const StepIn in, const double dt, double* __rest
     const bool edge = strip * OWN - 4 < 0 || strip * OWN - 4 + 32 > (long long)g.cols || lo - 11 < 0 || hi + 8 > (long long)g.rows;
     if (edge) march_body<S, true>(g, in, dt, y_out, lo, hi, gc, yring, sring);
     else march_body<S, false>(g, in, dt, y_out, lo, hi, gc, yring, sring);
+    if constexpr (P2P) {
+        p2p_push_rows(x, g, y_out, lo, hi, gc, has_up, has_down);
+        p2p_finish(x, has_up, has_down);
+    }
 }
 
 __global__ void grid_init_kernel(const size_t rows_local, const size_t cols, const size_t row_begin,
@@ -854,14 +981,14 @@ int launch_fused(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
 // quad topology: the marching kernel over local rows [ty_first * 16, (ty_first + n_ty) * 16) (callers count in tile rows of 16)
 template <bool S>
 int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const StepIn& in, double dt, double* y_out, unsigned ty_first,
-                 unsigned n_ty, unsigned fixed_chunk) {
+                 unsigned n_ty, unsigned fixed_chunk, MarchP2P* p2p = nullptr) {
     const unsigned r_lo = ty_first * kFusedTY;
     unsigned r_hi = (ty_first + n_ty) * kFusedTY;
     if (r_hi > g.rows_local) r_hi = (unsigned)g.rows_local;
     if (r_hi <= r_lo) return SOPOT_B200_OK;
     // Rows per chunk.  Every chunk runs its pipeline 10 ticks longer than it has rows, and the CTAs of a launch are scheduled in
-    // waves of (SMs x resident CTAs): the chunk length is chosen to minimise  waves x (rows per chunk + 10)  over all ways of
-    // cutting the rows into equal chunks of 64 .. 512 rows.  At 8192 rows on one GPU that is 128 +- a few rows (measured: 64 ->
+    // waves of (SMs x resident CTAs): the chunk length is chosen to minimise a simple model of the launch time over all ways
+    // of cutting the rows into equal chunks of 64 .. 512 rows.  At 8192 rows on one GPU that is 128 +- a few rows (measured: 64 ->
     // 3.06 ms, 128 -> 2.90, 256 -> 2.97, 512 -> 3.14 at that stage of development); on a 1/8 slab of 1024 rows it is 205 rows = 430
     // CTAs = one wave on 148 SMs instead of 688 CTAs = 1.55 waves with 128 (8 GPUs, strict: 1.00 -> 0.85 ms per step).
     static const unsigned env_rows = std::getenv("SOPOT_B200_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_MARCH_ROWS")) : 0u;
@@ -876,14 +1003,27 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
             const unsigned c = (rows + nch - 1) / nch;
             if (c > 512 && nch < rows) continue;
             if (c < 64 && nch > 1) break;
-            const unsigned long long waves = ((unsigned long long)ctas_x * nch + slots - 1) / slots, cost = waves * (c + 10);
+            // launch time in ticks x 1024: one CTA lives c + 10 ticks; up to one wave all CTAs run side by side, beyond that
+            // the SMs stay busy (work-conserving) and half a CTA lifetime is lost in the tail
+            const unsigned long long ctas = (unsigned long long)ctas_x * nch, life = c + 10;
+            const unsigned long long cost = ctas <= slots ? life * 1024 : life * 1024 * ctas / slots + life * 512;
             if (cost < best) { best = cost; chunk = c; }
         }
         if (!chunk) chunk = rows;
     }
     const dim3 grid(ctas_x, (r_hi - r_lo + chunk - 1) / chunk);
-    SB_CUDA(ctx, cudaFuncSetAttribute(grid_rk4_march<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarchSmem));
-    grid_rk4_march<S><<<grid, 32 * kMarchWarps, kMarchSmem, st>>>(g, in, dt, y_out, r_lo, r_hi, chunk);
+    SB_CUDA(ctx, cudaFuncSetAttribute(grid_rk4_march<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarchSmem));
+    SB_CUDA(ctx, cudaFuncSetAttribute(grid_rk4_march<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMarchSmem));
+    MarchP2P x;
+    if (p2p) {                                    // the warps of the bordering chunks count themselves: target = those of all launches so far
+        x = *p2p;
+        const bool up = g.row_begin > 0, down = g.row_begin + g.rows_local < g.rows;
+        const unsigned bordering = grid.y == 1 ? ((up || down) ? 1u : 0u) : (up ? 1u : 0u) + (down ? 1u : 0u);
+        x.done_target = p2p->done_target += grid.x * bordering * kMarchWarps;
+    }
+    static const bool force_p2p_variant = std::getenv("SOPOT_B200_MARCH_P2P_KERNEL") != nullptr;    // diagnosis: time that instantiation alone
+    if (p2p || force_p2p_variant) grid_rk4_march<S, true><<<grid, 32 * kMarchWarps, kMarchSmem, st>>>(g, in, dt, y_out, r_lo, r_hi, chunk, x);
+    else grid_rk4_march<S, false><<<grid, 32 * kMarchWarps, kMarchSmem, st>>>(g, in, dt, y_out, r_lo, r_hi, chunk, x);
     SB_CHECK_LAUNCH(ctx);
     return SOPOT_B200_OK;
 }
@@ -901,6 +1041,110 @@ int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo
     if (strict) { if (topo == 0) SB_FUSED_CASE(true, 0); else if (topo == 1) SB_FUSED_CASE(true, 1); else SB_FUSED_CASE(true, 2); }
     else        { if (topo == 0) SB_FUSED_CASE(false, 0); else if (topo == 1) SB_FUSED_CASE(false, 1); else SB_FUSED_CASE(false, 2); }
 #undef SB_FUSED_CASE
+}
+
+// ---- host side of the peer-memory exchange ----------------------------------------------------------------------------------
+// p2p_prepare is COLLECTIVE (every rank of the ctx calls it with the same slot size): allocate the ghost slots and the flags,
+// hand their CUDA IPC handles to the ranks above and below (two 128-byte messages over the existing NCCL communicator), map
+// theirs, and agree with one all-reduce(min) whether every rank succeeded.  If any did not (IPC unavailable in the sandbox, no
+// peer access), every rank keeps using the NCCL send/recv schedule.  SOPOT_B200_NO_P2P=1 skips the attempt.
+int p2p_prepare(sopot_b200_ctx* ctx, const size_t slot_doubles) {
+    auto& P = ctx->p2p;
+    if (std::getenv("SOPOT_B200_NO_P2P")) return SOPOT_B200_OK;
+    if (P.ready && P.slot_doubles >= slot_doubles) return SOPOT_B200_OK;
+    if (P.tried && !P.ready) return SOPOT_B200_OK;                 // failed before: stay on NCCL
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 2; ++k) {
+        if (P.peer_ghost[k]) cudaIpcCloseMemHandle(P.peer_ghost[k]);
+        if (P.peer_flags[k]) cudaIpcCloseMemHandle(P.peer_flags[k]);
+        P.peer_ghost[k] = nullptr; P.peer_flags[k] = nullptr;
+    }
+    if (P.ghost) cudaFree(P.ghost);
+    if (P.flags) cudaFree(P.flags);
+    P.ghost = nullptr; P.flags = nullptr; P.ready = false; P.tried = true; P.seq = 0;
+    bool ok = cudaMalloc(&P.ghost, 4 * slot_doubles * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&P.flags, 128 * sizeof(unsigned)) == cudaSuccess &&
+              cudaMemset(P.flags, 0, 128 * sizeof(unsigned)) == cudaSuccess;
+    struct Msg { cudaIpcMemHandle_t ghost, flags; };               // 2 x 64 bytes = 16 doubles
+    static_assert(sizeof(Msg) == 128, "IPC handles are 64 bytes each");
+    Msg mine{}, from_up{}, from_down{};
+    ok = ok && cudaIpcGetMemHandle(&mine.ghost, P.ghost) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, P.flags) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+    void* scr;
+    int rc = sb_scratch(ctx, 4096, &scr);
+    if (rc) return rc;
+    double* d_msg = static_cast<double*>(scr);                     // [0..16) mine, [16..32) from above, [32..48) from below, [48] verdict
+    SB_CUDA(ctx, cudaMemcpyAsync(d_msg, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    const bool up = ctx->rank > 0, down = ctx->rank + 1 < ctx->nranks;
+    const NcclApi* n = ctx->nccl;
+    SB_NCCL(ctx, n->GroupStart());
+    if (up) { SB_NCCL(ctx, n->Send(d_msg, 16, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream));
+              SB_NCCL(ctx, n->Recv(d_msg + 16, 16, SB_NCCL_FLOAT64, ctx->rank - 1, ctx->nccl_comm, ctx->stream)); }
+    if (down) { SB_NCCL(ctx, n->Send(d_msg, 16, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream));
+                SB_NCCL(ctx, n->Recv(d_msg + 32, 16, SB_NCCL_FLOAT64, ctx->rank + 1, ctx->nccl_comm, ctx->stream)); }
+    SB_NCCL(ctx, n->GroupEnd());
+    SB_CUDA(ctx, cudaMemcpyAsync(&from_up, d_msg + 16, sizeof from_up, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(&from_down, d_msg + 32, sizeof from_down, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const auto open = [&](const Msg& m, int k) {
+        const Msg zero{};
+        if (!memcmp(&m, &zero, sizeof m)) return false;            // that rank could not export its buffers
+        return cudaIpcOpenMemHandle((void**)&P.peer_ghost[k], m.ghost, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+               cudaIpcOpenMemHandle((void**)&P.peer_flags[k], m.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    };
+    if (ok && up) ok = open(from_up, 0);
+    if (ok && down) ok = open(from_down, 1);
+    if (!ok) cudaGetLastError();
+    const double verdict = ok ? 1.0 : 0.0;
+    double all = 0.0;
+    SB_CUDA(ctx, cudaMemcpyAsync(d_msg + 48, &verdict, 8, cudaMemcpyHostToDevice, ctx->stream));
+    SB_NCCL(ctx, n->AllReduce(d_msg + 48, d_msg + 48, 1, SB_NCCL_FLOAT64, SB_NCCL_MIN, ctx->nccl_comm, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(&all, d_msg + 48, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (all == 1.0) { P.ready = true; P.slot_doubles = slot_doubles; }
+    return SOPOT_B200_OK;
+}
+
+// the fused step with the exchange inside the kernel: publish the caller's boundary rows once, then one launch per step
+template <bool S>
+int grid_rk4_march_p2p(sopot_b200_ctx* ctx, const GridDev& g, double dt, size_t n_steps, double* y, double* alt) {
+    auto& P = ctx->p2p;
+    const size_t slot = P.slot_doubles, rows4 = 4 * g.cols * 4;
+    const bool up = g.row_begin > 0, down = g.row_begin + g.rows_local < g.rows;
+    const unsigned E0 = P.seq;
+    SB_CUDA(ctx, cudaMemsetAsync(P.flags + 64, 0, 2 * sizeof(unsigned), ctx->stream));     // the two warp / block counters
+    // slot(parity, side): side 0 = rows from the rank above (my ghost_top), 1 = from the rank below (my ghost_bot)
+    const auto mine = [&](unsigned e, int side) { return P.ghost + ((size_t)(e & 1u) * 2 + side) * slot; };
+    const auto peer = [&](int k, unsigned e, int side) { return P.peer_ghost[k] ? P.peer_ghost[k] + ((size_t)(e & 1u) * 2 + side) * slot : nullptr; };
+    MarchP2P x;
+    x.on = 1;
+    x.flag_up = P.flags; x.flag_down = P.flags + 32; x.err = P.flags + 96;
+    x.peer_up_flag = P.peer_flags[0] ? P.peer_flags[0] + 32 : nullptr;     // I am the rank BELOW my upper neighbour
+    x.peer_down_flag = P.peer_flags[1] ? P.peer_flags[1] : nullptr;        // ... and the rank ABOVE my lower one
+    {   // exchange E0 + 1: the caller's state; wait until both neighbours are past exchange E0 (their previous call)
+        MarchP2P pub = x;
+        pub.wait_seq = E0; pub.signal_seq = E0 + 1; pub.done = P.flags + 64; pub.done_target = 64;
+        pub.peer_up_slot = peer(0, E0 + 1, 1); pub.peer_down_slot = peer(1, E0 + 1, 0);
+        p2p_publish_kernel<<<64, 256, 0, ctx->stream>>>(pub, y, y + (g.rows_local - 4) * g.cols * 4, rows4 / 2, up ? 1 : 0, down ? 1 : 0);
+        SB_CHECK_LAUNCH(ctx);
+    }
+    x.done = P.flags + 65;
+    x.done_target = 0;
+    double* cur = y;
+    double* nxt = alt;
+    const unsigned nty = (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY);
+    for (size_t step = 0; step < n_steps; ++step) {
+        const unsigned e = E0 + 1 + (unsigned)step;
+        x.wait_seq = e; x.signal_seq = e + 1;
+        x.peer_up_slot = peer(0, e + 1, 1); x.peer_down_slot = peer(1, e + 1, 0);
+        const StepIn in{cur, mine(e, 0), mine(e, 1)};
+        int rc = launch_march<S>(ctx, ctx->stream, g, in, dt, nxt, 0, nty, 0, &x);
+        if (rc) return rc;
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    P.seq = E0 + 1 + (unsigned)n_steps;
+    if (cur != y) SB_CUDA(ctx, cudaMemcpyAsync(y, cur, g.rows_local * g.cols * 4 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SOPOT_B200_OK;
 }
 
 // One rank: one launch per step over all tiles.  Several ranks with slabs of more than 48 rows: the tiles that touch the
@@ -923,6 +1167,15 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
     double* alt = static_cast<double*>(scr);
     double* g_top = alt + slab;
     double* g_bot = g_top + ghost;
+    // several ranks, quad topology, slabs of at least 8 rows (a rank's first and last four rows are distinct): the exchange
+    // goes over NVLink peer memory from inside the step kernel when every rank could set that up (collective decision)
+    static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
+    static const bool tile_strict = std::getenv("SOPOT_B200_GRID_TILE_STRICT") != nullptr;
+    if (ctx->nranks > 1 && topo == 0 && g.rows / (size_t)ctx->nranks >= 8 && !tile_only && !(strict && tile_strict)) {
+        if ((rc = p2p_prepare(ctx, ghost))) return rc;
+        if (ctx->p2p.ready)
+            return strict ? grid_rk4_march_p2p<true>(ctx, g, dt, n_steps, y, alt) : grid_rk4_march_p2p<false>(ctx, g, dt, n_steps, y, alt);
+    }
     double* cur = y;
     double* nxt = alt;
     const unsigned nty = (unsigned)((g.rows_local + kFusedTY - 1) / kFusedTY);

@@ -78,18 +78,15 @@ for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2,
     for per_stage in (False, True):       # fused step (one 4-row exchange per step) and per-stage schedule (four 1-row)
         mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT, per_stage=per_stage)
         assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo, per_stage)
-    # contract mode: the marching kernel (quad topology) puts every mass through the same operations whatever the slab and
-    # chunk boundaries, so the slabs equal the single-rank run bit for bit in this mode too; the tile kernel of the diagonal
-    # topologies compiles boundary and interior tiles separately (different FMA contraction), there the slabs agree to rounding
+    # contract mode: the slabs agree with the single-rank run to rounding (the multi-rank step is a separately compiled
+    # instantiation -- exchange over peer memory inside the kernel, boundary tiles -- whose FMA contraction may differ; only
+    # strict arithmetic promises equal bits across decompositions)
     solo = Engine(local)
     ref_c = solo.grid2d_rk4(solo.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], steps,
                             s0.reshape(-1, 4).copy(), fp_mode=FP_CONTRACT).reshape(rows, cols, 4)
     solo.close()
     mine_c = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_CONTRACT)
-    if topo == 0:
-        assert np.array_equal(mine_c.reshape(rl, cols, 4), ref_c[rb:rb + rl]), (rank, rows, cols, topo, "contract")
-    else:
-        assert np.abs(mine_c.reshape(rl, cols, 4) - ref_c[rb:rb + rl]).max() <= 1e-12 * np.abs(ref_c).max(), (rank, rows, cols, topo)
+    assert np.abs(mine_c.reshape(rl, cols, 4) - ref_c[rb:rb + rl]).max() <= 1e-12 * np.abs(ref_c).max(), (rank, rows, cols, topo)
     dev = eng.to_device(s0[rb:rb + rl].reshape(-1, 4).copy())
     eng.grid2d_rk4(gp, p["dt"], steps, dev, fp_mode=FP_STRICT)
     assert np.array_equal(dev.download().reshape(rl, cols, 4), ref[rb:rb + rl])
