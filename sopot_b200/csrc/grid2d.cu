@@ -1004,9 +1004,9 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
             if (c > 512 && nch < rows) continue;
             if (c < 64 && nch > 1) break;
             // launch time in ticks x 1024: one CTA lives c + 10 ticks; up to one wave all CTAs run side by side, beyond that
-            // the SMs stay busy (work-conserving) and half a CTA lifetime is lost in the tail
+            // the SMs stay busy (work-conserving) and about one CTA lifetime is lost in the tail
             const unsigned long long ctas = (unsigned long long)ctas_x * nch, life = c + 10;
-            const unsigned long long cost = ctas <= slots ? life * 1024 : life * 1024 * ctas / slots + life * 512;
+            const unsigned long long cost = ctas <= slots ? life * 1024 : life * 1024 * ctas / slots + life * 1024;
             if (cost < best) { best = cost; chunk = c; }
         }
         if (!chunk) chunk = rows;
