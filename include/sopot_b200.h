@@ -262,6 +262,11 @@ int sopot_b200_dispersion_stats(sopot_b200_ctx* ctx, const double* values, size_
  * default the whole RK4 step is one kernel (all four stages on a shared-memory tile with a 4-cell halo) and
  * FOUR boundary rows are exchanged once per step -- same values bit for bit, a quarter of the messages and
  * 64 instead of 544 bytes of HBM traffic per mass and step.
+ * With the quad topology the fused step on several ranks carries the exchange itself: ghost rows and sequence flags live in
+ * buffers that the neighbouring ranks map with CUDA IPC, and the step kernel stores its boundary rows straight into them over
+ * NVLink (no collective call per step).  Set up on first use; if any rank cannot (no IPC / peer access) all ranks agree to use
+ * ncclSend/ncclRecv instead.  A timed-out wait is reported by the next sopot_b200_sync().  Environment switches for
+ * diagnosis: SOPOT_B200_NO_P2P=1 (NCCL schedule), SOPOT_B200_NO_HALO_OVERLAP=1, SOPOT_B200_GRID_TILE_KERNEL=1.
  * Slab contract (nranks > 1): rank r must own exactly the r-th block of the even contiguous partition of the
  * rows (base = rows / nranks rows each, the first rows % nranks ranks one more; sopot_b200/distributed.py::slab).
  * Every rank derives its exchange schedule from rows / nranks alone, so any other decomposition -- or fewer rows

@@ -165,6 +165,15 @@ SB_EXPORT const char* sopot_b200_last_error(const sopot_b200_ctx* ctx) {
 SB_EXPORT int sopot_b200_sync(sopot_b200_ctx* ctx) {
     if (!ctx) return SOPOT_B200_EINVAL;
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->p2p.flags) {
+        // a kernel of the peer-memory halo exchange gave up waiting for a neighbouring rank (grid2d.cu, p2p_wait)
+        unsigned err = 0;
+        SB_CUDA(ctx, cudaMemcpy(&err, ctx->p2p.flags + 96, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) {
+            cudaMemset(ctx->p2p.flags + 96, 0, sizeof err);
+            return sb_fail(ctx, SOPOT_B200_ENCCL, "halo exchange over peer memory timed out waiting for a neighbouring rank (its results are invalid)");
+        }
+    }
     return SOPOT_B200_OK;
 }
 
