@@ -11,8 +11,10 @@ LIB = os.path.join(ROOT, "sopot_b200", "lib", "libsopot_b200.so")
 OUT = os.path.join(ROOT, "profiles", "sass")
 WANT = {
     "dpend_contract": "rk4_ensemble_kernelI8DpendSysLb0",
-    "grid_march_contract": "grid_rk4_marchILb0",
-    "grid_march_strict": "grid_rk4_marchILb1",
+    "grid_march_contract": "grid_rk4_marchILb0ELb0",
+    "grid_march_contract_p2p": "grid_rk4_marchILb0ELb1",        # several ranks: exchange over NVLink peer memory inside the kernel
+    "grid_march_strict": "grid_rk4_marchILb1ELb0",
+    "ugrid_march_strict_stage2": "ugrid_stage_marchILb1ELi2",
     "rocket_contract": "rk4_ensemble_kernelI10RocketSysTILb0EELb0",
     "ho_contract": "rk4_ensemble_kernelI5HoSysLb0",
     "cartpole_linearize_contract": "cartpole_linearize_kernelILb0",
