@@ -108,7 +108,7 @@ struct CartPlant {
 // (15 FP64 instructions + 1 MUFU instead of the pivoted elimination with three IEEE divisions), and, as in the double
 // pendulum (ho_dpend.cu), every sin/cos argument of a step is the base angle plus a small increment: the pair
 // (sin th, cos th) is carried and rotated -- stage 2 and 4 from the base pair (rotate_small), stage 3 relative to stage 2
-// and the next base relative to stage 4 (rotate_tiny), full sincos every 16th step and whenever an increment leaves its
+// and the next base relative to stage 4 (rotate_micro, rotate_tiny as fall-back), full sincos every 16th step and whenever an increment leaves its
 // guarded range.  D >= mc, so the reference's singular-pivot throw cannot trigger for mc > 0; instances with
 // mc <= 1e-12 take the generic step, which reports it.
 struct CartFast {
@@ -136,28 +136,31 @@ struct CartFast {
         const double x = y[0].v, th = y[1].v, xd = y[2].v, w = y[3].v;
         double ax, aw;
         accel(s, c, w, F, ax, aw);
-        double F0 = xd, F1 = w, F2 = ax, F3 = aw;
-        double ux = fma(k.hdt, ax, xd), uw = fma(k.hdt, aw, w);
+        // Nystrom form of the two position-like rows (as ho_dpend.cu): y += dt v + dt^2/6 (a_1 + a_2 + a_3), with the sums
+        // Ax, Aw kept next to the velocity rows' F2, F3 = a_1 + 2 a_2 + 2 a_3
+        double F2 = ax, F3 = aw, Ax = ax, Aw = aw;
+        double uw = fma(k.hdt, aw, w);
         const double d = k.hdt2 * aw;                                  // stage 3 - stage 2 angle
         double ss, cs;
         rotate(s, c, k.hdt * w, k, th, ss, cs);
         accel(ss, cs, uw, F, ax, aw);
-        F0 = fma(2.0, ux, F0); F1 = fma(2.0, uw, F1); F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3);
+        F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3); Ax += ax; Aw += aw;
         if (sbtrig::tiny_angle(d)) sbtrig::rotate_tiny_k(ss, cs, d, k.rot3, ss, cs);
         else rotate(s, c, k.hdt * uw, k, th, ss, cs);
-        ux = fma(k.hdt, ax, xd); uw = fma(k.hdt, aw, w);
+        uw = fma(k.hdt, aw, w);
         accel(ss, cs, uw, F, ax, aw);
-        F0 = fma(2.0, ux, F0); F1 = fma(2.0, uw, F1); F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3);
+        F2 = fma(2.0, ax, F2); F3 = fma(2.0, aw, F3); Ax += ax; Aw += aw;
         const double h4 = k.dt * uw;
         rotate(s, c, h4, k, th, ss, cs);
-        ux = fma(k.dt, ax, xd); uw = fma(k.dt, aw, w);
+        uw = fma(k.dt, aw, w);
         accel(ss, cs, uw, F, ax, aw);
-        const double nth = fma(k.dt6, F1 + uw, th);
-        y[0].v = fma(k.dt6, F0 + ux, x); y[1].v = nth;
+        const double gth = fma(k.dt2_6, Aw, k.dt * w), nth = th + gth;
+        y[0].v = x + fma(k.dt2_6, Ax, k.dt * xd); y[1].v = nth;
         y[2].v = fma(k.dt6, F2 + ax, xd); y[3].v = fma(k.dt6, F3 + aw, w);
-        const double gth = nth - th, e = gth - h4;
+        const double e = gth - h4;                                     // dt^2/6 (a_1 - 2 a_2 + a_3) = O(dt^3)
         const bool refresh = ((step_no + 1) & 15) == 0;
-        if (!refresh && sbtrig::tiny_angle(e)) sbtrig::rotate_tiny_k(ss, cs, e, k.rot3, s, c);
+        if (!refresh && sbtrig::micro_angle(e)) sbtrig::rotate_micro(ss, cs, e, s, c);
+        else if (!refresh && sbtrig::tiny_angle(e)) sbtrig::rotate_tiny_k(ss, cs, e, k.rot3, s, c);
         else if (!refresh && sbtrig::small_angle(gth)) sbtrig::rotate_small_k(s, c, gth, k.rot3, k.rot5, k.cot4, s, c);
         else sbtrig::sincos<true>(nth, s, c);
     }
@@ -368,7 +371,6 @@ SB_EXPORT int sopot_b200_cartpole_linearize(sopot_b200_ctx* ctx, const sopot_b20
     if (!ctx) return SOPOT_B200_EINVAL;
     if (!plant || !x0 || !u0 || !opts || !A || !B) return sb_fail(ctx, SOPOT_B200_EINVAL, "NULL argument");
     if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts: mem and fp_mode must be 0 or 1");
-    if (opts->mem > 1 || opts->fp_mode > 1) return sb_fail(ctx, SOPOT_B200_EINVAL, "bad opts");
     Staging sg(ctx, opts->mem);
     int rc;
     if (sg.host && (rc = sb_arena_begin(ctx, 4 * sb_align(P * 8) + sb_align(4 * P * 8) + sb_align(P * 8) +

@@ -48,9 +48,9 @@ __device__ __forceinline__ int rk4_step(const typename Sys::template Inst<S>& in
 // the kernel (0.5 * dt is a per-thread DMUL) the same values sit in vector registers and every such FMA reads three
 // (3 cycles, profiles/r1_fp64_operand_rule.txt).  rot3/rot5/cot4: the full-precision coefficients of the small-angle
 // rotation (trig.cuh); its remaining coefficients are exact in the high word and become instruction immediates.
-struct StepConsts { double dt, hdt, dt6, hdt2, rot3, rot5, cot4; };
+struct StepConsts { double dt, hdt, dt6, hdt2, rot3, rot5, cot4, dt2_6; };
 __host__ __device__ __forceinline__ StepConsts make_step_consts(double dt) {
-    return StepConsts{dt, 0.5 * dt, dt / 6.0, (0.5 * dt) * (0.5 * dt), -1.0 / 6.0, 1.0 / 120.0, 1.0 / 24.0};
+    return StepConsts{dt, 0.5 * dt, dt / 6.0, (0.5 * dt) * (0.5 * dt), -1.0 / 6.0, 1.0 / 120.0, 1.0 / 24.0, dt * dt / 6.0};
 }
 
 template <class Sys>

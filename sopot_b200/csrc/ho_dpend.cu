@@ -104,6 +104,9 @@ SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
 #ifndef SB_DPEND_MINB
 #define SB_DPEND_MINB 1
 #endif
+#ifndef SB_DPEND_MICRO
+#define SB_DPEND_MICRO 1            // 0: the round-2 baseline step (rate sums for the angle rows, tiny rotation to the next base) for A/B runs
+#endif
 #ifndef SB_DPEND_REFRESH
 #define SB_DPEND_REFRESH 16         // full sincos of the carried pairs every this many steps (power of two)
 #endif
@@ -219,8 +222,9 @@ struct DpendSys {
     //   stage 2: th + (dt/2) w            -> rotate the base pair (sbtrig::rotate_small, |h| <= 2^-5)
     //   stage 3: stage 2 + (dt/2)^2 a_1   -> rotate the stage-2 pair by a tiny increment (rotate_tiny, |d| <= 2^-13)
     //   stage 4: th + dt u_3              -> rotate the base pair
-    //   next step: th_new - th            -> rotate the base pair; full sincos every SB_DPEND_REFRESH-th (16th) step bounds the accumulated
-    //                                        rounding of the carried pair to a few 1e-16
+    //   next step: th_new - stage 4       -> = dt^2/6 (a_1 - 2 a_2 + a_3): rotate the stage-4 pair by a micro increment (rotate_micro,
+    //                                        |e| <= 2^-18; tiny / small rotation as fall-backs); full sincos every SB_DPEND_REFRESH-th
+    //                                        (16th) step bounds the accumulated rounding of the carried pair to a few 1e-16
     // Every shortcut has an integer-compare guard on its increment and falls back to the full routine.
     // ~180 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
     static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
@@ -229,12 +233,17 @@ struct DpendSys {
         double a1, a2;
         accel(in, s1, c1, S, C, w1, w2, a1, a2);                                    // f1 = (w1, w2, a1, a2)
         double F0 = w1, F1 = w2, F2 = a1, F3 = a2;
+        double A1 = a1, A2 = a2;                                                    // a_1 + a_2 + a_3 per angle (SB_DPEND_MICRO)
         double u1 = fma(k.hdt, a1, w1), u2 = fma(k.hdt, a2, w2);                    // stage-2 rates
         const double d1 = k.hdt2 * a1, dd = k.hdt2 * (a1 - a2);                     // stage 3 - stage 2 angles
         double s1s, c1s, Ss, Cs;
         stage_trig(in, k, th1, th2, s1, c1, S, C, k.hdt * w1, k.hdt * (w1 - w2), s1s, c1s, Ss, Cs);
         accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f2 = (u1, u2, a1, a2)
+#if SB_DPEND_MICRO
+        F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3); A1 += a1; A2 += a2;
+#else
         F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
+#endif
         if (sbtrig::tiny_angle(d1) && sbtrig::tiny_angle(dd)) {
             sbtrig::rotate_tiny_k(s1s, c1s, d1, k.rot3, s1s, c1s);
             sbtrig::rotate_tiny_k(Ss, Cs, dd, k.rot3, Ss, Cs);
@@ -243,18 +252,40 @@ struct DpendSys {
         }
         u1 = fma(k.hdt, a1, w1); u2 = fma(k.hdt, a2, w2);                           // stage-3 rates
         accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f3
+#if SB_DPEND_MICRO
+        F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3); A1 += a1; A2 += a2;
+#else
         F0 = fma(2.0, u1, F0); F1 = fma(2.0, u2, F1); F2 = fma(2.0, a1, F2); F3 = fma(2.0, a2, F3);
+#endif
         const double h41 = k.dt * u1, h4d = k.dt * (u1 - u2);
         stage_trig(in, k, th1, th2, s1, c1, S, C, h41, h4d, s1s, c1s, Ss, Cs);
         u1 = fma(k.dt, a1, w1); u2 = fma(k.dt, a2, w2);                             // stage-4 rates
         accel(in, s1s, c1s, Ss, Cs, u1, u2, a1, a2);                                // f4
+#if SB_DPEND_MICRO
+        // angle increments of the whole step in Nystrom form: g = dt w + dt^2/6 (a_1 + a_2 + a_3) (A1, A2 = the sums, kept while
+        // F2, F3 were accumulated) -- two instructions fewer than the rate sums F0, F1, and the increment comes without the
+        // cancellation of (th + g) - th
+        const double g1 = fma(k.dt2_6, A1, k.dt * w1), g2 = fma(k.dt2_6, A2, k.dt * w2);
+        const double n1 = th1 + g1, n2 = th2 + g2;
+        y[0].v = n1; y[1].v = n2;
+        y[2].v = fma(k.dt6, F2 + a1, w1);  y[3].v = fma(k.dt6, F3 + a2, w2);
+        const double gd = g1 - g2;
+#else
         const double n1 = fma(k.dt6, F0 + u1, th1), n2 = fma(k.dt6, F1 + u2, th2);
         y[0].v = n1; y[1].v = n2;
         y[2].v = fma(k.dt6, F2 + a1, w1);  y[3].v = fma(k.dt6, F3 + a2, w2);
         const double g1 = n1 - th1, gd = g1 - (n2 - th2);
-        // the new base angle differs from the stage-4 angle by dt (F/6 - u_3) = O(dt^2 a): tiny rotation of the stage-4 pair
+#endif
+        // the new base angle differs from the stage-4 angle by dt (F/6 - u_3) = dt^2/6 (a_1 - 2 a_2 + a_3) = O(dt^3): a micro
+        // rotation of the stage-4 pair (tiny / small / full as fall-backs)
         const double e1 = g1 - h41, ed = gd - h4d;
         const bool refresh = ((step + 1) & (SB_DPEND_REFRESH - 1)) == 0;
+#if SB_DPEND_MICRO
+        if (!refresh && sbtrig::micro_angle(e1) && sbtrig::micro_angle(ed)) {
+            sbtrig::rotate_micro(s1s, c1s, e1, in.s1, in.c1);
+            sbtrig::rotate_micro(Ss, Cs, ed, in.sd, in.cd);
+        } else
+#endif
         if (!refresh && sbtrig::tiny_angle(e1) && sbtrig::tiny_angle(ed)) {
             sbtrig::rotate_tiny_k(s1s, c1s, e1, k.rot3, in.s1, in.c1);
             sbtrig::rotate_tiny_k(Ss, Cs, ed, k.rot3, in.sd, in.cd);

@@ -1,7 +1,7 @@
 // Host-side accuracy check of csrc/trig.cuh (the header compiles for the host with the same fma() sequence):
 // max error in ulp of sbtrig::sincos against long double libm over |x| <= 1e6 and near multiples of pi/2, and
 // of rotate_small / rotate_small_k (sin x, cos x, h) against sin/cos(x + h) for |h| <= 2^-5 and rotate_tiny / rotate_tiny_k
-// for |d| <= 2^-13 (the variants the double-pendulum step uses).  Pure CPU; run by tests/test_oracle.py.
+// for |d| <= 2^-13 and rotate_micro for |d| <= 2^-18 (the variants the double-pendulum step uses).  Pure CPU; run by tests/test_oracle.py.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,7 +18,7 @@ int main(int argc, char** argv) {
     const long n = argc > 1 ? std::atol(argv[1]) : 400000;
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-1.0, 1.0);
-    double worst_s = 0, worst_c = 0, worst_rs = 0, worst_rc = 0, worst_k = 0, worst_t = 0;
+    double worst_s = 0, worst_c = 0, worst_rs = 0, worst_rc = 0, worst_k = 0, worst_t = 0, worst_m = 0;
     for (long i = 0; i < n; ++i) {
         double x;
         switch (i & 3) {
@@ -55,6 +55,14 @@ int main(int argc, char** argv) {
         if (ts != ts2 || tc != tc2) { std::puts("rotate_tiny and rotate_tiny_k differ"); return 1; }
         worst_t = std::fmax(worst_t, (double)std::fabs((long double)ts - (sl * cdl + cl * sdl)) / 0x1p-52);
         worst_t = std::fmax(worst_t, (double)std::fabs((long double)tc - (cl * cdl - sl * sdl)) / 0x1p-52);
+        // micro increments (every 8th sample sits on the bound)
+        const double e = (i & 7) ? sbtrig::kMicroAngle * U(rng) : ((i & 8) ? sbtrig::kMicroAngle : -sbtrig::kMicroAngle);
+        if (!sbtrig::micro_angle(e)) { std::printf("micro_angle rejects %.17g\n", e); return 1; }
+        const long double sel = sinl((long double)e), cel = cosl((long double)e);
+        double ms, mc;
+        sbtrig::rotate_micro((double)sl, (double)cl, e, ms, mc);
+        worst_m = std::fmax(worst_m, (double)std::fabs((long double)ms - (sl * cel + cl * sel)) / 0x1p-52);
+        worst_m = std::fmax(worst_m, (double)std::fabs((long double)mc - (cl * cel - sl * sel)) / 0x1p-52);
     }
     // lean log(num/den) and exp (rocket atmosphere): relative error in ulp over the guarded ranges
     double worst_l = 0, worst_e = 0;
@@ -73,7 +81,8 @@ int main(int argc, char** argv) {
     if (worst_l > 3.0 || worst_e > 2.0) return 3;     // the quotient z carries ~2 ulp (sum, reciprocal, product roundings)
     if (sbtrig::small_angle(0.03126) || !sbtrig::small_angle(-0.03125)) { std::puts("small_angle threshold wrong"); return 1; }
     if (sbtrig::tiny_angle(0x1.0001p-13) || !sbtrig::tiny_angle(-0x1p-13)) { std::puts("tiny_angle threshold wrong"); return 1; }
-    std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f, _k %.3f, tiny %.3f\n",
-                worst_s, worst_c, worst_rs, worst_rc, worst_k, worst_t);
-    return (worst_s <= 2.0 && worst_c <= 2.0 && worst_rs <= 2.0 && worst_rc <= 2.0 && worst_k <= 2.0 && worst_t <= 2.0) ? 0 : 2;
+    if (sbtrig::micro_angle(0x1.0001p-18) || !sbtrig::micro_angle(-0x1p-18)) { std::puts("micro_angle threshold wrong"); return 1; }
+    std::printf("sincos max ulp: sin %.3f cos %.3f; rotate_small max abs error / 2^-52: sin %.3f cos %.3f, _k %.3f, tiny %.3f, micro %.3f\n",
+                worst_s, worst_c, worst_rs, worst_rc, worst_k, worst_t, worst_m);
+    return (worst_s <= 2.0 && worst_c <= 2.0 && worst_rs <= 2.0 && worst_rc <= 2.0 && worst_k <= 2.0 && worst_t <= 2.0 && worst_m <= 2.0) ? 0 : 2;
 }
