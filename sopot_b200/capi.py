@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("SOPOT_B200_LIB") or os.path.join(_HERE, "lib", "libso
 MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
+FLAG_GRID_MARCH, FLAG_GRID_TILE = 4, 8
 FLAG_UGRID_STAGE_PAIRS = 2
 ABI_VERSION = 5
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
@@ -616,11 +617,13 @@ class Engine:
         self.sync()
         return st
 
-    def grid2d_rk4(self, g: Grid2DParams, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, per_stage=False):
+    def grid2d_rk4(self, g: Grid2DParams, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, per_stage=False, kernel=None):
         """In place on `state` (numpy host array or DeviceArray).  per_stage=True: four stage kernels with a 1-row
-        halo exchange each instead of the fused step kernel (same values)."""
+        halo exchange each instead of the fused step kernel (same values).  kernel="march" / "tile": force the fused step's
+        kernel for the quad topology (default: chosen by size)."""
         mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
-        opts = RK4Opts(mem, fp_mode, 0, 0, FLAG_GRID_PER_STAGE if per_stage else 0)
+        flags = (FLAG_GRID_PER_STAGE if per_stage else 0) | {None: 0, "march": FLAG_GRID_MARCH, "tile": FLAG_GRID_TILE}[kernel]
+        opts = RK4Opts(mem, fp_mode, 0, 0, flags)
         self._ck(self.lib.sopot_b200_grid2d_rk4(self.ctx, byref(g), dt, n_steps, byref(opts), _ptr(state)))
         if sync:
             self.sync()

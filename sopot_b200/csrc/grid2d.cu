@@ -1028,13 +1028,28 @@ int launch_march(sopot_b200_ctx* ctx, cudaStream_t st, const GridDev& g, const S
     return SOPOT_B200_OK;
 }
 
-int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
-                     double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride, unsigned fixed_chunk = 0) {
-    // SOPOT_B200_GRID_TILE_KERNEL=1 keeps the shared-memory tile kernel for the quad topology too (comparison runs, tests)
-    // (SOPOT_B200_GRID_TILE_STRICT=1: tile kernel for strict arithmetic only)
+// Which kernel runs the fused step of the quad topology.  The marching kernel (one warp per 24-column strip, rows streamed) is
+// the fast one once it fills the GPU: 2048^2 0.195 ms per step against 0.281 for the tile kernel, 8192^2 2.4 against 4.3.  Its
+// parallelism is strips x row chunks, though, and a chunk shorter than 64 rows spends more ticks filling its pipeline than
+// working: below about one wave of CTAs the tile kernel (one CTA per 32 x 16 tile) wins -- 512^2: 0.025 ms per step against
+// 0.082 (strict 0.040 against 0.212), 1024^2: 0.074 against 0.099 (strict 0.123 against 0.242); profiles/r2_grid_small_sizes.txt.
+// Decided from the GLOBAL size (rows per rank of the even partition), so that all ranks of a slab decomposition agree.
+// opts->flags SOPOT_B200_FLAG_GRID_MARCH / _TILE and the environment (SOPOT_B200_GRID_TILE_KERNEL=1, and
+// SOPOT_B200_GRID_TILE_STRICT=1 for strict arithmetic only) override the choice.
+bool grid_use_march(const sopot_b200_ctx* ctx, const GridDev& g, int topo, bool strict, uint32_t flags) {
     static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
     static const bool tile_strict = std::getenv("SOPOT_B200_GRID_TILE_STRICT") != nullptr;
-    if (topo == 0 && ty_stride == 1 && !tile_only && !(strict && tile_strict))
+    if (topo != 0 || tile_only || (strict && tile_strict) || (flags & SOPOT_B200_FLAG_GRID_TILE)) return false;
+    static const bool march_only = std::getenv("SOPOT_B200_GRID_MARCH_KERNEL") != nullptr;
+    if ((flags & SOPOT_B200_FLAG_GRID_MARCH) || march_only) return true;
+    const size_t base_rows = g.rows / (size_t)(ctx->nranks > 0 ? ctx->nranks : 1);
+    const size_t ctas = ((g.cols + 23) / 24 + kMarchWarps - 1) / kMarchWarps * ((base_rows + 63) / 64);
+    return ctas >= (size_t)ctx->sm_count * SB_MARCH_MINB;
+}
+
+int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
+                     double* y_out, unsigned ty_first, unsigned n_ty, unsigned ty_stride, bool march, unsigned fixed_chunk = 0) {
+    if (topo == 0 && ty_stride == 1 && march)
         return strict ? launch_march<true>(ctx, st, g, in, dt, y_out, ty_first, n_ty, fixed_chunk)
                       : launch_march<false>(ctx, st, g, in, dt, y_out, ty_first, n_ty, fixed_chunk);
 #define SB_FUSED_CASE(SS, TT) return launch_fused<SS, TT>(ctx, st, g, in, dt, y_out, ty_first, n_ty, ty_stride)
@@ -1157,7 +1172,8 @@ int grid_rk4_march_p2p(sopot_b200_ctx* ctx, const GridDev& g, double dt, size_t 
 // B only.  The exchange and the boundary tiles hide behind the interior tiles; thinner slabs exchange first and launch
 // once, as before.  (A first version with all kernels on one stream, B before I, was SLOWER than no overlap at all --
 // 2.48 vs 2.37 ms per step on 2 GPUs: three partial waves instead of one launch cost more than the 30 us exchange.)
-int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool strict, double dt, size_t n_steps, double* y) {
+int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool strict, double dt, size_t n_steps, double* y, uint32_t flags) {
+    const bool march = grid_use_march(ctx, g, topo, strict, flags);
     const size_t slab = g.rows_local * g.cols * 4, ghost = 4 * g.cols * 4;
     if (ctx->nranks > 1 && g.rows_local < 4)
         return sb_fail(ctx, SOPOT_B200_EINVAL, "the fused grid step needs >= 4 rows per rank (use SOPOT_B200_FLAG_GRID_PER_STAGE)");
@@ -1169,9 +1185,8 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
     double* g_bot = g_top + ghost;
     // several ranks, quad topology, slabs of at least 8 rows (a rank's first and last four rows are distinct): the exchange
     // goes over NVLink peer memory from inside the step kernel when every rank could set that up (collective decision)
-    static const bool tile_only = std::getenv("SOPOT_B200_GRID_TILE_KERNEL") != nullptr;
-    static const bool tile_strict = std::getenv("SOPOT_B200_GRID_TILE_STRICT") != nullptr;
-    if (ctx->nranks > 1 && topo == 0 && g.rows / (size_t)ctx->nranks >= 8 && !tile_only && !(strict && tile_strict)) {
+    // (the marching kernel carries the exchange; slabs too small to fill the GPU with it take the tile kernel and NCCL below)
+    if (ctx->nranks > 1 && march && g.rows / (size_t)ctx->nranks >= 8) {
         if ((rc = p2p_prepare(ctx, ghost))) return rc;
         if (ctx->p2p.ready)
             return strict ? grid_rk4_march_p2p<true>(ctx, g, dt, n_steps, y, alt) : grid_rk4_march_p2p<false>(ctx, g, dt, n_steps, y, alt);
@@ -1186,16 +1201,16 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
     // boundary tiles end up BEHIND the interior ones (8 GPUs, strict: 0.98 ms per step against 0.85 for exchange-then-launch).
     // Decided from the global size alone (slabs differ by at most one row), so every rank takes the same branch.
     const size_t base_rows = g.rows / (size_t)ctx->nranks;
-    const size_t interior_ctas = (topo == 0)
+    const size_t interior_ctas = march
         ? ((g.cols + 23) / 24 + kMarchWarps - 1) / kMarchWarps * ((base_rows > 48 ? base_rows - 48 : 0) + 127) / 128
         : (g.cols + kFusedTX - 1) / kFusedTX * (base_rows / kFusedTY > 3 ? base_rows / kFusedTY - 3 : 0);
-    const size_t slots = (size_t)ctx->sm_count * (topo == 0 ? SB_MARCH_MINB : 2);
+    const size_t slots = (size_t)ctx->sm_count * (march ? SB_MARCH_MINB : 2);
     const bool overlap = ctx->nranks > 1 && base_rows > 3 * (size_t)kFusedTY && nty >= 4 && interior_ctas >= 2 * slots &&
                          !(std::getenv("SOPOT_B200_NO_HALO_OVERLAP"));
     if (!overlap) {
         for (size_t step = 0; step < n_steps; ++step) {
             if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4))) return rc;
-            if ((rc = launch_fused_any(ctx, ctx->stream, strict, topo, g, StepIn{cur, g_top, g_bot}, dt, nxt, 0, nty, 1))) return rc;
+            if ((rc = launch_fused_any(ctx, ctx->stream, strict, topo, g, StepIn{cur, g_top, g_bot}, dt, nxt, 0, nty, 1, march))) return rc;
             double* t = cur; cur = nxt; nxt = t;
         }
     } else {
@@ -1207,10 +1222,10 @@ int grid_rk4_fused_run(sopot_b200_ctx* ctx, const GridDev& g, int topo, bool str
             if (step > 0) SB_CUDA(ctx, cudaStreamWaitEvent(main_s, ev_b, 0));     // I(s) reads and overwrites rows B(s-1) used
             SB_CUDA(ctx, cudaStreamWaitEvent(copy_s, ev_i, 0));                   // B(s) reads rows I(s-1) wrote
             if ((rc = halo_exchange(ctx, g, cur, g_top, g_bot, 4, copy_s))) return rc;
-            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, 0, 1, 1))) return rc;                // B(s): top
-            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, nty - 2, 2, 1))) return rc;          //       bottom
+            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, 0, 1, 1, march))) return rc;         // B(s): top
+            if ((rc = launch_fused_any(ctx, copy_s, strict, topo, g, in, dt, nxt, nty - 2, 2, 1, march))) return rc;   //       bottom
             SB_CUDA(ctx, cudaEventRecord(ev_b, copy_s));
-            if ((rc = launch_fused_any(ctx, main_s, strict, topo, g, in, dt, nxt, 1, nty - 3, 1, 128))) return rc;     // I(s)
+            if ((rc = launch_fused_any(ctx, main_s, strict, topo, g, in, dt, nxt, 1, nty - 3, 1, march, 128))) return rc;     // I(s)
             SB_CUDA(ctx, cudaEventRecord(ev_i, main_s));
             double* t = cur; cur = nxt; nxt = t;
         }
@@ -1289,7 +1304,7 @@ SB_EXPORT int sopot_b200_grid2d_rk4(sopot_b200_ctx* ctx, const sopot_b200_grid2d
     // branch (the exchanges are collective), hence the test on the GLOBAL size (slabs differ by at most one row).
     const bool thin_slabs = ctx->nranks > 1 && g.rows / (size_t)ctx->nranks < 4;
     if (!(opts->flags & SOPOT_B200_FLAG_GRID_PER_STAGE) && !thin_slabs) {
-        rc = grid_rk4_fused_run(ctx, g, p->topology, strict, dt, n_steps, y);
+        rc = grid_rk4_fused_run(ctx, g, p->topology, strict, dt, n_steps, y, opts->flags);
         if (rc) return rc;
         return sg.finish();
     }

@@ -75,9 +75,11 @@ for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2,
     solo.close()
     rb, rl = slab(rows, rank, world)
     gp = eng.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], row_begin=rb, rows_local=rl)
-    for per_stage in (False, True):       # fused step (one 4-row exchange per step) and per-stage schedule (four 1-row)
-        mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT, per_stage=per_stage)
-        assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo, per_stage)
+    # fused step (one 4-row exchange per step) with the kernel chosen by size, with the marching kernel forced (it carries the
+    # exchange over peer memory) and with the tile kernel forced (NCCL exchange between launches); per-stage schedule (four 1-row)
+    for kw in (dict(), dict(kernel="march"), dict(kernel="tile"), dict(per_stage=True)):
+        mine = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_STRICT, **kw)
+        assert np.array_equal(mine.reshape(rl, cols, 4), ref[rb:rb + rl]), (rank, rows, cols, topo, kw)
     # contract mode: the slabs agree with the single-rank run to rounding (the multi-rank step is a separately compiled
     # instantiation -- exchange over peer memory inside the kernel, boundary tiles -- whose FMA contraction may differ; only
     # strict arithmetic promises equal bits across decompositions)
@@ -85,8 +87,9 @@ for rows, cols, topo, steps in ((64, 96, 0, 12), (37, 130, 1, 6), (world, 64, 2,
     ref_c = solo.grid2d_rk4(solo.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"]), p["dt"], steps,
                             s0.reshape(-1, 4).copy(), fp_mode=FP_CONTRACT).reshape(rows, cols, 4)
     solo.close()
-    mine_c = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_CONTRACT)
-    assert np.abs(mine_c.reshape(rl, cols, 4) - ref_c[rb:rb + rl]).max() <= 1e-12 * np.abs(ref_c).max(), (rank, rows, cols, topo)
+    for kernel in (None, "march", "tile"):
+        mine_c = eng.grid2d_rk4(gp, p["dt"], steps, s0[rb:rb + rl].reshape(-1, 4).copy(), fp_mode=FP_CONTRACT, kernel=kernel)
+        assert np.abs(mine_c.reshape(rl, cols, 4) - ref_c[rb:rb + rl]).max() <= 1e-12 * np.abs(ref_c).max(), (rank, rows, cols, topo, kernel)
     dev = eng.to_device(s0[rb:rb + rl].reshape(-1, 4).copy())
     eng.grid2d_rk4(gp, p["dt"], steps, dev, fp_mode=FP_STRICT)
     assert np.array_equal(dev.download().reshape(rl, cols, 4), ref[rb:rb + rl])

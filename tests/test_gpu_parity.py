@@ -433,10 +433,11 @@ def test_grid2d_golden_bit_exact(engine, r, c, t):
     assert np.array_equal(engine.grid2d_initial_state(gp).ravel(), g[key + "_init"])
     s = g[key + "_state"].reshape(-1, 4).copy()
     assert np.array_equal(engine.grid2d_rhs(gp, s, fp_mode=FP_STRICT).ravel(), g[key + "_rhs"])
-    out = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_STRICT)
-    assert np.array_equal(out.ravel(), g[key + "_rk4"])
-    fast = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_CONTRACT)
-    assert rel_err(fast.ravel(), g[key + "_rk4"]).max() <= FINAL
+    for kernel in ((None, "march", "tile") if t == 0 else (None,)):     # quad topology: both fused-step kernels
+        out = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_STRICT, kernel=kernel)
+        assert np.array_equal(out.ravel(), g[key + "_rk4"]), kernel
+        fast = engine.grid2d_rk4(gp, 1e-3, 200, s.copy(), fp_mode=FP_CONTRACT, kernel=kernel)
+        assert rel_err(fast.ravel(), g[key + "_rk4"]).max() <= FINAL, kernel
 
 
 def test_grid2d_degenerate_spring(engine):
@@ -454,13 +455,14 @@ def test_grid2d_medium_vs_oracle_bit_exact(engine, port, rows, cols, topo):
     ref_rhs = port.grid2d_rhs(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], s0)
     assert np.array_equal(engine.grid2d_rhs(gp, s0.copy(), fp_mode=FP_STRICT).ravel(), ref_rhs)
     ref = port.grid2d_rk4(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], 25, s0, nthreads=4)
-    got = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_STRICT)
-    assert np.array_equal(got.ravel(), ref)
-    dev = engine.to_device(s0)
-    engine.grid2d_rk4(gp, p["dt"], 25, dev, fp_mode=FP_STRICT)
-    assert np.array_equal(dev.download().ravel(), ref)
-    fast = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_CONTRACT)
-    assert rel_err(fast.ravel(), ref).max() <= FINAL
+    for kernel in ((None, "march", "tile") if topo == 0 else (None,)):
+        got = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_STRICT, kernel=kernel)
+        assert np.array_equal(got.ravel(), ref), kernel
+        dev = engine.to_device(s0)
+        engine.grid2d_rk4(gp, p["dt"], 25, dev, fp_mode=FP_STRICT, kernel=kernel)
+        assert np.array_equal(dev.download().ravel(), ref), kernel
+        fast = engine.grid2d_rk4(gp, p["dt"], 25, s0.copy(), fp_mode=FP_CONTRACT, kernel=kernel)
+        assert rel_err(fast.ravel(), ref).max() <= FINAL, kernel
 
 
 def test_grid2d_large_properties(engine, port):
@@ -483,6 +485,12 @@ def test_grid2d_large_properties(engine, port):
     crop = np.ascontiguousarray(s0.reshape(n, n, 4)[:512, :512]).reshape(-1, 4)
     ref = port.grid2d_rk4(512, 512, 0, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], 3, crop, nthreads=8).reshape(512, 512, 4)
     assert np.array_equal(out[:64, :64], ref[:64, :64])
+    # the size-based choice (marching kernel at this size), the forced tile kernel and the per-stage schedule: the same bits everywhere
+    for kw in (dict(kernel="tile"), dict(kernel="march"), dict(per_stage=True)):
+        dev2 = engine.to_device(s0)
+        engine.grid2d_rk4(gp, p["dt"], 3, dev2, fp_mode=FP_STRICT, **kw)
+        assert np.array_equal(dev2.download().reshape(n, n, 4), out), kw
+        dev2.free()
 
 
 @pytest.mark.parametrize("rows,cols,topo,steps", [(37, 45, 0, 7), (64, 64, 1, 4), (19, 130, 2, 5), (130, 33, 0, 6)])
@@ -494,13 +502,14 @@ def test_grid2d_fused_step_equals_per_stage_schedule(engine, port, rows, cols, t
     p = W.GRID2D_PARAMS
     s0 = W.grid2d_state(rows, cols, p["spacing"])
     gp = engine.grid2d_params(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"])
-    fused = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT)
     staged = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT, per_stage=True)
-    assert np.array_equal(fused, staged)
-    # contract mode: the two kernels contract different expressions, so they agree to rounding, not to the bit
-    fused_c = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_CONTRACT)
     staged_c = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_CONTRACT, per_stage=True)
-    assert rel_err(fused_c.ravel(), fused.ravel()).max() <= FINAL and rel_err(staged_c.ravel(), fused.ravel()).max() <= FINAL
+    for kernel in ((None, "march", "tile") if topo == 0 else (None,)):
+        fused = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT, kernel=kernel)
+        assert np.array_equal(fused, staged), kernel
+        # contract mode: the kernels contract different expressions, so they agree to rounding, not to the bit
+        fused_c = engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_CONTRACT, kernel=kernel)
+        assert rel_err(fused_c.ravel(), fused.ravel()).max() <= FINAL and rel_err(staged_c.ravel(), fused.ravel()).max() <= FINAL
     ref = port.grid2d_rk4(rows, cols, topo, p["mass"], p["spacing"], p["k"], p["c"], p["dt"], steps, s0, nthreads=4)
     assert np.array_equal(engine.grid2d_rk4(gp, p["dt"], steps, s0.copy(), fp_mode=FP_STRICT).ravel(), ref)
 
@@ -514,9 +523,10 @@ def test_grid2d_strict_guarded_route_tiny_and_huge_operands(engine, port, spacin
     rows, cols, steps = 70, 100, 3
     s0 = W.grid2d_state(rows, cols, 0.5) * spacing / 0.5
     gp = engine.grid2d_params(rows, cols, 0, 1.0, spacing, 50.0, 0.5)
-    fused = engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT)
+    fused = engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT, kernel="march")
     staged = engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT, per_stage=True)
     assert np.array_equal(fused, staged)
+    assert np.array_equal(engine.grid2d_rk4(gp, 1e-3, steps, s0.copy(), fp_mode=FP_STRICT, kernel="tile"), staged)
     ref = port.grid2d_rk4(rows, cols, 0, 1.0, spacing, 50.0, 0.5, 1e-3, steps, s0, nthreads=4)
     assert np.array_equal(fused.ravel(), ref) and np.all(np.isfinite(ref))
 
