@@ -1044,7 +1044,10 @@ bool grid_use_march(const sopot_b200_ctx* ctx, const GridDev& g, int topo, bool 
     if ((flags & SOPOT_B200_FLAG_GRID_MARCH) || march_only) return true;
     const size_t base_rows = g.rows / (size_t)(ctx->nranks > 0 ? ctx->nranks : 1);
     const size_t ctas = ((g.cols + 23) / 24 + kMarchWarps - 1) / kMarchWarps * ((base_rows + 63) / 64);
-    return ctas >= (size_t)ctx->sm_count * SB_MARCH_MINB;
+    // measured crossover (profiles/r2_grid_small_sizes.txt): strict arithmetic at one full wave of CTAs (between 1536^2 and 1792^2),
+    // contract arithmetic at 9/16 of a wave (between 1152^2 and 1280^2) -- its tile kernel is barrier-bound, not FP64-bound
+    const size_t slots = (size_t)ctx->sm_count * SB_MARCH_MINB;
+    return strict ? ctas >= slots : 16 * ctas >= 9 * slots;
 }
 
 int launch_fused_any(sopot_b200_ctx* ctx, cudaStream_t st, bool strict, int topo, const GridDev& g, const StepIn& in, double dt,
