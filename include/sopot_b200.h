@@ -56,7 +56,10 @@ enum { SOPOT_B200_FP_CONTRACT = 0, SOPOT_B200_FP_STRICT = 1 };
 enum { SOPOT_B200_FLAG_GRID_PER_STAGE = 1, SOPOT_B200_FLAG_UGRID_STAGE_PAIRS = 2,
        /* fused grid2d step, quad topology: force the row-marching kernel / the shared-memory tile kernel.  Default: by size
         * (tile kernel while the marching kernel would not fill the GPU, about <= 1024^2 per rank).  Same bits in FP_STRICT. */
-       SOPOT_B200_FLAG_GRID_MARCH = 4, SOPOT_B200_FLAG_GRID_TILE = 8 };
+       SOPOT_B200_FLAG_GRID_MARCH = 4, SOPOT_B200_FLAG_GRID_TILE = 8,
+       /* unified grid, quad topology: force the marching stage kernel (every spring once) / the gather kernel for every stage.
+        * Default: by arithmetic mode, integrator and global grid size.  Same bits in FP_STRICT. */
+       SOPOT_B200_FLAG_UGRID_MARCH = 16, SOPOT_B200_FLAG_UGRID_GATHER = 32 };
 enum { SOPOT_B200_ST_OK = 0, SOPOT_B200_ST_NONFINITE = 1, SOPOT_B200_ST_SINGULAR = 2,
        SOPOT_B200_ST_RANGE = 4 /* |angle| > 5e8 rad in FP_CONTRACT mode: rerun with FP_STRICT */,
        SOPOT_B200_ST_NOT_CONVERGED = 8 /* LQR::solve returned false (Riccati iteration diverged) */ };

@@ -22,6 +22,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 FP_CONTRACT, FP_STRICT = 0, 1
 FLAG_GRID_PER_STAGE = 1
 FLAG_GRID_MARCH, FLAG_GRID_TILE = 4, 8
+FLAG_UGRID_MARCH, FLAG_UGRID_GATHER = 16, 32
 FLAG_UGRID_STAGE_PAIRS = 2
 ABI_VERSION = 5
 INTEGRATOR_RK4, INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_VELOCITY_VERLET = 0, 1, 2      # sopot_b200_ugrid_integrate
@@ -597,11 +598,13 @@ class Engine:
         self.sync()
         return out
 
-    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, integrator=0, stage_pairs=False):
+    def ugrid_rk4(self, g, dt, n_steps, state, fp_mode=FP_STRICT, sync=True, integrator=0, stage_pairs=False, kernel=None):
         """integrator: 0 RK4, 1 symplectic Euler, 2 velocity Verlet (the reference Grid2DSimulator's three).
-        stage_pairs: RK4 with two stages per kernel instead of the default one kernel per stage (single rank, opt-in)."""
+        stage_pairs: RK4 with two stages per kernel instead of the default one kernel per stage (single rank, opt-in).
+        kernel="march" / "gather": force the stage kernel of the quad topology (default: by mode, integrator and size)."""
         mem = MEM_DEVICE if isinstance(state, DeviceArray) else MEM_HOST
-        opts = RK4Opts(mem, fp_mode, 0, 0, FLAG_UGRID_STAGE_PAIRS if stage_pairs else 0)
+        flags = (FLAG_UGRID_STAGE_PAIRS if stage_pairs else 0) | {None: 0, "march": FLAG_UGRID_MARCH, "gather": FLAG_UGRID_GATHER}[kernel]
+        opts = RK4Opts(mem, fp_mode, 0, 0, flags)
         self._ck(self.lib.sopot_b200_ugrid_integrate(self.ctx, byref(g), integrator, dt, n_steps, byref(opts), _ptr(state)))
         if sync:
             self.sync()

@@ -27,6 +27,7 @@ struct sopot_b200_ctx {
     cudaEvent_t events[16] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // internal cross-stream ordering
     uint64_t launches = 0;
+    uint32_t ugrid_kernel = 0;                   // SOPOT_B200_FLAG_UGRID_MARCH / _GATHER of the running ugrid call (0: by size)
     std::string error;
     // grow-only device arena used to stage HOST-pointer calls
     char* arena = nullptr;

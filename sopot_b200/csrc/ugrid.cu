@@ -533,7 +533,18 @@ void launch_ustage(sopot_b200_ctx* ctx, bool strict, const UGridDev& g, const UI
     static const bool gather_only = std::getenv("SOPOT_B200_UGRID_GATHER") != nullptr;
     static const bool march_all = std::getenv("SOPOT_B200_UGRID_MARCH") != nullptr;
     static const unsigned env_rows = std::getenv("SOPOT_B200_UGRID_MARCH_ROWS") ? (unsigned)std::atoi(std::getenv("SOPOT_B200_UGRID_MARCH_ROWS")) : 0u;
-    if (g.topo == 0 && STAGE != 0 && !gather_only && (strict || STAGE >= 5 || march_all)) {
+    // ... and only where it can fill the GPU: a warp marches a 30-column strip in chunks of 16 rows, so a 512^2 grid is 160 CTAs
+    // and the gather kernel (one thread per mass) is twice as fast there -- strict RK4 0.088 against 0.163 ms per step, contract
+    // Euler 0.013 against 0.020; from 1024^2 (576 CTAs) the marching kernel wins (strict RK4 0.232 against 0.282).  The
+    // contract-mode Verlet stages gain from it only on very large grids (4096^2: 1.02 against 1.06; 2048^2: 0.292 against 0.272).
+    // Decided from the GLOBAL grid size, so every rank of a slab decomposition and the single-domain run pick the same kernel
+    // (profiles/r2_ugrid_small_sizes.txt).
+    const size_t march_ctas = (((size_t)g.cols + kUMarchOwn - 1) / kUMarchOwn + kUMarchWarps - 1) / kUMarchWarps * (((size_t)g.rows + 15) / 16);
+    const bool verlet_contract = !strict && (STAGE == 6 || STAGE == 7);
+    const bool big_enough = march_ctas >= (verlet_contract ? 8192u : 2u * (unsigned)ctx->sm_count);
+    const bool force_march = march_all || (ctx->ugrid_kernel & SOPOT_B200_FLAG_UGRID_MARCH);
+    const bool force_gather = gather_only || (ctx->ugrid_kernel & SOPOT_B200_FLAG_UGRID_GATHER);
+    if (g.topo == 0 && STAGE != 0 && !force_gather && (force_march || (big_enough && (strict || STAGE >= 5)))) {
         // 16 rows per chunk (one extra tick each): 16 -> 2.83 ms, 32 -> 2.87, 64 -> 3.08, 128 -> 3.23 (strict RK4 step)
         const unsigned strips = (unsigned)((g.cols + kUMarchOwn - 1) / kUMarchOwn), chunk = env_rows ? env_rows : 16u;
         const dim3 mgrid((strips + kUMarchWarps - 1) / kUMarchWarps, (unsigned)((r_hi - r_lo + chunk - 1) / chunk));
@@ -619,6 +630,7 @@ SB_EXPORT int sopot_b200_ugrid_integrate(sopot_b200_ctx* ctx, const sopot_b200_u
     if (integrator < 0 || integrator > 2) return sb_fail(ctx, SOPOT_B200_EINVAL, "integrator must be RK4, SYMPLECTIC_EULER or VELOCITY_VERLET");
     if (!(dt > 0.0)) return sb_fail(ctx, SOPOT_B200_EINVAL, "dt must be positive");
     const bool strict = opts->fp_mode == SOPOT_B200_FP_STRICT;
+    ctx->ugrid_kernel = opts->flags & (SOPOT_B200_FLAG_UGRID_MARCH | SOPOT_B200_FLAG_UGRID_GATHER);
     const size_t n = g.rows_local * g.cols * 6, row_elems = g.cols * 6;
     Staging sg(ctx, opts->mem);
     if (sg.host && (rc = sb_arena_begin(ctx, sb_align(n * 8) + 4096))) return rc;

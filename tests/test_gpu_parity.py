@@ -655,6 +655,9 @@ def _ugrid_prm():
     return mg.UGRID_PARAMS
 
 
+UGRID_KERNELS = (None, "march", "gather")
+
+
 @pytest.mark.parametrize("rows,cols", [(3, 3), (4, 5), (2, 7), (6, 6), (10, 10)])
 def test_unified_grid_golden(engine, rows, cols):
     """Unified 6-state grid (PointMass2D + Spring2D with attachment points and torque) against the reference's ValidatedSystem:
@@ -667,8 +670,9 @@ def test_unified_grid_golden(engine, rows, cols):
         for mode in (FP_STRICT, FP_CONTRACT):
             d = engine.ugrid_rhs(gp, g[key + "_state"].copy(), fp_mode=mode)
             assert np.abs(d - g[key + "_rhs"]).max() <= 1e-12 * np.abs(g[key + "_rhs"]).max()
-            out = engine.ugrid_rk4(gp, 1e-3, 50, g[key + "_state"].copy(), fp_mode=mode)
-            assert rel_err(out.ravel(), g[key + "_rk4"].ravel()).max() <= FINAL
+            for kernel in UGRID_KERNELS:        # size-based choice, marching stage kernel forced, gather kernel forced
+                out = engine.ugrid_rk4(gp, 1e-3, 50, g[key + "_state"].copy(), fp_mode=mode, kernel=kernel)
+                assert rel_err(out.ravel(), g[key + "_rk4"].ravel()).max() <= FINAL, kernel
 
 
 def test_unified_grid_integrators(engine, port):
@@ -683,8 +687,9 @@ def test_unified_grid_integrators(engine, port):
         gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
         for name, integ in ids.items():
             for mode in (FP_STRICT, FP_CONTRACT):
-                out = engine.ugrid_rk4(gp, 1e-3, 80, g[f"u{rows}x{cols}_wasm_state"].copy(), fp_mode=mode, integrator=integ)
-                assert rel_err(out.ravel(), gi[f"u{rows}x{cols}_{name}"].ravel()).max() <= FINAL
+                for kernel in UGRID_KERNELS:
+                    out = engine.ugrid_rk4(gp, 1e-3, 80, g[f"u{rows}x{cols}_wasm_state"].copy(), fp_mode=mode, integrator=integ, kernel=kernel)
+                    assert rel_err(out.ravel(), gi[f"u{rows}x{cols}_{name}"].ravel()).max() <= FINAL, kernel
     rows, cols = 45, 77
     gp = engine.ugrid_params(rows, cols, *prm[:8], tuple(prm[8:12]))
     s0 = engine.ugrid_initial_state(gp)
@@ -693,11 +698,15 @@ def test_unified_grid_integrators(engine, port):
     for name, integ in ids.items():
         for n_steps in (1, 7, 12):
             ref = port.ugrid(rows, cols, prm, st, 2e-3, n_steps, name)
-            got = engine.ugrid_rk4(gp, 2e-3, n_steps, st.copy(), fp_mode=FP_STRICT, integrator=integ)
-            assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL
-            dev = engine.to_device(st)
-            engine.ugrid_rk4(gp, 2e-3, n_steps, dev, fp_mode=FP_CONTRACT, integrator=integ)
-            assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL
+            strict_bits = None
+            for kernel in UGRID_KERNELS:
+                got = engine.ugrid_rk4(gp, 2e-3, n_steps, st.copy(), fp_mode=FP_STRICT, integrator=integ, kernel=kernel)
+                assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL, kernel
+                assert strict_bits is None or np.array_equal(got, strict_bits), kernel      # strict: both kernels, the same bits
+                strict_bits = got
+                dev = engine.to_device(st)
+                engine.ugrid_rk4(gp, 2e-3, n_steps, dev, fp_mode=FP_CONTRACT, integrator=integ, kernel=kernel)
+                assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL, kernel
     with pytest.raises(Exception):
         engine.ugrid_rk4(gp, 1e-3, 1, st.copy(), integrator=9)
 
@@ -776,11 +785,15 @@ def test_unified_grid_medium_vs_oracle(engine, port):
         rng = np.random.default_rng(rows)
         st = s0 + rng.normal(0, 0.02, s0.shape); st[:, 4] = rng.normal(0, 0.2, rows * cols)
         ref = port.ugrid(rows, cols, prm, st, 1e-3, 10, "rk4")
-        got = engine.ugrid_rk4(gp, 1e-3, 10, st.copy(), fp_mode=FP_STRICT)
-        assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL
-        dev = engine.to_device(st)
-        engine.ugrid_rk4(gp, 1e-3, 10, dev, fp_mode=FP_CONTRACT)
-        assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL
+        strict_bits = None
+        for kernel in UGRID_KERNELS:
+            got = engine.ugrid_rk4(gp, 1e-3, 10, st.copy(), fp_mode=FP_STRICT, kernel=kernel)
+            assert rel_err(got.ravel(), ref.ravel()).max() <= FINAL, kernel
+            assert strict_bits is None or np.array_equal(got, strict_bits), kernel
+            strict_bits = got
+            dev = engine.to_device(st)
+            engine.ugrid_rk4(gp, 1e-3, 10, dev, fp_mode=FP_CONTRACT, kernel=kernel)
+            assert rel_err(dev.download().ravel(), ref.ravel()).max() <= FINAL, kernel
     rest = list(prm); rest[4] = 0.4                                   # 0.5 spacing - 2 * 0.05 radius
     gp = engine.ugrid_params(64, 64, *rest[:8], tuple(rest[8:12]))
     s0 = engine.ugrid_initial_state(gp)
