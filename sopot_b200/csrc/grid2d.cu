@@ -425,6 +425,7 @@ struct MarchP2P {
     double* peer_down_slot = nullptr;         // the rank below: its from-above ghost slot
     unsigned* done = nullptr;                 // warps of this launch series that have finished
     unsigned* err = nullptr;
+    long long timeout_clocks = 0;             // how long a CTA waits for a neighbouring rank before it raises err (p2p_timeout_clocks)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -437,15 +438,16 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 }
 // ONE thread of a CTA polls until *flag has reached seq (sequence numbers wrap: compare the difference), relaxed loads with a
 // back-off and one acquire fence at the end -- hundreds of warps hammering a flag with system-scope acquire loads slow down the
-// very stores they wait for; gives up after ~4 s and raises err
-__device__ __noinline__ void p2p_wait(const unsigned* flag, const unsigned seq, unsigned* err) {
+// very stores they wait for; gives up after timeout_clocks (one minute by default: a neighbour may be held up on its host for
+// seconds without anything being wrong, and a waiting CTA costs nothing but its slot) and raises err
+__device__ __noinline__ void p2p_wait(const unsigned* flag, const unsigned seq, unsigned* err, const long long timeout_clocks) {
     const long long t0 = clock64();
     unsigned v;
     for (;;) {
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - seq) >= 0) break;
         __nanosleep(500);
-        if (clock64() - t0 > 8000000000ll) { atomicExch(err, 1u); break; }
+        if (clock64() - t0 > timeout_clocks) { atomicExch(err, 1u); break; }
     }
     asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
@@ -495,8 +497,8 @@ __global__ void __launch_bounds__(256) p2p_publish_kernel(const MarchP2P x, cons
                                                           const double* __restrict__ last_rows, const size_t n2 /*double2 per slot*/,
                                                           const int has_up, const int has_down) {
     if (threadIdx.x == 0) {
-        if (has_up) p2p_wait(x.flag_up, x.wait_seq, x.err);
-        if (has_down) p2p_wait(x.flag_down, x.wait_seq, x.err);
+        if (has_up) p2p_wait(x.flag_up, x.wait_seq, x.err, x.timeout_clocks);
+        if (has_down) p2p_wait(x.flag_down, x.wait_seq, x.err, x.timeout_clocks);
     }
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
@@ -855,8 +857,8 @@ grid_rk4_march(const GridDev g, const StepIn in, const double dt, double* __rest
         const bool first = blockIdx.y == 0 && has_up, last = blockIdx.y == gridDim.y - 1 && has_down;
         if (first || last) {
             if (threadIdx.x == 0) {
-                if (first) p2p_wait(x.flag_up, x.wait_seq, x.err);
-                if (last) p2p_wait(x.flag_down, x.wait_seq, x.err);
+                if (first) p2p_wait(x.flag_up, x.wait_seq, x.err, x.timeout_clocks);
+                if (last) p2p_wait(x.flag_down, x.wait_seq, x.err, x.timeout_clocks);
             }
             __syncthreads();
         }
@@ -1123,6 +1125,14 @@ int p2p_prepare(sopot_b200_ctx* ctx, const size_t slot_doubles) {
     return SOPOT_B200_OK;
 }
 
+// SM clocks a CTA waits for a neighbouring rank: SOPOT_B200_P2P_TIMEOUT_S seconds (default 60) at the device's clock rate
+long long p2p_timeout_clocks(const sopot_b200_ctx* ctx) {
+    static const double seconds = std::getenv("SOPOT_B200_P2P_TIMEOUT_S") ? std::atof(std::getenv("SOPOT_B200_P2P_TIMEOUT_S")) : 60.0;
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device) != cudaSuccess || khz <= 0) { cudaGetLastError(); khz = 2000000; }
+    return (long long)((seconds > 0.0 ? seconds : 60.0) * 1e3 * (double)khz);
+}
+
 // the fused step with the exchange inside the kernel: publish the caller's boundary rows once, then one launch per step
 template <bool S>
 int grid_rk4_march_p2p(sopot_b200_ctx* ctx, const GridDev& g, double dt, size_t n_steps, double* y, double* alt) {
@@ -1136,6 +1146,7 @@ int grid_rk4_march_p2p(sopot_b200_ctx* ctx, const GridDev& g, double dt, size_t 
     const auto peer = [&](int k, unsigned e, int side) { return P.peer_ghost[k] ? P.peer_ghost[k] + ((size_t)(e & 1u) * 2 + side) * slot : nullptr; };
     MarchP2P x;
     x.on = 1;
+    x.timeout_clocks = p2p_timeout_clocks(ctx);
     x.flag_up = P.flags; x.flag_down = P.flags + 32; x.err = P.flags + 96;
     x.peer_up_flag = P.peer_flags[0] ? P.peer_flags[0] + 32 : nullptr;     // I am the rank BELOW my upper neighbour
     x.peer_down_flag = P.peer_flags[1] ? P.peer_flags[1] : nullptr;        // ... and the rank ABOVE my lower one
