@@ -8,6 +8,9 @@
 //   MODE 5  x = x * y             DMUL two vector
 //   MODE 6  x = x + y             DADD two vector
 //   MODE 7  x = fma(x, y, z) with y,z = neighbours in the chain array (more register banks in flight)
+//   MODE 8  x = fma(x, Y, z)      three distinct, but Y is ONE register shared by consecutive instructions (operand reuse cache, slot b)
+//   MODE 9  x = fma(x, y, Z)      the same with the shared register in slot c
+//   MODE 10 x = fma(Y, x, z)      shared register in slot a
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int MODE>
@@ -29,6 +32,9 @@ __global__ void __launch_bounds__(256) k(double* out, int iters, double a, doubl
                 if (MODE == 5) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(x[i]) : "d"(y[i]));
                 if (MODE == 6) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(x[i]) : "d"(y[i]));
                 if (MODE == 7) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[i]) : "d"(x[(i + 3) & 7]), "d"(x[(i + 5) & 7]));
+                if (MODE == 8) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[i]) : "d"(y[0]), "d"(z[i]));
+                if (MODE == 9) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[i]) : "d"(y[i]), "d"(z[0]));
+                if (MODE == 10) asm volatile("fma.rn.f64 %0, %1, %0, %2;" : "+d"(x[i]) : "d"(y[0]), "d"(z[i]));
             }
         }
     }
@@ -57,6 +63,7 @@ int main() {
     run<0>("fma(x,U,U)", d, n, ghz); run<1>("fma(x,y,U)", d, n, ghz); run<2>("fma(x,y,z)", d, n, ghz);
     run<3>("fma(y,z,x)", d, n, ghz); run<4>("fma(x,x,y)", d, n, ghz); run<5>("mul(x,y)", d, n, ghz);
     run<6>("add(x,y)", d, n, ghz); run<7>("fma(x,x3,x5)", d, n, ghz);
+    run<8>("fma(x,Yshared,z)", d, n, ghz); run<9>("fma(x,y,Zshared)", d, n, ghz); run<10>("fma(Yshared,x,z)", d, n, ghz);
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
