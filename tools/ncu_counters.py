@@ -58,6 +58,37 @@ for r in srows[hdr + 1:]:
             regs.add(q.group(1))
     if mm.group(2) == "DFMA" and len(regs) == 3:
         dfma3 += n
+# Three-register DFMAs whose third operand comes from the operand-reuse cache (the previous instruction of the warp read the same
+# register in the same slot and ptxas flagged it .reuse) issue in 2 cycles (profiles/r2_fp64_operand_reuse.txt).  ncu's source page
+# drops the flags, cuobjdump keeps them: when the library built HERE has the profiled kernel's SASS (same hash) the two listings
+# are joined instruction by instruction.
+dfma3_reuse = None
+try:
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    import kernel_hash as KH
+    sass = KH.kernel_sass(KH.DEFAULT_LIB, h["kernel"])
+    if KH.kernel_hash(KH.DEFAULT_LIB, h["kernel"])["sass_sha256"] == h["sass_sha256"]:
+        counts = [int(r[ei] or 0) for r in srows[hdr + 1:] if len(r) > ei]
+        if len(counts) == len(sass):
+            def operands(text):
+                q = re.match(r"(@!?U?P\d+\s+)?(\S+)\s*(.*)$", text)
+                return q.group(2), [o.strip() for o in q.group(3).split(",")] if q.group(3) else []
+            dfma3_reuse, prev = 0, []
+            for text, n in zip(sass, counts):
+                op, o = operands(text)
+                if op.startswith("DFMA"):
+                    srcs = o[1:]
+                    regs = [q.group(1) for q in (re.match(r"[-|]*R(\d+)", x) for x in srcs) if q]
+                    if len(set(regs)) == 3:
+                        for k, x in enumerate(srcs):
+                            a = re.match(r"[-|]*R(\d+)", prev[k + 1]) if k + 1 < len(prev) and ".reuse" in prev[k + 1] else None
+                            b = re.match(r"[-|]*R(\d+)", x)
+                            if a and b and a.group(1) == b.group(1):
+                                dfma3_reuse += n
+                                break
+                prev = o
+except Exception as ex:                                   # no cuobjdump / other library here: the field stays null
+    print(f"(reuse analysis skipped: {ex})", file=sys.stderr)
 w = units / 32.0                                  # warp-items per launch
 fp64 = sum(v for k, v in per_op.items() if k != "MUFU")
 out = {
@@ -67,7 +98,8 @@ out = {
     "dram_bytes_per_launch": (num("dram__bytes_read.sum", "bytes") or 0) + (num("dram__bytes_write.sum", "bytes") or 0),
     "fp64_instr_per_unit": fp64 / w, "dfma_per_unit": per_op["DFMA"] / w, "dmul_per_unit": per_op["DMUL"] / w,
     "dadd_per_unit": per_op["DADD"] / w, "mufu_per_unit": per_op["MUFU"] / w, "dfma3_per_unit": dfma3 / w,
-    "fp64_issue_cycles_per_warp_unit": (2.0 * fp64 + dfma3) / w, "thread_instr_per_unit": total / w,
+    "dfma3_served_by_reuse_per_unit": None if dfma3_reuse is None else dfma3_reuse / w,
+    "fp64_issue_cycles_per_warp_unit": (2.0 * fp64 + dfma3 - (dfma3_reuse or 0)) / w, "thread_instr_per_unit": total / w,
     "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
     "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
     "registers_per_thread": num("launch__registers_per_thread"),
