@@ -4,6 +4,12 @@
 #include "dual.cuh"
 #include "ensemble.cuh"
 #include "trig.cuh"
+#ifndef SB_DPEND_STEP
+#define SB_DPEND_STEP 2             // 3: the step of dpend_step.cuh (156 FP64 instructions per instance-step, tools/build_variant.py step3 ho_dpend.cu -DSB_DPEND_STEP=3); 2: the round-2 step below (172)
+#endif
+#if SB_DPEND_STEP >= 3
+#include "dpend_step.cuh"
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // HarmonicOscillator::derivatives: {v, T(-k/m)*x - T(c/m)*v}.  The two quotients are loop
@@ -227,6 +233,18 @@ struct DpendSys {
     //                                        (16th) step bounds the accumulated rounding of the carried pair to a few 1e-16
     // Every shortcut has an integer-compare guard on its increment and falls back to the full routine.
     // ~180 FP64 instructions per instance-step (228 with one full sincos pair per step, ~310 with four).
+#if SB_DPEND_STEP >= 3
+    // third form: csrc/dpend_step.cuh (host-compilable; tests/cpp/dpend_step_host.cpp checks it against a long-double RK4)
+    static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
+        const sbdp::Scales q{in.kol.v, in.lam.v, in.gL1.v};
+        sbdp::Pairs b{in.s1, in.c1, in.sd, in.cd};
+        double v[4] = {y[0].v, y[1].v, y[2].v, y[3].v};
+        sbdp::step(q, b, v, k, ((step + 1) & (SB_DPEND_REFRESH - 1)) == 0);
+        y[0].v = v[0]; y[1].v = v[1]; y[2].v = v[2]; y[3].v = v[3];
+        in.s1 = b.s1; in.c1 = b.c1; in.sd = b.S; in.cd = b.C;
+        return 0;
+    }
+#else
     static __device__ __forceinline__ int fast_step(Inst<false>& in, Real<false> (&y)[4], const StepConsts& k, const size_t step) {
         const double th1 = y[0].v, th2 = y[1].v, w1 = y[2].v, w2 = y[3].v;
         const double s1 = in.s1, c1 = in.c1, S = in.sd, C = in.cd;
@@ -297,6 +315,7 @@ struct DpendSys {
         }
         return 0;
     }
+#endif
     template <bool S> static __device__ __forceinline__ void observe(Inst<S>&, double, const Real<S> (&)[4]) {}
     template <bool S>
     static __device__ __forceinline__ int finish(const DevParams&, const Inst<S>&, size_t, size_t, const Real<S> (&y)[4]) {

@@ -177,6 +177,21 @@ def test_lean_trig_accuracy(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_dpend_fast_step_on_host(tmp_path):
+    """csrc/dpend_step.cuh (the FP_CONTRACT step of the double pendulum that carries its sin/cos pairs from stage to stage
+    and step to step) compiled for the host -- the kernel's own fma() sequence -- against a long-double RK4 of the
+    reference's equations, step by step from identical inputs along whole trajectories (so the rounding carried in the
+    pairs counts): a few 1e-15 relative per step on the BASELINE ensemble (the mode promises 1e-12), every fall-back tier
+    driven by fast spinners, coarse steps, g = 0 and m2 = 0; the two tiered rotations <= 1 ulp(1)."""
+    import subprocess
+    exe = tmp_path / "dpend_step_host"
+    src = os.path.join(ROOT, "tests", "cpp", "dpend_step_host.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", src, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count(" ok") == 9, r.stdout
+
+
 def test_golden_lqr_and_closed_loop(port):
     """Section 8f-1: the C restatement of LQR<4,1>::solve and of the sampled-data closed loop against the reference's
     own classes (golden vectors from oracle/ref_harness.cpp): gains, Riccati solutions, status codes incl. the
