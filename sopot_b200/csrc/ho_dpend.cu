@@ -5,7 +5,7 @@
 #include "ensemble.cuh"
 #include "trig.cuh"
 #ifndef SB_DPEND_STEP
-#define SB_DPEND_STEP 2             // 3: the step of dpend_step.cuh (156 FP64 instructions per instance-step, tools/build_variant.py step3 ho_dpend.cu -DSB_DPEND_STEP=3); 2: the round-2 step below (172)
+#define SB_DPEND_STEP 3             // 3: the step of dpend_step.cuh (156 FP64 instructions per instance-step, tools/build_variant.py step3 ho_dpend.cu -DSB_DPEND_STEP=3); 2: the round-2 step below (172)
 #endif
 #if SB_DPEND_STEP >= 3
 #include "dpend_step.cuh"
