@@ -10,6 +10,9 @@
 #if SB_DPEND_STEP >= 3
 #include "dpend_step.cuh"
 #endif
+#ifndef SB_DPEND_OPTIMISTIC
+#define SB_DPEND_OPTIMISTIC 0       // 1: sbdp::step_optimistic (one branch per step, second pass through step() when an increment leaves its tier)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // HarmonicOscillator::derivatives: {v, T(-k/m)*x - T(c/m)*v}.  The two quotients are loop
@@ -108,7 +111,11 @@ SB_EXPORT int sopot_b200_ho_rhs(sopot_b200_ctx* ctx, const sopot_b200_ho_params*
 #define SB_DPEND_IPT 1
 #endif
 #ifndef SB_DPEND_MINB
+#if SB_DPEND_STEP >= 3
+#define SB_DPEND_MINB 6             // 80 registers, six CTAs of four warps per SM: 42.08 -> 41.91 ms per 1000 steps of 4 Mi instances (7: 42.06, 8: 42.74)
+#else
 #define SB_DPEND_MINB 1
+#endif
 #endif
 #ifndef SB_DPEND_MICRO
 #define SB_DPEND_MICRO 1            // 0: the round-2 baseline step (rate sums for the angle rows, tiny rotation to the next base) for A/B runs
@@ -239,7 +246,11 @@ struct DpendSys {
         const sbdp::Scales q{in.kol.v, in.lam.v, in.gL1.v};
         sbdp::Pairs b{in.s1, in.c1, in.sd, in.cd};
         double v[4] = {y[0].v, y[1].v, y[2].v, y[3].v};
+#if SB_DPEND_OPTIMISTIC
+        sbdp::step_optimistic(q, b, v, k, ((step + 1) & (SB_DPEND_REFRESH - 1)) == 0);
+#else
         sbdp::step(q, b, v, k, ((step + 1) & (SB_DPEND_REFRESH - 1)) == 0);
+#endif
         y[0].v = v[0]; y[1].v = v[1]; y[2].v = v[2]; y[3].v = v[3];
         in.s1 = b.s1; in.c1 = b.c1; in.sd = b.S; in.cd = b.C;
         return 0;

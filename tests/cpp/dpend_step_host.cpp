@@ -4,7 +4,7 @@
 // trajectories, so that the rounding carried in the pairs between two refreshes is part of what is measured.  Beside it the
 // plain-double RK4 in the reference's own association against the same truth: the step must stay in that error class.
 // Ensembles: the BASELINE one (m = L = 1, g = 9.81, theta ~ U(-3, 3)), jittered parameters, g = 0, m2 = 0, fast spinners and
-// coarse steps that drive every fall-back tier.  Pure CPU; run by tests/test_oracle.py.  Prints one line per ensemble:
+// coarse steps that drive every fall-back tier; sbdp::step_optimistic (the one-branch form) must reproduce sbdp::step bit for bit.  Pure CPU; run by tests/test_oracle.py.  Prints one line per ensemble:
 //   name  max_rel_err_fast  max_rel_err_plain  tier counts
 #include <cmath>
 #include <cstdio>
@@ -66,7 +66,15 @@ static void run(const char* name, int n_inst, int n_steps, double dt, unsigned s
             rk4<double>(p, yp, dt);
             const double x1 = dt * y[2], xd = x1 - dt * y[3];
             r.half += sbdp::below_2m6(x1) && sbdp::below_2m6(xd);
+            // the one-branch form of the step must give the same bits from the same inputs
+            double yo[4] = {y[0], y[1], y[2], y[3]};
+            sbdp::Pairs bo = b;
+            sbdp::step_optimistic(q, bo, yo, k, ((s + 1) & 15) == 0);
             sbdp::step(q, b, y, k, ((s + 1) & 15) == 0);
+            if (std::memcmp(yo, y, sizeof y) != 0 || std::memcmp(&bo, &b, sizeof b) != 0) {
+                std::printf("%s: step_optimistic differs from step at instance %d step %d\n", name, i, s);
+                std::exit(1);
+            }
             r.steps++;
             for (int d = 0; d < 4; ++d) {
                 // relative to the magnitude of the component, angles and rates floored at 1 (an angle or a rate passing through

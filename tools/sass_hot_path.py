@@ -98,8 +98,9 @@ def hot_path(lib=DEFAULT_LIB, mangled=DPEND_KERNEL):
     def cost(i):
         _, t = ins[i]
         op = opcode(t)
-        f = 1 if op in FP64 else 0
-        return f
+        if op == "CALL":
+            return 10000                      # an out-of-line routine is never on the hot path (its instructions are not in this listing)
+        return 1 if op in FP64 else 0
 
     order = range(hi, lo - 1, -1)
     for i in order:
