@@ -3,7 +3,8 @@
 // the very same fma() sequence on the CPU against a long-double RK4 of the reference's equations.
 //
 // Same carried, scaled pairs as the second form (ho_dpend.cu):  (s1, c1) = (g/L1)(sin th1, cos th1),  (S, C) = lam (sin, cos)(th1 - th2),
-// kol = kap / lam, lam = L1/L2, kap = m2 L2 / ((m1+m2) L1).  What changed, in FP64 instructions per instance-step (174 -> 158):
+// kol = kap / lam, lam = L1/L2, kap = m2 L2 / ((m1+m2) L1).  What changed, in executed FP64 instructions per instance-step
+// (ncu: 174.0 -> 158.2; 45.57 -> 41.91 ms per 1000 steps of 4 Mi instances, profiles/r2_dpend_bench_step3.txt):
 //   * derivative 16 -> 15:  -B2 = lam w1^2 sd + (g/L2) sin th2 = S (w1^2 - c1) + s1 C   [(g/L2) sin th2 = s1 C - c1 S]
 //   * the increments of the difference angle by one FMA from the increment of th1 (h_d = h_1 - c w2) instead of (w1 - w2) c;
 //   * stage 2 rotates by HALF the full-step increment x = dt w, which the Nystrom angle row needs anyway (polynomials in x
@@ -191,7 +192,9 @@ SB_NOINLINE void step_out_of_line(const Scales& q, Pairs& b, double (&y)[4], con
 // The same step with ONE branch: the first-tier route of step() is computed unconditionally, the eight range tests are folded
 // into three integer maxima, and a step in which any increment leaves its tier is recomputed by step() from the saved
 // inputs -- bit-identical to step() in every case (on the BASELINE ensemble 0.4 % of the warp-steps take the second pass).
-// Removes the four divergence points (BSSY / BSYNC / BRA, 27 control instructions) from the hot path of a step.
+// Removes the four divergence points (BSSY / BSYNC / BRA, 27 control instructions) from the hot path of a step -- and measured
+// 3-4 % SLOWER on the B200 at every occupancy (43.3-43.8 against 41.9 ms, profiles/r2_dpend_step3_variants.txt): kept as an
+// opt-in (SB_DPEND_OPTIMISTIC=1) and as a second implementation the host test compares step() with.
 template <class K>
 SB_HD void step_optimistic(const Scales& q, Pairs& b, double (&y)[4], const K& k, const bool refresh) {
     const double th1 = y[0], th2 = y[1], w1 = y[2], w2 = y[3];
