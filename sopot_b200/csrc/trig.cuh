@@ -206,8 +206,21 @@ SB_HD bool micro_angle(double d) {
     return std::fabs(d) <= kMicroAngle;
 #endif
 }
+// -d/2 for the micro rotation.  SB_MICRO_INT_HALF (opt-in, measured 1 % SLOWER on the double pendulum: 42.36 against 41.93 ms per
+// 1000 steps -- two FP64 instructions fewer, but SEL / LOP3 / IADD on the step's loop-carried chain, profiles/r2_dpend_step3_variants.txt):
+// on the integer pipe (exponent field minus one, sign flipped) instead of a DMUL on the FP64 pipe the kernel is bound by; |d| below 2^-1021 (exponent field < 2, zero included) gives 0, which leaves the
+// rotation's second-order term out exactly where it underflows anyway.  Callers guarantee |d| <= 2^-18 (no inf / NaN).
+SB_HD double neg_half(double d) {
+#if defined(__CUDA_ARCH__) && defined(SB_MICRO_INT_HALF)
+    const int hi = __double2hiint(d);
+    const bool normal = (hi & 0x7fe00000) != 0;
+    return __hiloint2double(normal ? ((hi - 0x00100000) ^ (int)0x80000000) : 0, normal ? __double2loint(d) : 0);
+#else
+    return -0.5 * d;
+#endif
+}
 SB_HD void rotate_micro(double s, double c, double d, double& s_out, double& c_out) {
-    const double eh = -0.5 * d;
+    const double eh = neg_half(d);
     const double so = fma(d, fma(eh, s, c), s);
     const double co = fma(d, fma(eh, c, -s), c);
     s_out = so; c_out = co;
