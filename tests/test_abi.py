@@ -65,3 +65,25 @@ def test_num_steps_rule_matches_reference_loop():
     assert lib.sopot_b200_rk4_num_steps(0.0, 30.0, 0.01) == 3000
     assert lib.sopot_b200_rk4_num_steps(0.0, 0.016, 0.01) == 2
     assert lib.sopot_b200_rk4_num_steps(0.0, 1.0, 0.0) == 0
+
+
+def test_headline_kernel_counters_belong_to_the_built_code():
+    """profiles/dpend_bench_counters.json (the ncu counters bench.py reports as roofline.traffic / fp64_instr_per_unit) was
+    captured on exactly the kernel this tree builds -- same SHA-256 of its SASS -- and agrees with the static hot path of
+    that kernel's time loop (tools/sass_hot_path.py: the executed count exceeds the static one only by the 1-in-16 refresh
+    and the rare fall-back tiers; the three-register DFMA count likewise).  No GPU needed: cuobjdump on the built library."""
+    import json
+    import sys
+    from sopot_b200 import build
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from kernel_hash import kernel_hash
+    from sass_hot_path import hot_path
+    lib = build.build()
+    c = json.load(open(os.path.join(ROOT, "profiles", "dpend_bench_counters.json")))
+    assert kernel_hash(lib, c["kernel_mangled"])["sass_sha256"] == c["sass_sha256"], \
+        "the double-pendulum kernel changed: re-capture profiles/dpend_bench_counters.json (tools/ncu_counters.py)"
+    h = hot_path(lib, c["kernel_mangled"])
+    assert h["fp64"] <= c["fp64_instr_per_unit"] <= h["fp64"] + 4, (h["fp64"], c["fp64_instr_per_unit"])
+    assert abs(h["dfma_three_vector_sources"] - c["dfma3_per_unit"]) <= 2, (h["dfma_three_vector_sources"], c["dfma3_per_unit"])
+    assert h["mufu"] == 4 and h["dsetp"] == 0           # four reciprocal seeds, every range test on the integer pipe
+    assert h["fp64"] <= 156                             # the third form of the step (csrc/dpend_step.cuh); the second had 172
