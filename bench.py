@@ -123,6 +123,15 @@ def cpu_reference_rate(seconds_target: float, force_kind: str | None = None):
     return n * N_STEPS / el, cores, kind, sample, el
 
 
+def workload_config(n, world):
+    """`config` of the JSON line, the same object in both arms (ours and --impl reference)."""
+    return {"workload": "double pendulum ensemble (BASELINE configs[1]): m=L=1, g=9.81, theta~U(-3,3), "
+                        "RK4 dt=1e-3 over 10 s = 10000 steps/instance, one kernel launch per step",
+            "instances_per_gpu": n, "n_steps": N_STEPS, "dt": DT, "fp_mode": "contract",
+            "l2": "inputs larger than L2 (9 arrays x %d MiB per step)" % (n * 8 >> 20),
+            "parallelism": "ensemble sharded over %d GPU(s), no data-path collective" % world}
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -136,9 +145,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "double pendulum ensemble, RK4 dt=1e-3 over 10 s (10000 steps/instance); "
-                                   "each step = a bounded sample of the 4Mi-instance batch on the host CPU",
-                       "instances_per_gpu": N_PER_GPU, "n_steps": N_STEPS, "dt": DT},
+            # the product arm's config, verbatim (the driver compares the two); what this arm actually integrates per step -- a
+            # bounded sample of that batch on the host cores -- is stated in cpu_baseline.sample
+            "config": workload_config(args.instances, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -609,11 +618,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "double pendulum ensemble (BASELINE configs[1]): m=L=1, g=9.81, theta~U(-3,3), "
-                                   "RK4 dt=1e-3 over 10 s = 10000 steps/instance, one kernel launch per step",
-                       "instances_per_gpu": n, "n_steps": N_STEPS, "dt": DT, "fp_mode": "contract",
-                       "l2": "inputs larger than L2 (9 arrays x %d MiB per step)" % (n * 8 >> 20),
-                       "parallelism": "ensemble sharded over %d GPU(s), no data-path collective" % world},
+            "config": workload_config(n, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 9 * n * 8, "d2h_bytes_per_step": 4 * n * 8,
                     "ms_per_step": ms_e2e / args.steps},
