@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
+#include <vector>
 #include "../../sopot_b200/csrc/dpend_step.cuh"
 
 struct StepK { double dt, hdt, dt6, hdt2, rot3, rot5, cot4, dt2_6; };     // = StepConsts of csrc/ensemble.cuh
@@ -118,7 +120,45 @@ static void check_rotations(long n) {
     if (!(worst_half <= 1.0 && worst_full <= 1.0)) std::exit(1);
 }
 
+// integrate: dpend_step_host integrate <in.bin> <out.bin> <n> <steps> <dt> <store_every>
+// in.bin = 9 arrays of n doubles (m1, m2, L1, L2, g, th1, th2, w1, w2), out.bin = [snapshot][4][n] -- the kernel's loop
+// (load, refresh every 16th step, snapshots) on the host, for the full-horizon comparison with the oracle in tests/test_oracle.py
+static int integrate(int argc, char** argv) {
+    if (argc < 8) return 2;
+    const long n = std::atol(argv[4]), steps = std::atol(argv[5]), every = std::atol(argv[7]);
+    const double dt = std::atof(argv[6]);
+    std::FILE* f = std::fopen(argv[2], "rb");
+    if (!f) return 2;
+    std::vector<double> in(9 * n);
+    if (std::fread(in.data(), 8, in.size(), f) != in.size()) return 2;
+    std::fclose(f);
+    const long snaps = every ? steps / every : 0;
+    std::vector<double> out((snaps + 1) * 4 * n);
+    const StepK k = make_k(dt);
+    for (long i = 0; i < n; ++i) {
+        const double m1 = in[i], m2 = in[n + i], L1 = in[2 * n + i], L2 = in[3 * n + i], g = in[4 * n + i];
+        double y[4] = {in[5 * n + i], in[6 * n + i], in[7 * n + i], in[8 * n + i]};
+        sbdp::Scales q;
+        q.lam = L1 / L2;
+        q.kol = ((m2 * L2) / ((m1 + m2) * L1)) / q.lam;
+        q.gL1 = g / L1;
+        sbdp::Pairs b;
+        sbdp::pairs_of<false>(q, y[0], y[0] - y[1], b);
+        long snap = 0;
+        for (long s = 0; s < steps; ++s) {
+            sbdp::step(q, b, y, k, ((s + 1) & 15) == 0);
+            if (every && (s + 1) % every == 0) { for (int d = 0; d < 4; ++d) out[(snap * 4 + d) * n + i] = y[d]; ++snap; }
+        }
+        for (int d = 0; d < 4; ++d) out[(snaps * 4 + d) * n + i] = y[d];
+    }
+    f = std::fopen(argv[3], "wb");
+    if (!f || std::fwrite(out.data(), 8, out.size(), f) != out.size()) return 2;
+    std::fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "integrate") return integrate(argc, argv);
     const int scale = argc > 1 ? std::atoi(argv[1]) : 1;
     check_rotations(400000L * scale);
     // tolerance: 1e-12 relative per step is the mode's promise; the step is expected (and required here) to stay within a few ulp

@@ -192,6 +192,38 @@ def test_dpend_fast_step_on_host(tmp_path):
     assert r.stdout.count(" ok") == 9, r.stdout
 
 
+def test_dpend_fast_step_full_horizon_shadow_twin_on_host(tmp_path, port):
+    """The timed configuration without a GPU: the kernel's own step (csrc/dpend_step.cuh compiled for the host, the loop of
+    rk4_ensemble_kernel: load, refresh every 16th step, snapshots) over all 10 000 steps of the first 256 instances of
+    bench.py's inputs, against the oracle by the rule of SURVEY.md section 8c -- error <= C * (separation of the oracle's run
+    from its own run with theta1 nudged by one ulp) + 1e-9 at every stored second, <= 1e-9 outright at t = 1 s, C = 2 as in
+    tests/test_gpu_parity.py::test_dpend_bench_inputs_full_horizon_shadow_twin (observed here: max (err - 1e-9) / twin = 0.09,
+    5.2e-15 at t = 1 s -- the figure bench.py's parity_check reports from the GPU)."""
+    import subprocess
+    from sopot_b200 import workloads as W
+    exe = tmp_path / "dpend_step_host"
+    src = os.path.join(ROOT, "tests", "cpp", "dpend_step_host.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", src, "-o", str(exe)], check=True)
+    n = 256
+    w = W.dpend_ensemble(1 << 22, seed=2)
+    args = [np.ascontiguousarray(w[k][:n]) for k in ("m1", "m2", "L1", "L2", "g", "th1", "th2", "w1", "w2")]
+    _, ref, _ = port.dpend_rk4(*args, 0.0, 10.0, 1e-3, store_every=1000, n_snap=10, nthreads=4)
+    nudged = list(args)
+    nudged[5] = np.nextafter(args[5], np.inf)
+    _, ref_twin, _ = port.dpend_rk4(*nudged, 0.0, 10.0, 1e-3, store_every=1000, n_snap=10, nthreads=4)
+    np.concatenate(args).tofile(tmp_path / "in.bin")
+    subprocess.run([str(exe), "integrate", str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(n), "10000", "1e-3", "1000"], check=True)
+    out = np.fromfile(tmp_path / "out.bin").reshape(11, 4, n)
+    assert np.array_equal(out[9], out[10])                       # last snapshot == final state
+
+    def rel(a, b):
+        return np.max(np.abs(a - b), axis=1) / np.maximum(np.max(np.abs(b), axis=1), 1e-300)
+
+    twin, err = rel(ref_twin, ref), rel(out[:10], ref)
+    assert err[0].max() <= 1e-9, err[0].max()
+    assert np.all(err <= 2.0 * twin + 1e-9), (np.maximum(err - 1e-9, 0.0) / np.maximum(twin, 1e-300)).max()
+
+
 def test_golden_lqr_and_closed_loop(port):
     """Section 8f-1: the C restatement of LQR<4,1>::solve and of the sampled-data closed loop against the reference's
     own classes (golden vectors from oracle/ref_harness.cpp): gains, Riccati solutions, status codes incl. the
